@@ -1,0 +1,103 @@
+"""ctypes loader for libpacknet_b200.so (the C-ABI in include/packnet_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, the op raises."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpacknet_b200.so")
+PN_MAX_SCALES = 4
+PN_MAX_CONTEXT = 4
+
+_lock = threading.Lock()
+_lib = None
+
+
+class LossDesc(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("num_context", ctypes.c_int32), ("num_scales", ctypes.c_int32),
+        ("scale_h", ctypes.c_int32 * PN_MAX_SCALES), ("scale_w", ctypes.c_int32 * PN_MAX_SCALES),
+        ("ssim_loss_weight", ctypes.c_float), ("smooth_loss_weight", ctypes.c_float),
+        ("C1", ctypes.c_float), ("C2", ctypes.c_float),
+        ("reduce_min", ctypes.c_int32), ("automask", ctypes.c_int32),
+    ]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32),
+        ("precision", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
+def _declare(lib):
+    c = ctypes
+    vp, sz, fp = c.c_void_p, c.c_size_t, c.c_void_p
+    lib.pn_version.restype = c.c_int
+    lib.pn_last_error_string.restype = c.c_char_p
+    lib.pn_launch_count.restype = c.c_uint64
+    lib.pn_loss_workspace_bytes.argtypes = [c.POINTER(LossDesc), c.POINTER(sz)]
+    lib.pn_loss_forward.argtypes = [c.POINTER(LossDesc), fp, c.POINTER(vp), c.POINTER(vp), fp, fp, c.POINTER(vp), fp,
+                                    vp, sz, vp]
+    lib.pn_loss_backward.argtypes = [c.POINTER(LossDesc), fp, c.POINTER(vp), c.POINTER(vp), fp, fp, c.POINTER(vp), fp,
+                                     c.POINTER(vp), c.POINTER(vp), vp, sz, vp]
+    lib.pn_loss_warp_indices.argtypes = [c.POINTER(LossDesc), c.c_int, fp, fp, fp, fp, vp, vp, vp, sz, vp]
+    lib.pn_resize_bilinear_ac.argtypes = [fp, fp, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, vp]
+    for name in ("pn_loss_workspace_bytes", "pn_loss_forward", "pn_loss_backward", "pn_loss_warp_indices",
+                 "pn_resize_bilinear_ac"):
+        getattr(lib, name).restype = c.c_int
+    return lib
+
+
+def lib():
+    """The loaded library; raises RuntimeError (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "libpacknet_b200.so is not built (%s). Run `python -m packnet_sfm_b200.build` "
+                        "or __graft_entry__.build(); there is no CPU/PyTorch fallback." % LIB_PATH)
+                loaded = ctypes.CDLL(LIB_PATH)
+                _declare(loaded)
+                from . import _lib_conv
+                _lib_conv.declare(loaded)
+                _lib = loaded
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().pn_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(lib().pn_launch_count())
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("packnet_sfm_b200 ops run on CUDA tensors only (got %s); there is no CPU path"
+                               % t.device)

@@ -1,0 +1,39 @@
+// common.cuh -- shared host/device helpers of libpacknet_b200 (error reporting, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "packnet_b200.h"
+
+namespace pn {
+
+// thread-local last-error text behind pn_last_error_string()
+void set_error(const char* fmt, ...);
+// cudaGetLastError() -> return code (0 ok, >0 cudaError_t) with the error text recorded
+int check_launch(const char* what);
+// launch accounting behind pn_launch_count()
+void count_launch(int n = 1);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#define PN_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::pn::set_error(__VA_ARGS__);      \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define PN_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::pn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                  \
+    }                                                                                  \
+  } while (0)
+
+}  // namespace pn
