@@ -105,6 +105,88 @@ int pn_loss_warp_indices(const pn_loss_desc* desc, int scale, const float* inv_d
 int pn_resize_bilinear_ac(const float* src, float* dst, int batch, int channels, int h_in, int w_in,
                           int h_out, int w_out, pn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stride-1 "same" 2-D convolution on the tcgen05 tensor cores (implicit GEMM, NHWC activations)
+ *   replaces nn.Conv2d inside Conv2D / ResidualConv / PackLayerConv3d / UnpackLayerConv3d:
+ *     packnet_sfm/networks/layers/packnet/layers01.py:28-30,36 (ConstantPad2d + Conv2d), :58-60,:69-71,
+ *     :234 (pack conv on the 8x-inflated channel count), :272 (unpack conv) and their autograd backward.
+ * ------------------------------------------------------------------------------------------------ */
+enum { PN_PRECISION_TF32X1 = 1, PN_PRECISION_TF32X3 = 3 };
+enum { PN_CONV_MODE_AUTO = 0, PN_CONV_MODE_PER_TAP = 1, PN_CONV_MODE_HALO = 2 };
+
+typedef struct {
+  int32_t batch, height, width; /* input and output spatial size (stride 1, zero padding ksize/2) */
+  int32_t cin, cout;            /* multiples of 4 */
+  int32_t ksize;                /* 1, 3, 5 or 7 */
+  int32_t precision;            /* PN_PRECISION_* */
+  int32_t mode;                 /* PN_CONV_MODE_*: how the activation operand is staged (AUTO picks) */
+  int32_t debug_flags;          /* bit0: force base_offset=0 in shifted descriptors (bring-up tests) */
+} pn_conv_desc;
+
+/* y[B,H,W,Cout] = conv(x[B,H,W,Cin], w) + bias.  w_packed comes from pn_conv2d_pack_weight.
+ * x_lo / w_packed_lo (tf32 residuals, pn_tf32_residual / pack_weight) are required for TF32X3 and
+ * ignored for TF32X1.  error_flag: optional device word set to 0xDEADxxxx if a pipeline wait times out
+ * (the kernel traps instead of hanging). */
+int pn_conv2d_forward(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* w_packed,
+                      const float* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
+                      pn_stream_t stream);
+
+/* Weight packing: OIHW [Cout,Cin,k,k] (nn.Conv2d.weight) -> [Cout][k*k][ceil32(Cin)] (transposed=0, fprop)
+ * or -> [Cin][k*k flipped][ceil32(Cout)] (transposed=1: the operand of the data-gradient convolution).
+ * w_packed_lo may be NULL. */
+int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, size_t* elems);
+int pn_conv2d_pack_weight(const float* w_oihw, float* w_packed, float* w_packed_lo, int cout, int cin,
+                          int ksize, int transposed, pn_stream_t stream);
+
+/* Weight gradient (autograd backward of nn.Conv2d w.r.t. weight).  The reduction runs over pixels, so the
+ * operands are the NCHW (pixel-contiguous) copies: x_nchw [B,Cin,H,W], g_nchw [B,Cout,H,W] (+ tf32 residuals
+ * for TF32X3).  dw_packed [Cout][k*k][ceil32(Cin)] is zeroed and accumulated; pn_conv2d_unpack_weight_grad
+ * converts it to OIHW.  desc->width must be a multiple of 4. */
+int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x_nchw, const float* x_nchw_lo, const float* g_nchw,
+                    const float* g_nchw_lo, float* dw_packed, uint32_t* error_flag, pn_stream_t stream);
+int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize,
+                                 pn_stream_t stream);
+
+/* lo[i] = x[i] - trunc_tf32(x[i]) (the bits a tf32 tensor-core operand read drops); n % 4 == 0. */
+int pn_tf32_residual(const float* x, float* lo, size_t n, pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pack / unpack feature stencil: Conv3d(1->8, 3x3x3, pad 1) fused with space-to-depth (pack) or
+ * depth-to-space (unpack).  NHWC.
+ *   pack   (pack=1): in x[B,2h,2w,C]  -> out[B,h,w,8*4C] at channel f*4C + (4c+2i+j)
+ *          replaces packing() + unsqueeze + conv3d + view, layers01.py:126-148,:241-245
+ *   unpack (pack=0): in u[B,h,w,C]    -> out[B,2h,2w,2C], out[2y+i][2x+j][v/4] with v = f*C + c, i=(v%4)/2, j=v%2
+ *          replaces unsqueeze + conv3d + view + PixelShuffle(2), layers01.py:281-285
+ * The destination may be a wider buffer (out_cstride channels per pixel, first channel out_coffset): the
+ * decoder's torch.cat (PackNet01.py:138-175) becomes a pointer offset.  out_lo (optional) receives the tf32
+ * residual of every value written.  w3 = conv3d.weight [8,1,3,3,3] flattened, b3 = conv3d.bias [8].
+ * ------------------------------------------------------------------------------------------------ */
+int pn_feature_stencil_forward(int pack, const float* in, const float* w3, const float* b3, float* out,
+                               float* out_lo, int batch, int h_low, int w_low, int channels, int out_cstride,
+                               int out_coffset, pn_stream_t stream);
+/* g: gradient in the forward OUTPUT layout (g_cstride/g_coffset as above); gin: gradient in the forward INPUT
+ * layout (overwritten); gw3 [216], gb3 [8] (overwritten). */
+int pn_feature_stencil_backward(int pack, const float* in, const float* g, const float* w3, float* gin,
+                                float* gw3, float* gb3, int batch, int h_low, int w_low, int channels,
+                                int g_cstride, int g_coffset, pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm(16, eps) + ELU on NHWC maps (layers01.py:31-32,37; with x2 != NULL the input is x + x2, the
+ * residual sum of layers01.py:72).  stats: [B,16,2] doubles (sum, sum of squares), written by the forward
+ * and read by the backward.  The output may again be a channel window of a wider buffer.
+ * backward scratch `bc`: 2*C*B doubles followed by 2*16*B floats.
+ * ------------------------------------------------------------------------------------------------ */
+int pn_groupnorm_elu_forward(const float* x, const float* x2, const float* gamma, const float* beta, float eps,
+                             float* y, float* y_lo, double* stats, int batch, int hw, int channels,
+                             int out_cstride, int out_coffset, pn_stream_t stream);
+int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, const float* dy,
+                              const float* gamma, float eps, const double* stats, double* bc, float* dx,
+                              float* dx_lo, float* dgamma, float* dbeta, int batch, int hw, int channels,
+                              int y_cstride, int y_coffset, int dy_cstride, int dy_coffset, pn_stream_t stream);
+
+/* out[c] = sum over pixels of g[pixel][c] (conv bias gradient), g dense [pixels, channels]. */
+int pn_channel_sum(const float* g, float* out, size_t pixels, int channels, pn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,14 @@ def install():
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.cm"] = cm
 
+    if "termcolor" not in sys.modules:
+        try:
+            import termcolor  # noqa: F401
+        except Exception:
+            tc = types.ModuleType("termcolor")
+            tc.colored = lambda text, *a, **k: text
+            sys.modules["termcolor"] = tc
+
     if not getattr(torch.Tensor.get_device, "_pn_shim", False):
         _orig = torch.Tensor.get_device
 

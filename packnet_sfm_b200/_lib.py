@@ -25,12 +25,6 @@ class LossDesc(ctypes.Structure):
     ]
 
 
-class ConvDesc(ctypes.Structure):
-    _fields_ = [
-        ("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
-        ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32),
-        ("precision", ctypes.c_int32), ("reserved", ctypes.c_int32),
-    ]
 
 
 def _declare(lib):

@@ -1,5 +1,39 @@
-"""ctypes declarations for the convolution / layer entry points (filled in as they land)."""
+"""ctypes declarations for the convolution / layer entry points of include/packnet_b200.h."""
+import ctypes
+
+PRECISION_TF32X1 = 1
+PRECISION_TF32X3 = 3
+MODE_AUTO, MODE_PER_TAP, MODE_HALO = 0, 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("ksize", ctypes.c_int32),
+        ("precision", ctypes.c_int32), ("mode", ctypes.c_int32), ("debug_flags", ctypes.c_int32),
+    ]
 
 
 def declare(lib):
+    c = ctypes
+    vp, sz = c.c_void_p, c.c_size_t
+    lib.pn_conv2d_forward.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pn_conv2d_packed_weight_elems.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(sz)]
+    lib.pn_conv2d_pack_weight.argtypes = [vp, vp, vp, c.c_int, c.c_int, c.c_int, c.c_int, vp]
+    lib.pn_tf32_residual.argtypes = [vp, vp, sz, vp]
+    i, f = c.c_int, c.c_float
+    lib.pn_feature_stencil_forward.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.pn_feature_stencil_backward.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.pn_groupnorm_elu_forward.argtypes = [vp, vp, vp, vp, f, vp, vp, vp, i, i, i, i, i, vp]
+    lib.pn_groupnorm_elu_backward.argtypes = [vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.pn_channel_sum.argtypes = [vp, vp, sz, i, vp]
+    for name in ("pn_feature_stencil_forward", "pn_feature_stencil_backward", "pn_groupnorm_elu_forward",
+                 "pn_groupnorm_elu_backward", "pn_channel_sum"):
+        getattr(lib, name).restype = c.c_int
+    lib.pn_conv2d_wgrad.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]
+    lib.pn_conv2d_unpack_weight_grad.argtypes = [vp, vp, i, i, i, vp]
+    lib.pn_conv2d_wgrad.restype = c.c_int
+    lib.pn_conv2d_unpack_weight_grad.restype = c.c_int
+    for name in ("pn_conv2d_forward", "pn_conv2d_packed_weight_elems", "pn_conv2d_pack_weight", "pn_tf32_residual"):
+        getattr(lib, name).restype = c.c_int
     return lib

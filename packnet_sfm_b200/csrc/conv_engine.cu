@@ -1,0 +1,756 @@
+// conv_engine.cu -- stride-1 "same" 2-D convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+//   D[pixel, co] = sum_{tap, ci} X[pixel + tap, ci] * W[co, tap, ci]       (+ bias)
+//
+// * activations are NHWC fp32 (== torch.channels_last storage): an M-tile is an 8-wide x 16-tall (x nb
+//   images) patch of 128 output pixels, a K-chunk is 32 input channels = one 128-byte row per pixel, so a
+//   4-D TMA box IS the canonical K-major SWIZZLE_128B operand tile; the zero padding of the convolution
+//   (layers01.py:30 ConstantPad2d) is the TMA out-of-bounds fill -- no im2col, no padded copy.
+// * weights are pre-packed [Cout][tap][Cin] (K-major); one 3-D TMA box per (tap, K-chunk).
+// * tcgen05.mma kind::tf32, M=128, N=BN, accumulators in TMEM, issued by one thread; a TMA producer
+//   thread and four epilogue warps (tcgen05.ld -> +bias -> NHWC stores) run concurrently, linked by
+//   mbarriers (tcgen05.commit frees the shared-memory stages).
+// * HALO mode: the (16+k-1) x 16 pixel input patch of a tile is loaded ONCE per K-chunk and every tap
+//   reads it through a shifted shared-memory descriptor (start address + base_offset), cutting the
+//   activation traffic by ~k^2; PER-TAP mode reloads a shifted 8x16 box per tap (always 1024-B aligned).
+// * precision: tf32x1 (one MMA per product; what cuDNN does for the reference on Ampere+ GPUs) or
+//   tf32x3 (error-compensated: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with lo = x - trunc_tf32(x); fp32-grade
+//   results, needed for the 1e-3 depth parity bar -- DESIGN.md "precision").
+//
+// Reference call sites replaced: nn.Conv2d inside Conv2D / ResidualConv / PackLayerConv3d /
+// UnpackLayerConv3d (packnet_sfm/networks/layers/packnet/layers01.py:28-29,36,58-72,234,272) and their
+// autograd backward (dgrad = the same kernel on flipped/transposed weights).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace pn {
+namespace conv {
+
+constexpr int TILE_W = 8;        // pixels per tile row (one 8-row swizzle atom)
+constexpr int TILE_ROWS = 16;    // tile rows x images
+constexpr int KC = 32;           // K elements (fp32) per chunk = 128 bytes
+constexpr int PATCH_PITCH = 16;  // pixels per row of the HALO patch (2048 B: keeps 8-row groups 1024-B aligned)
+constexpr int NTHREADS = 192;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int MAX_STAGES = 8;
+
+struct KernelParams {
+  int B, H, W, Cin, Cout, ks, pad;
+  int th, nb;              // tile rows per image, images per tile (th * nb == 16)
+  int tiles_x, tiles_y;    // tiles per image group
+  int bn;                  // N tile (output channels per CTA)
+  int nsplit;              // 1: tf32x1, 3: tf32x3
+  int halo;                // 1: patch reuse across taps
+  int cchunks;             // ceil(Cin / 32)
+  int stages;
+  int force_base_offset0;  // debug knob for the descriptor bring-up tests
+  uint32_t a_stage_bytes, b_stage_bytes, patch_bytes;
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  const float* bias;
+  float* out;
+  unsigned int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must not hang the GPU box -- flag the error and trap instead
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* error_flag, int who) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      if (error_flag) atomicExch(error_flag, 0xDEAD0000u | (unsigned)who);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1) | [32,46) SBO>>4 | [46,48) version=1
+//   [49,52) base_offset | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                  const KernelParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
+  const int nops = (P.nsplit == 3) ? 2 : 1;
+  // carve: [HALO patches: 2 buffers x nops] [stages: (A x nops when per-tap) + (B x nops)] [barriers]
+  const uint32_t patch_region = P.halo ? 2u * nops * P.patch_bytes : 0u;
+  const uint32_t stage_bytes = (P.halo ? 0u : nops * P.a_stage_bytes) + nops * P.b_stage_bytes;
+  const uint32_t stages_base = smem_base + patch_region;
+  const uint32_t bars_base = stages_base + P.stages * stage_bytes;
+  // barriers: full[stages], empty[stages], full_a[2], empty_a[2], tmem_full ; then the TMEM address word
+  auto full_bar = [&](int s) { return bars_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bars_base + 8u * (MAX_STAGES + s); };
+  auto fulla_bar = [&](int s) { return bars_base + 8u * (2 * MAX_STAGES + s); };
+  auto emptya_bar = [&](int s) { return bars_base + 8u * (2 * MAX_STAGES + 2 + s); };
+  const uint32_t tmemfull_bar = bars_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t tmem_slot = bars_base + 8u * (2 * MAX_STAGES + 5);
+  auto patch_addr = [&](int buf, int op) { return smem_base + (uint32_t)(buf * nops + op) * P.patch_bytes; };
+  auto stage_a = [&](int s, int op) { return stages_base + s * stage_bytes + op * P.a_stage_bytes; };
+  auto stage_b = [&](int s, int op) {
+    return stages_base + s * stage_bytes + (P.halo ? 0u : nops * P.a_stage_bytes) + op * P.b_stage_bytes;
+  };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int m = blockIdx.x;
+  const int tx = m % P.tiles_x, ty = (m / P.tiles_x) % P.tiles_y, bg = m / (P.tiles_x * P.tiles_y);
+  const int x0 = tx * TILE_W, y0 = ty * P.th, b0 = bg * P.nb;
+  const int n0 = blockIdx.y * P.bn;
+  const int taps = P.ks * P.ks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 1); }
+    mbar_init(tmemfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================================== TMA producer ============================================
+    if (lane == 0) {
+      int s = 0, ph = 0, pa = 0, pha = 0;
+      for (int cc = 0; cc < P.cchunks; ++cc) {
+        if (P.halo) {
+          mbar_wait(emptya_bar(pa), pha ^ 1, P.error_flag, 1);
+          mbar_expect_tx(fulla_bar(pa), P.patch_bytes * nops);
+          tma_load_4d(patch_addr(pa, 0), &tmA, fulla_bar(pa), cc * KC, x0 - P.pad, y0 - P.pad, b0);
+          if (nops == 2) tma_load_4d(patch_addr(pa, 1), &tmAlo, fulla_bar(pa), cc * KC, x0 - P.pad, y0 - P.pad, b0);
+          pa ^= 1;
+          if (pa == 0) pha ^= 1;
+        }
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 2);
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          if (!P.halo) {
+            const int dy = tap / P.ks, dx = tap % P.ks;
+            tma_load_4d(stage_a(s, 0), &tmA, full_bar(s), cc * KC, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+            if (nops == 2) tma_load_4d(stage_a(s, 1), &tmAlo, full_bar(s), cc * KC, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+          }
+          tma_load_3d(stage_b(s, 0), &tmB, full_bar(s), cc * KC, tap, n0);
+          if (nops == 2) tma_load_3d(stage_b(s, 1), &tmBlo, full_bar(s), cc * KC, tap, n0);
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ==============================================
+    if (lane == 0) {
+      int s = 0, ph = 0, pa = 0, pha = 0;
+      uint32_t acc = 0;
+      for (int cc = 0; cc < P.cchunks; ++cc) {
+        if (P.halo) {
+          mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
+          tc_fence_after();
+        }
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(full_bar(s), ph, P.error_flag, 4);
+          tc_fence_after();
+          uint32_t a_hi, a_lo, sbo, boff;
+          if (P.halo) {
+            const int dy = tap / P.ks, dx = tap % P.ks;
+            const uint32_t shift = (uint32_t)(dy * PATCH_PITCH + dx) * 128u;
+            a_hi = patch_addr(pa, 0) + shift;
+            a_lo = patch_addr(pa, 1) + shift;
+            sbo = PATCH_PITCH * 128u;
+            boff = P.force_base_offset0 ? 0u : ((a_hi >> 7) & 7u);
+          } else {
+            a_hi = stage_a(s, 0);
+            a_lo = stage_a(s, 1);
+            sbo = 1024u;
+            boff = 0u;
+          }
+          const uint32_t b_hi = stage_b(s, 0), b_lo = stage_b(s, 1);
+#pragma unroll
+          for (int k = 0; k < KC / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+            const uint64_t da = make_smem_desc(a_hi + k * 32u, sbo, boff);
+            const uint64_t db = make_smem_desc(b_hi + k * 32u, 1024u, 0u);
+            if (nops == 2) {
+              const uint64_t dal = make_smem_desc(a_lo + k * 32u, sbo, boff);
+              const uint64_t dbl = make_smem_desc(b_lo + k * 32u, 1024u, 0u);
+              umma_tf32(tmem_base, dal, db, P.idesc, acc);   // small terms first
+              umma_tf32(tmem_base, da, dbl, P.idesc, 1u);
+              umma_tf32(tmem_base, da, db, P.idesc, 1u);
+            } else {
+              umma_tf32(tmem_base, da, db, P.idesc, acc);
+            }
+            acc = 1u;
+          }
+          umma_commit(empty_bar(s));  // frees this stage when the MMAs above have read it
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+        if (P.halo) {
+          umma_commit(emptya_bar(pa));
+          pa ^= 1;
+          if (pa == 0) pha ^= 1;
+        }
+      }
+      umma_commit(tmemfull_bar);
+    }
+  } else {
+    // ===================================== epilogue ================================================
+    mbar_wait(tmemfull_bar, 0, P.error_flag, 5);
+    tc_fence_after();
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;     // tile row == TMEM lane
+    const int i = row & 7, g = row >> 3;
+    const int x = x0 + i, y = y0 + (g % P.th), n = b0 + (g / P.th);
+    const bool valid = (x < P.W) && (y < P.H) && (n < P.B);
+    float* orow = P.out + (((size_t)n * P.H + y) * P.W + x) * P.Cout + n0;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < P.bn; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int co = n0 + c0 + j;
+          if (co < P.Cout) {
+            float4 o;
+            o.x = __uint_as_float(v[j + 0]); o.y = __uint_as_float(v[j + 1]);
+            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+            if (P.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + co));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight gradient:  dW[co, tap, ci] = sum_{b,y,x} dZ[b,y,x,co] * X[b, y+dy-p, x+dx-p, ci]
+//   The reduction runs over pixels, so the K-major operands are the NCHW (pixel-contiguous) copies:
+//   A = X^T  : rows = 128 input channels, K-chunk = 32 consecutive x positions of one image row, shifted by
+//              the tap (TMA zero-fills the padding),  B = dZ^T : rows = BN output channels, same pixels.
+//   One CTA owns (128-channel block, group of TG taps, BN block, K split) and keeps TG accumulators in TMEM;
+//   the dZ tile of a K-chunk is loaded once and reused by the TG taps.  Partial sums of the K splits are
+//   combined with red.global.add.f32 into the zero-initialised packed gradient [Cout][tap][ceil32(Cin)].
+// ---------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int B, H, W, Cin, Cout, ks, pad;
+  int kpad;              // ceil32(Cin): row pitch of the packed gradient
+  int bn, tg;            // N tile, taps per CTA
+  int tap_groups;
+  int xchunks;           // ceil(W / 32)
+  int kiters;            // B * H * xchunks
+  int ksplits;
+  int nsplit, stages;
+  uint32_t tmem_cols, idesc;
+  float* dwp;            // [Cout][taps][kpad]
+  unsigned int* error_flag;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmGlo, const WgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nops = (P.nsplit == 3) ? 2 : 1;
+  const uint32_t a_bytes = 128u * 128u, b_bytes = (uint32_t)P.bn * 128u;
+  const uint32_t stage_bytes = nops * (b_bytes + (uint32_t)P.tg * a_bytes);
+  const uint32_t bars_base = smem_base + P.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bars_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bars_base + 8u * (MAX_STAGES + s); };
+  const uint32_t tmemfull_bar = bars_base + 8u * (2 * MAX_STAGES);
+  const uint32_t tmem_slot = bars_base + 8u * (2 * MAX_STAGES + 1);
+  auto stage_b = [&](int s, int op) { return smem_base + s * stage_bytes + op * b_bytes; };
+  auto stage_a = [&](int s, int t, int op) { return smem_base + s * stage_bytes + nops * b_bytes + (uint32_t)(t * nops + op) * a_bytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci0 = blockIdx.x * 128;
+  const int tgi = blockIdx.y % P.tap_groups, nblk = blockIdx.y / P.tap_groups;
+  const int n0 = nblk * P.bn;
+  const int tap0 = tgi * P.tg;
+  const int taps = P.ks * P.ks;
+  const int ntap = min(P.tg, taps - tap0);
+  const int split = blockIdx.z;
+  const int per = (P.kiters + P.ksplits - 1) / P.ksplits;
+  const int k_begin = split * per, k_end = min(P.kiters, k_begin + per);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmemfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const bool has_work = k_end > k_begin;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      int s = 0, ph = 0;
+      for (int kit = k_begin; kit < k_end; ++kit) {
+        const int xc = kit % P.xchunks, y = (kit / P.xchunks) % P.H, b = kit / (P.xchunks * P.H);
+        mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 6);
+        mbar_expect_tx(full_bar(s), nops * (b_bytes + (uint32_t)ntap * a_bytes));
+        tma_load_4d(stage_b(s, 0), &tmG, full_bar(s), xc * KC, y, n0, b);
+        if (nops == 2) tma_load_4d(stage_b(s, 1), &tmGlo, full_bar(s), xc * KC, y, n0, b);
+        for (int t = 0; t < ntap; ++t) {
+          const int tap = tap0 + t, dy = tap / P.ks, dx = tap % P.ks;
+          tma_load_4d(stage_a(s, t, 0), &tmX, full_bar(s), xc * KC + dx - P.pad, y + dy - P.pad, ci0, b);
+          if (nops == 2) tma_load_4d(stage_a(s, t, 1), &tmXlo, full_bar(s), xc * KC + dx - P.pad, y + dy - P.pad, ci0, b);
+        }
+        if (++s == P.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      int s = 0, ph = 0;
+      uint32_t acc = 0;
+      for (int kit = k_begin; kit < k_end; ++kit) {
+        mbar_wait(full_bar(s), ph, P.error_flag, 7);
+        tc_fence_after();
+        for (int t = 0; t < ntap; ++t) {
+          const uint32_t d_t = tmem_base + (uint32_t)(t * P.bn);
+#pragma unroll
+          for (int k = 0; k < KC / 8; ++k) {
+            const uint64_t da = make_smem_desc(stage_a(s, t, 0) + k * 32u, 1024u, 0u);
+            const uint64_t db = make_smem_desc(stage_b(s, 0) + k * 32u, 1024u, 0u);
+            if (nops == 2) {
+              const uint64_t dal = make_smem_desc(stage_a(s, t, 1) + k * 32u, 1024u, 0u);
+              const uint64_t dbl = make_smem_desc(stage_b(s, 1) + k * 32u, 1024u, 0u);
+              umma_tf32(d_t, dal, db, P.idesc, (k == 0) ? acc : 1u);
+              umma_tf32(d_t, da, dbl, P.idesc, 1u);
+              umma_tf32(d_t, da, db, P.idesc, 1u);
+            } else {
+              umma_tf32(d_t, da, db, P.idesc, (k == 0) ? acc : 1u);
+            }
+          }
+        }
+        acc = 1u;
+        umma_commit(empty_bar(s));
+        if (++s == P.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tmemfull_bar);
+    }
+  } else if (has_work) {
+    mbar_wait(tmemfull_bar, 0, P.error_flag, 8);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int ci = ci0 + q * 32 + lane;
+    const bool valid = ci < P.kpad;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int t = 0; t < ntap; ++t) {
+      const int tap = tap0 + t;
+      for (int c0 = 0; c0 < P.bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)(t * P.bn + c0), v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = n0 + c0 + j;
+            if (co < P.Cout) atomicAdd(P.dwp + ((size_t)co * taps + tap) * P.kpad + ci, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// packed gradient [Cout][tap][kpad] -> OIHW [Cout][Cin][k][k]
+__global__ void unpack_weight_grad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int taps, int kpad) {
+  const size_t total = (size_t)Cout * Cin * taps;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(idx % taps);
+    const int ci = (int)((idx / taps) % Cin);
+    const int co = (int)(idx / ((size_t)taps * Cin));
+    dw[idx] = dwp[((size_t)co * taps + tap) * kpad + ci];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// operand preparation kernels
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// lo = x - trunc_tf32(x): the part of x a tf32 tensor-core operand read drops
+__global__ void tf32_residual_kernel(const float4* __restrict__ x, float4* __restrict__ lo, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    float4 r;
+    r.x = v.x - tf32_trunc(v.x); r.y = v.y - tf32_trunc(v.y); r.z = v.z - tf32_trunc(v.z); r.w = v.w - tf32_trunc(v.w);
+    lo[i] = r;
+  }
+}
+
+// OIHW [Cout][Cin][k][k] -> [Cout][tap][Cin_pad] (+ residual);  transposed: dgrad weights
+//   [Cin][tap'][Cout_pad] with tap' = (k-1-dy, k-1-dx)  (correlation with the flipped kernel)
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wp_lo, int Cout,
+                                   int Cin, int ks, int kpad, int transposed) {
+  const int taps = ks * ks;
+  const int rows = transposed ? Cin : Cout;
+  const size_t total = (size_t)rows * taps * kpad;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % kpad);
+    const int tap = (int)((idx / kpad) % taps);
+    const int r = (int)(idx / ((size_t)kpad * taps));
+    float v = 0.0f;
+    if (!transposed) {
+      if (k < Cin) v = w[((size_t)r * Cin + k) * taps + tap];
+    } else {
+      if (k < Cout) v = w[((size_t)k * Cin + r) * taps + (taps - 1 - tap)];
+    }
+    wp[idx] = v;
+    if (wp_lo) wp_lo[idx] = v - tf32_trunc(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  PN_REQUIRE(fn != nullptr, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_BAD_ARGUMENT, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return PN_OK;
+}
+
+static uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while ((int)c < n) c <<= 1;
+  return c;
+}
+
+int kpad_of(int c) { return (c + KC - 1) / KC * KC; }
+
+// x [B,H,W,Cin] NHWC, wp [Cout][k*k][kpad(Cin)] -> y [B,H,W,Cout]
+static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo, const float* wp, const float* wp_lo,
+                        const float* bias, float* y, unsigned int* error_flag, cudaStream_t stream) {
+  PN_REQUIRE(d && x && wp && y, PN_ERR_BAD_ARGUMENT, "pn_conv2d: null argument");
+  PN_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0 && d->cin > 0 && d->cout > 0, PN_ERR_BAD_ARGUMENT,
+             "pn_conv2d: bad shape");
+  PN_REQUIRE(d->ksize >= 1 && d->ksize <= 7 && (d->ksize & 1), PN_ERR_UNSUPPORTED, "pn_conv2d: ksize %d (odd, <= 7)", d->ksize);
+  PN_REQUIRE(d->cin % 4 == 0 && d->cout % 4 == 0, PN_ERR_UNSUPPORTED, "pn_conv2d: Cin (%d) and Cout (%d) must be multiples of 4",
+             d->cin, d->cout);
+  PN_REQUIRE(d->precision == PN_PRECISION_TF32X1 || d->precision == PN_PRECISION_TF32X3, PN_ERR_BAD_ARGUMENT,
+             "pn_conv2d: precision %d", d->precision);
+  PN_REQUIRE(d->precision == PN_PRECISION_TF32X1 || (x_lo && wp_lo), PN_ERR_BAD_ARGUMENT,
+             "pn_conv2d: tf32x3 needs the residual operands x_lo and w_lo");
+  PN_REQUIRE(aligned16(x) && aligned16(wp) && aligned16(y) && (!bias || aligned16(bias)), PN_ERR_ALIGNMENT,
+             "pn_conv2d: pointers must be 16-byte aligned");
+
+  KernelParams P{};
+  P.B = d->batch; P.H = d->height; P.W = d->width; P.Cin = d->cin; P.Cout = d->cout; P.ks = d->ksize; P.pad = d->ksize / 2;
+  P.nsplit = (d->precision == PN_PRECISION_TF32X3) ? 3 : 1;
+  const int nops = (P.nsplit == 3) ? 2 : 1;
+  // tile rows: tall tiles for big maps, batch folding for small ones
+  P.th = TILE_ROWS;
+  while (P.th > 1 && P.th / 2 >= d->height) P.th /= 2;
+  P.nb = TILE_ROWS / P.th;
+  P.halo = (d->mode == PN_CONV_MODE_HALO) || (d->mode == PN_CONV_MODE_AUTO && P.nb == 1 && d->ksize > 1);
+  if (d->mode == PN_CONV_MODE_PER_TAP) P.halo = 0;
+  PN_REQUIRE(!(P.halo && P.nb != 1), PN_ERR_UNSUPPORTED, "pn_conv2d: halo mode needs maps at least 9 rows tall");
+  P.force_base_offset0 = (d->debug_flags & 1) ? 1 : 0;
+  P.tiles_x = (d->width + TILE_W - 1) / TILE_W;
+  P.tiles_y = (d->height + P.th - 1) / P.th;
+  const int bgroups = (d->batch + P.nb - 1) / P.nb;
+  // N tile: as wide as TMEM/smem allow (<= 256, multiple of 16)
+  int bn = (d->cout + 15) / 16 * 16;
+  const int bn_cap = (P.nsplit == 3) ? 128 : 256;
+  if (bn > bn_cap) bn = bn_cap;
+  P.bn = bn;
+  P.cchunks = (d->cin + KC - 1) / KC;
+  P.a_stage_bytes = TILE_W * TILE_ROWS * 128u;
+  P.b_stage_bytes = (uint32_t)bn * 128u;
+  P.patch_bytes = (uint32_t)PATCH_PITCH * (P.th + d->ksize - 1) * 128u;
+  P.tmem_cols = pow2_cols(bn);
+  P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.bias = bias; P.out = y; P.error_flag = error_flag;
+
+  const uint32_t patch_region = P.halo ? 2u * nops * P.patch_bytes : 0u;
+  const uint32_t stage_bytes = (P.halo ? 0u : nops * P.a_stage_bytes) + nops * P.b_stage_bytes;
+  const uint32_t budget = 227u * 1024u - 1024u /*alignment slack*/ - 512u /*barriers*/;
+  PN_REQUIRE(patch_region + 2 * stage_bytes <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d: tile does not fit in shared memory");
+  int stages = (int)((budget - patch_region) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  P.stages = stages;
+  const size_t smem = 1024 + patch_region + (size_t)stages * stage_bytes + 512;
+
+  // tensor maps
+  alignas(64) CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
+    const uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)d->width * d->cin * 4,
+                                 (uint64_t)d->height * d->width * d->cin * 4};
+    uint32_t box[4];
+    if (P.halo) { box[0] = KC; box[1] = PATCH_PITCH; box[2] = P.th + d->ksize - 1; box[3] = 1; }
+    else        { box[0] = KC; box[1] = TILE_W;      box[2] = P.th;                box[3] = P.nb; }
+    int rc = make_map(&tmA, x, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = make_map(&tmAlo, x_lo ? x_lo : x, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const int kp = kpad_of(d->cin), taps = d->ksize * d->ksize;
+    const uint64_t dims[3] = {(uint64_t)kp, (uint64_t)taps, (uint64_t)d->cout};
+    const uint64_t strides[2] = {(uint64_t)kp * 4, (uint64_t)kp * taps * 4};
+    const uint32_t box[3] = {KC, 1, (uint32_t)bn};
+    int rc = make_map(&tmB, wp, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_map(&tmBlo, wp_lo ? wp_lo : wp, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  PN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(P.tiles_x * P.tiles_y * bgroups, (d->cout + bn - 1) / bn);
+  conv_igemm_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmAlo, tmB, tmBlo, P);
+  count_launch();
+  return check_launch("conv_igemm_kernel");
+}
+
+// x_nchw [B,Cin,H,W], g_nchw [B,Cout,H,W] (+ tf32 residuals) -> dwp [Cout][k*k][ceil32(Cin)] (accumulated into zeros)
+static int conv_wgrad(const pn_conv_desc* d, const float* x_nchw, const float* x_lo, const float* g_nchw, const float* g_lo,
+                      float* dwp, unsigned int* error_flag, cudaStream_t stream) {
+  PN_REQUIRE(d && x_nchw && g_nchw && dwp, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
+  PN_REQUIRE(d->ksize >= 1 && d->ksize <= 7 && (d->ksize & 1), PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: ksize %d", d->ksize);
+  PN_REQUIRE(d->width % 4 == 0, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: width %d must be a multiple of 4 (TMA row pitch)", d->width);
+  PN_REQUIRE(d->precision == PN_PRECISION_TF32X1 || (x_lo && g_lo), PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: tf32x3 needs residuals");
+  PN_REQUIRE(aligned16(x_nchw) && aligned16(g_nchw) && aligned16(dwp), PN_ERR_ALIGNMENT, "pn_conv2d_wgrad: alignment");
+  WgradParams P{};
+  P.B = d->batch; P.H = d->height; P.W = d->width; P.Cin = d->cin; P.Cout = d->cout; P.ks = d->ksize; P.pad = d->ksize / 2;
+  P.kpad = kpad_of(d->cin);
+  P.nsplit = (d->precision == PN_PRECISION_TF32X3) ? 3 : 1;
+  const int nops = (P.nsplit == 3) ? 2 : 1;
+  const int taps = d->ksize * d->ksize;
+  int bn = (d->cout + 15) / 16 * 16;
+  if (bn > 128) bn = 128;
+  P.bn = bn;
+  int tg = (P.nsplit == 3) ? 2 : 4;
+  if (tg > taps) tg = taps;
+  while (tg * bn > 512) --tg;
+  P.tg = tg;
+  P.tap_groups = (taps + tg - 1) / tg;
+  P.xchunks = (d->width + KC - 1) / KC;
+  P.kiters = d->batch * d->height * P.xchunks;
+  const int mblocks = (P.kpad + 127) / 128, nblocks = (d->cout + bn - 1) / bn;
+  const int base_ctas = mblocks * P.tap_groups * nblocks;
+  int ksplits = (2 * 148 + base_ctas - 1) / base_ctas;
+  if (ksplits > P.kiters) ksplits = P.kiters;
+  if (ksplits < 1) ksplits = 1;
+  P.ksplits = ksplits;
+  P.tmem_cols = pow2_cols(tg * bn);
+  P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.dwp = dwp; P.error_flag = error_flag;
+  const uint32_t stage_bytes = nops * ((uint32_t)bn * 128u + (uint32_t)tg * 16384u);
+  const uint32_t budget = 227u * 1024u - 1024u - 512u;
+  PN_REQUIRE(2 * stage_bytes <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: stage does not fit");
+  int stages = (int)(budget / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  P.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
+
+  alignas(64) CUtensorMap tmX, tmXlo, tmG, tmGlo;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->cin, (uint64_t)d->batch};
+    const uint64_t strides[3] = {(uint64_t)d->width * 4, (uint64_t)d->width * d->height * 4,
+                                 (uint64_t)d->width * d->height * d->cin * 4};
+    const uint32_t box[4] = {KC, 1, 128, 1};
+    int rc = make_map(&tmX, x_nchw, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = make_map(&tmXlo, x_lo ? x_lo : x_nchw, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->cout, (uint64_t)d->batch};
+    const uint64_t strides[3] = {(uint64_t)d->width * 4, (uint64_t)d->width * d->height * 4,
+                                 (uint64_t)d->width * d->height * d->cout * 4};
+    const uint32_t box[4] = {KC, 1, (uint32_t)bn, 1};
+    int rc = make_map(&tmG, g_nchw, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = make_map(&tmGlo, g_lo ? g_lo : g_nchw, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  PN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)d->cout * taps * P.kpad, stream));
+  PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(mblocks, P.tap_groups * nblocks, ksplits);
+  conv_wgrad_kernel<<<grid, NTHREADS, smem, stream>>>(tmX, tmXlo, tmG, tmGlo, P);
+  count_launch();
+  return check_launch("conv_wgrad_kernel");
+}
+
+}  // namespace conv
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_conv2d_forward(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* w_packed,
+                                 const float* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
+                                 pn_stream_t stream) {
+  return conv::conv_forward(desc, x, x_lo, w_packed, w_packed_lo, bias, y, error_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, size_t* elems) {
+  PN_REQUIRE(elems && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_packed_weight_elems: bad argument");
+  const int rows = transposed ? cin : cout, k = transposed ? cout : cin;
+  *elems = (size_t)rows * ksize * ksize * conv::kpad_of(k);
+  return PN_OK;
+}
+
+extern "C" int pn_conv2d_pack_weight(const float* w_oihw, float* w_packed, float* w_packed_lo, int cout, int cin, int ksize,
+                                     int transposed, pn_stream_t stream) {
+  PN_REQUIRE(w_oihw && w_packed && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_pack_weight: bad argument");
+  const int rows = transposed ? cin : cout, k = transposed ? cout : cin;
+  const size_t total = (size_t)rows * ksize * ksize * conv::kpad_of(k);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  conv::pack_weight_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w_oihw, w_packed, w_packed_lo, cout, cin,
+                                                                                     ksize, conv::kpad_of(k), transposed);
+  count_launch();
+  return check_launch("pack_weight_kernel");
+}
+
+extern "C" int pn_tf32_residual(const float* x, float* lo, size_t n, pn_stream_t stream) {
+  PN_REQUIRE(x && lo && (n % 4 == 0) && aligned16(x) && aligned16(lo), PN_ERR_BAD_ARGUMENT,
+             "pn_tf32_residual: need 16-byte aligned pointers and n %% 4 == 0");
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  conv::tf32_residual_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n / 4);
+  count_launch();
+  return check_launch("tf32_residual_kernel");
+}
+
+extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x_nchw, const float* x_nchw_lo, const float* g_nchw,
+                               const float* g_nchw_lo, float* dw_packed, uint32_t* error_flag, pn_stream_t stream) {
+  return conv::conv_wgrad(desc, x_nchw, x_nchw_lo, g_nchw, g_nchw_lo, dw_packed, error_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, pn_stream_t stream) {
+  PN_REQUIRE(dw_packed && dw_oihw && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_unpack_weight_grad: bad argument");
+  const size_t total = (size_t)cout * cin * ksize * ksize;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  conv::unpack_weight_grad_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dw_packed, dw_oihw, cout, cin,
+                                                                                            ksize * ksize, conv::kpad_of(cin));
+  count_launch();
+  return check_launch("unpack_weight_grad_kernel");
+}

@@ -1,0 +1,561 @@
+// layer_kernels.cu -- the HBM-bound pieces of the pack / unpack blocks (NHWC fp32), sm_100a.
+//
+//   * feature stencil: the Conv3d(1->8, 3x3x3, pad 1) of PackLayerConv3d / UnpackLayerConv3d fused with
+//     the surrounding data movement, so neither the space-to-depth tensor nor a separately shuffled copy
+//     ever exists in HBM:
+//        pack  : x[B,2H,2W,C] --(space-to-depth read)--> 27-tap stencil over (4C,H,W) --> Y[B,H,W,8*4C]
+//                layers01.py:126-148 (packing), :236-237,:241-245 (conv3d + view)
+//        unpack: u[B,H,W,Cu] --> stencil over (Cu,H,W) --(depth-to-space write)--> out[B,2H,2W,2Cu]
+//                layers01.py:274-276,:281-285 (conv3d + view + PixelShuffle), written straight into the
+//                decoder's concat buffer (channel stride/offset) -- torch.cat (PackNet01.py:138-175) by pointer
+//     and their backward (data gradient, conv3d weight/bias gradient).
+//   * GroupNorm(16) + ELU (layers01.py:31-32,37 / :61-62,72): statistics pass + fused apply pass, and backward.
+//   * tf32 residual outputs (x - trunc_tf32(x)) are emitted by the producers for the tf32x3 GEMM path.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace pn {
+namespace layers {
+
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---------------------------------------------------------------------------------------------------
+// feature stencil
+// ---------------------------------------------------------------------------------------------------
+// "virtual" input volume V[d][h][w], d in [0,D): pack: D = 4C, V[4c+2i+j][h][w] = x[2h+i][2w+j][c];
+//                                               unpack: D = Cu, V[d][h][w] = u[h][w][d]
+// output feature (f, d, h, w), f in [0,8): pack: Y[h][w][f*D + d]; unpack: v = f*D+d -> out[2h+i][2w+j][v/4], i=(v%4)/2, j=v%2
+struct StencilParams {
+  int B, H, W, D;          // volume dims (H, W are the LOW resolution for both pack and unpack)
+  int C;                   // pack: input channels (D = 4C); unpack: Cu (D = Cu)
+  int tw;                  // output pixels per CTA along w
+  int out_cstride;         // channels per output pixel in the destination buffer
+  int out_coffset;         // first channel written
+  const float* in;         // pack: x [B,2H,2W,C]; unpack: u [B,H,W,Cu]
+  const float* w3;         // [8][27]
+  const float* b3;         // [8]
+  float* out;              // pack: [B,H,W,out_cstride]; unpack: [B,2H,2W,out_cstride]
+  float* out_lo;           // optional tf32 residual of out (same layout) or nullptr
+};
+
+template <bool PACK>
+__device__ __forceinline__ float load_volume(const StencilParams& P, int b, int d, int h, int w) {
+  if (PACK) {
+    const int c = d >> 2, i = (d >> 1) & 1, j = d & 1;
+    return __ldg(P.in + (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.C + c);
+  } else {
+    return __ldg(P.in + (((size_t)b * P.H + h) * P.W + w) * P.C + d);
+  }
+}
+
+// smem: s_v[3][tw+2][D+2] (zero padded in all three dims), s_w[8*27 + 8]
+template <bool PACK>
+__global__ void __launch_bounds__(256) stencil_fwd_kernel(const StencilParams P) {
+  extern __shared__ float sm[];
+  const int D = P.D, DP = D + 2, TWP = P.tw + 2;
+  float* s_v = sm;
+  float* s_w = sm + 3 * TWP * DP;
+  const int w0 = blockIdx.x * P.tw, h = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 8 * 27 + 8; i += blockDim.x) s_w[i] = (i < 216) ? P.w3[i] : P.b3[i - 216];
+  // stage the 3 x (tw+2) x (D+2) neighbourhood; for PACK read x pixel-major so the global loads coalesce
+  const int total = 3 * TWP * DP;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    int dd, cw, r;
+    if (PACK) {
+      // idx enumerates (r, cw, i, j, c) with c fastest: consecutive threads read consecutive channels of one x pixel
+      const int per_px = DP;  // keep the generic decomposition; the remap below orders reads by (i,j,c)
+      dd = idx % per_px; cw = (idx / per_px) % TWP; r = idx / (per_px * TWP);
+      // remap dd in [1,D] from "d order" to "(ij, c) order" so that a warp touches one x pixel at a time
+      if (dd >= 1 && dd <= D) {
+        const int lin = dd - 1, ij = lin / P.C, c = lin % P.C;
+        dd = 1 + (c << 2) + ij;
+      }
+    } else {
+      dd = idx % DP; cw = (idx / DP) % TWP; r = idx / (DP * TWP);
+    }
+    const int d = dd - 1, ww = w0 + cw - 1, hh = h + r - 1;
+    float v = 0.0f;
+    if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) v = load_volume<PACK>(P, b, d, hh, ww);
+    s_v[(r * TWP + cw) * DP + dd] = v;
+  }
+  __syncthreads();
+  // one (pixel, d) item per thread iteration -> 8 features from 27 shared-memory reads
+  const int items = P.tw * D;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int d = it % D, pw = it / D;
+    const int w = w0 + pw;
+    if (w >= P.W) continue;
+    float acc[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) acc[f] = s_w[216 + f];
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float v = s_v[(dy * TWP + pw + dx) * DP + d + dz];
+          const int t = (dz * 3 + dy) * 3 + dx;
+#pragma unroll
+          for (int f = 0; f < 8; ++f) acc[f] = fmaf(s_w[f * 27 + t], v, acc[f]);
+        }
+    if (PACK) {
+      float* o = P.out + (((size_t)b * P.H + h) * P.W + w) * P.out_cstride + P.out_coffset + d;
+      float* ol = P.out_lo ? P.out_lo + (((size_t)b * P.H + h) * P.W + w) * P.out_cstride + P.out_coffset + d : nullptr;
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        o[(size_t)f * D] = acc[f];
+        if (ol) ol[(size_t)f * D] = acc[f] - tf32_trunc(acc[f]);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        const int v = f * D + d, co = v >> 2, i = (v >> 1) & 1, j = v & 1;
+        const size_t o = (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.out_cstride + P.out_coffset + co;
+        P.out[o] = acc[f];
+        if (P.out_lo) P.out_lo[o] = acc[f] - tf32_trunc(acc[f]);
+      }
+    }
+  }
+}
+
+// backward: g = dL/d(out features) in the forward's OUTPUT layout; produces dL/d(in) in the forward's INPUT
+// layout, and accumulates dL/dw3 [8][27], dL/db3 [8] (atomicAdd into zeroed buffers).
+struct StencilBwdParams {
+  int B, H, W, D, C, tw;
+  int g_cstride, g_coffset;  // layout of g (same meaning as out_cstride/out_coffset of the forward)
+  const float* in;           // forward input (for the weight gradient)
+  const float* g;            // gradient w.r.t. the forward output
+  const float* w3;
+  float* gin;                // gradient w.r.t. the forward input (same layout as `in`)
+  float* gw3;                // [8*27] accumulated
+  float* gb3;                // [8] accumulated
+};
+
+template <bool PACK>
+__device__ __forceinline__ float load_gout(const StencilBwdParams& P, int b, int f, int d, int h, int w) {
+  if (PACK) {
+    return __ldg(P.g + (((size_t)b * P.H + h) * P.W + w) * P.g_cstride + P.g_coffset + (size_t)f * P.D + d);
+  } else {
+    const int v = f * P.D + d, co = v >> 2, i = (v >> 1) & 1, j = v & 1;
+    return __ldg(P.g + (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.g_cstride + P.g_coffset + co);
+  }
+}
+
+// smem: s_v[3][tw+2][D+2] (forward input neighbourhood), s_g[3][tw+2][D+2] (one feature plane of g, with halo),
+//       s_w[216], s_red[256]
+template <bool PACK>
+__global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams P) {
+  extern __shared__ float sm[];
+  const int D = P.D, DP = D + 2, TWP = P.tw + 2;
+  float* s_v = sm;
+  float* s_g = s_v + 3 * TWP * DP;
+  float* s_w = s_g + 3 * TWP * DP;
+  float* s_red = s_w + 216;
+  const int w0 = blockIdx.x * P.tw, h = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 216; i += blockDim.x) s_w[i] = P.w3[i];
+  const int total = 3 * TWP * DP;
+  StencilParams Q{};
+  Q.B = P.B; Q.H = P.H; Q.W = P.W; Q.D = P.D; Q.C = P.C; Q.in = P.in;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int dd = idx % DP, cw = (idx / DP) % TWP, r = idx / (DP * TWP);
+    const int d = dd - 1, ww = w0 + cw - 1, hh = h + r - 1;
+    float v = 0.0f;
+    if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) v = load_volume<PACK>(Q, b, d, hh, ww);
+    s_v[idx] = v;
+  }
+  const int items = P.tw * D;
+  constexpr int MAXI = 8;  // items per thread kept in registers (tw*D <= 256*MAXI is enforced by the host)
+  float gin_acc[MAXI];
+#pragma unroll
+  for (int k = 0; k < MAXI; ++k) gin_acc[k] = 0.0f;
+  for (int f = 0; f < 8; ++f) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int dd = idx % DP, cw = (idx / DP) % TWP, r = idx / (DP * TWP);
+      const int d = dd - 1, ww = w0 + cw - 1, hh = h + r - 1;
+      float v = 0.0f;
+      if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) v = load_gout<PACK>(P, b, f, d, hh, ww);
+      s_g[idx] = v;
+    }
+    __syncthreads();
+    float wacc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) wacc[t] = 0.0f;
+    float bacc = 0.0f;
+    int slot = 0;
+    for (int it = threadIdx.x; it < items; it += blockDim.x, ++slot) {
+      const int d = it % D, pw = it / D;
+      if (w0 + pw >= P.W) continue;
+      const float gc = s_g[(1 * TWP + pw + 1) * DP + d + 1];  // g at the centre (this pixel, this depth)
+      bacc += gc;
+      float a = 0.0f;
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int t = (dz * 3 + dy) * 3 + dx;
+            // weight gradient: g(centre) * V(centre + offset)
+            wacc[t] = fmaf(gc, s_v[(dy * TWP + pw + dx) * DP + d + dz], wacc[t]);
+            // data gradient: sum_t w[t] * g(centre - offset)  (transpose of the forward stencil)
+            a = fmaf(s_w[f * 27 + t], s_g[((2 - dy) * TWP + pw + (2 - dx)) * DP + d + (2 - dz)], a);
+          }
+      if (slot < MAXI) gin_acc[slot] += a;
+    }
+    // block-reduce the 27 weight-gradient partials + bias partial of this feature
+#pragma unroll
+    for (int t = 0; t < 28; ++t) {
+      float v = (t < 27) ? wacc[t < 27 ? t : 0] : bacc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) s_red[(threadIdx.x >> 5) * 28 + t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 28) {
+      float v = 0.0f;
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += s_red[wv * 28 + threadIdx.x];
+      if (threadIdx.x < 27) atomicAdd(P.gw3 + f * 27 + threadIdx.x, v);
+      else atomicAdd(P.gb3 + f, v);
+    }
+  }
+  // write the data gradient in the forward INPUT layout
+  int slot = 0;
+  for (int it = threadIdx.x; it < items; it += blockDim.x, ++slot) {
+    const int d = it % D, pw = it / D;
+    const int w = w0 + pw;
+    if (w >= P.W || slot >= MAXI) continue;
+    if (PACK) {
+      const int c = d >> 2, i = (d >> 1) & 1, j = d & 1;
+      P.gin[(((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.C + c] = gin_acc[slot];
+    } else {
+      P.gin[(((size_t)b * P.H + h) * P.W + w) * P.C + d] = gin_acc[slot];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm(16) + ELU   (NHWC; x may be the sum of two tensors for the residual block, layers01.py:72)
+// ---------------------------------------------------------------------------------------------------
+// stats[b][g] = (sum, sumsq) in double, accumulated atomically into a zeroed buffer
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ x2, int HW, int C,
+                                                       int in_cstride, int pixels_per_cta, double* __restrict__ stats) {
+  __shared__ double s_sum[16], s_sq[16];
+  const int b = blockIdx.y;
+  const int cg = C / 16;
+  if (threadIdx.x < 16) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int p0 = blockIdx.x * pixels_per_cta;
+  const int p1 = min(p0 + pixels_per_cta, HW);
+  const int c4 = C / 4;  // float4 columns
+  // thread -> (pixel lane, float4 column); a float4 never straddles a group because cg % 4 == 0 or cg in {1,2,4..}
+  const int lanes = blockDim.x / c4 > 0 ? blockDim.x / c4 : 1;
+  const int col = threadIdx.x % c4, pl = threadIdx.x / c4;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (pl < lanes) {
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const size_t o = ((size_t)b * HW + p) * in_cstride + col * 4;
+      float4 v = *reinterpret_cast<const float4*>(x + o);
+      if (x2) {
+        const float4 u = *reinterpret_cast<const float4*>(x2 + o);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = (col * 4 + k) / cg;
+      atomicAdd(&s_sum[g], (double)s[k]);
+      atomicAdd(&s_sq[g], (double)q[k]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    atomicAdd(stats + ((size_t)b * 16 + threadIdx.x) * 2 + 0, s_sum[threadIdx.x]);
+    atomicAdd(stats + ((size_t)b * 16 + threadIdx.x) * 2 + 1, s_sq[threadIdx.x]);
+  }
+}
+
+// y = ELU(gamma * (x - mean) * rstd + beta), written at (out_cstride, out_coffset); optional tf32 residual copy
+__global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restrict__ x, const float* __restrict__ x2, int HW, int C,
+                                                           int in_cstride, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                           float* __restrict__ y, float* __restrict__ y_lo, int out_cstride,
+                                                           int out_coffset, int B) {
+  const int c4 = C / 4, cg = C / 16;
+  const size_t total = (size_t)B * HW * c4;
+  const double cnt = (double)HW * cg;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % c4);
+    const size_t pix = idx / c4;
+    const int b = (int)(pix / HW);
+    const size_t o = pix * in_cstride + col * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + o);
+    if (x2) {
+      const float4 u = *reinterpret_cast<const float4*>(x2 + o);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    float in[4] = {v.x, v.y, v.z, v.w}, out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = col * 4 + k, g = c / cg;
+      const double su = stats[((size_t)b * 16 + g) * 2 + 0], sq = stats[((size_t)b * 16 + g) * 2 + 1];
+      const double mean = su / cnt;
+      double var = sq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float z = (in[k] - (float)mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      out[k] = z > 0.0f ? z : expm1f(z);   // nn.ELU(alpha=1)
+    }
+    const size_t oo = pix * out_cstride + out_coffset + col * 4;
+    *reinterpret_cast<float4*>(y + oo) = make_float4(out[0], out[1], out[2], out[3]);
+    if (y_lo)
+      *reinterpret_cast<float4*>(y_lo + oo) = make_float4(out[0] - tf32_trunc(out[0]), out[1] - tf32_trunc(out[1]),
+                                                          out[2] - tf32_trunc(out[2]), out[3] - tf32_trunc(out[3]));
+  }
+}
+
+// backward, pass 1: per (b, c): sum dz, sum dz*xhat with dz = dy * ELU'(z) (ELU' = 1 for y>0 else y+1)
+//   -> bc[b][c][2] (double, zeroed)
+__global__ void __launch_bounds__(256) gn_elu_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                                const float* __restrict__ y, const float* __restrict__ dy, int HW, int C,
+                                                                int in_cstride, int y_cstride, int y_coffset, int dy_cstride,
+                                                                int dy_coffset, const double* __restrict__ stats, float eps,
+                                                                int pixels_per_cta, double* __restrict__ bc) {
+  const int b = blockIdx.y;
+  const int cg = C / 16;
+  const double cnt = (double)HW * cg;
+  const int p0 = blockIdx.x * pixels_per_cta, p1 = min(p0 + pixels_per_cta, HW);
+  // thread -> channel (c = threadIdx.x % C), pixel lane
+  const int lanes = blockDim.x / C > 0 ? blockDim.x / C : 1;
+  for (int c = threadIdx.x % C + (threadIdx.x / C >= lanes ? C : 0); c < C; c += blockDim.x) {
+    const int pl = (blockDim.x >= C) ? threadIdx.x / C : 0;
+    const int g = c / cg;
+    const double su = stats[((size_t)b * 16 + g) * 2 + 0], sq = stats[((size_t)b * 16 + g) * 2 + 1];
+    const double mean = su / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps)), fmean = (float)mean;
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const size_t pix = (size_t)b * HW + p;
+      float xv = x[pix * in_cstride + c];
+      if (x2) xv += x2[pix * in_cstride + c];
+      const float yv = y[pix * y_cstride + y_coffset + c];
+      const float dz = dy[pix * dy_cstride + dy_coffset + c] * (yv > 0.0f ? 1.0f : yv + 1.0f);
+      s1 += dz;
+      s2 += dz * (xv - fmean) * rstd;
+    }
+    atomicAdd(bc + ((size_t)b * C + c) * 2 + 0, (double)s1);
+    atomicAdd(bc + ((size_t)b * C + c) * 2 + 1, (double)s2);
+  }
+}
+
+// backward, pass 2: dx = rstd * (gamma*dz - mean_g(gamma*dz) - xhat * mean_g(gamma*dz*xhat)); also dgamma/dbeta
+// (first CTA column only) from bc
+__global__ void __launch_bounds__(256) gn_elu_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                               const float* __restrict__ y, const float* __restrict__ dy, int HW, int C,
+                                                               int in_cstride, int y_cstride, int y_coffset, int dy_cstride,
+                                                               int dy_coffset, const double* __restrict__ stats,
+                                                               const float* __restrict__ gmeans, const float* __restrict__ gamma, float eps,
+                                                               float* __restrict__ dx, float* __restrict__ dx_lo, int B) {
+  const int cg = C / 16;
+  const double cnt = (double)HW * cg;
+  const size_t total = (size_t)B * HW * C;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const size_t pix = idx / C;
+    const int b = (int)(pix / HW), g = c / cg;
+    const double su = stats[((size_t)b * 16 + g) * 2 + 0], sq = stats[((size_t)b * 16 + g) * 2 + 1];
+    const double mean = su / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps)), fmean = (float)mean;
+    const float m1 = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 0), m2 = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 1);
+    float xv = x[pix * in_cstride + c];
+    if (x2) xv += x2[pix * in_cstride + c];
+    const float xhat = (xv - fmean) * rstd;
+    const float yv = y[pix * y_cstride + y_coffset + c];
+    const float dz = dy[pix * dy_cstride + dy_coffset + c] * (yv > 0.0f ? 1.0f : yv + 1.0f);
+    const float r = rstd * (__ldg(gamma + c) * dz - m1 - xhat * m2);
+    dx[idx] = r;
+    if (dx_lo) dx_lo[idx] = r - tf32_trunc(r);
+  }
+}
+
+// dgamma[c] = sum_b bc[b][c][1], dbeta[c] = sum_b bc[b][c][0];
+// gmeans[b][g] = (mean_g(gamma*dz), mean_g(gamma*dz*xhat)) over the (HW * C/16) elements of the group
+__global__ void gn_bwd_finalize_kernel(const double* __restrict__ bc, const float* __restrict__ gamma, int B, int C, double cnt,
+                                       float* __restrict__ gmeans, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int cg = C / 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * 16 + C; i += gridDim.x * blockDim.x) {
+    if (i < B * 16) {
+      const int b = i / 16, g = i % 16;
+      double m1 = 0.0, m2 = 0.0;
+      for (int k = 0; k < cg; ++k) {
+        const int cc = g * cg + k;
+        const double gm = (double)gamma[cc];
+        m1 += gm * bc[((size_t)b * C + cc) * 2 + 0];
+        m2 += gm * bc[((size_t)b * C + cc) * 2 + 1];
+      }
+      gmeans[i * 2 + 0] = (float)(m1 / cnt);
+      gmeans[i * 2 + 1] = (float)(m2 / cnt);
+    } else {
+      const int c = i - B * 16;
+      double a = 0.0, d = 0.0;
+      for (int b = 0; b < B; ++b) { d += bc[((size_t)b * C + c) * 2 + 0]; a += bc[((size_t)b * C + c) * 2 + 1]; }
+      dgamma[c] = (float)a;
+      dbeta[c] = (float)d;
+    }
+  }
+}
+
+// bias gradient of an NHWC tensor: db[c] = sum over pixels (conv bias, layers01.py:28)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ g, size_t pixels, int C, int pixels_per_cta,
+                                                          float* __restrict__ out) {
+  const size_t p0 = (size_t)blockIdx.x * pixels_per_cta;
+  const size_t p1 = p0 + pixels_per_cta < pixels ? p0 + pixels_per_cta : pixels;
+  const int lanes = blockDim.x / C > 0 ? blockDim.x / C : 1;
+  for (int c = threadIdx.x % C + (threadIdx.x / C >= lanes ? C : 0); c < C; c += blockDim.x) {
+    const int pl = (blockDim.x >= C) ? threadIdx.x / C : 0;
+    float s = 0.0f;
+    for (size_t p = p0 + pl; p < p1; p += lanes) s += g[p * C + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static int pick_tw(int D, int W, bool bwd) {
+  // shared memory: (bwd ? 2 : 1) * 3 * (tw+2) * (D+2) floats; keep it under ~96 KB and tw*D <= 2048 for bwd
+  const size_t budget = 96 * 1024;
+  int tw = 8;
+  while (tw > 1 && ((size_t)(bwd ? 2 : 1) * 3 * (tw + 2) * (D + 2) * 4 > budget || (bwd && tw * D > 2048))) tw >>= 1;
+  if (tw > W) tw = W;
+  return tw;
+}
+
+}  // namespace layers
+}  // namespace pn
+
+using namespace pn;
+using namespace pn::layers;
+
+extern "C" int pn_feature_stencil_forward(int pack, const float* in, const float* w3, const float* b3, float* out, float* out_lo,
+                                          int batch, int h_low, int w_low, int channels, int out_cstride, int out_coffset,
+                                          pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(in && w3 && b3 && out && batch > 0 && h_low > 0 && w_low > 0 && channels > 0, PN_ERR_BAD_ARGUMENT,
+             "pn_feature_stencil_forward: bad argument");
+  StencilParams P{};
+  P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
+  P.in = in; P.w3 = w3; P.b3 = b3; P.out = out; P.out_lo = out_lo;
+  P.out_cstride = out_cstride; P.out_coffset = out_coffset;
+  P.tw = pick_tw(P.D, P.W, false);
+  PN_REQUIRE((size_t)3 * 3 * (P.D + 2) * 4 <= 200 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_forward: depth %d too large", P.D);
+  const size_t smem = ((size_t)3 * (P.tw + 2) * (P.D + 2) + 224) * sizeof(float);
+  dim3 grid((P.W + P.tw - 1) / P.tw, P.H, P.B);
+  if (pack) {
+    PN_CUDA(cudaFuncSetAttribute(stencil_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stencil_fwd_kernel<true><<<grid, 256, smem, stream>>>(P);
+  } else {
+    PN_CUDA(cudaFuncSetAttribute(stencil_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stencil_fwd_kernel<false><<<grid, 256, smem, stream>>>(P);
+  }
+  count_launch();
+  return check_launch("stencil_fwd_kernel");
+}
+
+extern "C" int pn_feature_stencil_backward(int pack, const float* in, const float* g, const float* w3, float* gin, float* gw3,
+                                           float* gb3, int batch, int h_low, int w_low, int channels, int g_cstride, int g_coffset,
+                                           pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(in && g && w3 && gin && gw3 && gb3 && batch > 0 && h_low > 0 && w_low > 0 && channels > 0, PN_ERR_BAD_ARGUMENT,
+             "pn_feature_stencil_backward: bad argument");
+  StencilBwdParams P{};
+  P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
+  P.in = in; P.g = g; P.w3 = w3; P.gin = gin; P.gw3 = gw3; P.gb3 = gb3;
+  P.g_cstride = g_cstride; P.g_coffset = g_coffset;
+  P.tw = pick_tw(P.D, P.W, true);
+  PN_REQUIRE(P.tw * P.D <= 2048, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large", P.D);
+  PN_CUDA(cudaMemsetAsync(gw3, 0, sizeof(float) * 216, stream));
+  PN_CUDA(cudaMemsetAsync(gb3, 0, sizeof(float) * 8, stream));
+  const size_t smem = ((size_t)2 * 3 * (P.tw + 2) * (P.D + 2) + 216 + 8 * 28 + 32) * sizeof(float);
+  dim3 grid((P.W + P.tw - 1) / P.tw, P.H, P.B);
+  if (pack) {
+    PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stencil_bwd_kernel<true><<<grid, 256, smem, stream>>>(P);
+  } else {
+    PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stencil_bwd_kernel<false><<<grid, 256, smem, stream>>>(P);
+  }
+  count_launch();
+  return check_launch("stencil_bwd_kernel");
+}
+
+extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const float* gamma, const float* beta, float eps, float* y,
+                                        float* y_lo, double* stats, int batch, int hw, int channels, int out_cstride, int out_coffset,
+                                        pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(x && gamma && beta && y && stats && batch > 0 && hw > 0, PN_ERR_BAD_ARGUMENT, "pn_groupnorm_elu_forward: bad argument");
+  PN_REQUIRE(channels % 16 == 0 && channels % 4 == 0 && channels <= 1024, PN_ERR_UNSUPPORTED,
+             "pn_groupnorm_elu_forward: channels %d (need a multiple of 16, <= 1024)", channels);
+  PN_REQUIRE(out_cstride % 4 == 0 && out_coffset % 4 == 0, PN_ERR_ALIGNMENT, "pn_groupnorm_elu_forward: output channel window");
+  PN_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * 16 * batch, stream));
+  int ppc = (hw + 147) / 148;
+  if (ppc < 32) ppc = 32;
+  dim3 g1((hw + ppc - 1) / ppc, batch);
+  gn_stats_kernel<<<g1, 256, 0, stream>>>(x, x2, hw, channels, channels, ppc, stats);
+  count_launch();
+  const size_t total = (size_t)batch * hw * (channels / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gn_elu_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, hw, channels, channels, stats, gamma, beta, eps, y, y_lo, out_cstride,
+                                                  out_coffset, batch);
+  count_launch();
+  return check_launch("gn_elu_apply_kernel");
+}
+
+extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, const float* dy, const float* gamma,
+                                         float eps, const double* stats, double* bc, float* dx, float* dx_lo, float* dgamma,
+                                         float* dbeta, int batch, int hw, int channels, int y_cstride, int y_coffset, int dy_cstride,
+                                         int dy_coffset, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(x && y && dy && gamma && stats && bc && dx && dgamma && dbeta && batch > 0 && hw > 0, PN_ERR_BAD_ARGUMENT,
+             "pn_groupnorm_elu_backward: bad argument");
+  PN_REQUIRE(channels % 16 == 0 && channels <= 1024, PN_ERR_UNSUPPORTED, "pn_groupnorm_elu_backward: channels %d", channels);
+  PN_CUDA(cudaMemsetAsync(bc, 0, sizeof(double) * 2 * channels * batch, stream));
+  int ppc = (hw + 147) / 148;
+  if (ppc < 32) ppc = 32;
+  dim3 g1((hw + ppc - 1) / ppc, batch);
+  gn_elu_bwd_reduce_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
+                                                   stats, eps, ppc, bc);
+  count_launch();
+  const size_t total = (size_t)batch * hw * channels;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  // bc holds 2*C*B doubles followed by 2*16*B floats of scratch for the group means
+  float* gmeans = reinterpret_cast<float*>(bc + (size_t)2 * channels * batch);
+  gn_bwd_finalize_kernel<<<(batch * 16 + channels + 127) / 128, 128, 0, stream>>>(bc, gamma, batch, channels,
+                                                                                 (double)hw * (channels / 16), gmeans, dgamma, dbeta);
+  count_launch();
+  gn_elu_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
+                                                      dy_coffset, stats, gmeans, gamma, eps, dx, dx_lo, batch);
+  count_launch();
+  return check_launch("gn_elu_bwd kernels");
+}
+
+extern "C" int pn_channel_sum(const float* g, float* out, size_t pixels, int channels, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(g && out && pixels > 0 && channels > 0 && channels <= 1024, PN_ERR_BAD_ARGUMENT, "pn_channel_sum: bad argument");
+  PN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * channels, stream));
+  int ppc = (int)((pixels + 147 * 4) / (148 * 4));
+  if (ppc < 64) ppc = 64;
+  channel_sum_kernel<<<(int)((pixels + ppc - 1) / ppc), 256, 0, stream>>>(g, pixels, channels, ppc, out);
+  count_launch();
+  return check_launch("channel_sum_kernel");
+}

@@ -1,0 +1,224 @@
+"""Autograd functions over the C-ABI layer kernels.  Every tensor here is an NHWC feature map stored as a
+plain contiguous [B,H,W,C] CUDA tensor (the same bytes as a torch.channels_last NCHW tensor).
+
+  conv2d            tcgen05 implicit-GEMM convolution (+bias); backward = data gradient through the same
+                    kernel on the flipped/transposed packed weight, weight gradient through the wgrad kernel
+  groupnorm_elu     GroupNorm(16)+ELU (optionally of x + x2), output optionally into a channel window
+  pack_features     space-to-depth + Conv3d(1->8) feature stencil   (PackLayerConv3d, layers01.py:239-245)
+  unpack_features   Conv3d(1->8) feature stencil + depth-to-space   (UnpackLayerConv3d, layers01.py:281-285)
+
+Precision of the tensor-core GEMMs: PRECISION_TF32X3 (default; fp32-grade, needed for the 1e-3 parity
+bar) or PRECISION_TF32X1 (what cuDNN gives the reference on Ampere+ with PyTorch defaults)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_TF32X3, MODE_AUTO
+
+_state = {"precision": PRECISION_TF32X3, "mode": MODE_AUTO}
+
+
+def set_precision(p):
+    assert p in (PRECISION_TF32X1, PRECISION_TF32X3)
+    _state["precision"] = p
+
+
+def get_precision():
+    return _state["precision"]
+
+
+def set_conv_mode(m):
+    _state["mode"] = m
+
+
+def _stream():
+    return _lib.current_stream()
+
+
+def _p(t):
+    return _lib.ptr(t) if t is not None else None
+
+
+def _residual(x):
+    lo = torch.empty_like(x)
+    _lib.check(_lib.lib().pn_tf32_residual(_lib.ptr(x), _lib.ptr(lo), x.numel(), _stream()), "pn_tf32_residual")
+    return lo
+
+
+def _pack_weight(w, transposed, with_lo):
+    cout, cin, k, _ = w.shape
+    n = ctypes.c_size_t(0)
+    lib = _lib.lib()
+    _lib.check(lib.pn_conv2d_packed_weight_elems(cout, cin, k, int(transposed), ctypes.byref(n)), "packed_weight_elems")
+    wp = torch.empty(int(n.value), dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(wp) if with_lo else None
+    _lib.check(lib.pn_conv2d_pack_weight(_lib.ptr(w), _lib.ptr(wp), _p(lo), cout, cin, k, int(transposed), _stream()),
+               "pn_conv2d_pack_weight")
+    return wp, lo
+
+
+def _conv_raw(x, x_lo, wp, wp_lo, bias, cout, ksize, precision):
+    B, H, W, Cin = x.shape
+    y = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
+    d = ConvDesc(B, H, W, Cin, cout, ksize, precision, _state["mode"], 0)
+    _lib.check(_lib.lib().pn_conv2d_forward(ctypes.byref(d), _lib.ptr(x), _p(x_lo), _lib.ptr(wp), _p(wp_lo), _p(bias),
+                                            _lib.ptr(y), None, _stream()), "pn_conv2d_forward")
+    return y
+
+
+def _pad_channels(w, cin_tensor):
+    """weight [Cout,Cin,k,k] whose Cin is smaller than the (4-aligned) channel count of the activation tensor."""
+    if w.shape[1] == cin_tensor:
+        return w
+    pad = torch.zeros(w.shape[0], cin_tensor - w.shape[1], w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+    return torch.cat([w, pad], 1).contiguous()
+
+
+class _Conv2d(torch.autograd.Function):
+    """y = conv2d(x, weight, stride 1, zero pad k//2) + bias on NHWC tensors (nn.Conv2d + ConstantPad2d,
+    layers01.py:28-30,36)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, x_lo):
+        _lib.require_cuda(x, weight)
+        x = x.contiguous()
+        precision = _state["precision"]
+        three = precision == PRECISION_TF32X3
+        cout, cin_w, k, _ = weight.shape
+        w_eff = _pad_channels(weight.detach().contiguous(), x.shape[3])
+        wp, wp_lo = _pack_weight(w_eff, False, three)
+        if three and x_lo is None:
+            x_lo = _residual(x)
+        y = _conv_raw(x, x_lo if three else None, wp, wp_lo, bias.detach().contiguous() if bias is not None else None,
+                      cout, k, precision)
+        ctx.save_for_backward(x, weight, x_lo if three else None)
+        ctx.has_bias = bias is not None
+        ctx.precision = precision
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, x_lo = ctx.saved_tensors
+        precision = ctx.precision
+        three = precision == PRECISION_TF32X3
+        lib = _lib.lib()
+        gy = gy.contiguous()
+        B, H, W, Cin = x.shape
+        cout, cin_w, k, _ = weight.shape
+        gy_lo = _residual(gy) if three else None
+        gx = gw = gb = None
+        w_eff = _pad_channels(weight.detach().contiguous(), Cin)
+        if ctx.needs_input_grad[0]:
+            # data gradient: correlation of gy with the flipped kernel, contraction over Cout
+            wt, wt_lo = _pack_weight(w_eff, True, three)
+            gx = _conv_raw(gy, gy_lo, wt, wt_lo, None, Cin, k, precision)
+        if ctx.needs_input_grad[1]:
+            # weight gradient: reduction over pixels -> pixel-contiguous (NCHW) operand copies
+            x_t = x.permute(0, 3, 1, 2).contiguous()
+            g_t = gy.permute(0, 3, 1, 2).contiguous()
+            x_t_lo = x_lo.permute(0, 3, 1, 2).contiguous() if three else None
+            g_t_lo = gy_lo.permute(0, 3, 1, 2).contiguous() if three else None
+            n = ctypes.c_size_t(0)
+            _lib.check(lib.pn_conv2d_packed_weight_elems(cout, Cin, k, 0, ctypes.byref(n)), "packed_weight_elems")
+            dwp = torch.empty(int(n.value), dtype=torch.float32, device=x.device)
+            d = ConvDesc(B, H, W, Cin, cout, k, precision, 0, 0)
+            _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_t), _p(x_t_lo), _lib.ptr(g_t), _p(g_t_lo),
+                                           _lib.ptr(dwp), None, _stream()), "pn_conv2d_wgrad")
+            gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=x.device)
+            _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, _stream()),
+                       "pn_conv2d_unpack_weight_grad")
+            gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = torch.empty(cout, dtype=torch.float32, device=x.device)
+            _lib.check(lib.pn_channel_sum(_lib.ptr(gy), _lib.ptr(gb), B * H * W, cout, _stream()), "pn_channel_sum")
+        return gx, gw, gb, None
+
+
+def conv2d(x, weight, bias=None, x_lo=None):
+    return _Conv2d.apply(x, weight, bias, x_lo)
+
+
+class _GroupNormELU(torch.autograd.Function):
+    """y = ELU(GroupNorm16(x [+ x2])) (layers01.py:31-32,37 and :61-62,72)."""
+
+    @staticmethod
+    def forward(ctx, x, x2, gamma, beta, eps):
+        _lib.require_cuda(x, gamma, beta)
+        x = x.contiguous()
+        x2c = x2.contiguous() if x2 is not None else None
+        B, H, W, C = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(B * 16 * 2, dtype=torch.float64, device=x.device)
+        _lib.check(_lib.lib().pn_groupnorm_elu_forward(_lib.ptr(x), _p(x2c), _lib.ptr(gamma.detach().contiguous()),
+                                                       _lib.ptr(beta.detach().contiguous()), float(eps), _lib.ptr(y), None,
+                                                       _lib.ptr(stats), B, H * W, C, C, 0, _stream()),
+                   "pn_groupnorm_elu_forward")
+        ctx.save_for_backward(x, x2c, y, gamma, stats)
+        ctx.eps = float(eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, x2, y, gamma, stats = ctx.saved_tensors
+        gy = gy.contiguous()
+        B, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        bc = torch.empty(2 * C * B + 16 * B, dtype=torch.float64, device=x.device)   # doubles + float scratch tail
+        _lib.check(_lib.lib().pn_groupnorm_elu_backward(_lib.ptr(x), _p(x2), _lib.ptr(y), _lib.ptr(gy),
+                                                        _lib.ptr(gamma.detach().contiguous()), ctx.eps, _lib.ptr(stats),
+                                                        _lib.ptr(bc), _lib.ptr(dx), None, _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                                        B, H * W, C, C, 0, C, 0, _stream()), "pn_groupnorm_elu_backward")
+        return dx, (dx if x2 is not None else None), dgamma, dbeta, None
+
+
+def groupnorm_elu(x, gamma, beta, eps=1e-5, x2=None):
+    return _GroupNormELU.apply(x, x2, gamma, beta, eps)
+
+
+class _FeatureStencil(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w3, b3, pack):
+        _lib.require_cuda(x, w3, b3)
+        x = x.contiguous()
+        B = x.shape[0]
+        if pack:
+            h, w, C = x.shape[1] // 2, x.shape[2] // 2, x.shape[3]
+            out = torch.empty(B, h, w, 32 * C, dtype=torch.float32, device=x.device)
+            cs = 32 * C
+        else:
+            h, w, C = x.shape[1], x.shape[2], x.shape[3]
+            out = torch.empty(B, 2 * h, 2 * w, 2 * C, dtype=torch.float32, device=x.device)
+            cs = 2 * C
+        w3c = w3.detach().contiguous()
+        _lib.check(_lib.lib().pn_feature_stencil_forward(int(pack), _lib.ptr(x), _lib.ptr(w3c), _lib.ptr(b3.detach().contiguous()),
+                                                         _lib.ptr(out), None, B, h, w, C, cs, 0, _stream()),
+                   "pn_feature_stencil_forward")
+        ctx.save_for_backward(x, w3c)
+        ctx.pack, ctx.dims, ctx.cs = bool(pack), (B, h, w, C), cs
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w3 = ctx.saved_tensors
+        g = g.contiguous()
+        B, h, w, C = ctx.dims
+        gin = torch.empty_like(x)
+        gw3 = torch.empty(216, dtype=torch.float32, device=x.device)
+        gb3 = torch.empty(8, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().pn_feature_stencil_backward(int(ctx.pack), _lib.ptr(x), _lib.ptr(g), _lib.ptr(w3), _lib.ptr(gin),
+                                                          _lib.ptr(gw3), _lib.ptr(gb3), B, h, w, C, ctx.cs, 0, _stream()),
+                   "pn_feature_stencil_backward")
+        return gin, gw3.view(8, 1, 3, 3, 3), gb3, None
+
+
+def pack_features(x, w3, b3):
+    """[B,2h,2w,C] -> [B,h,w,32C]"""
+    return _FeatureStencil.apply(x, w3, b3, True)
+
+
+def unpack_features(u, w3, b3):
+    """[B,h,w,Cu] -> [B,2h,2w,2Cu]"""
+    return _FeatureStencil.apply(u, w3, b3, False)

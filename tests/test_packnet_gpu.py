@@ -1,0 +1,82 @@
+"""GPU parity of the whole PackNet01 depth network against the golden vectors from the live reference and
+against the CPU oracle (depth maps within 1e-3 relative, north_star)."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from oracle import packnet_oracle as PO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _net(sd):
+    from packnet_sfm_b200.networks import PackNet01
+    net = PackNet01(version="1A")
+    net.load_state_dict(sd, strict=True)
+    return net.to(DEV).train()
+
+
+def test_packnet01_depth_maps_match_reference_golden():
+    z = load_golden("packnet01_64x96")
+    net = _net(PO.packnet01_state_dict(seed=42, randomize_affine=True))
+    with torch.no_grad():
+        out = net(z["rgb"].to(DEV))["inv_depths"]
+    for i, d in enumerate(out):
+        ref = z["disp%d" % (i + 1)]
+        rel = ((d.cpu() - ref).abs() / ref.abs()).max().item()
+        print("disp%d max-rel %.3e rel-l2 %.3e" % (i + 1, rel, rel_l2(d.cpu(), ref)))
+        assert d.shape == ref.shape
+        assert rel < 1e-3
+
+
+def test_packnet01_tf32x1_is_looser_but_sane():
+    from packnet_sfm_b200 import functional as PF
+    z = load_golden("packnet01_64x96")
+    net = _net(PO.packnet01_state_dict(seed=42, randomize_affine=True))
+    PF.set_precision(PF.PRECISION_TF32X1)
+    try:
+        with torch.no_grad():
+            out = net(z["rgb"].to(DEV))["inv_depths"]
+    finally:
+        PF.set_precision(PF.PRECISION_TF32X3)
+    for i, d in enumerate(out):
+        r = rel_l2(d.cpu(), z["disp%d" % (i + 1)])
+        print("tf32x1 disp%d rel-l2 %.3e" % (i + 1, r))
+        assert r < 3e-2
+
+
+def test_packnet01_gradients_match_oracle_autograd():
+    """Full backward through every custom kernel against CPU autograd of the oracle restatement."""
+    from packnet_sfm_b200 import synthetic
+    sd = PO.packnet01_state_dict(seed=7, randomize_affine=True)
+    net = _net(sd)
+    x = synthetic.make_frames(1, 64, 96, seed=9)["rgb"]
+    out = net(x.to(DEV))["inv_depths"]
+    g = torch.Generator().manual_seed(1)
+    gouts = [torch.rand(d.shape, generator=g) - 0.5 for d in out]
+    torch.autograd.backward(out, [t.to(DEV) for t in gouts])
+    torch.cuda.synchronize()
+    sdc = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = PO.packnet01_forward(x, sdc)
+    torch.autograd.backward(ref, gouts)
+    for a, b in zip(out, ref):
+        assert rel_l2(a.detach().cpu(), b.detach()) < 1e-3
+    worst = ("", 0.0)
+    for k, p in net.named_parameters():
+        r = sdc[k].grad
+        err = float((p.grad.cpu().double() - r.double()).norm())
+        bound = 2e-3 * float(r.double().norm()) + 1e-5 * r.numel() ** 0.5
+        if err / max(bound, 1e-30) > worst[1]:
+            worst = (k, err / max(bound, 1e-30))
+        assert err <= bound, (k, err, bound)
+    print("worst parameter-gradient error/bound: %s %.3f" % worst)
+
+
+def test_eval_mode_contract_and_shape_errors():
+    net = _net(PO.packnet01_state_dict(seed=1)).eval()
+    with torch.no_grad():
+        out = net(torch.rand(1, 3, 32, 64, device=DEV))
+    assert torch.is_tensor(out["inv_depths"]) and out["inv_depths"].shape == (1, 1, 32, 64)
+    with pytest.raises(ValueError):
+        net(torch.rand(1, 3, 30, 64, device=DEV))

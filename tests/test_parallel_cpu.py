@@ -1,0 +1,76 @@
+"""CPU tier: the data-parallel plumbing with gloo, world_size 2 (N>1 host logic without GPUs)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _model():
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.GroupNorm(4, 8), nn.ELU(), nn.Conv2d(8, 1, 3, padding=1))
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from packnet_sfm_b200 import parallel
+    torch.manual_seed(100 + rank)                      # deliberately different init per rank
+    model = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.GroupNorm(4, 8), nn.ELU(), nn.Conv2d(8, 1, 3, padding=1))
+    parallel.broadcast_parameters(model, src=0)
+    bucket = parallel.FlatBucket(model.parameters())
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(4, 3, 8, 8, generator=g)
+    sl = parallel.shard_batch(4, rank, world)
+    bucket.zero_grad()
+    model(x[sl]).pow(2).mean().backward()
+    bucket.allreduce_mean()
+    ret[rank] = (bucket.flat_grad.clone(), torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_equals_full_batch_gradient():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    g0, p0 = ret[0]
+    g1, p1 = ret[1]
+    assert torch.equal(p0, p1), "broadcast_parameters must make the replicas identical"
+    assert torch.allclose(g0, g1, rtol=0, atol=0)
+    # single-process gradient of the concatenated batch with rank 0's parameters
+    torch.manual_seed(100)
+    model = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.GroupNorm(4, 8), nn.ELU(), nn.Conv2d(8, 1, 3, padding=1))
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(4, 3, 8, 8, generator=g)
+    # mean over the full batch == mean of the per-shard means (equal shard sizes)
+    loss = 0.5 * (model(x[:2]).pow(2).mean() + model(x[2:]).pow(2).mean())
+    loss.backward()
+    full = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.allclose(g0, full, rtol=1e-5, atol=1e-7)
+
+
+def test_flat_bucket_views_survive_zero_grad_and_backward():
+    from packnet_sfm_b200 import parallel
+    m = _model()
+    b = parallel.FlatBucket(m.parameters())
+    for _ in range(2):
+        b.zero_grad()
+        m(torch.rand(1, 3, 8, 8)).sum().backward()
+        off = 0
+        for p in m.parameters():
+            assert p.grad.data_ptr() == b.flat_grad.data_ptr() + 4 * off
+            off += p.numel()
+    assert b.nbytes() == 4 * sum(p.numel() for p in m.parameters())
+    assert b.allreduce_mean() is None      # no process group: a no-op
