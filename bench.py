@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the PackNet01 640x192 self-supervised training step on N B200s (one process
+per GPU, NCCL), plus the roofline numbers of the hot kernels and the CPU baseline (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W          our arm (sm_100a kernels)
+  python bench.py --impl reference ...                   the reference's algorithm on the host CPU cores
+                                                         (oracle port: the Python reference cannot travel)
+For N>1 the driver launches `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`.
+A step = forward (PackNet01 + PoseNet) + photometric loss + backward + gradient all-reduce + Adam."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="images per GPU (BASELINE configs[1]: 4)")
+    ap.add_argument("--height", type=int, default=192)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32x1"])
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_host_batch(B, H, W, rank):
+    from packnet_sfm_b200 import synthetic
+    fr = synthetic.make_frames(B, H, W, seed=1234 + rank)
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+    return {"rgb": pin(fr["rgb"]), "rgb_context": [pin(c) for c in fr["rgb_context"]], "intrinsics": pin(fr["intrinsics"])}
+
+
+def to_device(hb, dev):
+    b = {"rgb": hb["rgb"].to(dev, non_blocking=True), "rgb_context": [c.to(dev, non_blocking=True) for c in hb["rgb_context"]],
+         "intrinsics": hb["intrinsics"].to(dev, non_blocking=True)}
+    b["rgb_original"], b["rgb_context_original"] = b["rgb"], b["rgb_context"]   # synthetic frames: no colour jitter
+    return b
+
+
+def cpu_baseline(args, steps):
+    """The oracle port of the reference step on the host cores, B=1 sample of the workload."""
+    from oracle.step_oracle import StepOracle
+    from packnet_sfm_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fr = synthetic.make_frames(1, args.height, args.width, seed=1234)
+    orc = StepOracle()
+    orc.step(fr)                                     # warm-up (allocations, oneDNN primitive caches)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.step(fr)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 1.0 / dt, "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": "B=1 %dx%d full step (PackNet01+PoseNet fwd, loss, bwd, Adam), %d timed after 1 warm-up, "
+                      "torch %s CPU fp32" % (args.height, args.width, steps, torch.__version__), "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    cb = cpu_baseline(args, steps)
+    line = {"impl": "reference", "metric": "images/sec PackNet01 self-sup step (fwd+loss+bwd+Adam)", "value": cb["value"],
+            "unit": "images/sec", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PackNet01+MultiViewPhotometricLoss self-sup step, %dx%d, B=1 sample on CPU"
+                                   % (args.width, args.height)},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def time_kernels(args, dev, pk):
+    """Roofline numbers of the two hot kernels, timed alone with CUDA events on the launching stream."""
+    from packnet_sfm_b200 import functional as PF, synthetic, _lib
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    from packnet_sfm_b200.geometry import Pose
+    from packnet_sfm_b200.models import YACS_LOSS_DEFAULTS
+    B, H, W = args.batch, args.height, args.width
+    res = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+
+    def timed(fn, iters=10):
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    # fused warp + SSIM + L1 + automask-min + smoothness (HBM bound). Algorithmic bytes: SURVEY.md §8(d)
+    fr = synthetic.make_frames(B, H, W, seed=5)
+    inv = [d.to(dev).requires_grad_(True) for d in synthetic.make_inv_depths(B, H, W, seed=6)]
+    vec = synthetic.make_pose_vecs(B, seed=7).to(dev)
+    mats = [Pose.from_vec(vec[:, j], "euler").mat.requires_grad_(True) for j in range(2)]
+    loss_fn = MultiViewPhotometricLoss(**YACS_LOSS_DEFAULTS)
+    img, ctx, K = fr["rgb"].to(dev), [c.to(dev) for c in fr["rgb_context"]], fr["intrinsics"].to(dev)
+    out = {}
+
+    def fwd():
+        out["o"] = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats])
+
+    def bwd():
+        out["o"]["loss"].backward(retain_graph=True)
+
+    for _ in range(3):
+        fwd(); bwd()
+    t_f = timed(fwd)
+    t_b = timed(bwd)
+    P_s = B * H * W * 4
+    bytes_f, bytes_b = 48 * P_s, 44 * P_s
+    res["roofline_loss"] = {"bound": "hbm", "kernel": "loss_tile_kernel fwd+bwd (incl. prep launches)",
+                            "achieved": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                            "fwd_ms": t_f, "bwd_ms": t_b, "algorithmic_bytes": bytes_f + bytes_b, "peak_source": pk["source"]}
+    # pack1 convolution (tensor bound): [B,96,320,2048] x [64,2048,5,5]
+    h2, w2, cin, cout, k = H // 2, W // 2, 2048, 64, 5
+    x = torch.rand(B, h2, w2, cin, device=dev) - 0.5
+    w = (torch.rand(cout, cin, k, k, device=dev) - 0.5) * 0.01
+    with torch.no_grad():
+        for _ in range(2):
+            PF.conv2d(x, w, None)
+        three = PF.get_precision() == PF.PRECISION_TF32X3
+        wp, wlo = PF._pack_weight(w, False, three)
+        xlo = PF._residual(x) if three else None
+        t_c = timed(lambda: PF._conv_raw(x, xlo, wp, wlo, None, cout, k, PF.get_precision()), iters=5)
+    flops = 2.0 * B * h2 * w2 * cout * cin * k * k
+    tf32_peak = pk["bf16_tflops"] / 2.0
+    res["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (pack1 conv2d, %s)" % args.precision,
+                       "achieved": flops / (t_c * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                       "frac": flops / (t_c * 1e-3) / 1e12 / tf32_peak, "traffic": None, "ms": t_c,
+                       "algorithmic_flops": flops,
+                       "peak_source": pk["source"] + " cuBLAS bf16 / 2 (tf32 dense rate is half the bf16 rate)"}
+    return res
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from packnet_sfm_b200 import _lib, functional as PF, parallel
+    from packnet_sfm_b200.models import SelfSupModel
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    PF.set_precision(PF.PRECISION_TF32X3 if args.precision == "tf32x3" else PF.PRECISION_TF32X1)
+    _lib.lib()          # fail loudly if the extension is missing
+    torch.manual_seed(42)
+    import random
+    random.seed(42)
+    model = SelfSupModel().to(dev).train()
+    parallel.broadcast_parameters(model)
+    bucket = parallel.FlatBucket(model.parameters())
+    groups = [{"name": "Depth", "params": list(model.depth_net.parameters()), "lr": 2e-4},
+              {"name": "Pose", "params": list(model.pose_net.parameters()), "lr": 2e-4}]
+    opt = torch.optim.Adam(groups, fused=True)
+    B, H, W = args.batch, args.height, args.width
+    hb = make_host_batch(B, H, W, rank)
+    dbatch = to_device(hb, dev)
+    state = {}
+
+    def step(batch):
+        bucket.zero_grad()
+        out = model(batch)
+        out["loss"].backward()
+        bucket.allreduce_mean()
+        opt.step()
+        state["loss"] = out["loss"]
+
+    def timed_region(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(dbatch)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed_region(lambda: step(dbatch), args.steps)
+    launches = _lib.launch_count() - launches0
+
+    def e2e_step():
+        step(to_device(hb, dev))
+        state["loss_host"] = float(state["loss"].item())     # D2H read of the step's result
+
+    e2e_step()
+    ms_e2e = timed_region(e2e_step, args.steps)
+    h2d = sum(t.numel() * 4 for t in [hb["rgb"], hb["intrinsics"]] + hb["rgb_context"])
+
+    if rank == 0:
+        pk = peaks()
+        extra = time_kernels(args, dev, pk) if world == 1 else {}
+        imgs = B * world * args.steps
+        line = {"metric": "images/sec PackNet01 640x192 self-sup step (fwd+loss+bwd+allreduce+Adam)",
+                "value": imgs / (ms * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (tensor-core GEMMs: %s)" % args.precision, "data": "synthetic",
+                "config": {"workload": "PackNet01(1A)+PoseNet+MultiViewPhotometricLoss, synthetic %dx%d 3-frame triplets, "
+                                       "batch=%d/GPU, 4 scales upsampled, Adam lr 2e-4" % (H, W, B),
+                           "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "l2": "no flush between steps: weights (0.5 GB) + activations (GBs) exceed the 126 MB L2",
+                           "grad_allreduce_bytes": bucket.nbytes()},
+                "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "loss": state.get("loss_host")}
+        line.update(extra)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -11,6 +11,11 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# the CPU oracle runs small ops: dozens of OpenMP threads only add spin-wait overhead (and a cgroup-limited
+# box may report far more cores than it grants)
+torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "ref: needs the live reference tree at /root/reference (build container)")
