@@ -120,7 +120,7 @@ typedef struct {
   int32_t ksize;                /* 1, 3, 5 or 7 */
   int32_t precision;            /* PN_PRECISION_* */
   int32_t mode;                 /* PN_CONV_MODE_*: how the activation operand is staged (AUTO picks) */
-  int32_t debug_flags;          /* bit0: force base_offset=0 in shifted descriptors (bring-up tests) */
+  int32_t debug_flags;          /* bit0: bring-up knob, sets base_offset=(addr>>7)&7 in shifted descriptors (wrong on B200) */
 } pn_conv_desc;
 
 /* y[B,H,W,Cout] = conv(x[B,H,W,Cin], w) + bias.  w_packed comes from pn_conv2d_pack_weight.

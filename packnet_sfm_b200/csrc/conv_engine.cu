@@ -45,7 +45,7 @@ struct KernelParams {
   int halo;                // 1: patch reuse across taps
   int cchunks;             // ceil(Cin / 32)
   int stages;
-  int force_base_offset0;  // debug knob for the descriptor bring-up tests
+  int force_base_offset0;  // debug knob (bring-up): 1 = put (addr>>7)&7 into base_offset (known to be WRONG)
   uint32_t a_stage_bytes, b_stage_bytes, patch_bytes;
   uint32_t tmem_cols;
   uint32_t idesc;
@@ -242,7 +242,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             a_hi = patch_addr(pa, 0) + shift;
             a_lo = patch_addr(pa, 1) + shift;
             sbo = PATCH_PITCH * 128u;
-            boff = P.force_base_offset0 ? 0u : ((a_hi >> 7) & 7u);
+            // Measured on B200 (tools/conv_probe.py, profiles/r01_conv_probe.txt): the SWIZZLE_128B XOR is a pure
+            // function of the shared-memory ADDRESS bits, exactly like the TMA write, so a 128-B-shifted start
+            // needs base_offset = 0; setting it to (addr>>7)&7 double-applies the phase and scrambles the rows.
+            boff = P.force_base_offset0 ? ((a_hi >> 7) & 7u) : 0u;
           } else {
             a_hi = stage_a(s, 0);
             a_lo = stage_a(s, 1);

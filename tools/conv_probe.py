@@ -64,9 +64,9 @@ def main():
         run("k3 Cout512 (2 n-tiles)", 1, 16, 16, 64, 512, 3, X1, PT)
     if group in ("halo", "all"):
         run("k3 halo 1 tile", 1, 16, 8, 32, 32, 3, X1, HL)
-        run("k3 halo 1 tile boff0", 1, 16, 8, 32, 32, 3, X1, HL, 1)
+        run("k3 halo 1 tile boff=addr", 1, 16, 8, 32, 32, 3, X1, HL, 1)
         run("k5 halo B2 48x40 Cin64", 2, 48, 40, 64, 64, 5, X1, HL)
-        run("k5 halo boff0", 2, 48, 40, 64, 64, 5, X1, HL, 1)
+        run("k5 halo boff=addr", 2, 48, 40, 64, 64, 5, X1, HL, 1)
         run("k7 halo 32x24", 1, 32, 24, 64, 64, 7, X1, HL)
     if group in ("x3", "all"):
         run("x3 gemm k1", 1, 16, 8, 32, 16, 1, X3, PT)
