@@ -44,6 +44,7 @@ struct KernelParams {
   int nsplit;              // 1: tf32x1, 3: tf32x3
   int halo;                // 1: patch reuse across taps
   int cchunks;             // ceil(Cin / 32)
+  int ksplits;             // split of the channel-chunk loop over blockIdx.z (small maps: fill the 148 SMs)
   int stages;
   int force_base_offset0;  // debug knob (bring-up): 1 = put (addr>>7)&7 into base_offset (known to be WRONG)
   uint32_t a_stage_bytes, b_stage_bytes, patch_bytes;
@@ -180,6 +181,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int x0 = tx * TILE_W, y0 = ty * P.th, b0 = bg * P.nb;
   const int n0 = blockIdx.y * P.bn;
   const int taps = P.ks * P.ks;
+  const int cc_per = (P.cchunks + P.ksplits - 1) / P.ksplits;
+  const int cc_begin = blockIdx.z * cc_per, cc_end = min(P.cchunks, cc_begin + cc_per);
+  const bool has_work = cc_end > cc_begin;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -197,9 +201,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer ============================================
-    if (lane == 0) {
+    if (lane == 0 && has_work) {
       int s = 0, ph = 0, pa = 0, pha = 0;
-      for (int cc = 0; cc < P.cchunks; ++cc) {
+      for (int cc = cc_begin; cc < cc_end; ++cc) {
         if (P.halo) {
           mbar_wait(emptya_bar(pa), pha ^ 1, P.error_flag, 1);
           mbar_expect_tx(fulla_bar(pa), P.patch_bytes * nops);
@@ -224,10 +228,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ==============================================
-    if (lane == 0) {
+    if (lane == 0 && has_work) {
       int s = 0, ph = 0, pa = 0, pha = 0;
       uint32_t acc = 0;
-      for (int cc = 0; cc < P.cchunks; ++cc) {
+      for (int cc = cc_begin; cc < cc_end; ++cc) {
         if (P.halo) {
           mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
           tc_fence_after();
@@ -279,7 +283,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       umma_commit(tmemfull_bar);
     }
-  } else {
+  } else if (has_work) {
     // ===================================== epilogue ================================================
     mbar_wait(tmemfull_bar, 0, P.error_flag, 5);
     tc_fence_after();
@@ -301,11 +305,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float4 o;
             o.x = __uint_as_float(v[j + 0]); o.y = __uint_as_float(v[j + 1]);
             o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-            if (P.bias) {
+            if (P.bias && blockIdx.z == 0) {
               const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + co));
               o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             }
-            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+            if (P.ksplits == 1) {
+              *reinterpret_cast<float4*>(orow + c0 + j) = o;
+            } else {  // K-split partial sums meet in the zero-initialised output
+              atomicAdd(orow + c0 + j + 0, o.x); atomicAdd(orow + c0 + j + 1, o.y);
+              atomicAdd(orow + c0 + j + 2, o.z); atomicAdd(orow + c0 + j + 3, o.w);
+            }
           }
         }
       }
@@ -329,6 +338,7 @@ struct WgradParams {
   int B, H, W, Cin, Cout, ks, pad;
   int kpad;              // ceil32(Cin): row pitch of the packed gradient
   int bn, tg;            // N tile, taps per CTA
+  int acc_stride;        // TMEM columns between the accumulators of two taps (power of two >= bn)
   int tap_groups;
   int xchunks;           // ceil(W / 32)
   int kiters;            // B * H * xchunks
@@ -405,7 +415,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(full_bar(s), ph, P.error_flag, 7);
         tc_fence_after();
         for (int t = 0; t < ntap; ++t) {
-          const uint32_t d_t = tmem_base + (uint32_t)(t * P.bn);
+          const uint32_t d_t = tmem_base + (uint32_t)(t * P.acc_stride);
 #pragma unroll
           for (int k = 0; k < KC / 8; ++k) {
             const uint64_t da = make_smem_desc(stage_a(s, t, 0) + k * 32u, 1024u, 0u);
@@ -438,7 +448,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int tap = tap0 + t;
       for (int c0 = 0; c0 < P.bn; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)(t * P.bn + c0), v);
+        tmem_ld16(trow + (uint32_t)(t * P.acc_stride + c0), v);
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -622,8 +632,21 @@ static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo
     rc = make_map(&tmBlo, wp_lo ? wp_lo : wp, 3, dims, strides, box);
     if (rc) return rc;
   }
+  // small maps: split the channel-chunk loop so that the grid covers the 148 SMs
+  {
+    const int base = P.tiles_x * P.tiles_y * bgroups * ((d->cout + bn - 1) / bn);
+    int ks = 1;
+    if (base < 120) ks = (148 + base - 1) / base;
+    if (ks > P.cchunks) ks = P.cchunks;
+    if (ks > 1) {
+      const int per = (P.cchunks + ks - 1) / ks;
+      ks = (P.cchunks + per - 1) / per;   // no empty splits
+    }
+    P.ksplits = ks;
+    if (ks > 1) PN_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)d->batch * d->height * d->width * d->cout, stream));
+  }
   PN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(P.tiles_x * P.tiles_y * bgroups, (d->cout + bn - 1) / bn);
+  dim3 grid(P.tiles_x * P.tiles_y * bgroups, (d->cout + bn - 1) / bn, P.ksplits);
   conv_igemm_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmAlo, tmB, tmBlo, P);
   count_launch();
   return check_launch("conv_igemm_kernel");
@@ -646,9 +669,10 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x_nchw, const float* x
   int bn = (d->cout + 15) / 16 * 16;
   if (bn > 128) bn = 128;
   P.bn = bn;
+  P.acc_stride = (int)pow2_cols(bn);
   int tg = (P.nsplit == 3) ? 2 : 4;
   if (tg > taps) tg = taps;
-  while (tg * bn > 512) --tg;
+  while (tg * P.acc_stride > 512) --tg;
   P.tg = tg;
   P.tap_groups = (taps + tg - 1) / tg;
   P.xchunks = (d->width + KC - 1) / KC;
@@ -659,7 +683,7 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x_nchw, const float* x
   if (ksplits > P.kiters) ksplits = P.kiters;
   if (ksplits < 1) ksplits = 1;
   P.ksplits = ksplits;
-  P.tmem_cols = pow2_cols(tg * bn);
+  P.tmem_cols = pow2_cols(tg * P.acc_stride);
   P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   P.dwp = dwp; P.error_flag = error_flag;
   const uint32_t stage_bytes = nops * ((uint32_t)bn * 128u + (uint32_t)tg * 16384u);

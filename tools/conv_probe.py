@@ -46,6 +46,31 @@ def run(tag, B, H, W, Cin, Cout, k, precision, mode, debug=0, seed=0):
     return True
 
 
+def run_bwd(tag, B, H, W, Cin, Cout, k, precision, which, seed=0):
+    """which: 'dgrad' or 'wgrad' -- exercises the backward kernels in isolation."""
+    from packnet_sfm_b200 import functional as PF
+    torch.manual_seed(seed)
+    dev = torch.device("cuda:0")
+    PF.set_precision(precision)
+    x = (torch.rand(B, H, W, Cin, device=dev) - 0.5).requires_grad_(which == "dgrad")
+    w = ((torch.rand(Cout, Cin, k, k, device=dev) - 0.5) * (2.0 / (Cin * k * k) ** 0.5)).requires_grad_(which == "wgrad")
+    gy = torch.rand(B, H, W, Cout, device=dev) - 0.5
+    try:
+        y = PF.conv2d(x, w, None)
+        torch.cuda.synchronize()
+        y.backward(gy)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print("%-40s EXCEPTION %s" % (tag, str(e)[:120]))
+        return False
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    yr = F.conv2d(xd.permute(0, 3, 1, 2), wd, None, padding=k // 2).permute(0, 2, 3, 1)
+    yr.backward(gy.double())
+    got, ref = (x.grad, xd.grad) if which == "dgrad" else (w.grad, wd.grad)
+    print("%-40s %s rel_l2=%.3e" % (tag, which, float((got.double() - ref).norm() / ref.norm())))
+    return True
+
+
 def main():
     group = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.backends.cudnn.allow_tf32 = False
@@ -76,5 +101,21 @@ def main():
         run("x1 k3 pertap K=2048", 1, 16, 16, 2048, 64, 3, X1, PT)
 
 
+def main_bwd(group):
+    torch.backends.cudnn.allow_tf32 = False
+    X1, X3 = ops.PRECISION_TF32X1, ops.PRECISION_TF32X3
+    cases = [(2, 40, 36, 64, 48, 3), (1, 32, 24, 96, 64, 5), (4, 6, 20, 64, 128, 3), (1, 16, 16, 36, 32, 3),
+             (1, 16, 16, 64, 512, 3), (1, 32, 24, 64, 64, 7), (2, 12, 40, 256, 256, 3)]
+    only = int(sys.argv[2]) if len(sys.argv) > 2 else -1
+    for i, c in enumerate(cases):
+        if only >= 0 and i != only:
+            continue
+        for prec in (X1, X3):
+            run_bwd("%s x%d %s" % (group, prec, c), *c, prec, group)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] in ("dgrad", "wgrad"):
+        main_bwd(sys.argv[1])
+        sys.exit(0)
     main()
