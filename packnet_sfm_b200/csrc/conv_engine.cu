@@ -673,6 +673,7 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x_nchw, const float* x
   int tg = (P.nsplit == 3) ? 2 : 4;
   if (tg > taps) tg = taps;
   while (tg * P.acc_stride > 512) --tg;
+  if (d->debug_flags & 2) tg = 1;   // bring-up knob: one tap (one accumulator) per CTA
   P.tg = tg;
   P.tap_groups = (taps + tg - 1) / tg;
   P.xchunks = (d->width + KC - 1) / KC;

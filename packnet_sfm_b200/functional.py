@@ -36,6 +36,21 @@ def _stream():
     return _lib.current_stream()
 
 
+_errflag = {}
+
+
+def error_flag():
+    """Pinned host word the conv kernels write 0xDEAD00xx into when a pipeline wait times out (they trap
+    instead of hanging); being host memory it stays readable after the CUDA context died."""
+    if "t" not in _errflag:
+        _errflag["t"] = torch.zeros(4, dtype=torch.int32).pin_memory()
+    return _errflag["t"]
+
+
+def read_error_flag():
+    return int(error_flag()[0].item()) & 0xFFFFFFFF
+
+
 def _p(t):
     return _lib.ptr(t) if t is not None else None
 
@@ -63,7 +78,7 @@ def _conv_raw(x, x_lo, wp, wp_lo, bias, cout, ksize, precision):
     y = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
     d = ConvDesc(B, H, W, Cin, cout, ksize, precision, _state["mode"], 0)
     _lib.check(_lib.lib().pn_conv2d_forward(ctypes.byref(d), _lib.ptr(x), _p(x_lo), _lib.ptr(wp), _p(wp_lo), _p(bias),
-                                            _lib.ptr(y), None, _stream()), "pn_conv2d_forward")
+                                            _lib.ptr(y), _lib.ptr(error_flag()), _stream()), "pn_conv2d_forward")
     return y
 
 
@@ -124,7 +139,7 @@ class _Conv2d(torch.autograd.Function):
             dwp = torch.empty(int(n.value), dtype=torch.float32, device=x.device)
             d = ConvDesc(B, H, W, Cin, cout, k, precision, 0, 0)
             _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_t), _p(x_t_lo), _lib.ptr(g_t), _p(g_t_lo),
-                                           _lib.ptr(dwp), None, _stream()), "pn_conv2d_wgrad")
+                                           _lib.ptr(dwp), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
             gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=x.device)
             _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, _stream()),
                        "pn_conv2d_unpack_weight_grad")
