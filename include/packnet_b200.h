@@ -138,12 +138,12 @@ int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, 
 int pn_conv2d_pack_weight(const float* w_oihw, float* w_packed, float* w_packed_lo, int cout, int cin,
                           int ksize, int transposed, pn_stream_t stream);
 
-/* Weight gradient (autograd backward of nn.Conv2d w.r.t. weight).  The reduction runs over pixels, so the
- * operands are the NCHW (pixel-contiguous) copies: x_nchw [B,Cin,H,W], g_nchw [B,Cout,H,W] (+ tf32 residuals
- * for TF32X3).  dw_packed [Cout][k*k][ceil32(Cin)] is zeroed and accumulated; pn_conv2d_unpack_weight_grad
- * converts it to OIHW.  desc->width must be a multiple of 4. */
-int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x_nchw, const float* x_nchw_lo, const float* g_nchw,
-                    const float* g_nchw_lo, float* dw_packed, uint32_t* error_flag, pn_stream_t stream);
+/* Weight gradient (autograd backward of nn.Conv2d w.r.t. weight).  x [B,H,W,Cin] and g = dL/dy [B,H,W,Cout]
+ * are the NHWC tensors themselves (read as MN-major operand tiles; the reduction runs over pixels); x_lo / g_lo
+ * are their tf32 residuals (TF32X3 only).  dw_packed [Cout][k*k][ceil32(Cin)] is zeroed and accumulated;
+ * pn_conv2d_unpack_weight_grad converts it to OIHW. */
+int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* g, const float* g_lo,
+                    float* dw_packed, uint32_t* error_flag, pn_stream_t stream);
 int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize,
                                  pn_stream_t stream);
 

@@ -327,43 +327,60 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------
 // weight gradient:  dW[co, tap, ci] = sum_{b,y,x} dZ[b,y,x,co] * X[b, y+dy-p, x+dx-p, ci]
-//   The reduction runs over pixels, so the K-major operands are the NCHW (pixel-contiguous) copies:
-//   A = X^T  : rows = 128 input channels, K-chunk = 32 consecutive x positions of one image row, shifted by
-//              the tap (TMA zero-fills the padding),  B = dZ^T : rows = BN output channels, same pixels.
-//   One CTA owns (128-channel block, group of TG taps, BN block, K split) and keeps TG accumulators in TMEM;
-//   the dZ tile of a K-chunk is loaded once and reused by the TG taps.  Partial sums of the K splits are
-//   combined with red.global.add.f32 into the zero-initialised packed gradient [Cout][tap][ceil32(Cin)].
+//   The reduction runs over pixels.  Both operands are read straight from the NHWC tensors as MN-MAJOR tiles:
+//   a TMA box of (32 channels x 8 px x th rows) puts one pixel per 128-byte row, i.e. K (= pixels) along the
+//   rows and 32 M/N elements (= channels) contiguous -- the canonical MN-major SWIZZLE_128B operand; a block of
+//   128 input channels is four such boxes (LBO = bytes per box).  One MMA covers K = 8 pixels = one 1024-byte
+//   swizzle atom.  The X patch of a pixel tile is loaded ONCE with its halo and every tap reads it through a
+//   shifted descriptor (same trick as the forward HALO mode); the dZ tile is shared by all taps.  One CTA owns
+//   (128-channel block, group of TG taps, BN block, pixel split) with TG accumulators side by side in TMEM;
+//   partial sums of the pixel splits meet in the zero-initialised packed gradient via red.global.add.f32.
+//   tf32x3 = three launches of this tf32x1 kernel on (X_lo,dZ), (X,dZ_lo), (X,dZ).
+//   (A K-major formulation over NCHW copies was tried first: TMA rejects the 4-byte-misaligned innermost
+//   coordinate a tap shift along x produces -- profiles/r01_conv_probe.txt.)
 // ---------------------------------------------------------------------------------------------------
 struct WgradParams {
   int B, H, W, Cin, Cout, ks, pad;
   int kpad;              // ceil32(Cin): row pitch of the packed gradient
-  int bn, tg;            // N tile, taps per CTA
+  int bn, tg;            // N tile (multiple of 32), taps per CTA
   int acc_stride;        // TMEM columns between the accumulators of two taps (power of two >= bn)
   int tap_groups;
-  int xchunks;           // ceil(W / 32)
-  int kiters;            // B * H * xchunks
-  int ksplits;
-  int nsplit, stages;
+  int th;                // pixel-tile rows (tile = 8 x th pixels = th MMA k-steps)
+  int tiles_x, tiles_y, ntiles;   // pixel tiles per image / in total (B * tiles_y * tiles_x)
+  int psplits;
+  int stages;
+  uint32_t patch_bytes;  // PATCH_PITCH * (th + ks - 1) * 128: one 32-channel block of the X patch
+  uint32_t gblk_bytes;   // 8 * th * 128: one 32-channel block of the dZ tile
   uint32_t tmem_cols, idesc;
   float* dwp;            // [Cout][taps][kpad]
   unsigned int* error_flag;
 };
 
+// MN-major SWIZZLE_128B descriptor: LBO = byte distance between 32-element blocks along M/N,
+// SBO = byte distance between 8-row groups along K (one group per MMA here)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
-                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmGlo, const WgradParams P) {
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int nops = (P.nsplit == 3) ? 2 : 1;
-  const uint32_t a_bytes = 128u * 128u, b_bytes = (uint32_t)P.bn * 128u;
-  const uint32_t stage_bytes = nops * (b_bytes + (uint32_t)P.tg * a_bytes);
+  const int nblk_n = P.bn / 32;
+  const uint32_t stage_bytes = 4u * P.patch_bytes + (uint32_t)nblk_n * P.gblk_bytes;
   const uint32_t bars_base = smem_base + P.stages * stage_bytes;
   auto full_bar = [&](int s) { return bars_base + 8u * s; };
   auto empty_bar = [&](int s) { return bars_base + 8u * (MAX_STAGES + s); };
   const uint32_t tmemfull_bar = bars_base + 8u * (2 * MAX_STAGES);
   const uint32_t tmem_slot = bars_base + 8u * (2 * MAX_STAGES + 1);
-  auto stage_b = [&](int s, int op) { return smem_base + s * stage_bytes + op * b_bytes; };
-  auto stage_a = [&](int s, int t, int op) { return smem_base + s * stage_bytes + nops * b_bytes + (uint32_t)(t * nops + op) * a_bytes; };
+  auto stage_x = [&](int s, int j) { return smem_base + s * stage_bytes + (uint32_t)j * P.patch_bytes; };
+  auto stage_g = [&](int s, int i) { return smem_base + s * stage_bytes + 4u * P.patch_bytes + (uint32_t)i * P.gblk_bytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci0 = blockIdx.x * 128;
@@ -372,9 +389,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tap0 = tgi * P.tg;
   const int taps = P.ks * P.ks;
   const int ntap = min(P.tg, taps - tap0);
-  const int split = blockIdx.z;
-  const int per = (P.kiters + P.ksplits - 1) / P.ksplits;
-  const int k_begin = split * per, k_end = min(P.kiters, k_begin + per);
+  const int per = (P.ntiles + P.psplits - 1) / P.psplits;
+  const int t_begin = blockIdx.z * per, t_end = min(P.ntiles, t_begin + per);
+  const bool has_work = t_end > t_begin;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -388,22 +405,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const bool has_work = k_end > k_begin;
 
   if (warp == 0) {
     if (lane == 0 && has_work) {
       int s = 0, ph = 0;
-      for (int kit = k_begin; kit < k_end; ++kit) {
-        const int xc = kit % P.xchunks, y = (kit / P.xchunks) % P.H, b = kit / (P.xchunks * P.H);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int tx = t % P.tiles_x, ty = (t / P.tiles_x) % P.tiles_y, b = t / (P.tiles_x * P.tiles_y);
+        const int x0 = tx * TILE_W, y0 = ty * P.th;
         mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 6);
-        mbar_expect_tx(full_bar(s), nops * (b_bytes + (uint32_t)ntap * a_bytes));
-        tma_load_4d(stage_b(s, 0), &tmG, full_bar(s), xc * KC, y, n0, b);
-        if (nops == 2) tma_load_4d(stage_b(s, 1), &tmGlo, full_bar(s), xc * KC, y, n0, b);
-        for (int t = 0; t < ntap; ++t) {
-          const int tap = tap0 + t, dy = tap / P.ks, dx = tap % P.ks;
-          tma_load_4d(stage_a(s, t, 0), &tmX, full_bar(s), xc * KC + dx - P.pad, y + dy - P.pad, ci0, b);
-          if (nops == 2) tma_load_4d(stage_a(s, t, 1), &tmXlo, full_bar(s), xc * KC + dx - P.pad, y + dy - P.pad, ci0, b);
-        }
+        mbar_expect_tx(full_bar(s), stage_bytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_4d(stage_x(s, j), &tmX, full_bar(s), ci0 + 32 * j, x0 - P.pad, y0 - P.pad, b);
+        for (int i = 0; i < nblk_n; ++i) tma_load_4d(stage_g(s, i), &tmG, full_bar(s), n0 + 32 * i, x0, y0, b);
         if (++s == P.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -411,24 +424,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (lane == 0 && has_work) {
       int s = 0, ph = 0;
       uint32_t acc = 0;
-      for (int kit = k_begin; kit < k_end; ++kit) {
+      for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(full_bar(s), ph, P.error_flag, 7);
         tc_fence_after();
-        for (int t = 0; t < ntap; ++t) {
-          const uint32_t d_t = tmem_base + (uint32_t)(t * P.acc_stride);
-#pragma unroll
-          for (int k = 0; k < KC / 8; ++k) {
-            const uint64_t da = make_smem_desc(stage_a(s, t, 0) + k * 32u, 1024u, 0u);
-            const uint64_t db = make_smem_desc(stage_b(s, 0) + k * 32u, 1024u, 0u);
-            if (nops == 2) {
-              const uint64_t dal = make_smem_desc(stage_a(s, t, 1) + k * 32u, 1024u, 0u);
-              const uint64_t dbl = make_smem_desc(stage_b(s, 1) + k * 32u, 1024u, 0u);
-              umma_tf32(d_t, dal, db, P.idesc, (k == 0) ? acc : 1u);
-              umma_tf32(d_t, da, dbl, P.idesc, 1u);
-              umma_tf32(d_t, da, db, P.idesc, 1u);
-            } else {
-              umma_tf32(d_t, da, db, P.idesc, (k == 0) ? acc : 1u);
-            }
+        for (int tt = 0; tt < ntap; ++tt) {
+          const int tap = tap0 + tt, dy = tap / P.ks, dx = tap % P.ks;
+          const uint32_t d_t = tmem_base + (uint32_t)(tt * P.acc_stride);
+          for (int kk = 0; kk < P.th; ++kk) {  // one MMA per tile row: K = 8 pixels
+            const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
+            const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
+            umma_tf32(d_t, make_smem_desc_mn(a, P.patch_bytes, 1024u), make_smem_desc_mn(bb, P.gblk_bytes, 1024u), P.idesc,
+                      (kk == 0) ? acc : 1u);
           }
         }
         acc = 1u;
@@ -652,74 +658,79 @@ static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo
   return check_launch("conv_igemm_kernel");
 }
 
-// x_nchw [B,Cin,H,W], g_nchw [B,Cout,H,W] (+ tf32 residuals) -> dwp [Cout][k*k][ceil32(Cin)] (accumulated into zeros)
-static int conv_wgrad(const pn_conv_desc* d, const float* x_nchw, const float* x_lo, const float* g_nchw, const float* g_lo,
-                      float* dwp, unsigned int* error_flag, cudaStream_t stream) {
-  PN_REQUIRE(d && x_nchw && g_nchw && dwp, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
+// x [B,H,W,Cin], g [B,H,W,Cout] (NHWC) -> dwp [Cout][k*k][ceil32(Cin)], ACCUMULATED (the caller zeroes it)
+static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, float* dwp, unsigned int* error_flag,
+                      cudaStream_t stream) {
+  PN_REQUIRE(d && x && g && dwp, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
   PN_REQUIRE(d->ksize >= 1 && d->ksize <= 7 && (d->ksize & 1), PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: ksize %d", d->ksize);
-  PN_REQUIRE(d->width % 4 == 0, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: width %d must be a multiple of 4 (TMA row pitch)", d->width);
-  PN_REQUIRE(d->precision == PN_PRECISION_TF32X1 || (x_lo && g_lo), PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: tf32x3 needs residuals");
-  PN_REQUIRE(aligned16(x_nchw) && aligned16(g_nchw) && aligned16(dwp), PN_ERR_ALIGNMENT, "pn_conv2d_wgrad: alignment");
+  PN_REQUIRE(d->cin % 4 == 0 && d->cout % 4 == 0, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: Cin/Cout must be multiples of 4");
+  PN_REQUIRE(aligned16(x) && aligned16(g) && aligned16(dwp), PN_ERR_ALIGNMENT, "pn_conv2d_wgrad: alignment");
   WgradParams P{};
   P.B = d->batch; P.H = d->height; P.W = d->width; P.Cin = d->cin; P.Cout = d->cout; P.ks = d->ksize; P.pad = d->ksize / 2;
   P.kpad = kpad_of(d->cin);
-  P.nsplit = (d->precision == PN_PRECISION_TF32X3) ? 3 : 1;
-  const int nops = (P.nsplit == 3) ? 2 : 1;
   const int taps = d->ksize * d->ksize;
-  int bn = (d->cout + 15) / 16 * 16;
-  if (bn > 128) bn = 128;
+  int bn = (d->cout + 31) / 32 * 32;
+  if (bn > 256) bn = 256;
   P.bn = bn;
   P.acc_stride = (int)pow2_cols(bn);
-  int tg = (P.nsplit == 3) ? 2 : 4;
+  int tg = 512 / P.acc_stride;
   if (tg > taps) tg = taps;
-  while (tg * P.acc_stride > 512) --tg;
-  if (d->debug_flags & 2) tg = 1;   // bring-up knob: one tap (one accumulator) per CTA
+  if (d->debug_flags & 2) tg = 1;
   P.tg = tg;
   P.tap_groups = (taps + tg - 1) / tg;
-  P.xchunks = (d->width + KC - 1) / KC;
-  P.kiters = d->batch * d->height * P.xchunks;
-  const int mblocks = (P.kpad + 127) / 128, nblocks = (d->cout + bn - 1) / bn;
-  const int base_ctas = mblocks * P.tap_groups * nblocks;
-  int ksplits = (2 * 148 + base_ctas - 1) / base_ctas;
-  if (ksplits > P.kiters) ksplits = P.kiters;
-  if (ksplits < 1) ksplits = 1;
-  P.ksplits = ksplits;
-  P.tmem_cols = pow2_cols(tg * P.acc_stride);
-  P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  P.dwp = dwp; P.error_flag = error_flag;
-  const uint32_t stage_bytes = nops * ((uint32_t)bn * 128u + (uint32_t)tg * 16384u);
+  // pixel tile height: as tall as shared memory allows with >= 2 stages (4 X-patch blocks + bn/32 dZ blocks per stage)
   const uint32_t budget = 227u * 1024u - 1024u - 512u;
-  PN_REQUIRE(2 * stage_bytes <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: stage does not fit");
+  int th = d->height < TILE_ROWS ? d->height : TILE_ROWS;
+  auto stage_bytes_of = [&](int t) {
+    return 4u * (uint32_t)PATCH_PITCH * (t + d->ksize - 1) * 128u + (uint32_t)(bn / 32) * 8u * t * 128u;
+  };
+  while (th > 1 && 2u * stage_bytes_of(th) > budget) th = (th + 1) / 2;
+  PN_REQUIRE(stage_bytes_of(th) <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: tile does not fit in shared memory");
+  P.th = th;
+  P.patch_bytes = (uint32_t)PATCH_PITCH * (th + d->ksize - 1) * 128u;
+  P.gblk_bytes = 8u * th * 128u;
+  const uint32_t stage_bytes = stage_bytes_of(th);
   int stages = (int)(budget / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 1) stages = 1;
   P.stages = stages;
+  P.tiles_x = (d->width + TILE_W - 1) / TILE_W;
+  P.tiles_y = (d->height + th - 1) / th;
+  P.ntiles = d->batch * P.tiles_x * P.tiles_y;
+  const int mblocks = (P.kpad + 127) / 128, nblocks = (d->cout + bn - 1) / bn;
+  const int base_ctas = mblocks * P.tap_groups * nblocks;
+  int psplits = (2 * 148 + base_ctas - 1) / base_ctas;
+  if (psplits > P.ntiles) psplits = P.ntiles;
+  if (psplits < 1) psplits = 1;
+  {
+    const int per = (P.ntiles + psplits - 1) / psplits;
+    psplits = (P.ntiles + per - 1) / per;
+  }
+  P.psplits = psplits;
+  P.tmem_cols = pow2_cols(tg * P.acc_stride);
+  // kind::tf32, fp32 accumulate, M=128, N=bn, A and B MN-major (bits 15, 16)
+  P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.dwp = dwp; P.error_flag = error_flag;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
 
-  alignas(64) CUtensorMap tmX, tmXlo, tmG, tmGlo;
+  alignas(64) CUtensorMap tmX, tmG;
   {
-    const uint64_t dims[4] = {(uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->cin, (uint64_t)d->batch};
-    const uint64_t strides[3] = {(uint64_t)d->width * 4, (uint64_t)d->width * d->height * 4,
-                                 (uint64_t)d->width * d->height * d->cin * 4};
-    const uint32_t box[4] = {KC, 1, 128, 1};
-    int rc = make_map(&tmX, x_nchw, 4, dims, strides, box);
-    if (rc) return rc;
-    rc = make_map(&tmXlo, x_lo ? x_lo : x_nchw, 4, dims, strides, box);
+    const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
+    const uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)d->width * d->cin * 4, (uint64_t)d->height * d->width * d->cin * 4};
+    const uint32_t box[4] = {KC, PATCH_PITCH, (uint32_t)(th + d->ksize - 1), 1};
+    int rc = make_map(&tmX, x, 4, dims, strides, box);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->cout, (uint64_t)d->batch};
-    const uint64_t strides[3] = {(uint64_t)d->width * 4, (uint64_t)d->width * d->height * 4,
-                                 (uint64_t)d->width * d->height * d->cout * 4};
-    const uint32_t box[4] = {KC, 1, (uint32_t)bn, 1};
-    int rc = make_map(&tmG, g_nchw, 4, dims, strides, box);
-    if (rc) return rc;
-    rc = make_map(&tmGlo, g_lo ? g_lo : g_nchw, 4, dims, strides, box);
+    const uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
+    const uint64_t strides[3] = {(uint64_t)d->cout * 4, (uint64_t)d->width * d->cout * 4, (uint64_t)d->height * d->width * d->cout * 4};
+    const uint32_t box[4] = {KC, TILE_W, (uint32_t)th, 1};
+    int rc = make_map(&tmG, g, 4, dims, strides, box);
     if (rc) return rc;
   }
-  PN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)d->cout * taps * P.kpad, stream));
   PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(mblocks, P.tap_groups * nblocks, ksplits);
-  conv_wgrad_kernel<<<grid, NTHREADS, smem, stream>>>(tmX, tmXlo, tmG, tmGlo, P);
+  dim3 grid(mblocks, P.tap_groups * nblocks, psplits);
+  conv_wgrad_kernel<<<grid, NTHREADS, smem, stream>>>(tmX, tmG, P);
   count_launch();
   return check_launch("conv_wgrad_kernel");
 }
@@ -767,9 +778,21 @@ extern "C" int pn_tf32_residual(const float* x, float* lo, size_t n, pn_stream_t
   return check_launch("tf32_residual_kernel");
 }
 
-extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x_nchw, const float* x_nchw_lo, const float* g_nchw,
-                               const float* g_nchw_lo, float* dw_packed, uint32_t* error_flag, pn_stream_t stream) {
-  return conv::conv_wgrad(desc, x_nchw, x_nchw_lo, g_nchw, g_nchw_lo, dw_packed, error_flag, reinterpret_cast<cudaStream_t>(stream));
+extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* g, const float* g_lo,
+                               float* dw_packed, uint32_t* error_flag, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(desc && dw_packed, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
+  PN_REQUIRE(desc->precision == PN_PRECISION_TF32X1 || (desc->precision == PN_PRECISION_TF32X3 && x_lo && g_lo),
+             PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: tf32x3 needs the residual operands");
+  const size_t n = (size_t)desc->cout * desc->ksize * desc->ksize * conv::kpad_of(desc->cin);
+  PN_CUDA(cudaMemsetAsync(dw_packed, 0, sizeof(float) * n, stream));
+  if (desc->precision == PN_PRECISION_TF32X3) {   // error-compensated: small terms first
+    int rc = conv::conv_wgrad(desc, x_lo, g, dw_packed, error_flag, stream);
+    if (rc) return rc;
+    rc = conv::conv_wgrad(desc, x, g_lo, dw_packed, error_flag, stream);
+    if (rc) return rc;
+  }
+  return conv::conv_wgrad(desc, x, g, dw_packed, error_flag, stream);
 }
 
 extern "C" int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, pn_stream_t stream) {

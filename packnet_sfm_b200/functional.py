@@ -129,11 +129,8 @@ class _Conv2d(torch.autograd.Function):
             wt, wt_lo = _pack_weight(w_eff, True, three)
             gx = _conv_raw(gy, gy_lo, wt, wt_lo, None, Cin, k, precision)
         if ctx.needs_input_grad[1]:
-            # weight gradient: reduction over pixels -> pixel-contiguous (NCHW) operand copies
-            x_t = x.permute(0, 3, 1, 2).contiguous()
-            g_t = gy.permute(0, 3, 1, 2).contiguous()
-            x_t_lo = x_lo.permute(0, 3, 1, 2).contiguous() if three else None
-            g_t_lo = gy_lo.permute(0, 3, 1, 2).contiguous() if three else None
+            # weight gradient: reduction over pixels, operands read in place as MN-major tiles
+            x_t, g_t, x_t_lo, g_t_lo = x, gy, (x_lo if three else None), gy_lo
             n = ctypes.c_size_t(0)
             _lib.check(lib.pn_conv2d_packed_weight_elems(cout, Cin, k, 0, ctypes.byref(n)), "packed_weight_elems")
             dwp = torch.empty(int(n.value), dtype=torch.float32, device=x.device)

@@ -108,8 +108,8 @@ def wgrad_direct(tag, B, H, W, Cin, Cout, k, precision, debug):
     from packnet_sfm_b200._lib_conv import ConvDesc
     dev = torch.device("cuda:0")
     torch.manual_seed(1)
-    x = torch.rand(B, Cin, H, W, device=dev) - 0.5
-    g = torch.rand(B, Cout, H, W, device=dev) - 0.5
+    x = torch.rand(B, H, W, Cin, device=dev) - 0.5
+    g = torch.rand(B, H, W, Cout, device=dev) - 0.5
     lib = _lib.lib()
     n = ctypes.c_size_t(0)
     lib.pn_conv2d_packed_weight_elems(Cout, Cin, k, 0, ctypes.byref(n))
@@ -129,7 +129,7 @@ def wgrad_direct(tag, B, H, W, Cin, Cout, k, precision, debug):
     gw = torch.empty(Cout, Cin, k, k, device=dev)
     lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw), Cout, Cin, k, _lib.current_stream())
     w = torch.zeros(Cout, Cin, k, k, device=dev, dtype=torch.float64, requires_grad=True)
-    F.conv2d(x.double(), w, padding=k // 2).backward(g.double())
+    F.conv2d(x.double().permute(0, 3, 1, 2), w, padding=k // 2).backward(g.double().permute(0, 3, 1, 2))
     print("%-46s ok rel_l2=%.3e" % (tag, float((gw.double() - w.grad).norm() / w.grad.norm())))
 
 
