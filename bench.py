@@ -167,7 +167,7 @@ def time_kernels(args, dev, pk):
         out["o"] = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats])
 
     def bwd():
-        out["o"]["loss"].backward(retain_graph=True)
+        torch.autograd.grad(out["o"]["loss"], inv + mats, retain_graph=True)
 
     for _ in range(3):
         fwd(); bwd()
