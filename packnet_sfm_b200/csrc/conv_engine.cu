@@ -352,6 +352,7 @@ struct WgradParams {
   uint32_t patch_bytes;  // PATCH_PITCH * (th + ks - 1) * 128: one 32-channel block of the X patch
   uint32_t gblk_bytes;   // 8 * th * 128: one 32-channel block of the dZ tile
   uint32_t tmem_cols, idesc;
+  int swap_lbo_sbo;      // bring-up knob
   float* dwp;            // [Cout][taps][kpad]
   unsigned int* error_flag;
 };
@@ -433,8 +434,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int kk = 0; kk < P.th; ++kk) {  // one MMA per tile row: K = 8 pixels
             const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
             const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
-            umma_tf32(d_t, make_smem_desc_mn(a, P.patch_bytes, 1024u), make_smem_desc_mn(bb, P.gblk_bytes, 1024u), P.idesc,
-                      (kk == 0) ? acc : 1u);
+            const uint64_t da = P.swap_lbo_sbo ? make_smem_desc_mn(a, 1024u, P.patch_bytes) : make_smem_desc_mn(a, P.patch_bytes, 1024u);
+            const uint64_t db = P.swap_lbo_sbo ? make_smem_desc_mn(bb, 1024u, P.gblk_bytes) : make_smem_desc_mn(bb, P.gblk_bytes, 1024u);
+            umma_tf32(d_t, da, db, P.idesc, (kk == 0) ? acc : 1u);
           }
         }
         acc = 1u;
@@ -710,6 +712,7 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, flo
   P.tmem_cols = pow2_cols(tg * P.acc_stride);
   // kind::tf32, fp32 accumulate, M=128, N=bn, A and B MN-major (bits 15, 16)
   P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.swap_lbo_sbo = (d->debug_flags & 4) ? 1 : 0;   // bring-up knob
   P.dwp = dwp; P.error_flag = error_flag;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
 

@@ -607,7 +607,9 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
       const int ridx = (qj + HALO) * RW + (qi + HALO);
       float gq = 0.0f;
       if (do_smooth) {
-        const float d0 = s_inv[ridx] * inv_mcl;
+        // explicit single roundings: an FMA-contracted (d0 - d1) would turn exact ties of the nearest-upsampled
+        // scales into +-1 ulp noise and sign() of noise into a full-size gradient
+        const float d0 = __fmul_rn(s_inv[ridx], inv_mcl);
         float i0[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) i0[c] = s_tgt[c * RP + ridx];
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) ad += fabsf(i0[c] - s_tgt[c * RP + ridx + 1]);
           const float wx = expf(-ad / 3.0f);
-          const float sx = (d0 - s_inv[ridx + 1] * inv_mcl) * wx;
+          const float sx = __fsub_rn(d0, __fmul_rn(s_inv[ridx + 1], inv_mcl)) * wx;
           smooth_acc += fabsf(sx) * S.sx_coef;
           gq += sgnf(sx) * wx * S.sx_coef;
         }
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) ad += fabsf(i0[c] - s_tgt[c * RP + ridx + RW]);
           const float wy = expf(-ad / 3.0f);
-          const float sy = (d0 - s_inv[ridx + RW] * inv_mcl) * wy;
+          const float sy = __fsub_rn(d0, __fmul_rn(s_inv[ridx + RW], inv_mcl)) * wy;
           smooth_acc += fabsf(sy) * S.sy_coef;
           gq += sgnf(sy) * wy * S.sy_coef;
         }
@@ -635,7 +637,7 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) ad += fabsf(s_tgt[c * RP + ridx - 1] - i0[c]);
             const float wx = expf(-ad / 3.0f);
-            const float sx = (s_inv[ridx - 1] * inv_mcl - d0) * wx;
+            const float sx = __fsub_rn(__fmul_rn(s_inv[ridx - 1], inv_mcl), d0) * wx;
             gq -= sgnf(sx) * wx * S.sx_coef;
           }
           if (y >= 1) {
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) ad += fabsf(s_tgt[c * RP + ridx - RW] - i0[c]);
             const float wy = expf(-ad / 3.0f);
-            const float sy = (s_inv[ridx - RW] * inv_mcl - d0) * wy;
+            const float sy = __fsub_rn(__fmul_rn(s_inv[ridx - RW], inv_mcl), d0) * wy;
             gq -= sgnf(sy) * wy * S.sy_coef;
           }
         }
