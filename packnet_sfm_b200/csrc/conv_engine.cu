@@ -713,6 +713,9 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, flo
   // kind::tf32, fp32 accumulate, M=128, N=bn, A and B MN-major (bits 15, 16)
   P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   P.swap_lbo_sbo = (d->debug_flags & 4) ? 1 : 0;   // bring-up knob
+  if (d->debug_flags & 8) P.idesc &= ~((1u << 15) | (1u << 16));   // bring-up: K-major interpretation of both
+  if (d->debug_flags & 16) P.idesc &= ~(1u << 16);                  // bring-up: only A MN-major
+  if (d->debug_flags & 32) P.idesc &= ~(1u << 15);                  // bring-up: only B MN-major
   P.dwp = dwp; P.error_flag = error_flag;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
 

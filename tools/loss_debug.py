@@ -52,9 +52,10 @@ def run(tag, B, H, W, full_res, **kw):
 
 
 run("default fullres", 1, 32, 64, True)
-run("photometric only (smooth=0)", 1, 32, 64, True, smooth_loss_weight=0.0)
-run("smooth only-ish (smooth=10)", 1, 32, 64, True, smooth_loss_weight=10.0)
-run("no automask", 1, 32, 64, True, automask_loss=False, smooth_loss_weight=0.0)
-run("mean no automask smooth=0", 1, 32, 64, True, automask_loss=False, photometric_reduce_op="mean", smooth_loss_weight=0.0)
-run("multires default", 1, 32, 64, False)
-run("B2 ragged", 2, 35, 70, True)
+run("smooth=10 fullres", 1, 32, 64, True, smooth_loss_weight=10.0)
+run("B3 17x33", 3, 17, 33, True)
+run("B3 17x33 smooth=0", 3, 17, 33, True, smooth_loss_weight=0.0)
+run("B3 17x33 smooth=10", 3, 17, 33, True, smooth_loss_weight=10.0)
+run("B3 32x64 smooth=10", 3, 32, 64, True, smooth_loss_weight=10.0)
+run("B1 17x33 smooth=10", 1, 17, 33, True, smooth_loss_weight=10.0)
+run("bench shape", 4, 192, 640, True)
