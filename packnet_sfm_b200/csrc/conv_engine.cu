@@ -357,15 +357,18 @@ struct WgradParams {
   unsigned int* error_flag;
 };
 
-// MN-major SWIZZLE_128B descriptor: LBO = byte distance between 32-element blocks along M/N,
-// SBO = byte distance between 8-row groups along K (one group per MMA here)
+// MN-major descriptor for 32-bit (tf32) operands.  Transposing 4-byte elements needs the 32-byte-atom flavour of
+// the 128-byte swizzle on BOTH sides: TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and descriptor layout type 1
+// (SWIZZLE_128B_BASE32B, cute Swizzle<2,5,2>, K atom = 4 rows); with the plain SWIZZLE_128B layout type the MMA
+// returns zeros on B200 (measured, profiles/r01_conv_probe.txt).  LBO = byte distance between 32-element blocks
+// along M/N, SBO = byte distance between the 4-row groups along K (UMMA_K = 8 rows = 2 groups).
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 
@@ -434,8 +437,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int kk = 0; kk < P.th; ++kk) {  // one MMA per tile row: K = 8 pixels
             const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
             const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
-            const uint64_t da = P.swap_lbo_sbo ? make_smem_desc_mn(a, 1024u, P.patch_bytes) : make_smem_desc_mn(a, P.patch_bytes, 1024u);
-            const uint64_t db = P.swap_lbo_sbo ? make_smem_desc_mn(bb, 1024u, P.gblk_bytes) : make_smem_desc_mn(bb, P.gblk_bytes, 1024u);
+            const uint64_t da = P.swap_lbo_sbo ? make_smem_desc_mn(a, 512u, P.patch_bytes) : make_smem_desc_mn(a, P.patch_bytes, 512u);
+            const uint64_t db = P.swap_lbo_sbo ? make_smem_desc_mn(bb, 512u, P.gblk_bytes) : make_smem_desc_mn(bb, P.gblk_bytes, 512u);
             umma_tf32(d_t, da, db, P.idesc, (kk == 0) ? acc : 1u);
           }
         }
@@ -541,7 +544,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+                    const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   PN_REQUIRE(fn != nullptr, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gd[5], gs[5];
@@ -549,7 +552,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_BAD_ARGUMENT, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return PN_OK;
@@ -724,14 +727,14 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, flo
     const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
     const uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)d->width * d->cin * 4, (uint64_t)d->height * d->width * d->cin * 4};
     const uint32_t box[4] = {KC, PATCH_PITCH, (uint32_t)(th + d->ksize - 1), 1};
-    int rc = make_map(&tmX, x, 4, dims, strides, box);
+    int rc = make_map(&tmX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
     const uint64_t strides[3] = {(uint64_t)d->cout * 4, (uint64_t)d->width * d->cout * 4, (uint64_t)d->height * d->width * d->cout * 4};
     const uint32_t box[4] = {KC, TILE_W, (uint32_t)th, 1};
-    int rc = make_map(&tmG, g, 4, dims, strides, box);
+    int rc = make_map(&tmG, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

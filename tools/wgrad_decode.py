@@ -39,13 +39,16 @@ g = torch.zeros(B, H, W, C, device=dev)
 p = torch.arange(H * W, device=dev)
 x.view(-1, C)[p, p % C] = 1.0                         # one-hot over channels
 g.view(-1, C)[:] = (p[:, None] * 100 + torch.arange(C, device=dev)[None, :]).float()
-for dbg in (0, 8, 16, 32, 4):
+for dbg in (0, 4):
     run("onehot k1 debug=%d" % dbg, B, H, W, C, C, 1, dbg, x, g)
 torch.manual_seed(0)
 x = torch.rand(B, H, W, C, device=dev)
 g = torch.rand(B, H, W, C, device=dev)
-for dbg in (0, 8, 16, 32):
+for dbg in (0, 4):
     run("random k1 debug=%d" % dbg, B, H, W, C, C, 1, dbg, x, g)
 x = torch.rand(1, 16, 16, 64, device=dev)
 g = torch.rand(1, 16, 16, 64, device=dev)
 run("random 16x16 C64 k1", 1, 16, 16, 64, 64, 1, 0, x, g)
+x = torch.rand(2, 20, 24, 96, device=dev)
+g = torch.rand(2, 20, 24, 64, device=dev)
+run("random B2 20x24 Cin96 Cout64 k1", 2, 20, 24, 96, 64, 1, 0, x, g)
