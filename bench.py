@@ -21,6 +21,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress to stderr (stdout carries exactly one JSON line)"""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.time() - _T0, msg))
+    sys.stderr.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -105,7 +114,9 @@ def cpu_baseline(args, steps):
     torch.set_num_threads(cores)
     fr = synthetic.make_frames(1, args.height, args.width, seed=1234)
     orc = StepOracle()
+    t0 = time.perf_counter()
     orc.step(fr)                                     # warm-up (allocations, oneDNN primitive caches)
+    log("cpu baseline warm-up step: %.1f s on %d threads" % (time.perf_counter() - t0, cores))
     t0 = time.perf_counter()
     for _ in range(steps):
         orc.step(fr)
@@ -218,7 +229,9 @@ def run_ours(args):
     torch.manual_seed(42)
     import random
     random.seed(42)
+    log("building model")
     model = SelfSupModel().to(dev).train()
+    log("model on device")
     parallel.broadcast_parameters(model)
     bucket = parallel.FlatBucket(model.parameters())
     groups = [{"name": "Depth", "params": list(model.depth_net.parameters()), "lr": 2e-4},
@@ -252,12 +265,16 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
+        t_w = time.time()
         step(dbatch)
+        torch.cuda.synchronize()
+        log("warm-up step %d: %.1f ms (loss %.5f)" % (i, (time.time() - t_w) * 1e3, float(state["loss"].item())))
     launches0 = _lib.launch_count()
     with ClockSampler(local) as clk:
         ms = timed_region(lambda: step(dbatch), args.steps)
     launches = _lib.launch_count() - launches0
+    log("timed region: %.1f ms/step, %d library launches" % (ms / args.steps, launches))
 
     def e2e_step():
         step(to_device(hb, dev))
@@ -265,11 +282,13 @@ def run_ours(args):
 
     e2e_step()
     ms_e2e = timed_region(e2e_step, args.steps)
+    log("e2e region: %.1f ms/step" % (ms_e2e / args.steps))
     h2d = sum(t.numel() * 4 for t in [hb["rgb"], hb["intrinsics"]] + hb["rgb_context"])
 
     if rank == 0:
         pk = peaks()
         extra = time_kernels(args, dev, pk) if world == 1 else {}
+        log("kernel rooflines done")
         imgs = B * world * args.steps
         line = {"metric": "images/sec PackNet01 640x192 self-sup step (fwd+loss+bwd+allreduce+Adam)",
                 "value": imgs / (ms * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
