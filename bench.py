@@ -106,13 +106,24 @@ def to_device(hb, dev):
     return b
 
 
+def usable_cpus():
+    """Host threads the process can really use: min(affinity, cgroup CPU quota).  The GPU box reports 128 logical
+    CPUs but its cgroup grants 16 (cpu.max = "1600000 100000"); 128 OpenMP threads on 16 CPUs ran 10x slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return int(os.environ.get("PN_CPU_THREADS", n))
+
+
 def cpu_baseline(args, steps):
     """The oracle port of the reference step on the host cores, B=1 sample of the workload."""
     from oracle.step_oracle import StepOracle
     from packnet_sfm_b200 import synthetic
-    # "all the host threads it can use": beyond ~32 OpenMP threads the small ops of this network get SLOWER on the
-    # GPU box (measured: 44 s/step with 128 threads vs ~4 s/step with 8 in the build container), so cap it
-    cores = min(os.cpu_count() or 1, int(os.environ.get("PN_CPU_THREADS", "32")))
+    cores = usable_cpus()
     torch.set_num_threads(cores)
     fr = synthetic.make_frames(1, args.height, args.width, seed=1234)
     orc = StepOracle()

@@ -49,7 +49,8 @@ struct KernelParams {
   int force_base_offset0;  // debug knob (bring-up): 1 = put (addr>>7)&7 into base_offset (known to be WRONG)
   uint32_t a_stage_bytes, b_stage_bytes, patch_bytes;
   uint32_t tmem_cols;
-  uint32_t idesc;
+  uint32_t idesc;          // N = bn
+  uint32_t idesc2;         // N = 2*bn (tf32x3: A_hi x [B_hi ; B_lo])
   const float* bias;
   float* out;
   unsigned int* error_flag;
@@ -228,49 +229,56 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ==============================================
+    // One thread feeds the tensor core, so the loop is kept lean: descriptors are (constant high word | start
+    // address), advanced by adding 2 (= 32 bytes >> 4) per K step.
+    // tf32x3 issues TWO MMAs per K step instead of three: B_hi and B_lo of a stage are adjacent in shared memory,
+    // so A_hi x [B_hi ; B_lo] is one N = 2*bn instruction (TMEM columns [0, 2bn)) and A_lo x B_hi a second one
+    // (columns [2bn, 3bn)); the epilogue adds the three column ranges.  Same math time, 22 % fewer operand bytes
+    // read from shared memory (the N = 64 tf32 tile is shared-memory-read bound: DESIGN.md 3.2).
     if (lane == 0 && has_work) {
       int s = 0, ph = 0, pa = 0, pha = 0;
       uint32_t acc = 0;
+      const uint32_t sbo_a = P.halo ? PATCH_PITCH * 128u : 1024u;
+      const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      auto lo_of = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
+      auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+      const uint32_t tm_d2 = tmem_base + 2u * (uint32_t)P.bn;
       for (int cc = cc_begin; cc < cc_end; ++cc) {
         if (P.halo) {
           mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
           tc_fence_after();
         }
+        int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap) {
           mbar_wait(full_bar(s), ph, P.error_flag, 4);
           tc_fence_after();
-          uint32_t a_hi, a_lo, sbo, boff;
+          uint32_t la_hi, la_lo;
           if (P.halo) {
-            const int dy = tap / P.ks, dx = tap % P.ks;
+            // Measured on B200 (profiles/r01_conv_probe.txt): the SWIZZLE_128B XOR is a pure function of the
+            // shared-memory ADDRESS bits, exactly like the TMA write, so a 128-B-shifted start keeps base_offset 0.
             const uint32_t shift = (uint32_t)(dy * PATCH_PITCH + dx) * 128u;
-            a_hi = patch_addr(pa, 0) + shift;
-            a_lo = patch_addr(pa, 1) + shift;
-            sbo = PATCH_PITCH * 128u;
-            // Measured on B200 (tools/conv_probe.py, profiles/r01_conv_probe.txt): the SWIZZLE_128B XOR is a pure
-            // function of the shared-memory ADDRESS bits, exactly like the TMA write, so a 128-B-shifted start
-            // needs base_offset = 0; setting it to (addr>>7)&7 double-applies the phase and scrambles the rows.
-            boff = P.force_base_offset0 ? ((a_hi >> 7) & 7u) : 0u;
+            la_hi = lo_of(patch_addr(pa, 0) + shift);
+            la_lo = lo_of(patch_addr(pa, 1) + shift);
+            if (++dx == P.ks) { dx = 0; ++dy; }
           } else {
-            a_hi = stage_a(s, 0);
-            a_lo = stage_a(s, 1);
-            sbo = 1024u;
-            boff = 0u;
+            la_hi = lo_of(stage_a(s, 0));
+            la_lo = lo_of(stage_a(s, 1));
           }
-          const uint32_t b_hi = stage_b(s, 0), b_lo = stage_b(s, 1);
+          const uint32_t lb = lo_of(stage_b(s, 0));
+          if (nops == 2) {
 #pragma unroll
-          for (int k = 0; k < KC / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t da = make_smem_desc(a_hi + k * 32u, sbo, boff);
-            const uint64_t db = make_smem_desc(b_hi + k * 32u, 1024u, 0u);
-            if (nops == 2) {
-              const uint64_t dal = make_smem_desc(a_lo + k * 32u, sbo, boff);
-              const uint64_t dbl = make_smem_desc(b_lo + k * 32u, 1024u, 0u);
-              umma_tf32(tmem_base, dal, db, P.idesc, acc);   // small terms first
-              umma_tf32(tmem_base, da, dbl, P.idesc, 1u);
-              umma_tf32(tmem_base, da, db, P.idesc, 1u);
-            } else {
-              umma_tf32(tmem_base, da, db, P.idesc, acc);
+            for (int k = 0; k < KC / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+              umma_tf32(tm_d2, desc(hi_a, la_lo + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);       // A_lo x B_hi
+              umma_tf32(tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, acc);  // A_hi x [B_hi;B_lo]
+              acc = 1u;
             }
-            acc = 1u;
+          } else {
+#pragma unroll
+            for (int k = 0; k < KC / 8; ++k) {
+              umma_tf32(tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);
+              acc = 1u;
+            }
           }
           umma_commit(empty_bar(s));  // frees this stage when the MMAs above have read it
           if (++s == P.stages) { s = 0; ph ^= 1; }
@@ -297,6 +305,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int c0 = 0; c0 < P.bn; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(trow + (uint32_t)c0, v);
+      if (nops == 2) {  // tf32x3: add A_hi*B_lo (columns bn..) and A_lo*B_hi (columns 2bn..)
+        uint32_t u[16], t[16];
+        tmem_ld16(trow + (uint32_t)(P.bn + c0), u);
+        tmem_ld16(trow + (uint32_t)(2 * P.bn + c0), t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = __float_as_uint((__uint_as_float(u[j]) + __uint_as_float(t[j])) + __uint_as_float(v[j]));
+      }
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -606,8 +622,9 @@ static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo
   P.a_stage_bytes = TILE_W * TILE_ROWS * 128u;
   P.b_stage_bytes = (uint32_t)bn * 128u;
   P.patch_bytes = (uint32_t)PATCH_PITCH * (P.th + d->ksize - 1) * 128u;
-  P.tmem_cols = pow2_cols(bn);
+  P.tmem_cols = pow2_cols(P.nsplit == 3 ? 3 * bn : bn);
   P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   P.bias = bias; P.out = y; P.error_flag = error_flag;
 
   const uint32_t patch_region = P.halo ? 2u * nops * P.patch_bytes : 0u;

@@ -153,9 +153,24 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
   float* s_g = s_v + 3 * TWP * DP;
   float* s_w = s_g + 3 * TWP * DP;
   float* s_red = s_w + 216;
+  float* s_gh = s_red + 8 * 28 + 32;  // unpack only: the high-res gradient neighbourhood [6][2*TWP][2*D], loaded once
   const int w0 = blockIdx.x * P.tw, h = blockIdx.y, b = blockIdx.z;
   for (int i = threadIdx.x; i < 216; i += blockDim.x) s_w[i] = P.w3[i];
   const int total = 3 * TWP * DP;
+  if (!PACK) {
+    // g lives at high resolution with 2*D channels per pixel: stage rows 2(h-1)..2(h+1)+1, cols 2(w0-1)..2(w0+tw)+1
+    // pixel-major (coalesced), then every feature plane f is re-indexed out of shared memory
+    const int CG = 2 * D, GW = 2 * TWP;
+    const int gtotal = 6 * GW * CG;
+    for (int idx = threadIdx.x; idx < gtotal; idx += blockDim.x) {
+      const int c = idx % CG, gx = (idx / CG) % GW, gy = idx / (CG * GW);
+      const int yy = 2 * (h - 1) + gy, xx = 2 * (w0 - 1) + gx;
+      float v = 0.0f;
+      if (yy >= 0 && yy < 2 * P.H && xx >= 0 && xx < 2 * P.W)
+        v = __ldg(P.g + (((size_t)b * 2 * P.H + yy) * 2 * P.W + xx) * P.g_cstride + P.g_coffset + c);
+      s_gh[idx] = v;
+    }
+  }
   StencilParams Q{};
   Q.B = P.B; Q.H = P.H; Q.W = P.W; Q.D = P.D; Q.C = P.C; Q.in = P.in;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -176,7 +191,14 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
       const int dd = idx % DP, cw = (idx / DP) % TWP, r = idx / (DP * TWP);
       const int d = dd - 1, ww = w0 + cw - 1, hh = h + r - 1;
       float v = 0.0f;
-      if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) v = load_gout<PACK>(P, b, f, d, hh, ww);
+      if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) {
+        if (PACK) {
+          v = load_gout<PACK>(P, b, f, d, hh, ww);
+        } else {
+          const int vv = f * D + d, co = vv >> 2, i = (vv >> 1) & 1, j = vv & 1;
+          v = s_gh[((2 * r + i) * (2 * TWP) + (2 * cw + j)) * (2 * D) + co];
+        }
+      }
       s_g[idx] = v;
     }
     __syncthreads();
@@ -430,11 +452,19 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static int pick_tw(int D, int W, bool bwd) {
-  // shared memory: (bwd ? 2 : 1) * 3 * (tw+2) * (D+2) floats; keep it under ~96 KB and tw*D <= 2048 for bwd
-  const size_t budget = 96 * 1024;
+static size_t stencil_smem_bytes(int D, int tw, bool bwd, bool unpack_bwd) {
+  size_t f = (size_t)(bwd ? 2 : 1) * 3 * (tw + 2) * (D + 2) + 224;
+  if (bwd) f += 216 + 8 * 28 + 32;
+  if (unpack_bwd) f += (size_t)6 * 2 * (tw + 2) * 2 * D;
+  return f * sizeof(float);
+}
+
+static int pick_tw(int D, int W, bool bwd, bool unpack_bwd = false) {
+  // keep the working set under ~96 KB (200 KB for the unpack backward, which also stages the high-res gradient)
+  // and tw*D <= 2048 items for the backward's per-thread accumulators
+  const size_t budget = unpack_bwd ? 200 * 1024 : 96 * 1024;
   int tw = 8;
-  while (tw > 1 && ((size_t)(bwd ? 2 : 1) * 3 * (tw + 2) * (D + 2) * 4 > budget || (bwd && tw * D > 2048))) tw >>= 1;
+  while (tw > 1 && (stencil_smem_bytes(D, tw, bwd, unpack_bwd) > budget || (bwd && tw * D > 2048))) tw >>= 1;
   if (tw > W) tw = W;
   return tw;
 }
@@ -480,11 +510,12 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
   P.in = in; P.g = g; P.w3 = w3; P.gin = gin; P.gw3 = gw3; P.gb3 = gb3;
   P.g_cstride = g_cstride; P.g_coffset = g_coffset;
-  P.tw = pick_tw(P.D, P.W, true);
+  P.tw = pick_tw(P.D, P.W, true, !pack);
   PN_REQUIRE(P.tw * P.D <= 2048, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large", P.D);
   PN_CUDA(cudaMemsetAsync(gw3, 0, sizeof(float) * 216, stream));
   PN_CUDA(cudaMemsetAsync(gb3, 0, sizeof(float) * 8, stream));
-  const size_t smem = ((size_t)2 * 3 * (P.tw + 2) * (P.D + 2) + 216 + 8 * 28 + 32) * sizeof(float);
+  const size_t smem = stencil_smem_bytes(P.D, P.tw, true, !pack);
+  PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d needs %zu bytes of shared memory", P.D, smem);
   dim3 grid((P.W + P.tw - 1) / P.tw, P.H, P.B);
   if (pack) {
     PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -11,8 +11,8 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-# the CPU oracle runs small ops: dozens of OpenMP threads only add spin-wait overhead (and a cgroup-limited
-# box may report far more cores than it grants)
+# the CPU oracle runs small ops: dozens of OpenMP threads only add spin-wait overhead, and the GPU box reports
+# 128 logical CPUs while its cgroup grants 16 (cpu.max)
 torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
 
 
