@@ -111,44 +111,55 @@ int pn_resize_bilinear_ac(const float* src, float* dst, int batch, int channels,
  *     packnet_sfm/networks/layers/packnet/layers01.py:28-30,36 (ConstantPad2d + Conv2d), :58-60,:69-71,
  *     :234 (pack conv on the 8x-inflated channel count), :272 (unpack conv) and their autograd backward.
  * ------------------------------------------------------------------------------------------------ */
-enum { PN_PRECISION_TF32X1 = 1, PN_PRECISION_TF32X3 = 3 };
+/* Tensor-core precision of the GEMMs (fp32 accumulate in TMEM in every mode):
+ *   TF32X1  one kind::tf32 MMA per product on the fp32 operands (what cuDNN gives the reference on Ampere+ with
+ *           PyTorch's default cudnn.allow_tf32=True); depth maps off by ~1e-2 max-relative vs fp32
+ *   TF32X3  error-compensated split, operands fp32 x and x - trunc_tf32(x)            (~22 mantissa bits)
+ *   BF16X3  error-compensated split, operands bf16 hi = rn(x), lo = rn(x - hi)         (16 mantissa bits; kind::f16
+ *           runs at twice the tf32 rate on half the operand bytes; PackNet01 depth maps stay within ~2.5e-4
+ *           max-relative of fp32 -- DESIGN.md "precision") -- the default of the Python layer
+ *   BF16X1  one bf16 MMA per product (8 mantissa bits; for experiments only) */
+enum { PN_PRECISION_TF32X1 = 1, PN_PRECISION_BF16X1 = 2, PN_PRECISION_TF32X3 = 3, PN_PRECISION_BF16X3 = 4 };
 enum { PN_CONV_MODE_AUTO = 0, PN_CONV_MODE_PER_TAP = 1, PN_CONV_MODE_HALO = 2 };
 
 typedef struct {
   int32_t batch, height, width; /* input and output spatial size (stride 1, zero padding ksize/2) */
-  int32_t cin, cout;            /* multiples of 4 */
+  int32_t cin, cout;            /* cin: multiple of 4 (fp32 operands) or 8 (bf16 operands); cout: multiple of 4 */
   int32_t ksize;                /* 1, 3, 5 or 7 */
   int32_t precision;            /* PN_PRECISION_* */
   int32_t mode;                 /* PN_CONV_MODE_*: how the activation operand is staged (AUTO picks) */
-  int32_t debug_flags;          /* bit0: bring-up knob, sets base_offset=(addr>>7)&7 in shifted descriptors (wrong on B200) */
+  int32_t debug_flags;          /* bring-up knobs, 0 in production */
 } pn_conv_desc;
 
-/* y[B,H,W,Cout] = conv(x[B,H,W,Cin], w) + bias.  w_packed comes from pn_conv2d_pack_weight.
- * x_lo / w_packed_lo (tf32 residuals, pn_tf32_residual / pack_weight) are required for TF32X3 and
- * ignored for TF32X1.  error_flag: optional device word set to 0xDEADxxxx if a pipeline wait times out
- * (the kernel traps instead of hanging). */
-int pn_conv2d_forward(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* w_packed,
-                      const float* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
+/* y[B,H,W,Cout] (fp32) = conv(x[B,H,W,Cin], w) + bias.  Operand element type follows desc->precision: fp32 for the
+ * TF32 modes, bf16 for the BF16 modes.  w_packed comes from pn_conv2d_pack_weight; x_lo / w_packed_lo are the
+ * residual operands (pn_tf32_residual / pn_split_bf16 / pack_weight), required by the X3 modes, ignored otherwise.
+ * error_flag: optional (pinned host or device) word set to 0xDEADxxxx if a pipeline wait times out (the kernel
+ * traps instead of hanging). */
+int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const void* x_lo, const void* w_packed,
+                      const void* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
                       pn_stream_t stream);
 
-/* Weight packing: OIHW [Cout,Cin,k,k] (nn.Conv2d.weight) -> [Cout][k*k][ceil32(Cin)] (transposed=0, fprop)
- * or -> [Cin][k*k flipped][ceil32(Cout)] (transposed=1: the operand of the data-gradient convolution).
- * w_packed_lo may be NULL. */
-int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, size_t* elems);
-int pn_conv2d_pack_weight(const float* w_oihw, float* w_packed, float* w_packed_lo, int cout, int cin,
-                          int ksize, int transposed, pn_stream_t stream);
+/* Weight packing: OIHW fp32 [Cout,Cin,k,k] (nn.Conv2d.weight) -> [Cout][k*k][kpad(Cin)] (transposed=0, fprop) or
+ * -> [Cin][k*k flipped][kpad(Cout)] (transposed=1: the operand of the data-gradient convolution); kpad rounds up
+ * to 32 (fp32 operands) or 64 (bf16 operands).  w_packed_lo may be NULL. */
+int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, int precision, size_t* elems);
+int pn_conv2d_pack_weight(const float* w_oihw, void* w_packed, void* w_packed_lo, int cout, int cin, int ksize,
+                          int transposed, int precision, pn_stream_t stream);
 
 /* Weight gradient (autograd backward of nn.Conv2d w.r.t. weight).  x [B,H,W,Cin] and g = dL/dy [B,H,W,Cout]
  * are the NHWC tensors themselves (read as MN-major operand tiles; the reduction runs over pixels); x_lo / g_lo
- * are their tf32 residuals (TF32X3 only).  dw_packed [Cout][k*k][ceil32(Cin)] is zeroed and accumulated;
+ * are their residuals (X3 modes).  dw_packed fp32 [Cout][k*k][kpad(Cin)] is zeroed and accumulated;
  * pn_conv2d_unpack_weight_grad converts it to OIHW. */
-int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* g, const float* g_lo,
+int pn_conv2d_wgrad(const pn_conv_desc* desc, const void* x, const void* x_lo, const void* g, const void* g_lo,
                     float* dw_packed, uint32_t* error_flag, pn_stream_t stream);
-int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize,
+int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, int precision,
                                  pn_stream_t stream);
 
 /* lo[i] = x[i] - trunc_tf32(x[i]) (the bits a tf32 tensor-core operand read drops); n % 4 == 0. */
 int pn_tf32_residual(const float* x, float* lo, size_t n, pn_stream_t stream);
+/* hi[i] = bf16_rn(x[i]), lo[i] = bf16_rn(x[i] - hi[i]); n % 4 == 0. */
+int pn_split_bf16(const float* x, void* hi, void* lo, size_t n, pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pack / unpack feature stencil: Conv3d(1->8, 3x3x3, pad 1) fused with space-to-depth (pack) or

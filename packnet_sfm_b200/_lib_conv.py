@@ -2,7 +2,9 @@
 import ctypes
 
 PRECISION_TF32X1 = 1
+PRECISION_BF16X1 = 2
 PRECISION_TF32X3 = 3
+PRECISION_BF16X3 = 4
 MODE_AUTO, MODE_PER_TAP, MODE_HALO = 0, 1, 2
 
 
@@ -18,9 +20,11 @@ def declare(lib):
     c = ctypes
     vp, sz = c.c_void_p, c.c_size_t
     lib.pn_conv2d_forward.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.pn_conv2d_packed_weight_elems.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(sz)]
-    lib.pn_conv2d_pack_weight.argtypes = [vp, vp, vp, c.c_int, c.c_int, c.c_int, c.c_int, vp]
+    lib.pn_conv2d_packed_weight_elems.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(sz)]
+    lib.pn_conv2d_pack_weight.argtypes = [vp, vp, vp, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, vp]
     lib.pn_tf32_residual.argtypes = [vp, vp, sz, vp]
+    lib.pn_split_bf16.argtypes = [vp, vp, vp, sz, vp]
+    lib.pn_split_bf16.restype = c.c_int
     i, f = c.c_int, c.c_float
     lib.pn_feature_stencil_forward.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     lib.pn_feature_stencil_backward.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
@@ -31,7 +35,7 @@ def declare(lib):
                  "pn_groupnorm_elu_backward", "pn_channel_sum"):
         getattr(lib, name).restype = c.c_int
     lib.pn_conv2d_wgrad.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]
-    lib.pn_conv2d_unpack_weight_grad.argtypes = [vp, vp, i, i, i, vp]
+    lib.pn_conv2d_unpack_weight_grad.argtypes = [vp, vp, i, i, i, i, vp]
     lib.pn_conv2d_wgrad.restype = c.c_int
     lib.pn_conv2d_unpack_weight_grad.restype = c.c_int
     for name in ("pn_conv2d_forward", "pn_conv2d_packed_weight_elems", "pn_conv2d_pack_weight", "pn_tf32_residual"):

@@ -21,6 +21,7 @@
 // UnpackLayerConv3d (packnet_sfm/networks/layers/packnet/layers01.py:28-29,36,58-72,234,272) and their
 // autograd backward (dgrad = the same kernel on flipped/transposed weights).
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <mutex>
 
@@ -31,7 +32,6 @@ namespace conv {
 
 constexpr int TILE_W = 8;        // pixels per tile row (one 8-row swizzle atom)
 constexpr int TILE_ROWS = 16;    // tile rows x images
-constexpr int KC = 32;           // K elements (fp32) per chunk = 128 bytes
 constexpr int PATCH_PITCH = 16;  // pixels per row of the HALO patch (2048 B: keeps 8-row groups 1024-B aligned)
 constexpr int NTHREADS = 192;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 constexpr int MAX_STAGES = 8;
@@ -41,7 +41,9 @@ struct KernelParams {
   int th, nb;              // tile rows per image, images per tile (th * nb == 16)
   int tiles_x, tiles_y;    // tiles per image group
   int bn;                  // N tile (output channels per CTA)
-  int nsplit;              // 1: tf32x1, 3: tf32x3
+  int nsplit;              // 1: single product, 3: error-compensated hi/lo split
+  int kc;                  // K elements per 128-byte chunk: 32 (tf32 operands) or 64 (bf16 operands)
+  int bf16;                // 1: operands are bf16 (kind::f16), 0: fp32 read as tf32 (kind::tf32)
   int halo;                // 1: patch reuse across taps
   int cchunks;             // ceil(Cin / 32)
   int ksplits;             // split of the channel-chunk loop over blockIdx.z (small maps: fill the 148 SMs)
@@ -116,6 +118,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (bf16) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -208,8 +222,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (P.halo) {
           mbar_wait(emptya_bar(pa), pha ^ 1, P.error_flag, 1);
           mbar_expect_tx(fulla_bar(pa), P.patch_bytes * nops);
-          tma_load_4d(patch_addr(pa, 0), &tmA, fulla_bar(pa), cc * KC, x0 - P.pad, y0 - P.pad, b0);
-          if (nops == 2) tma_load_4d(patch_addr(pa, 1), &tmAlo, fulla_bar(pa), cc * KC, x0 - P.pad, y0 - P.pad, b0);
+          tma_load_4d(patch_addr(pa, 0), &tmA, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
+          if (nops == 2) tma_load_4d(patch_addr(pa, 1), &tmAlo, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
           pa ^= 1;
           if (pa == 0) pha ^= 1;
         }
@@ -218,11 +232,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_expect_tx(full_bar(s), stage_bytes);
           if (!P.halo) {
             const int dy = tap / P.ks, dx = tap % P.ks;
-            tma_load_4d(stage_a(s, 0), &tmA, full_bar(s), cc * KC, x0 + dx - P.pad, y0 + dy - P.pad, b0);
-            if (nops == 2) tma_load_4d(stage_a(s, 1), &tmAlo, full_bar(s), cc * KC, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+            tma_load_4d(stage_a(s, 0), &tmA, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+            if (nops == 2) tma_load_4d(stage_a(s, 1), &tmAlo, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
           }
-          tma_load_3d(stage_b(s, 0), &tmB, full_bar(s), cc * KC, tap, n0);
-          if (nops == 2) tma_load_3d(stage_b(s, 1), &tmBlo, full_bar(s), cc * KC, tap, n0);
+          tma_load_3d(stage_b(s, 0), &tmB, full_bar(s), cc * P.kc, tap, n0);
+          if (nops == 2) tma_load_3d(stage_b(s, 1), &tmBlo, full_bar(s), cc * P.kc, tap, n0);
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -244,6 +258,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       auto lo_of = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
       auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
       const uint32_t tm_d2 = tmem_base + 2u * (uint32_t)P.bn;
+      const bool bf16 = P.bf16 != 0;
       for (int cc = cc_begin; cc < cc_end; ++cc) {
         if (P.halo) {
           mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
@@ -268,15 +283,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t lb = lo_of(stage_b(s, 0));
           if (nops == 2) {
 #pragma unroll
-            for (int k = 0; k < KC / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-              umma_tf32(tm_d2, desc(hi_a, la_lo + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);       // A_lo x B_hi
-              umma_tf32(tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, acc);  // A_hi x [B_hi;B_lo]
+            for (int k = 0; k < 4; ++k) {  // one UMMA_K (8 tf32 / 16 bf16) = 32 bytes inside the 128-byte swizzle row
+              umma(bf16, tm_d2, desc(hi_a, la_lo + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);       // A_lo x B_hi
+              umma(bf16, tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, acc);  // A_hi x [B_hi;B_lo]
               acc = 1u;
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < KC / 8; ++k) {
-              umma_tf32(tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);
+            for (int k = 0; k < 4; ++k) {
+              umma(bf16, tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);
               acc = 1u;
             }
           }
@@ -357,8 +372,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ---------------------------------------------------------------------------------------------------
 struct WgradParams {
   int B, H, W, Cin, Cout, ks, pad;
-  int kpad;              // ceil32(Cin): row pitch of the packed gradient
-  int bn, tg;            // N tile (multiple of 32), taps per CTA
+  int kpad;              // ceil32/ceil64(Cin): row pitch of the packed gradient
+  int bf16;              // 1: bf16 operands (kind::f16, 64 channels per 128-byte block, plain SWIZZLE_128B)
+  int blk_ch, mblks;     // channels per 128-byte block (32 tf32 / 64 bf16) and X blocks per CTA (128 / blk_ch)
+  int bn, tg;            // N tile (multiple of blk_ch), taps per CTA
   int acc_stride;        // TMEM columns between the accumulators of two taps (power of two >= bn)
   int tap_groups;
   int th;                // pixel-tile rows (tile = 8 x th pixels = th MMA k-steps)
@@ -378,13 +395,14 @@ struct WgradParams {
 // (SWIZZLE_128B_BASE32B, cute Swizzle<2,5,2>, K atom = 4 rows); with the plain SWIZZLE_128B layout type the MMA
 // returns zeros on B200 (measured, profiles/r01_conv_probe.txt).  LBO = byte distance between 32-element blocks
 // along M/N, SBO = byte distance between the 4-row groups along K (UMMA_K = 8 rows = 2 groups).
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// 16-bit (bf16) MN-major operands use the ordinary SWIZZLE_128B (layout type 2, K atom = 8 rows).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 1u) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -392,15 +410,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int nblk_n = P.bn / 32;
-  const uint32_t stage_bytes = 4u * P.patch_bytes + (uint32_t)nblk_n * P.gblk_bytes;
+  const int nblk_n = P.bn / P.blk_ch;
+  const uint32_t stage_bytes = (uint32_t)P.mblks * P.patch_bytes + (uint32_t)nblk_n * P.gblk_bytes;
   const uint32_t bars_base = smem_base + P.stages * stage_bytes;
   auto full_bar = [&](int s) { return bars_base + 8u * s; };
   auto empty_bar = [&](int s) { return bars_base + 8u * (MAX_STAGES + s); };
   const uint32_t tmemfull_bar = bars_base + 8u * (2 * MAX_STAGES);
   const uint32_t tmem_slot = bars_base + 8u * (2 * MAX_STAGES + 1);
   auto stage_x = [&](int s, int j) { return smem_base + s * stage_bytes + (uint32_t)j * P.patch_bytes; };
-  auto stage_g = [&](int s, int i) { return smem_base + s * stage_bytes + 4u * P.patch_bytes + (uint32_t)i * P.gblk_bytes; };
+  auto stage_g = [&](int s, int i) { return smem_base + s * stage_bytes + (uint32_t)P.mblks * P.patch_bytes + (uint32_t)i * P.gblk_bytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci0 = blockIdx.x * 128;
@@ -434,9 +452,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int x0 = tx * TILE_W, y0 = ty * P.th;
         mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 6);
         mbar_expect_tx(full_bar(s), stage_bytes);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_4d(stage_x(s, j), &tmX, full_bar(s), ci0 + 32 * j, x0 - P.pad, y0 - P.pad, b);
-        for (int i = 0; i < nblk_n; ++i) tma_load_4d(stage_g(s, i), &tmG, full_bar(s), n0 + 32 * i, x0, y0, b);
+        for (int j = 0; j < P.mblks; ++j) tma_load_4d(stage_x(s, j), &tmX, full_bar(s), ci0 + P.blk_ch * j, x0 - P.pad, y0 - P.pad, b);
+        for (int i = 0; i < nblk_n; ++i) tma_load_4d(stage_g(s, i), &tmG, full_bar(s), n0 + P.blk_ch * i, x0, y0, b);
         if (++s == P.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -450,12 +467,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int tt = 0; tt < ntap; ++tt) {
           const int tap = tap0 + tt, dy = tap / P.ks, dx = tap % P.ks;
           const uint32_t d_t = tmem_base + (uint32_t)(tt * P.acc_stride);
-          for (int kk = 0; kk < P.th; ++kk) {  // one MMA per tile row: K = 8 pixels
-            const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
-            const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
-            const uint64_t da = P.swap_lbo_sbo ? make_smem_desc_mn(a, 512u, P.patch_bytes) : make_smem_desc_mn(a, P.patch_bytes, 512u);
-            const uint64_t db = P.swap_lbo_sbo ? make_smem_desc_mn(bb, 512u, P.gblk_bytes) : make_smem_desc_mn(bb, P.gblk_bytes, 512u);
-            umma_tf32(d_t, da, db, P.idesc, (kk == 0) ? acc : 1u);
+          if (P.bf16) {
+            // one MMA per PAIR of tile rows: K = 16 pixels = two 8-row groups (patch rows are 2048 B apart, dZ rows 1024 B)
+            for (int kk = 0; kk < P.th; kk += 2) {
+              const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
+              const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
+              umma_bf16(d_t, make_smem_desc_mn(a, P.patch_bytes, PATCH_PITCH * 128u, 2u), make_smem_desc_mn(bb, P.gblk_bytes, 1024u, 2u),
+                        P.idesc, (kk == 0) ? acc : 1u);
+            }
+          } else {
+            for (int kk = 0; kk < P.th; ++kk) {  // one MMA per tile row: K = 8 pixels
+              const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
+              const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
+              const uint64_t da = P.swap_lbo_sbo ? make_smem_desc_mn(a, 512u, P.patch_bytes) : make_smem_desc_mn(a, P.patch_bytes, 512u);
+              const uint64_t db = P.swap_lbo_sbo ? make_smem_desc_mn(bb, 512u, P.gblk_bytes) : make_smem_desc_mn(bb, P.gblk_bytes, 512u);
+              umma_tf32(d_t, da, db, P.idesc, (kk == 0) ? acc : 1u);
+            }
           }
         }
         acc = 1u;
@@ -539,6 +566,45 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+// bf16 flavour: hi = bf16_rn(v), lo = bf16_rn(v - hi)  (hi + lo carries 16 mantissa bits of v)
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ wp_lo,
+                                        int Cout, int Cin, int ks, int kpad, int transposed) {
+  const int taps = ks * ks;
+  const int rows = transposed ? Cin : Cout;
+  const size_t total = (size_t)rows * taps * kpad;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % kpad);
+    const int tap = (int)((idx / kpad) % taps);
+    const int r = (int)(idx / ((size_t)kpad * taps));
+    float v = 0.0f;
+    if (!transposed) {
+      if (k < Cin) v = w[((size_t)r * Cin + k) * taps + tap];
+    } else {
+      if (k < Cout) v = w[((size_t)k * Cin + r) * taps + (taps - 1 - tap)];
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    wp[idx] = h;
+    if (wp_lo) wp_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+__global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(in[k]);
+      const __nv_bfloat16 lb = __float2bfloat16_rn(in[k] - __bfloat162float(hb));
+      h[k] = __bfloat16_as_ushort(hb);
+      l[k] = __bfloat16_as_ushort(lb);
+    }
+    hi[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    lo[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -560,14 +626,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, bool bf16 = false) {
   EncodeTiledFn fn = encode_fn();
   PN_REQUIRE(fn != nullptr, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gd[5], gs[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_BAD_ARGUMENT, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -580,27 +646,33 @@ static uint32_t pow2_cols(int n) {
   return c;
 }
 
-int kpad_of(int c) { return (c + KC - 1) / KC * KC; }
+static bool is_bf16(int precision) { return precision == PN_PRECISION_BF16X3 || precision == PN_PRECISION_BF16X1; }
+static bool is_split(int precision) { return precision == PN_PRECISION_BF16X3 || precision == PN_PRECISION_TF32X3; }
+int kc_of(int precision) { return is_bf16(precision) ? 64 : 32; }
+int kpad_of(int c, int precision) { const int kc = kc_of(precision); return (c + kc - 1) / kc * kc; }
 
 // x [B,H,W,Cin] NHWC, wp [Cout][k*k][kpad(Cin)] -> y [B,H,W,Cout]
-static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo, const float* wp, const float* wp_lo,
+static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, const void* wp, const void* wp_lo,
                         const float* bias, float* y, unsigned int* error_flag, cudaStream_t stream) {
   PN_REQUIRE(d && x && wp && y, PN_ERR_BAD_ARGUMENT, "pn_conv2d: null argument");
   PN_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0 && d->cin > 0 && d->cout > 0, PN_ERR_BAD_ARGUMENT,
              "pn_conv2d: bad shape");
   PN_REQUIRE(d->ksize >= 1 && d->ksize <= 7 && (d->ksize & 1), PN_ERR_UNSUPPORTED, "pn_conv2d: ksize %d (odd, <= 7)", d->ksize);
-  PN_REQUIRE(d->cin % 4 == 0 && d->cout % 4 == 0, PN_ERR_UNSUPPORTED, "pn_conv2d: Cin (%d) and Cout (%d) must be multiples of 4",
-             d->cin, d->cout);
-  PN_REQUIRE(d->precision == PN_PRECISION_TF32X1 || d->precision == PN_PRECISION_TF32X3, PN_ERR_BAD_ARGUMENT,
-             "pn_conv2d: precision %d", d->precision);
-  PN_REQUIRE(d->precision == PN_PRECISION_TF32X1 || (x_lo && wp_lo), PN_ERR_BAD_ARGUMENT,
-             "pn_conv2d: tf32x3 needs the residual operands x_lo and w_lo");
+  PN_REQUIRE(d->precision == PN_PRECISION_TF32X1 || d->precision == PN_PRECISION_TF32X3 || is_bf16(d->precision),
+             PN_ERR_BAD_ARGUMENT, "pn_conv2d: precision %d", d->precision);
+  const bool bf16 = is_bf16(d->precision);
+  const int esize = bf16 ? 2 : 4, kc = kc_of(d->precision);
+  PN_REQUIRE(d->cin % (16 / esize) == 0 && d->cout % 4 == 0, PN_ERR_UNSUPPORTED,
+             "pn_conv2d: Cin (%d) must be a multiple of %d (16-byte TMA pitch) and Cout (%d) of 4", d->cin, 16 / esize, d->cout);
+  PN_REQUIRE(!is_split(d->precision) || (x_lo && wp_lo), PN_ERR_BAD_ARGUMENT,
+             "pn_conv2d: the x3 precisions need the residual operands x_lo and w_lo");
   PN_REQUIRE(aligned16(x) && aligned16(wp) && aligned16(y) && (!bias || aligned16(bias)), PN_ERR_ALIGNMENT,
              "pn_conv2d: pointers must be 16-byte aligned");
 
   KernelParams P{};
   P.B = d->batch; P.H = d->height; P.W = d->width; P.Cin = d->cin; P.Cout = d->cout; P.ks = d->ksize; P.pad = d->ksize / 2;
-  P.nsplit = (d->precision == PN_PRECISION_TF32X3) ? 3 : 1;
+  P.nsplit = is_split(d->precision) ? 3 : 1;
+  P.kc = kc; P.bf16 = bf16 ? 1 : 0;
   const int nops = (P.nsplit == 3) ? 2 : 1;
   // tile rows: tall tiles for big maps, batch folding for small ones
   P.th = TILE_ROWS;
@@ -618,13 +690,15 @@ static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo
   const int bn_cap = (P.nsplit == 3) ? 128 : 256;
   if (bn > bn_cap) bn = bn_cap;
   P.bn = bn;
-  P.cchunks = (d->cin + KC - 1) / KC;
+  P.cchunks = (d->cin + kc - 1) / kc;
   P.a_stage_bytes = TILE_W * TILE_ROWS * 128u;
   P.b_stage_bytes = (uint32_t)bn * 128u;
   P.patch_bytes = (uint32_t)PATCH_PITCH * (P.th + d->ksize - 1) * 128u;
   P.tmem_cols = pow2_cols(P.nsplit == 3 ? 3 * bn : bn);
-  P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  P.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // instruction descriptor: fp32 accumulate, A/B format 2 = TF32 (kind::tf32) or 1 = BF16 (kind::f16), K-major, M = 128
+  const uint32_t fmt = bf16 ? 1u : 2u;
+  P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   P.bias = bias; P.out = y; P.error_flag = error_flag;
 
   const uint32_t patch_region = P.halo ? 2u * nops * P.patch_bytes : 0u;
@@ -640,24 +714,24 @@ static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo
   alignas(64) CUtensorMap tmA, tmAlo, tmB, tmBlo;
   {
     const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
-    const uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)d->width * d->cin * 4,
-                                 (uint64_t)d->height * d->width * d->cin * 4};
+    const uint64_t strides[3] = {(uint64_t)d->cin * esize, (uint64_t)d->width * d->cin * esize,
+                                 (uint64_t)d->height * d->width * d->cin * esize};
     uint32_t box[4];
-    if (P.halo) { box[0] = KC; box[1] = PATCH_PITCH; box[2] = P.th + d->ksize - 1; box[3] = 1; }
-    else        { box[0] = KC; box[1] = TILE_W;      box[2] = P.th;                box[3] = P.nb; }
-    int rc = make_map(&tmA, x, 4, dims, strides, box);
+    if (P.halo) { box[0] = kc; box[1] = PATCH_PITCH; box[2] = P.th + d->ksize - 1; box[3] = 1; }
+    else        { box[0] = kc; box[1] = TILE_W;      box[2] = P.th;                box[3] = P.nb; }
+    int rc = make_map(&tmA, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
-    rc = make_map(&tmAlo, x_lo ? x_lo : x, 4, dims, strides, box);
+    rc = make_map(&tmAlo, x_lo ? x_lo : x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
   }
   {
-    const int kp = kpad_of(d->cin), taps = d->ksize * d->ksize;
+    const int kp = kpad_of(d->cin, d->precision), taps = d->ksize * d->ksize;
     const uint64_t dims[3] = {(uint64_t)kp, (uint64_t)taps, (uint64_t)d->cout};
-    const uint64_t strides[2] = {(uint64_t)kp * 4, (uint64_t)kp * taps * 4};
-    const uint32_t box[3] = {KC, 1, (uint32_t)bn};
-    int rc = make_map(&tmB, wp, 3, dims, strides, box);
+    const uint64_t strides[2] = {(uint64_t)kp * esize, (uint64_t)kp * taps * esize};
+    const uint32_t box[3] = {(uint32_t)kc, 1, (uint32_t)bn};
+    int rc = make_map(&tmB, wp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
-    rc = make_map(&tmBlo, wp_lo ? wp_lo : wp, 3, dims, strides, box);
+    rc = make_map(&tmBlo, wp_lo ? wp_lo : wp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
   }
   // small maps: split the channel-chunk loop so that the grid covers the 148 SMs
@@ -680,18 +754,22 @@ static int conv_forward(const pn_conv_desc* d, const float* x, const float* x_lo
   return check_launch("conv_igemm_kernel");
 }
 
-// x [B,H,W,Cin], g [B,H,W,Cout] (NHWC) -> dwp [Cout][k*k][ceil32(Cin)], ACCUMULATED (the caller zeroes it)
-static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, float* dwp, unsigned int* error_flag,
+// x [B,H,W,Cin], g [B,H,W,Cout] (NHWC; fp32 or bf16) -> dwp [Cout][k*k][kpad(Cin)] fp32, ACCUMULATED (caller zeroes it)
+static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* g, float* dwp, unsigned int* error_flag,
                       cudaStream_t stream) {
   PN_REQUIRE(d && x && g && dwp, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
   PN_REQUIRE(d->ksize >= 1 && d->ksize <= 7 && (d->ksize & 1), PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: ksize %d", d->ksize);
-  PN_REQUIRE(d->cin % 4 == 0 && d->cout % 4 == 0, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: Cin/Cout must be multiples of 4");
+  const bool bf16 = is_bf16(d->precision);
+  const int esize = bf16 ? 2 : 4, blk_ch = bf16 ? 64 : 32;
+  PN_REQUIRE(d->cin % (16 / esize) == 0 && d->cout % (16 / esize) == 0, PN_ERR_UNSUPPORTED,
+             "pn_conv2d_wgrad: Cin/Cout must be multiples of %d", 16 / esize);
   PN_REQUIRE(aligned16(x) && aligned16(g) && aligned16(dwp), PN_ERR_ALIGNMENT, "pn_conv2d_wgrad: alignment");
   WgradParams P{};
   P.B = d->batch; P.H = d->height; P.W = d->width; P.Cin = d->cin; P.Cout = d->cout; P.ks = d->ksize; P.pad = d->ksize / 2;
-  P.kpad = kpad_of(d->cin);
+  P.kpad = kpad_of(d->cin, d->precision);
+  P.bf16 = bf16 ? 1 : 0; P.blk_ch = blk_ch; P.mblks = 128 / blk_ch;
   const int taps = d->ksize * d->ksize;
-  int bn = (d->cout + 31) / 32 * 32;
+  int bn = (d->cout + blk_ch - 1) / blk_ch * blk_ch;
   if (bn > 256) bn = 256;
   P.bn = bn;
   P.acc_stride = (int)pow2_cols(bn);
@@ -700,13 +778,16 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, flo
   if (d->debug_flags & 2) tg = 1;
   P.tg = tg;
   P.tap_groups = (taps + tg - 1) / tg;
-  // pixel tile height: as tall as shared memory allows with >= 2 stages (4 X-patch blocks + bn/32 dZ blocks per stage)
+  // pixel tile height: as tall as shared memory allows with >= 2 stages (X-patch blocks + dZ blocks per stage);
+  // bf16 consumes tile rows in pairs (K = 16 pixels per MMA), so its height is even
   const uint32_t budget = 227u * 1024u - 1024u - 512u;
-  int th = d->height < TILE_ROWS ? d->height : TILE_ROWS;
+  int th = TILE_ROWS;
+  while (th > 2 && th / 2 >= d->height) th /= 2;
+  if (!bf16 && d->height < th) th = d->height;
   auto stage_bytes_of = [&](int t) {
-    return 4u * (uint32_t)PATCH_PITCH * (t + d->ksize - 1) * 128u + (uint32_t)(bn / 32) * 8u * t * 128u;
+    return (uint32_t)P.mblks * PATCH_PITCH * (t + d->ksize - 1) * 128u + (uint32_t)(bn / blk_ch) * 8u * t * 128u;
   };
-  while (th > 1 && 2u * stage_bytes_of(th) > budget) th = (th + 1) / 2;
+  while (th > (bf16 ? 2 : 1) && 2u * stage_bytes_of(th) > budget) th = bf16 ? th / 2 : (th + 1) / 2;
   PN_REQUIRE(stage_bytes_of(th) <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: tile does not fit in shared memory");
   P.th = th;
   P.patch_bytes = (uint32_t)PATCH_PITCH * (th + d->ksize - 1) * 128u;
@@ -730,28 +811,30 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, flo
   }
   P.psplits = psplits;
   P.tmem_cols = pow2_cols(tg * P.acc_stride);
-  // kind::tf32, fp32 accumulate, M=128, N=bn, A and B MN-major (bits 15, 16)
-  P.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // fp32 accumulate, M=128, N=bn, A and B MN-major (bits 15, 16); formats 2 = TF32 / 1 = BF16
+  const uint32_t fmt = bf16 ? 1u : 2u;
+  P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   P.swap_lbo_sbo = (d->debug_flags & 4) ? 1 : 0;   // bring-up knob
   if (d->debug_flags & 8) P.idesc &= ~((1u << 15) | (1u << 16));   // bring-up: K-major interpretation of both
-  if (d->debug_flags & 16) P.idesc &= ~(1u << 16);                  // bring-up: only A MN-major
-  if (d->debug_flags & 32) P.idesc &= ~(1u << 15);                  // bring-up: only B MN-major
   P.dwp = dwp; P.error_flag = error_flag;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
+  const CUtensorMapSwizzle sw = bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 
   alignas(64) CUtensorMap tmX, tmG;
   {
     const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
-    const uint64_t strides[3] = {(uint64_t)d->cin * 4, (uint64_t)d->width * d->cin * 4, (uint64_t)d->height * d->width * d->cin * 4};
-    const uint32_t box[4] = {KC, PATCH_PITCH, (uint32_t)(th + d->ksize - 1), 1};
-    int rc = make_map(&tmX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    const uint64_t strides[3] = {(uint64_t)d->cin * esize, (uint64_t)d->width * d->cin * esize,
+                                 (uint64_t)d->height * d->width * d->cin * esize};
+    const uint32_t box[4] = {(uint32_t)blk_ch, PATCH_PITCH, (uint32_t)(th + d->ksize - 1), 1};
+    int rc = make_map(&tmX, x, 4, dims, strides, box, sw, bf16);
     if (rc) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
-    const uint64_t strides[3] = {(uint64_t)d->cout * 4, (uint64_t)d->width * d->cout * 4, (uint64_t)d->height * d->width * d->cout * 4};
-    const uint32_t box[4] = {KC, TILE_W, (uint32_t)th, 1};
-    int rc = make_map(&tmG, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    const uint64_t strides[3] = {(uint64_t)d->cout * esize, (uint64_t)d->width * d->cout * esize,
+                                 (uint64_t)d->height * d->width * d->cout * esize};
+    const uint32_t box[4] = {(uint32_t)blk_ch, TILE_W, (uint32_t)th, 1};
+    int rc = make_map(&tmG, g, 4, dims, strides, box, sw, bf16);
     if (rc) return rc;
   }
   PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -766,28 +849,34 @@ static int conv_wgrad(const pn_conv_desc* d, const float* x, const float* g, flo
 
 using namespace pn;
 
-extern "C" int pn_conv2d_forward(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* w_packed,
-                                 const float* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
+extern "C" int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const void* x_lo, const void* w_packed,
+                                 const void* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
                                  pn_stream_t stream) {
   return conv::conv_forward(desc, x, x_lo, w_packed, w_packed_lo, bias, y, error_flag, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, size_t* elems) {
+extern "C" int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, int precision, size_t* elems) {
   PN_REQUIRE(elems && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_packed_weight_elems: bad argument");
   const int rows = transposed ? cin : cout, k = transposed ? cout : cin;
-  *elems = (size_t)rows * ksize * ksize * conv::kpad_of(k);
+  *elems = (size_t)rows * ksize * ksize * conv::kpad_of(k, precision);
   return PN_OK;
 }
 
-extern "C" int pn_conv2d_pack_weight(const float* w_oihw, float* w_packed, float* w_packed_lo, int cout, int cin, int ksize,
-                                     int transposed, pn_stream_t stream) {
+extern "C" int pn_conv2d_pack_weight(const float* w_oihw, void* w_packed, void* w_packed_lo, int cout, int cin, int ksize,
+                                     int transposed, int precision, pn_stream_t stream) {
   PN_REQUIRE(w_oihw && w_packed && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_pack_weight: bad argument");
   const int rows = transposed ? cin : cout, k = transposed ? cout : cin;
-  const size_t total = (size_t)rows * ksize * ksize * conv::kpad_of(k);
+  const int kpad = conv::kpad_of(k, precision);
+  const size_t total = (size_t)rows * ksize * ksize * kpad;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  conv::pack_weight_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w_oihw, w_packed, w_packed_lo, cout, cin,
-                                                                                     ksize, conv::kpad_of(k), transposed);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == PN_PRECISION_BF16X3 || precision == PN_PRECISION_BF16X1)
+    conv::pack_weight_bf16_kernel<<<blocks, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
+                                                         static_cast<__nv_bfloat16*>(w_packed_lo), cout, cin, ksize, kpad, transposed);
+  else
+    conv::pack_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, static_cast<float*>(w_packed), static_cast<float*>(w_packed_lo), cout,
+                                                    cin, ksize, kpad, transposed);
   count_launch();
   return check_launch("pack_weight_kernel");
 }
@@ -804,15 +893,28 @@ extern "C" int pn_tf32_residual(const float* x, float* lo, size_t n, pn_stream_t
   return check_launch("tf32_residual_kernel");
 }
 
-extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x, const float* x_lo, const float* g, const float* g_lo,
+extern "C" int pn_split_bf16(const float* x, void* hi, void* lo, size_t n, pn_stream_t stream) {
+  PN_REQUIRE(x && hi && lo && (n % 4 == 0) && aligned16(x) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(lo) & 7) == 0,
+             PN_ERR_BAD_ARGUMENT, "pn_split_bf16: need aligned pointers and n %% 4 == 0");
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  conv::split_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), static_cast<uint2*>(hi), static_cast<uint2*>(lo), n / 4);
+  count_launch();
+  return check_launch("split_bf16_kernel");
+}
+
+extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const void* x, const void* x_lo, const void* g, const void* g_lo,
                                float* dw_packed, uint32_t* error_flag, pn_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PN_REQUIRE(desc && dw_packed, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
-  PN_REQUIRE(desc->precision == PN_PRECISION_TF32X1 || (desc->precision == PN_PRECISION_TF32X3 && x_lo && g_lo),
-             PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: tf32x3 needs the residual operands");
-  const size_t n = (size_t)desc->cout * desc->ksize * desc->ksize * conv::kpad_of(desc->cin);
+  const bool split = desc->precision == PN_PRECISION_TF32X3 || desc->precision == PN_PRECISION_BF16X3;
+  PN_REQUIRE(!split || (x_lo && g_lo), PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: the x3 precisions need the residual operands");
+  const size_t n = (size_t)desc->cout * desc->ksize * desc->ksize * conv::kpad_of(desc->cin, desc->precision);
   PN_CUDA(cudaMemsetAsync(dw_packed, 0, sizeof(float) * n, stream));
-  if (desc->precision == PN_PRECISION_TF32X3) {   // error-compensated: small terms first
+  if (split) {   // error-compensated: small terms first
     int rc = conv::conv_wgrad(desc, x_lo, g, dw_packed, error_flag, stream);
     if (rc) return rc;
     rc = conv::conv_wgrad(desc, x, g_lo, dw_packed, error_flag, stream);
@@ -821,13 +923,14 @@ extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const float* x, const f
   return conv::conv_wgrad(desc, x, g, dw_packed, error_flag, stream);
 }
 
-extern "C" int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, pn_stream_t stream) {
+extern "C" int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, int precision,
+                                            pn_stream_t stream) {
   PN_REQUIRE(dw_packed && dw_oihw && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_unpack_weight_grad: bad argument");
   const size_t total = (size_t)cout * cin * ksize * ksize;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   conv::unpack_weight_grad_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dw_packed, dw_oihw, cout, cin,
-                                                                                            ksize * ksize, conv::kpad_of(cin));
+                                                                                            ksize * ksize, conv::kpad_of(cin, precision));
   count_launch();
   return check_launch("unpack_weight_grad_kernel");
 }

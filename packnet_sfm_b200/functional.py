@@ -7,21 +7,35 @@ plain contiguous [B,H,W,C] CUDA tensor (the same bytes as a torch.channels_last 
   pack_features     space-to-depth + Conv3d(1->8) feature stencil   (PackLayerConv3d, layers01.py:239-245)
   unpack_features   Conv3d(1->8) feature stencil + depth-to-space   (UnpackLayerConv3d, layers01.py:281-285)
 
-Precision of the tensor-core GEMMs: PRECISION_TF32X3 (default; fp32-grade, needed for the 1e-3 parity
-bar) or PRECISION_TF32X1 (what cuDNN gives the reference on Ampere+ with PyTorch defaults)."""
+Precision of the tensor-core GEMMs (include/packnet_b200.h): PRECISION_BF16X3 (default: error-compensated bf16
+split, 16 mantissa bits, meets the 1e-3 depth parity bar at twice the tf32 MMA rate), PRECISION_TF32X3 (22 bits),
+PRECISION_TF32X1 (what cuDNN gives the reference on Ampere+ with PyTorch defaults; fails the parity bar)."""
 import ctypes
 
 import torch
 
 from . import _lib
-from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_TF32X3, MODE_AUTO
+from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3, MODE_AUTO
 
-_state = {"precision": PRECISION_TF32X3, "mode": MODE_AUTO}
+_state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO}
 
 
 def set_precision(p):
-    assert p in (PRECISION_TF32X1, PRECISION_TF32X3)
+    assert p in (PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3)
     _state["precision"] = p
+
+
+def is_bf16(p):
+    return p in (PRECISION_BF16X1, PRECISION_BF16X3)
+
+
+def is_split(p):
+    return p in (PRECISION_TF32X3, PRECISION_BF16X3)
+
+
+def channel_align(p=None):
+    """Channel multiple an NHWC operand needs (16-byte TMA row pitch): 4 fp32 or 8 bf16 elements."""
+    return 8 if is_bf16(_state["precision"] if p is None else p) else 4
 
 
 def get_precision():
@@ -61,14 +75,25 @@ def _residual(x):
     return lo
 
 
-def _pack_weight(w, transposed, with_lo):
+def _operands(x, precision):
+    """fp32 NHWC tensor -> (hi, lo) tensor-core operands of the given precision (lo is None for the X1 modes)."""
+    if is_bf16(precision):
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        _lib.check(_lib.lib().pn_split_bf16(_lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), _stream()), "pn_split_bf16")
+        return hi, (lo if is_split(precision) else None)
+    return x, (_residual(x) if is_split(precision) else None)
+
+
+def _pack_weight(w, transposed, precision):
     cout, cin, k, _ = w.shape
     n = ctypes.c_size_t(0)
     lib = _lib.lib()
-    _lib.check(lib.pn_conv2d_packed_weight_elems(cout, cin, k, int(transposed), ctypes.byref(n)), "packed_weight_elems")
-    wp = torch.empty(int(n.value), dtype=torch.float32, device=w.device)
-    lo = torch.empty_like(wp) if with_lo else None
-    _lib.check(lib.pn_conv2d_pack_weight(_lib.ptr(w), _lib.ptr(wp), _p(lo), cout, cin, k, int(transposed), _stream()),
+    _lib.check(lib.pn_conv2d_packed_weight_elems(cout, cin, k, int(transposed), precision, ctypes.byref(n)), "packed_weight_elems")
+    dt = torch.bfloat16 if is_bf16(precision) else torch.float32
+    wp = torch.empty(int(n.value), dtype=dt, device=w.device)
+    lo = torch.empty_like(wp) if is_split(precision) else None
+    _lib.check(lib.pn_conv2d_pack_weight(_lib.ptr(w), _lib.ptr(wp), _p(lo), cout, cin, k, int(transposed), precision, _stream()),
                "pn_conv2d_pack_weight")
     return wp, lo
 
@@ -95,60 +120,59 @@ class _Conv2d(torch.autograd.Function):
     layers01.py:28-30,36)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, x_lo):
+    def forward(ctx, x, weight, bias):
         _lib.require_cuda(x, weight)
         x = x.contiguous()
         precision = _state["precision"]
-        three = precision == PRECISION_TF32X3
         cout, cin_w, k, _ = weight.shape
         w_eff = _pad_channels(weight.detach().contiguous(), x.shape[3])
-        wp, wp_lo = _pack_weight(w_eff, False, three)
-        if three and x_lo is None:
-            x_lo = _residual(x)
-        y = _conv_raw(x, x_lo if three else None, wp, wp_lo, bias.detach().contiguous() if bias is not None else None,
-                      cout, k, precision)
-        ctx.save_for_backward(x, weight, x_lo if three else None)
+        wp, wp_lo = _pack_weight(w_eff, False, precision)
+        x_hi, x_lo = _operands(x, precision)
+        y = _conv_raw(x_hi, x_lo, wp, wp_lo, bias.detach().contiguous() if bias is not None else None, cout, k, precision)
+        # the weight gradient needs exactly the operand pair the forward used
+        ctx.save_for_backward(x_hi, x_lo, weight)
         ctx.has_bias = bias is not None
         ctx.precision = precision
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight, x_lo = ctx.saved_tensors
+        x_hi, x_lo, weight = ctx.saved_tensors
         precision = ctx.precision
-        three = precision == PRECISION_TF32X3
         lib = _lib.lib()
         gy = gy.contiguous()
-        B, H, W, Cin = x.shape
+        B, H, W, Cin = x_hi.shape
         cout, cin_w, k, _ = weight.shape
-        gy_lo = _residual(gy) if three else None
         gx = gw = gb = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            # the output gradient has `cout` channels; bf16 operands need a multiple of 8
+            g_hi, g_lo = _operands(gy, precision)
         w_eff = _pad_channels(weight.detach().contiguous(), Cin)
         if ctx.needs_input_grad[0]:
             # data gradient: correlation of gy with the flipped kernel, contraction over Cout
-            wt, wt_lo = _pack_weight(w_eff, True, three)
-            gx = _conv_raw(gy, gy_lo, wt, wt_lo, None, Cin, k, precision)
+            wt, wt_lo = _pack_weight(w_eff, True, precision)
+            gx = _conv_raw(g_hi, g_lo, wt, wt_lo, None, Cin, k, precision)
         if ctx.needs_input_grad[1]:
             # weight gradient: reduction over pixels, operands read in place as MN-major tiles
-            x_t, g_t, x_t_lo, g_t_lo = x, gy, (x_lo if three else None), gy_lo
             n = ctypes.c_size_t(0)
-            _lib.check(lib.pn_conv2d_packed_weight_elems(cout, Cin, k, 0, ctypes.byref(n)), "packed_weight_elems")
-            dwp = torch.empty(int(n.value), dtype=torch.float32, device=x.device)
+            _lib.check(lib.pn_conv2d_packed_weight_elems(cout, Cin, k, 0, precision, ctypes.byref(n)), "packed_weight_elems")
+            dwp = torch.empty(int(n.value), dtype=torch.float32, device=gy.device)
             d = ConvDesc(B, H, W, Cin, cout, k, precision, 0, 0)
-            _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_t), _p(x_t_lo), _lib.ptr(g_t), _p(g_t_lo),
+            _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
                                            _lib.ptr(dwp), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
-            gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=x.device)
-            _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, _stream()),
+            gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=gy.device)
+            _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, precision, _stream()),
                        "pn_conv2d_unpack_weight_grad")
             gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = torch.empty(cout, dtype=torch.float32, device=x.device)
+            gb = torch.empty(cout, dtype=torch.float32, device=gy.device)
             _lib.check(lib.pn_channel_sum(_lib.ptr(gy), _lib.ptr(gb), B * H * W, cout, _stream()), "pn_channel_sum")
-        return gx, gw, gb, None
+        return gx, gw, gb
 
 
-def conv2d(x, weight, bias=None, x_lo=None):
-    return _Conv2d.apply(x, weight, bias, x_lo)
+def conv2d(x, weight, bias=None):
+    """x: [B,H,W,C] with C a multiple of channel_align(); weight may have fewer input channels (zero-padded)."""
+    return _Conv2d.apply(x, weight, bias)
 
 
 class _GroupNormELU(torch.autograd.Function):

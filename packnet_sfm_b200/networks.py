@@ -15,10 +15,10 @@ from . import functional as PF
 
 
 def _cat_channels(tensors):
-    """torch.cat along channels (PackNet01.py:138-175) on NHWC maps, zero-padded to a multiple of 4 channels
-    (the TMA row pitch of the following convolution)."""
+    """torch.cat along channels (PackNet01.py:138-175) on NHWC maps, zero-padded to the channel multiple the
+    following convolution's operand needs (16-byte TMA row pitch: 4 fp32 / 8 bf16 elements)."""
     c = sum(t.shape[-1] for t in tensors)
-    pad = (-c) % 4
+    pad = (-c) % PF.channel_align()
     if pad:
         b, h, w, _ = tensors[0].shape
         tensors = list(tensors) + [torch.zeros(b, h, w, pad, dtype=tensors[0].dtype, device=tensors[0].device)]
@@ -209,8 +209,9 @@ class PackNet01(nn.Module):
         B, _, H, W = rgb.shape
         if H % 32 or W % 32:
             raise ValueError("PackNet01 needs H and W divisible by 32 (got %dx%d)" % (H, W))
-        # NCHW image -> NHWC, zero-padded to 4 channels (TMA row pitch)
-        x_in = torch.cat([rgb.permute(0, 2, 3, 1), torch.zeros(B, H, W, 1, dtype=rgb.dtype, device=rgb.device)], -1)
+        # NCHW image -> NHWC, zero-padded to the operand's channel multiple (TMA row pitch)
+        cpad = PF.channel_align() - 3
+        x_in = torch.cat([rgb.permute(0, 2, 3, 1), torch.zeros(B, H, W, cpad, dtype=rgb.dtype, device=rgb.device)], -1)
         x = self.pre_calc(x_in.contiguous())
 
         x1 = self.conv1(x)

@@ -30,20 +30,24 @@ def test_packnet01_depth_maps_match_reference_golden():
         assert rel < 1e-3
 
 
-def test_packnet01_tf32x1_is_looser_but_sane():
+def test_packnet01_other_precisions():
+    """tf32x3 (22-bit split) is tighter than the default bf16x3; tf32x1 (cuDNN's default on the reference's GPUs)
+    misses the 1e-3 bar but stays sane."""
     from packnet_sfm_b200 import functional as PF
     z = load_golden("packnet01_64x96")
     net = _net(PO.packnet01_state_dict(seed=42, randomize_affine=True))
-    PF.set_precision(PF.PRECISION_TF32X1)
     try:
-        with torch.no_grad():
-            out = net(z["rgb"].to(DEV))["inv_depths"]
+        for prec, name, bound in ((PF.PRECISION_TF32X3, "tf32x3", 1e-3), (PF.PRECISION_TF32X1, "tf32x1", 2e-1)):
+            PF.set_precision(prec)
+            with torch.no_grad():
+                out = net(z["rgb"].to(DEV))["inv_depths"]
+            for i, d in enumerate(out):
+                ref = z["disp%d" % (i + 1)]
+                rel = ((d.cpu() - ref).abs() / ref.abs()).max().item()
+                print("%s disp%d max-rel %.3e rel-l2 %.3e" % (name, i + 1, rel, rel_l2(d.cpu(), ref)))
+                assert rel < bound
     finally:
-        PF.set_precision(PF.PRECISION_TF32X3)
-    for i, d in enumerate(out):
-        r = rel_l2(d.cpu(), z["disp%d" % (i + 1)])
-        print("tf32x1 disp%d rel-l2 %.3e" % (i + 1, r))
-        assert r < 3e-2
+        PF.set_precision(PF.PRECISION_BF16X3)
 
 
 def test_packnet01_gradients_match_oracle_autograd():

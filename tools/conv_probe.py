@@ -93,6 +93,16 @@ def main():
         run("k5 halo B2 48x40 Cin64", 2, 48, 40, 64, 64, 5, X1, HL)
         run("k5 halo boff=addr", 2, 48, 40, 64, 64, 5, X1, HL, 1)
         run("k7 halo 32x24", 1, 32, 24, 64, 64, 7, X1, HL)
+    if group in ("bf16", "all"):
+        B3 = ops.PRECISION_BF16X3
+        run("bf16x3 gemm k1", 1, 16, 8, 64, 16, 1, B3, PT)
+        run("bf16x3 k3 pertap", 2, 40, 36, 64, 48, 3, B3, PT)
+        run("bf16x3 k3 halo", 2, 40, 36, 64, 48, 3, B3, HL)
+        run("bf16x3 k5 halo", 2, 48, 40, 64, 64, 5, B3, HL)
+        run("bf16x3 k3 pertap K=2048", 1, 16, 16, 2048, 64, 3, B3, PT)
+        run("bf16x3 fold H6 W20 B4", 4, 6, 20, 64, 128, 3, B3, PT)
+        run("bf16x3 Cin40 ragged", 1, 16, 16, 40, 32, 3, B3, HL)
+        run("bf16x1 k3", 1, 16, 16, 64, 32, 3, ops.PRECISION_BF16X1, HL)
     if group in ("x3", "all"):
         run("x3 gemm k1", 1, 16, 8, 32, 16, 1, X3, PT)
         run("x3 k3 pertap", 2, 40, 36, 64, 48, 3, X3, PT)
@@ -101,42 +111,10 @@ def main():
         run("x1 k3 pertap K=2048", 1, 16, 16, 2048, 64, 3, X1, PT)
 
 
-def wgrad_direct(tag, B, H, W, Cin, Cout, k, precision, debug):
-    """pn_conv2d_wgrad called directly (debug flags reachable), checked against autograd."""
-    import ctypes
-    from packnet_sfm_b200 import _lib, functional as PF
-    from packnet_sfm_b200._lib_conv import ConvDesc
-    dev = torch.device("cuda:0")
-    torch.manual_seed(1)
-    x = torch.rand(B, H, W, Cin, device=dev) - 0.5
-    g = torch.rand(B, H, W, Cout, device=dev) - 0.5
-    lib = _lib.lib()
-    n = ctypes.c_size_t(0)
-    lib.pn_conv2d_packed_weight_elems(Cout, Cin, k, 0, ctypes.byref(n))
-    dwp = torch.empty(int(n.value), device=dev)
-    three = precision == 3
-    xlo = PF._residual(x) if three else None
-    glo = PF._residual(g) if three else None
-    d = ConvDesc(B, H, W, Cin, Cout, k, precision, 0, debug)
-    t0 = __import__("time").time()
-    try:
-        _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x), PF._p(xlo), _lib.ptr(g), PF._p(glo), _lib.ptr(dwp),
-                                       _lib.ptr(PF.error_flag()), _lib.current_stream()), "pn_conv2d_wgrad")
-        torch.cuda.synchronize()
-    except Exception as e:  # noqa: BLE001
-        print("%-46s EXCEPTION after %.2fs: %s flag=%x" % (tag, __import__("time").time() - t0, str(e)[:90], PF.read_error_flag()))
-        return
-    gw = torch.empty(Cout, Cin, k, k, device=dev)
-    lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw), Cout, Cin, k, _lib.current_stream())
-    w = torch.zeros(Cout, Cin, k, k, device=dev, dtype=torch.float64, requires_grad=True)
-    F.conv2d(x.double().permute(0, 3, 1, 2), w, padding=k // 2).backward(g.double().permute(0, 3, 1, 2))
-    print("%-46s ok rel_l2=%.3e" % (tag, float((gw.double() - w.grad).norm() / w.grad.norm())))
-
-
 def main_bwd(group):
     torch.backends.cudnn.allow_tf32 = False
-    X1, X3 = ops.PRECISION_TF32X1, ops.PRECISION_TF32X3
-    cases = [(2, 40, 36, 64, 48, 3), (1, 32, 24, 96, 64, 5), (4, 6, 20, 64, 128, 3), (1, 16, 16, 36, 32, 3),
+    X1, X3 = ops.PRECISION_TF32X1, ops.PRECISION_BF16X3
+    cases = [(2, 40, 36, 64, 48, 3), (1, 32, 24, 96, 64, 5), (4, 6, 20, 64, 128, 3), (1, 16, 16, 40, 32, 3),
              (1, 16, 16, 64, 512, 3), (1, 32, 24, 64, 64, 7), (2, 12, 40, 256, 256, 3)]
     only = int(sys.argv[2]) if len(sys.argv) > 2 else -1
     for i, c in enumerate(cases):
@@ -147,14 +125,6 @@ def main_bwd(group):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "wdirect":
-        torch.backends.cudnn.allow_tf32 = False
-        i = int(sys.argv[2])
-        cfgs = [("k3 tg1 W16", 1, 16, 16, 64, 64, 3, 1, 2), ("k3 tgN W16", 1, 16, 16, 64, 64, 3, 1, 0),
-                ("k3 tg1 W36 ragged", 2, 40, 36, 64, 48, 3, 1, 2), ("k1 W36", 2, 40, 36, 64, 48, 1, 1, 0),
-                ("k5 tgN x3", 1, 32, 24, 96, 64, 5, 3, 0), ("k3 fold x3", 4, 6, 20, 64, 128, 3, 3, 0)]
-        wgrad_direct(*cfgs[i])
-        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] in ("dgrad", "wgrad"):
         main_bwd(sys.argv[1])
         sys.exit(0)
