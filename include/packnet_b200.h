@@ -183,8 +183,8 @@ int pn_feature_stencil_backward(int pack, const float* in, const float* g, const
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm(16, eps) + ELU on NHWC maps (layers01.py:31-32,37; with x2 != NULL the input is x + x2, the
- * residual sum of layers01.py:72).  stats: [B,16,2] doubles (sum, sum of squares), written by the forward
- * and read by the backward.  The output may again be a channel window of a wider buffer.
+ * residual sum of layers01.py:72).  stats: B*16*3 doubles of scratch -- [B,16,2] doubles (sum, sum of squares)
+ * followed by [B,16,2] floats (mean, rstd) -- written by the forward and read by the backward.  The output may again be a channel window of a wider buffer.
  * backward scratch `bc`: 2*C*B doubles followed by 2*16*B floats.
  * ------------------------------------------------------------------------------------------------ */
 int pn_groupnorm_elu_forward(const float* x, const float* x2, const float* gamma, const float* beta, float eps,

@@ -49,6 +49,37 @@ __device__ __forceinline__ float load_volume(const StencilParams& P, int b, int 
   }
 }
 
+// Stage the 3 x (tw+2) x (D+2) zero-padded neighbourhood of the virtual volume into shared memory.  One warp takes
+// one (row, column[, sub-pixel]) combination at a time -- the index arithmetic is warp-uniform -- and its lanes run
+// over the contiguous channels of ONE source pixel, so every global load is coalesced.
+template <bool PACK>
+__device__ __forceinline__ void stage_volume(const float* __restrict__ in, int b, int H, int W, int C, int D, int h, int w0,
+                                             int TWP, float* __restrict__ s_v) {
+  const int DP = D + 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int ncombo = 3 * TWP * (PACK ? 4 : 1);
+  for (int cb = warp; cb < ncombo; cb += nwarps) {
+    const int ij = PACK ? (cb & 3) : 0;
+    const int rc = PACK ? (cb >> 2) : cb;
+    const int cw = rc % TWP, r = rc / TWP;
+    const int ww = w0 + cw - 1, hh = h + r - 1;
+    float* row = s_v + (r * TWP + cw) * DP;
+    const bool inside = (ww >= 0) && (ww < W) && (hh >= 0) && (hh < H);
+    if (ij == 0) {
+      if (lane == 0) row[0] = 0.0f;
+      if (lane == 1) row[DP - 1] = 0.0f;
+    }
+    if (PACK) {
+      const int i = ij >> 1, j = ij & 1;
+      const float* src = in + (((size_t)b * 2 * H + (2 * hh + i)) * 2 * W + (2 * ww + j)) * C;
+      for (int c = lane; c < C; c += 32) row[1 + 4 * c + ij] = inside ? __ldg(src + c) : 0.0f;
+    } else {
+      const float* src = in + (((size_t)b * H + hh) * W + ww) * C;
+      for (int d = lane; d < D; d += 32) row[1 + d] = inside ? __ldg(src + d) : 0.0f;
+    }
+  }
+}
+
 // smem: s_v[3][tw+2][D+2] (zero padded in all three dims), s_w[8*27 + 8]
 template <bool PACK>
 __global__ void __launch_bounds__(256) stencil_fwd_kernel(const StencilParams P) {
@@ -58,27 +89,7 @@ __global__ void __launch_bounds__(256) stencil_fwd_kernel(const StencilParams P)
   float* s_w = sm + 3 * TWP * DP;
   const int w0 = blockIdx.x * P.tw, h = blockIdx.y, b = blockIdx.z;
   for (int i = threadIdx.x; i < 8 * 27 + 8; i += blockDim.x) s_w[i] = (i < 216) ? P.w3[i] : P.b3[i - 216];
-  // stage the 3 x (tw+2) x (D+2) neighbourhood; for PACK read x pixel-major so the global loads coalesce
-  const int total = 3 * TWP * DP;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    int dd, cw, r;
-    if (PACK) {
-      // idx enumerates (r, cw, i, j, c) with c fastest: consecutive threads read consecutive channels of one x pixel
-      const int per_px = DP;  // keep the generic decomposition; the remap below orders reads by (i,j,c)
-      dd = idx % per_px; cw = (idx / per_px) % TWP; r = idx / (per_px * TWP);
-      // remap dd in [1,D] from "d order" to "(ij, c) order" so that a warp touches one x pixel at a time
-      if (dd >= 1 && dd <= D) {
-        const int lin = dd - 1, ij = lin / P.C, c = lin % P.C;
-        dd = 1 + (c << 2) + ij;
-      }
-    } else {
-      dd = idx % DP; cw = (idx / DP) % TWP; r = idx / (DP * TWP);
-    }
-    const int d = dd - 1, ww = w0 + cw - 1, hh = h + r - 1;
-    float v = 0.0f;
-    if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) v = load_volume<PACK>(P, b, d, hh, ww);
-    s_v[(r * TWP + cw) * DP + dd] = v;
-  }
+  stage_volume<PACK>(P.in, b, P.H, P.W, P.C, D, h, w0, TWP, s_v);
   __syncthreads();
   // one (pixel, d) item per thread iteration -> 8 features from 27 shared-memory reads
   const int items = P.tw * D;
@@ -171,15 +182,8 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
       s_gh[idx] = v;
     }
   }
-  StencilParams Q{};
-  Q.B = P.B; Q.H = P.H; Q.W = P.W; Q.D = P.D; Q.C = P.C; Q.in = P.in;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int dd = idx % DP, cw = (idx / DP) % TWP, r = idx / (DP * TWP);
-    const int d = dd - 1, ww = w0 + cw - 1, hh = h + r - 1;
-    float v = 0.0f;
-    if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) v = load_volume<PACK>(Q, b, d, hh, ww);
-    s_v[idx] = v;
-  }
+  stage_volume<PACK>(P.in, b, P.H, P.W, P.C, D, h, w0, TWP, s_v);
+  (void)total;
   const int items = P.tw * D;
   constexpr int MAXI = 8;  // items per thread kept in registers (tw*D <= 256*MAXI is enforced by the host)
   float gin_acc[MAXI];
@@ -187,19 +191,25 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
   for (int k = 0; k < MAXI; ++k) gin_acc[k] = 0.0f;
   for (int f = 0; f < 8; ++f) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int dd = idx % DP, cw = (idx / DP) % TWP, r = idx / (DP * TWP);
-      const int d = dd - 1, ww = w0 + cw - 1, hh = h + r - 1;
-      float v = 0.0f;
-      if (d >= 0 && d < D && ww >= 0 && ww < P.W && hh >= 0 && hh < P.H) {
+    {  // feature plane f of g with its halo: one warp per (row, column), lanes over the depth
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+      for (int rc = warp; rc < 3 * TWP; rc += nwarps) {
+        const int cw = rc % TWP, r = rc / TWP;
+        const int ww = w0 + cw - 1, hh = h + r - 1;
+        float* row = s_g + (r * TWP + cw) * DP;
+        const bool inside = (ww >= 0) && (ww < P.W) && (hh >= 0) && (hh < P.H);
+        if (lane == 0) row[0] = 0.0f;
+        if (lane == 1) row[DP - 1] = 0.0f;
         if (PACK) {
-          v = load_gout<PACK>(P, b, f, d, hh, ww);
+          const float* src = P.g + (((size_t)b * P.H + hh) * P.W + ww) * P.g_cstride + P.g_coffset + (size_t)f * D;
+          for (int d = lane; d < D; d += 32) row[1 + d] = inside ? __ldg(src + d) : 0.0f;
         } else {
-          const int vv = f * D + d, co = vv >> 2, i = (vv >> 1) & 1, j = vv & 1;
-          v = s_gh[((2 * r + i) * (2 * TWP) + (2 * cw + j)) * (2 * D) + co];
+          for (int d = lane; d < D; d += 32) {
+            const int vv = f * D + d, co = vv >> 2, i = (vv >> 1) & 1, j = vv & 1;
+            row[1 + d] = inside ? s_gh[((2 * r + i) * (2 * TWP) + (2 * cw + j)) * (2 * D) + co] : 0.0f;
+          }
         }
       }
-      s_g[idx] = v;
     }
     __syncthreads();
     float wacc[27];
@@ -243,17 +253,30 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
       else atomicAdd(P.gb3 + f, v);
     }
   }
-  // write the data gradient in the forward INPUT layout
-  int slot = 0;
-  for (int it = threadIdx.x; it < items; it += blockDim.x, ++slot) {
-    const int d = it % D, pw = it / D;
-    const int w = w0 + pw;
-    if (w >= P.W || slot >= MAXI) continue;
-    if (PACK) {
-      const int c = d >> 2, i = (d >> 1) & 1, j = d & 1;
-      P.gin[(((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.C + c] = gin_acc[slot];
-    } else {
-      P.gin[(((size_t)b * P.H + h) * P.W + w) * P.C + d] = gin_acc[slot];
+  // write the data gradient in the forward INPUT layout, through shared memory so the stores are pixel-major
+  __syncthreads();
+  float* s_out = s_g;  // tw * D floats (<= 3*(tw+2)*(D+2))
+  {
+    int slot = 0;
+    for (int it = threadIdx.x; it < items; it += blockDim.x, ++slot)
+      if (slot < MAXI) s_out[it] = gin_acc[slot];
+  }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int ncombo = P.tw * (PACK ? 4 : 1);
+    for (int cb = warp; cb < ncombo; cb += nwarps) {
+      const int ij = PACK ? (cb & 3) : 0, pw = PACK ? (cb >> 2) : cb;
+      const int w = w0 + pw;
+      if (w >= P.W) continue;
+      if (PACK) {
+        const int i = ij >> 1, j = ij & 1;
+        float* dst = P.gin + (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.C;
+        for (int c = lane; c < P.C; c += 32) dst[c] = s_out[pw * D + 4 * c + ij];
+      } else {
+        float* dst = P.gin + (((size_t)b * P.H + h) * P.W + w) * P.C;
+        for (int d = lane; d < D; d += 32) dst[d] = s_out[pw * D + d];
+      }
     }
   }
 }
@@ -301,15 +324,25 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   }
 }
 
+// (sum, sumsq) doubles -> (mean, rstd) floats, once per (sample, group); stored behind the doubles in `stats`
+__global__ void gn_finalize_stats_kernel(const double* __restrict__ stats, float* __restrict__ mr, int n, double cnt, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = stats[2 * i] / cnt;
+  double var = stats[2 * i + 1] / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mr[2 * i] = (float)mean;
+  mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 // y = ELU(gamma * (x - mean) * rstd + beta), written at (out_cstride, out_coffset); optional tf32 residual copy
 __global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restrict__ x, const float* __restrict__ x2, int HW, int C,
-                                                           int in_cstride, const double* __restrict__ stats,
+                                                           int in_cstride, const float* __restrict__ mr,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                            float* __restrict__ y, float* __restrict__ y_lo, int out_cstride,
                                                            int out_coffset, int B) {
   const int c4 = C / 4, cg = C / 16;
   const size_t total = (size_t)B * HW * c4;
-  const double cnt = (double)HW * cg;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int col = (int)(idx % c4);
     const size_t pix = idx / c4;
@@ -324,12 +357,8 @@ __global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restri
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = col * 4 + k, g = c / cg;
-      const double su = stats[((size_t)b * 16 + g) * 2 + 0], sq = stats[((size_t)b * 16 + g) * 2 + 1];
-      const double mean = su / cnt;
-      double var = sq / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-      const float z = (in[k] - (float)mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      const float mean = __ldg(mr + ((size_t)b * 16 + g) * 2 + 0), rstd = __ldg(mr + ((size_t)b * 16 + g) * 2 + 1);
+      const float z = (in[k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
       out[k] = z > 0.0f ? z : expm1f(z);   // nn.ELU(alpha=1)
     }
     const size_t oo = pix * out_cstride + out_coffset + col * 4;
@@ -345,22 +374,17 @@ __global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restri
 __global__ void __launch_bounds__(256) gn_elu_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                                 const float* __restrict__ y, const float* __restrict__ dy, int HW, int C,
                                                                 int in_cstride, int y_cstride, int y_coffset, int dy_cstride,
-                                                                int dy_coffset, const double* __restrict__ stats, float eps,
+                                                                int dy_coffset, const float* __restrict__ mr, float eps,
                                                                 int pixels_per_cta, double* __restrict__ bc) {
   const int b = blockIdx.y;
   const int cg = C / 16;
-  const double cnt = (double)HW * cg;
   const int p0 = blockIdx.x * pixels_per_cta, p1 = min(p0 + pixels_per_cta, HW);
   // thread -> channel (c = threadIdx.x % C), pixel lane
   const int lanes = blockDim.x / C > 0 ? blockDim.x / C : 1;
   for (int c = threadIdx.x % C + (threadIdx.x / C >= lanes ? C : 0); c < C; c += blockDim.x) {
     const int pl = (blockDim.x >= C) ? threadIdx.x / C : 0;
     const int g = c / cg;
-    const double su = stats[((size_t)b * 16 + g) * 2 + 0], sq = stats[((size_t)b * 16 + g) * 2 + 1];
-    const double mean = su / cnt;
-    double var = sq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps)), fmean = (float)mean;
+    const float fmean = __ldg(mr + ((size_t)b * 16 + g) * 2 + 0), rstd = __ldg(mr + ((size_t)b * 16 + g) * 2 + 1);
     float s1 = 0.0f, s2 = 0.0f;
     for (int p = p0 + pl; p < p1; p += lanes) {
       const size_t pix = (size_t)b * HW + p;
@@ -381,21 +405,16 @@ __global__ void __launch_bounds__(256) gn_elu_bwd_reduce_kernel(const float* __r
 __global__ void __launch_bounds__(256) gn_elu_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                                const float* __restrict__ y, const float* __restrict__ dy, int HW, int C,
                                                                int in_cstride, int y_cstride, int y_coffset, int dy_cstride,
-                                                               int dy_coffset, const double* __restrict__ stats,
+                                                               int dy_coffset, const float* __restrict__ mr,
                                                                const float* __restrict__ gmeans, const float* __restrict__ gamma, float eps,
                                                                float* __restrict__ dx, float* __restrict__ dx_lo, int B) {
   const int cg = C / 16;
-  const double cnt = (double)HW * cg;
   const size_t total = (size_t)B * HW * C;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C);
     const size_t pix = idx / C;
     const int b = (int)(pix / HW), g = c / cg;
-    const double su = stats[((size_t)b * 16 + g) * 2 + 0], sq = stats[((size_t)b * 16 + g) * 2 + 1];
-    const double mean = su / cnt;
-    double var = sq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps)), fmean = (float)mean;
+    const float fmean = __ldg(mr + ((size_t)b * 16 + g) * 2 + 0), rstd = __ldg(mr + ((size_t)b * 16 + g) * 2 + 1);
     const float m1 = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 0), m2 = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 1);
     float xv = x[pix * in_cstride + c];
     if (x2) xv += x2[pix * in_cstride + c];
@@ -440,13 +459,18 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
                                                           float* __restrict__ out) {
   const size_t p0 = (size_t)blockIdx.x * pixels_per_cta;
   const size_t p1 = p0 + pixels_per_cta < pixels ? p0 + pixels_per_cta : pixels;
+  __shared__ float s_acc[1024];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_acc[c] = 0.0f;
+  __syncthreads();
   const int lanes = blockDim.x / C > 0 ? blockDim.x / C : 1;
   for (int c = threadIdx.x % C + (threadIdx.x / C >= lanes ? C : 0); c < C; c += blockDim.x) {
     const int pl = (blockDim.x >= C) ? threadIdx.x / C : 0;
     float s = 0.0f;
     for (size_t p = p0 + pl; p < p1; p += lanes) s += g[p * C + c];
-    atomicAdd(out + c, s);
+    atomicAdd(&s_acc[c], s);
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, s_acc[c]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -542,10 +566,13 @@ extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const f
   dim3 g1((hw + ppc - 1) / ppc, batch);
   gn_stats_kernel<<<g1, 256, 0, stream>>>(x, x2, hw, channels, channels, ppc, stats);
   count_launch();
+  float* mr = reinterpret_cast<float*>(stats + (size_t)2 * 16 * batch);   // (mean, rstd) floats behind the doubles
+  gn_finalize_stats_kernel<<<(16 * batch + 127) / 128, 128, 0, stream>>>(stats, mr, 16 * batch, (double)hw * (channels / 16), eps);
+  count_launch();
   const size_t total = (size_t)batch * hw * (channels / 4);
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  gn_elu_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, hw, channels, channels, stats, gamma, beta, eps, y, y_lo, out_cstride,
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gn_elu_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, hw, channels, channels, mr, gamma, beta, eps, y, y_lo, out_cstride,
                                                   out_coffset, batch);
   count_launch();
   return check_launch("gn_elu_apply_kernel");
@@ -563,19 +590,20 @@ extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const 
   int ppc = (hw + 147) / 148;
   if (ppc < 32) ppc = 32;
   dim3 g1((hw + ppc - 1) / ppc, batch);
+  const float* mr = reinterpret_cast<const float*>(stats + (size_t)2 * 16 * batch);
   gn_elu_bwd_reduce_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
-                                                   stats, eps, ppc, bc);
+                                                   mr, eps, ppc, bc);
   count_launch();
   const size_t total = (size_t)batch * hw * channels;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   // bc holds 2*C*B doubles followed by 2*16*B floats of scratch for the group means
   float* gmeans = reinterpret_cast<float*>(bc + (size_t)2 * channels * batch);
   gn_bwd_finalize_kernel<<<(batch * 16 + channels + 127) / 128, 128, 0, stream>>>(bc, gamma, batch, channels,
                                                                                  (double)hw * (channels / 16), gmeans, dgamma, dbeta);
   count_launch();
   gn_elu_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
-                                                      dy_coffset, stats, gmeans, gamma, eps, dx, dx_lo, batch);
+                                                      dy_coffset, mr, gmeans, gamma, eps, dx, dx_lo, batch);
   count_launch();
   return check_launch("gn_elu_bwd kernels");
 }

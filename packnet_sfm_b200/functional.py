@@ -185,7 +185,7 @@ class _GroupNormELU(torch.autograd.Function):
         x2c = x2.contiguous() if x2 is not None else None
         B, H, W, C = x.shape
         y = torch.empty_like(x)
-        stats = torch.empty(B * 16 * 2, dtype=torch.float64, device=x.device)
+        stats = torch.empty(B * 16 * 3, dtype=torch.float64, device=x.device)   # sums (double) + mean/rstd (float)
         _lib.check(_lib.lib().pn_groupnorm_elu_forward(_lib.ptr(x), _p(x2c), _lib.ptr(gamma.detach().contiguous()),
                                                        _lib.ptr(beta.detach().contiguous()), float(eps), _lib.ptr(y), None,
                                                        _lib.ptr(stats), B, H * W, C, C, 0, _stream()),
