@@ -290,10 +290,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         log("warm-up step %d: %.1f ms (loss %.5f)" % (i, (time.time() - t_w) * 1e3, float(state["loss"].item())))
     launches0 = _lib.launch_count()
+    cpu0 = time.process_time()
     with ClockSampler(local) as clk:
         ms = timed_region(lambda: step(dbatch), args.steps)
+    cpu_ms = (time.process_time() - cpu0) * 1e3 / args.steps     # host CPU time (all threads) per step
     launches = _lib.launch_count() - launches0
-    log("timed region: %.1f ms/step, %d library launches" % (ms / args.steps, launches))
+    log("timed region: %.1f ms/step (host CPU %.1f ms/step), %d library launches" % (ms / args.steps, cpu_ms, launches))
 
     def e2e_step():
         step(to_device(hb, dev))
@@ -320,7 +322,8 @@ def run_ours(args):
                            "grad_allreduce_bytes": bucket.nbytes()},
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clk.summary(), "loss": state.get("loss_host")}
+                "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "clocks": clk.summary(),
+                "loss": state.get("loss_host")}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)

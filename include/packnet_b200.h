@@ -140,19 +140,23 @@ int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const void* x_lo,
                       const void* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
                       pn_stream_t stream);
 
-/* Weight packing: OIHW fp32 [Cout,Cin,k,k] (nn.Conv2d.weight) -> [Cout][k*k][kpad(Cin)] (transposed=0, fprop) or
- * -> [Cin][k*k flipped][kpad(Cout)] (transposed=1: the operand of the data-gradient convolution); kpad rounds up
- * to 32 (fp32 operands) or 64 (bf16 operands).  w_packed_lo may be NULL. */
+/* Weight packing: OIHW fp32 [Cout,Cin,k,k] (nn.Conv2d.weight) -> the shared-memory image of every B-operand tile,
+ * [channel chunk][tap][rows padded to the N tile][128 bytes, SWIZZLE_128B applied], so that the kernel fetches a
+ * tile with one contiguous bulk copy.  transposed=0: rows = Cout (fprop); transposed=1: rows = Cin, taps flipped
+ * (the operand of the data-gradient convolution).  A channel chunk is 32 (fp32) or 64 (bf16) reduction channels.
+ * w_packed_lo (residual operand of the X3 modes) may be NULL. */
 int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, int precision, size_t* elems);
 int pn_conv2d_pack_weight(const float* w_oihw, void* w_packed, void* w_packed_lo, int cout, int cin, int ksize,
                           int transposed, int precision, pn_stream_t stream);
 
 /* Weight gradient (autograd backward of nn.Conv2d w.r.t. weight).  x [B,H,W,Cin] and g = dL/dy [B,H,W,Cout]
  * are the NHWC tensors themselves (read as MN-major operand tiles; the reduction runs over pixels); x_lo / g_lo
- * are their residuals (X3 modes).  dw_packed fp32 [Cout][k*k][kpad(Cin)] is zeroed and accumulated;
+ * are their residuals (X3 modes).  dw_packed fp32 [Cout][k*k][kpad(Cin)] (kpad = Cin rounded up to 32 / 64;
+ * pn_conv2d_wgrad_packed_elems) is zeroed and accumulated;
  * pn_conv2d_unpack_weight_grad converts it to OIHW. */
 int pn_conv2d_wgrad(const pn_conv_desc* desc, const void* x, const void* x_lo, const void* g, const void* g_lo,
                     float* dw_packed, uint32_t* error_flag, pn_stream_t stream);
+int pn_conv2d_wgrad_packed_elems(int cout, int cin, int ksize, int precision, size_t* elems);
 int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, int precision,
                                  pn_stream_t stream);
 

@@ -38,6 +38,8 @@ def declare(lib):
     lib.pn_conv2d_unpack_weight_grad.argtypes = [vp, vp, i, i, i, i, vp]
     lib.pn_conv2d_wgrad.restype = c.c_int
     lib.pn_conv2d_unpack_weight_grad.restype = c.c_int
+    lib.pn_conv2d_wgrad_packed_elems.argtypes = [i, i, i, i, c.POINTER(sz)]
+    lib.pn_conv2d_wgrad_packed_elems.restype = c.c_int
     for name in ("pn_conv2d_forward", "pn_conv2d_packed_weight_elems", "pn_conv2d_pack_weight", "pn_tf32_residual"):
         getattr(lib, name).restype = c.c_int
     return lib

@@ -53,6 +53,9 @@ struct KernelParams {
   uint32_t tmem_cols;
   uint32_t idesc;          // N = bn
   uint32_t idesc2;         // N = 2*bn (tf32x3: A_hi x [B_hi ; B_lo])
+  const uint8_t* wp;       // packed, pre-swizzled weight tiles [cchunk][tap][rows_pad][128 B] (see pack_weight kernels)
+  const uint8_t* wp_lo;
+  int rows_pad;            // rows of one (cchunk, tap) tile group: Cout rounded up to a multiple of bn
   const float* bias;
   float* out;
   unsigned int* error_flag;
@@ -103,6 +106,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// 1-D bulk copy global -> shared (UBLKCP): one request for a whole contiguous tile
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -165,7 +174,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_b
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                   const KernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
@@ -235,8 +243,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_4d(stage_a(s, 0), &tmA, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
             if (nops == 2) tma_load_4d(stage_a(s, 1), &tmAlo, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
           }
-          tma_load_3d(stage_b(s, 0), &tmB, full_bar(s), cc * P.kc, tap, n0);
-          if (nops == 2) tma_load_3d(stage_b(s, 1), &tmBlo, full_bar(s), cc * P.kc, tap, n0);
+          // the weight tile of (channel chunk, tap, N block) is ONE contiguous, pre-swizzled run of bn*128 bytes
+          const size_t woff = ((size_t)(cc * taps + tap) * P.rows_pad + n0) * 128u;
+          bulk_load_1d(stage_b(s, 0), P.wp + woff, P.b_stage_bytes, full_bar(s));
+          if (nops == 2) bulk_load_1d(stage_b(s, 1), P.wp_lo + woff, P.b_stage_bytes, full_bar(s));
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -544,47 +554,48 @@ __global__ void tf32_residual_kernel(const float4* __restrict__ x, float4* __res
   }
 }
 
-// OIHW [Cout][Cin][k][k] -> [Cout][tap][Cin_pad] (+ residual);  transposed: dgrad weights
-//   [Cin][tap'][Cout_pad] with tap' = (k-1-dy, k-1-dx)  (correlation with the flipped kernel)
-__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wp_lo, int Cout,
-                                   int Cin, int ks, int kpad, int transposed) {
-  const int taps = ks * ks;
-  const int rows = transposed ? Cin : Cout;
-  const size_t total = (size_t)rows * taps * kpad;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % kpad);
-    const int tap = (int)((idx / kpad) % taps);
-    const int r = (int)(idx / ((size_t)kpad * taps));
-    float v = 0.0f;
-    if (!transposed) {
-      if (k < Cin) v = w[((size_t)r * Cin + k) * taps + tap];
-    } else {
-      if (k < Cout) v = w[((size_t)k * Cin + r) * taps + (taps - 1 - tap)];
-    }
-    wp[idx] = v;
-    if (wp_lo) wp_lo[idx] = v - tf32_trunc(v);
-  }
+// Weight packing.  Output = the exact shared-memory image of every B stage tile, so the kernel fetches a tile with ONE
+// contiguous bulk copy:   [cchunk][tap][rows_pad][128 bytes],  row = output channel (fprop) / input channel (dgrad),
+// 128 bytes = kc consecutive reduction channels of that chunk, 16-byte groups XOR-swizzled with (row & 7) exactly as
+// SWIZZLE_128B lays a K-major tile out (rows are 128 B apart, tiles start at multiples of 8 rows).
+//   fprop  (transposed=0): value(row=co, k=ci, tap) = w[co][ci][tap]
+//   dgrad  (transposed=1): value(row=ci, k=co, tap) = w[co][ci][taps-1-tap]     (correlation with the flipped kernel)
+// Rows >= the real row count and k >= the real reduction size are zero.
+template <typename T>
+__device__ __forceinline__ void store_split(T* hi, T* lo, size_t idx, float v);
+template <>
+__device__ __forceinline__ void store_split<float>(float* hi, float* lo, size_t idx, float v) {
+  hi[idx] = v;
+  if (lo) lo[idx] = v - tf32_trunc(v);
+}
+template <>
+__device__ __forceinline__ void store_split<__nv_bfloat16>(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  if (lo) lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// bf16 flavour: hi = bf16_rn(v), lo = bf16_rn(v - hi)  (hi + lo carries 16 mantissa bits of v)
-__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ wp_lo,
-                                        int Cout, int Cin, int ks, int kpad, int transposed) {
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wp_lo, int Cout, int Cin,
+                                   int ks, int kc, int rows_pad, int transposed) {
   const int taps = ks * ks;
-  const int rows = transposed ? Cin : Cout;
-  const size_t total = (size_t)rows * taps * kpad;
+  const int rows = transposed ? Cin : Cout, kred = transposed ? Cout : Cin;
+  const int cchunks = (kred + kc - 1) / kc;
+  const int epc = 16 / (int)sizeof(T);            // elements per 16-byte swizzle group
+  const size_t total = (size_t)cchunks * taps * rows_pad * kc;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % kpad);
-    const int tap = (int)((idx / kpad) % taps);
-    const int r = (int)(idx / ((size_t)kpad * taps));
+    const int e = (int)(idx % kc);                 // position inside the (swizzled) 128-byte row
+    const int r = (int)((idx / kc) % rows_pad);
+    const int tap = (int)((idx / ((size_t)kc * rows_pad)) % taps);
+    const int cc = (int)(idx / ((size_t)kc * rows_pad * taps));
+    const int grp = e / epc, within = e % epc;
+    const int k = cc * kc + ((grp ^ (r & 7)) * epc + within);   // logical reduction index stored at this position
     float v = 0.0f;
-    if (!transposed) {
-      if (k < Cin) v = w[((size_t)r * Cin + k) * taps + tap];
-    } else {
-      if (k < Cout) v = w[((size_t)k * Cin + r) * taps + (taps - 1 - tap)];
+    if (r < rows && k < kred) {
+      if (!transposed) v = w[((size_t)r * Cin + k) * taps + tap];
+      else v = w[((size_t)k * Cin + r) * taps + (taps - 1 - tap)];
     }
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    wp[idx] = h;
-    if (wp_lo) wp_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    store_split<T>(wp, wp_lo, idx, v);
   }
 }
 
@@ -650,6 +661,13 @@ static bool is_bf16(int precision) { return precision == PN_PRECISION_BF16X3 || 
 static bool is_split(int precision) { return precision == PN_PRECISION_BF16X3 || precision == PN_PRECISION_TF32X3; }
 int kc_of(int precision) { return is_bf16(precision) ? 64 : 32; }
 int kpad_of(int c, int precision) { const int kc = kc_of(precision); return (c + kc - 1) / kc * kc; }
+// N tile of the forward/dgrad kernel and the row padding of the packed weight (a multiple of the N tile)
+int bn_of(int rows) { const int r16 = (rows + 15) / 16 * 16; return r16 < 128 ? r16 : 128; }
+int rows_pad_of(int rows) { const int bn = bn_of(rows); return (rows + bn - 1) / bn * bn; }
+size_t packed_weight_elems(int rows, int kred, int ksize, int precision) {
+  const int kc = kc_of(precision);
+  return (size_t)((kred + kc - 1) / kc) * ksize * ksize * rows_pad_of(rows) * kc;
+}
 
 // x [B,H,W,Cin] NHWC, wp [Cout][k*k][kpad(Cin)] -> y [B,H,W,Cout]
 static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, const void* wp, const void* wp_lo,
@@ -685,11 +703,12 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   P.tiles_x = (d->width + TILE_W - 1) / TILE_W;
   P.tiles_y = (d->height + P.th - 1) / P.th;
   const int bgroups = (d->batch + P.nb - 1) / P.nb;
-  // N tile: as wide as TMEM/smem allow (<= 256, multiple of 16)
-  int bn = (d->cout + 15) / 16 * 16;
-  const int bn_cap = (P.nsplit == 3) ? 128 : 256;
-  if (bn > bn_cap) bn = bn_cap;
+  // N tile (<= 128, multiple of 16); the packed weight is padded to a multiple of it
+  const int bn = bn_of(d->cout);
   P.bn = bn;
+  P.rows_pad = rows_pad_of(d->cout);
+  P.wp = static_cast<const uint8_t*>(wp);
+  P.wp_lo = static_cast<const uint8_t*>(wp_lo ? wp_lo : wp);
   P.cchunks = (d->cin + kc - 1) / kc;
   P.a_stage_bytes = TILE_W * TILE_ROWS * 128u;
   P.b_stage_bytes = (uint32_t)bn * 128u;
@@ -711,7 +730,7 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   const size_t smem = 1024 + patch_region + (size_t)stages * stage_bytes + 512;
 
   // tensor maps
-  alignas(64) CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  alignas(64) CUtensorMap tmA, tmAlo;
   {
     const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
     const uint64_t strides[3] = {(uint64_t)d->cin * esize, (uint64_t)d->width * d->cin * esize,
@@ -722,16 +741,6 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
     int rc = make_map(&tmA, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
     rc = make_map(&tmAlo, x_lo ? x_lo : x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
-    if (rc) return rc;
-  }
-  {
-    const int kp = kpad_of(d->cin, d->precision), taps = d->ksize * d->ksize;
-    const uint64_t dims[3] = {(uint64_t)kp, (uint64_t)taps, (uint64_t)d->cout};
-    const uint64_t strides[2] = {(uint64_t)kp * esize, (uint64_t)kp * taps * esize};
-    const uint32_t box[3] = {(uint32_t)kc, 1, (uint32_t)bn};
-    int rc = make_map(&tmB, wp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
-    if (rc) return rc;
-    rc = make_map(&tmBlo, wp_lo ? wp_lo : wp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
   }
   // small maps: split the channel-chunk loop so that the grid covers the 148 SMs
@@ -749,7 +758,7 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   }
   PN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(P.tiles_x * P.tiles_y * bgroups, (d->cout + bn - 1) / bn, P.ksplits);
-  conv_igemm_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmAlo, tmB, tmBlo, P);
+  conv_igemm_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmAlo, P);
   count_launch();
   return check_launch("conv_igemm_kernel");
 }
@@ -858,7 +867,7 @@ extern "C" int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const 
 extern "C" int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, int precision, size_t* elems) {
   PN_REQUIRE(elems && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_packed_weight_elems: bad argument");
   const int rows = transposed ? cin : cout, k = transposed ? cout : cin;
-  *elems = (size_t)rows * ksize * ksize * conv::kpad_of(k, precision);
+  *elems = conv::packed_weight_elems(rows, k, ksize, precision);
   return PN_OK;
 }
 
@@ -866,17 +875,18 @@ extern "C" int pn_conv2d_pack_weight(const float* w_oihw, void* w_packed, void* 
                                      int transposed, int precision, pn_stream_t stream) {
   PN_REQUIRE(w_oihw && w_packed && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_pack_weight: bad argument");
   const int rows = transposed ? cin : cout, k = transposed ? cout : cin;
-  const int kpad = conv::kpad_of(k, precision);
-  const size_t total = (size_t)rows * ksize * ksize * kpad;
+  const size_t total = conv::packed_weight_elems(rows, k, ksize, precision);
+  const int kc = conv::kc_of(precision), rows_pad = conv::rows_pad_of(rows);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (precision == PN_PRECISION_BF16X3 || precision == PN_PRECISION_BF16X1)
-    conv::pack_weight_bf16_kernel<<<blocks, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
-                                                         static_cast<__nv_bfloat16*>(w_packed_lo), cout, cin, ksize, kpad, transposed);
+    conv::pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
+                                                                    static_cast<__nv_bfloat16*>(w_packed_lo), cout, cin, ksize, kc,
+                                                                    rows_pad, transposed);
   else
-    conv::pack_weight_kernel<<<blocks, 256, 0, st>>>(w_oihw, static_cast<float*>(w_packed), static_cast<float*>(w_packed_lo), cout,
-                                                    cin, ksize, kpad, transposed);
+    conv::pack_weight_kernel<float><<<blocks, 256, 0, st>>>(w_oihw, static_cast<float*>(w_packed), static_cast<float*>(w_packed_lo),
+                                                            cout, cin, ksize, kc, rows_pad, transposed);
   count_launch();
   return check_launch("pack_weight_kernel");
 }
@@ -921,6 +931,12 @@ extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const void* x, const vo
     if (rc) return rc;
   }
   return conv::conv_wgrad(desc, x, g, dw_packed, error_flag, stream);
+}
+
+extern "C" int pn_conv2d_wgrad_packed_elems(int cout, int cin, int ksize, int precision, size_t* elems) {
+  PN_REQUIRE(elems && cout > 0 && cin > 0 && ksize > 0, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad_packed_elems: bad argument");
+  *elems = (size_t)cout * ksize * ksize * conv::kpad_of(cin, precision);
+  return PN_OK;
 }
 
 extern "C" int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, int precision,

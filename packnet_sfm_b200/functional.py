@@ -155,7 +155,7 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             # weight gradient: reduction over pixels, operands read in place as MN-major tiles
             n = ctypes.c_size_t(0)
-            _lib.check(lib.pn_conv2d_packed_weight_elems(cout, Cin, k, 0, precision, ctypes.byref(n)), "packed_weight_elems")
+            _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, Cin, k, precision, ctypes.byref(n)), "wgrad_packed_elems")
             dwp = torch.empty(int(n.value), dtype=torch.float32, device=gy.device)
             d = ConvDesc(B, H, W, Cin, cout, k, precision, 0, 0)
             _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
