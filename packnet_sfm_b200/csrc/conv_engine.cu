@@ -94,6 +94,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
     }
   }
 }
+// long wait of a whole warp (the epilogue waiting for the accumulator): ONE lane polls, with a sleep between probes, so
+// 128 spinning threads do not hammer the mbarrier unit the TMA producer and the MMA issuer depend on (ncu r01: 74 % of
+// all stall samples of the convolution kernel sat in this loop and every pipeline stage took ~1500 cycles)
+__device__ __forceinline__ void mbar_wait_warp_backoff(uint32_t bar, uint32_t parity, unsigned int* error_flag, int who) {
+  if ((threadIdx.x & 31) == 0) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(256);
+      if (clock64() - t0 > 4000000000LL) {
+        if (error_flag) atomicExch(error_flag, 0xDEAD0000u | (unsigned)who);
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -318,7 +335,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (has_work) {
     // ===================================== epilogue ================================================
-    mbar_wait(tmemfull_bar, 0, P.error_flag, 5);
+    mbar_wait_warp_backoff(tmemfull_bar, 0, P.error_flag, 5);
     tc_fence_after();
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;     // tile row == TMEM lane
@@ -502,7 +519,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       umma_commit(tmemfull_bar);
     }
   } else if (has_work) {
-    mbar_wait(tmemfull_bar, 0, P.error_flag, 8);
+    mbar_wait_warp_backoff(tmemfull_bar, 0, P.error_flag, 8);
     tc_fence_after();
     const int q = warp & 3;
     const int ci = ci0 + q * 32 + lane;

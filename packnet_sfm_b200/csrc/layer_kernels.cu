@@ -182,8 +182,7 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
       s_gh[idx] = v;
     }
   }
-  stage_volume<PACK>(P.in, b, P.H, P.W, P.C, D, h, w0, TWP, s_v);
-  (void)total;
+  (void)total; (void)s_v;   // the weight gradient (which needs the forward input) lives in stencil_wgrad_kernel
   const int items = P.tw * D;
   constexpr int MAXI = 8;  // items per thread kept in registers (tw*D <= 256*MAXI is enforced by the host)
   float gin_acc[MAXI];
@@ -212,16 +211,10 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
       }
     }
     __syncthreads();
-    float wacc[27];
-#pragma unroll
-    for (int t = 0; t < 27; ++t) wacc[t] = 0.0f;
-    float bacc = 0.0f;
     int slot = 0;
     for (int it = threadIdx.x; it < items; it += blockDim.x, ++slot) {
       const int d = it % D, pw = it / D;
       if (w0 + pw >= P.W) continue;
-      const float gc = s_g[(1 * TWP + pw + 1) * DP + d + 1];  // g at the centre (this pixel, this depth)
-      bacc += gc;
       float a = 0.0f;
 #pragma unroll
       for (int dz = 0; dz < 3; ++dz)
@@ -230,27 +223,10 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
             const int t = (dz * 3 + dy) * 3 + dx;
-            // weight gradient: g(centre) * V(centre + offset)
-            wacc[t] = fmaf(gc, s_v[(dy * TWP + pw + dx) * DP + d + dz], wacc[t]);
             // data gradient: sum_t w[t] * g(centre - offset)  (transpose of the forward stencil)
             a = fmaf(s_w[f * 27 + t], s_g[((2 - dy) * TWP + pw + (2 - dx)) * DP + d + (2 - dz)], a);
           }
       if (slot < MAXI) gin_acc[slot] += a;
-    }
-    // block-reduce the 27 weight-gradient partials + bias partial of this feature
-#pragma unroll
-    for (int t = 0; t < 28; ++t) {
-      float v = (t < 27) ? wacc[t < 27 ? t : 0] : bacc;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((threadIdx.x & 31) == 0) s_red[(threadIdx.x >> 5) * 28 + t] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 28) {
-      float v = 0.0f;
-      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += s_red[wv * 28 + threadIdx.x];
-      if (threadIdx.x < 27) atomicAdd(P.gw3 + f * 27 + threadIdx.x, v);
-      else atomicAdd(P.gb3 + f, v);
     }
   }
   // write the data gradient in the forward INPUT layout, through shared memory so the stores are pixel-major
@@ -277,6 +253,80 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
         float* dst = P.gin + (((size_t)b * P.H + h) * P.W + w) * P.C;
         for (int d = lane; d < D; d += 32) dst[d] = s_out[pw * D + d];
       }
+    }
+  }
+}
+
+// Conv3d weight / bias gradient: dW[f][t] = sum over (b, d, h, w) of g[f][d][h][w] * V[d+dz-1][h+dy-1][w+dx-1], db[f] = sum g.
+// One CTA walks a strided set of (sample, row) pairs and all pixel tiles of each row; warp f owns feature f and keeps its
+// 27 + 1 partial sums in registers across the whole walk, so there is ONE warp reduction and 28 atomics per warp at the
+// very end (the previous per-tile block reductions + 224 contended atomics per tile dominated the backward).
+// smem: s_v[3][tw+2][D+2] (forward input with halo), s_gc[8][tw][D] (g at the tile's pixels, all 8 features)
+template <bool PACK>
+__global__ void __launch_bounds__(256) stencil_wgrad_kernel(const StencilBwdParams P) {
+  extern __shared__ float sm[];
+  const int D = P.D, DP = D + 2, TWP = P.tw + 2;
+  float* s_v = sm;
+  float* s_gc = s_v + 3 * TWP * DP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = warp;  // 8 warps <-> 8 features
+  float wacc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) wacc[t] = 0.0f;
+  float bacc = 0.0f;
+  const int rows = P.B * P.H;
+  const int wtiles = (P.W + P.tw - 1) / P.tw;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / P.H, h = row % P.H;
+    for (int wt = 0; wt < wtiles; ++wt) {
+      const int w0 = wt * P.tw;
+      __syncthreads();
+      stage_volume<PACK>(P.in, b, P.H, P.W, P.C, D, h, w0, TWP, s_v);
+      if (PACK) {
+        // g[b][h][w][f*D + d]: one warp per (pixel, feature), lanes over the depth
+        for (int cb = warp; cb < P.tw * 8; cb += 8) {
+          const int ff = cb & 7, pw = cb >> 3;
+          const int w = w0 + pw;
+          const float* src = P.g + (((size_t)b * P.H + h) * P.W + w) * P.g_cstride + P.g_coffset + (size_t)ff * D;
+          float* dst = s_gc + ((size_t)ff * P.tw + pw) * D;
+          for (int d = lane; d < D; d += 32) dst[d] = (w < P.W) ? __ldg(src + d) : 0.0f;
+        }
+      } else {
+        // g lives at high resolution: pixel (2h+i, 2w+j), channel co holds feature value v = 4*co + 2*i + j = f*D + d
+        for (int cb = warp; cb < P.tw * 4; cb += 8) {
+          const int ij = cb & 3, pw = cb >> 2;
+          const int i = ij >> 1, j = ij & 1, w = w0 + pw;
+          const float* src = P.g + (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.g_cstride + P.g_coffset;
+          for (int co = lane; co < 2 * D; co += 32) {
+            const int v = 4 * co + ij, ff = v / D, d = v - ff * D;
+            s_gc[((size_t)ff * P.tw + pw) * D + d] = (w < P.W) ? __ldg(src + co) : 0.0f;
+          }
+        }
+      }
+      __syncthreads();
+      const float* gc_f = s_gc + (size_t)f * P.tw * D;
+      for (int it = lane; it < P.tw * D; it += 32) {
+        const int d = it % D, pw = it / D;
+        const float gc = gc_f[it];
+        bacc += gc;
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              wacc[(dz * 3 + dy) * 3 + dx] = fmaf(gc, s_v[(dy * TWP + pw + dx) * DP + d + dz], wacc[(dz * 3 + dy) * 3 + dx]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 28; ++t) {
+    float v = (t < 27) ? wacc[t < 27 ? t : 0] : bacc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+      if (t < 27) atomicAdd(P.gw3 + f * 27 + t, v);
+      else atomicAdd(P.gb3 + f, v);
     }
   }
 }
@@ -549,7 +599,26 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
     stencil_bwd_kernel<false><<<grid, 256, smem, stream>>>(P);
   }
   count_launch();
-  return check_launch("stencil_bwd_kernel");
+  int rc = check_launch("stencil_bwd_kernel");
+  if (rc) return rc;
+  // weight / bias gradient
+  StencilBwdParams Q = P;
+  Q.tw = 8;
+  while (Q.tw > 1 && ((size_t)3 * (Q.tw + 2) * (Q.D + 2) + (size_t)8 * Q.tw * Q.D) * sizeof(float) > 200 * 1024) Q.tw >>= 1;
+  if (Q.tw > Q.W) Q.tw = Q.W;
+  const size_t smem_w = ((size_t)3 * (Q.tw + 2) * (Q.D + 2) + (size_t)8 * Q.tw * Q.D) * sizeof(float);
+  PN_REQUIRE(smem_w <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large for the weight gradient", Q.D);
+  int ctas = Q.B * Q.H;
+  if (ctas > 148 * 2) ctas = 148 * 2;
+  if (pack) {
+    PN_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    stencil_wgrad_kernel<true><<<ctas, 256, smem_w, stream>>>(Q);
+  } else {
+    PN_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    stencil_wgrad_kernel<false><<<ctas, 256, smem_w, stream>>>(Q);
+  }
+  count_launch();
+  return check_launch("stencil_wgrad_kernel");
 }
 
 extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const float* gamma, const float* beta, float eps, float* y,
