@@ -224,6 +224,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int cc_per = (P.cchunks + P.ksplits - 1) / P.ksplits;
   const int cc_begin = blockIdx.z * cc_per, cc_end = min(P.cchunks, cc_begin + cc_per);
   const bool has_work = cc_end > cc_begin;
+  // De-synchronise the CTAs: every CTA walks the same (channel chunk, tap) weight tiles, and when all 148 SMs ask the
+  // L2 for the SAME lines at the same moment the few slices that hold them serialise the requests (measured: every
+  // pipeline stage took ~1500 cycles whatever the tile layout, L2->SM pinned at 3.3 TB/s).  Each CTA therefore starts
+  // its reduction at its own rotation of the chunk and tap order; the sum is order-independent up to fp32 rounding.
+  const int ncc = cc_end - cc_begin;
+  const unsigned rot_seed = blockIdx.x * 2654435761u + blockIdx.y * 40503u;
+  const int rot_c = has_work ? (int)((rot_seed >> 8) % (unsigned)ncc) : 0;
+  const int rot_t = (int)((rot_seed >> 4) % (unsigned)taps);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -243,7 +251,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================== TMA producer ============================================
     if (lane == 0 && has_work) {
       int s = 0, ph = 0, pa = 0, pha = 0;
-      for (int cc = cc_begin; cc < cc_end; ++cc) {
+      for (int ci = 0; ci < ncc; ++ci) {
+        const int cc = cc_begin + (ci + rot_c) % ncc;
         if (P.halo) {
           mbar_wait(emptya_bar(pa), pha ^ 1, P.error_flag, 1);
           mbar_expect_tx(fulla_bar(pa), P.patch_bytes * nops);
@@ -252,7 +261,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           pa ^= 1;
           if (pa == 0) pha ^= 1;
         }
-        for (int tap = 0; tap < taps; ++tap) {
+        for (int ti = 0; ti < taps; ++ti) {
+          const int tap = (ti + rot_t) % taps;
           mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 2);
           mbar_expect_tx(full_bar(s), stage_bytes);
           if (!P.halo) {
@@ -286,13 +296,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
       const uint32_t tm_d2 = tmem_base + 2u * (uint32_t)P.bn;
       const bool bf16 = P.bf16 != 0;
-      for (int cc = cc_begin; cc < cc_end; ++cc) {
+      for (int ci = 0; ci < ncc; ++ci) {
         if (P.halo) {
           mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
           tc_fence_after();
         }
-        int dy = 0, dx = 0;
-        for (int tap = 0; tap < taps; ++tap) {
+        int dy = rot_t / P.ks, dx = rot_t % P.ks;   // same rotated tap order as the producer
+        for (int ti = 0; ti < taps; ++ti) {
           mbar_wait(full_bar(s), ph, P.error_flag, 4);
           tc_fence_after();
           uint32_t la_hi, la_lo;
@@ -302,7 +312,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t shift = (uint32_t)(dy * PATCH_PITCH + dx) * 128u;
             la_hi = lo_of(patch_addr(pa, 0) + shift);
             la_lo = lo_of(patch_addr(pa, 1) + shift);
-            if (++dx == P.ks) { dx = 0; ++dy; }
+            if (++dx == P.ks) { dx = 0; if (++dy == P.ks) dy = 0; }
           } else {
             la_hi = lo_of(stage_a(s, 0));
             la_lo = lo_of(stage_a(s, 1));
@@ -474,7 +484,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 0) {
     if (lane == 0 && has_work) {
       int s = 0, ph = 0;
-      for (int t = t_begin; t < t_end; ++t) {
+      // CTAs that share a pixel split walk the same tiles: start each at its own rotation (L2 hot-spot avoidance)
+      const int nt = t_end - t_begin;
+      const int rot = (int)((blockIdx.x * 2654435761u + blockIdx.y * 40503u) >> 8) % nt;
+      for (int ti = 0; ti < nt; ++ti) {
+        const int t = t_begin + (ti + rot) % nt;
         const int tx = t % P.tiles_x, ty = (t / P.tiles_x) % P.tiles_y, b = t / (P.tiles_x * P.tiles_y);
         const int x0 = tx * TILE_W, y0 = ty * P.th;
         mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 6);
