@@ -289,6 +289,13 @@ def run_ours(args):
         step(dbatch)
         torch.cuda.synchronize()
         log("warm-up step %d: %.1f ms (loss %.5f)" % (i, (time.time() - t_w) * 1e3, float(state["loss"].item())))
+    # host time to ENQUEUE one step on an idle GPU (no sync inside): step time close to this = launch-bound
+    torch.cuda.synchronize()
+    t_q = time.perf_counter()
+    step(dbatch)
+    enqueue_ms = (time.perf_counter() - t_q) * 1e3
+    torch.cuda.synchronize()
+    log("host enqueue of one step: %.1f ms" % enqueue_ms)
     launches0 = _lib.launch_count()
     cpu0 = time.process_time()
     with ClockSampler(local) as clk:
@@ -322,7 +329,7 @@ def run_ours(args):
                            "grad_allreduce_bytes": bucket.nbytes()},
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "clocks": clk.summary(),
+                "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
                 "loss": state.get("loss_host")}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:

@@ -47,7 +47,10 @@ struct KernelParams {
   int halo;                // 1: patch reuse across taps
   int cchunks;             // ceil(Cin / 32)
   int ksplits;             // split of the channel-chunk loop over blockIdx.z (small maps: fill the 148 SMs)
-  int stages;
+  int stages;              // pipeline slots
+  int group;               // (chunk, tap) items per slot
+  int pitch;               // HALO patch: pixels per patch row (8 + k - 1)
+  uint32_t patch_tx;       // bytes one patch load delivers (patch_bytes is rounded up to 1024)
   int force_base_offset0;  // debug knob (bring-up): 1 = put (addr>>7)&7 into base_offset (known to be WRONG)
   uint32_t a_stage_bytes, b_stage_bytes, patch_bytes;
   uint32_t tmem_cols;
@@ -84,7 +87,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a protocol bug must not hang the GPU box -- flag the error and trap instead
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* error_flag, int who) {
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned int* error_flag, int who) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s
@@ -93,6 +96,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
       __trap();
     }
   }
+}
+// the fast path is ONE probe: the watchdog clock reads stay out of the issuer's steady state
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* error_flag, int who) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, error_flag, who);
 }
 // long wait of a whole warp (the epilogue waiting for the accumulator): ONE lane polls, with a sleep between probes, so
 // 128 spinning threads do not hammer the mbarrier unit the TMA producer and the MMA issuer depend on (ncu r01: 74 % of
@@ -157,6 +164,17 @@ __device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t adesc,
   if (bf16) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
   else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
+// one lane of a fully converged warp; the region it guards is what the compiler keeps on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+template <bool BF16>
+__device__ __forceinline__ void umma_k(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (BF16) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -189,17 +207,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_b
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
+template <bool BF16, bool SPLIT, bool HALO>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const KernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
-  const int nops = (P.nsplit == 3) ? 2 : 1;
-  // carve: [HALO patches: 2 buffers x nops] [stages: (A x nops when per-tap) + (B x nops)] [barriers]
-  const uint32_t patch_region = P.halo ? 2u * nops * P.patch_bytes : 0u;
-  const uint32_t stage_bytes = (P.halo ? 0u : nops * P.a_stage_bytes) + nops * P.b_stage_bytes;
-  const uint32_t stages_base = smem_base + patch_region;
-  const uint32_t bars_base = stages_base + P.stages * stage_bytes;
+  constexpr int nops = SPLIT ? 2 : 1;
+  // An ITEM is one (channel chunk, tap): its weight tile(s) [B_hi][B_lo] and, in per-tap mode, its activation tile(s)
+  // [A_hi][A_lo] in front of them.  A pipeline SLOT holds a GROUP of P.group consecutive items behind ONE full/empty
+  // barrier pair: the wait + fence + commit hand-off costs ~100 issue cycles the tensor pipe cannot hide
+  // (tools/ubench_tc2.cu), so it is paid once per group instead of once per tap.
+  // carve: [HALO patches: 2 buffers x nops] [slots] [barriers]
+  const uint32_t patch_region = HALO ? 2u * nops * P.patch_bytes : 0u;
+  const uint32_t item_bytes = (HALO ? 0u : nops * P.a_stage_bytes) + nops * P.b_stage_bytes;
+  const uint32_t slot_bytes = (uint32_t)P.group * item_bytes;
+  const uint32_t slots_base = smem_base + patch_region;
+  const uint32_t bars_base = slots_base + P.stages * slot_bytes;
   // barriers: full[stages], empty[stages], full_a[2], empty_a[2], tmem_full ; then the TMEM address word
   auto full_bar = [&](int s) { return bars_base + 8u * s; };
   auto empty_bar = [&](int s) { return bars_base + 8u * (MAX_STAGES + s); };
@@ -208,10 +232,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmemfull_bar = bars_base + 8u * (2 * MAX_STAGES + 4);
   const uint32_t tmem_slot = bars_base + 8u * (2 * MAX_STAGES + 5);
   auto patch_addr = [&](int buf, int op) { return smem_base + (uint32_t)(buf * nops + op) * P.patch_bytes; };
-  auto stage_a = [&](int s, int op) { return stages_base + s * stage_bytes + op * P.a_stage_bytes; };
-  auto stage_b = [&](int s, int op) {
-    return stages_base + s * stage_bytes + (P.halo ? 0u : nops * P.a_stage_bytes) + op * P.b_stage_bytes;
-  };
+  const uint32_t b_off = HALO ? 0u : nops * P.a_stage_bytes;   // weight tiles inside an item
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -224,14 +245,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int cc_per = (P.cchunks + P.ksplits - 1) / P.ksplits;
   const int cc_begin = blockIdx.z * cc_per, cc_end = min(P.cchunks, cc_begin + cc_per);
   const bool has_work = cc_end > cc_begin;
-  // De-synchronise the CTAs: every CTA walks the same (channel chunk, tap) weight tiles, and when all 148 SMs ask the
-  // L2 for the SAME lines at the same moment the few slices that hold them serialise the requests (measured: every
-  // pipeline stage took ~1500 cycles whatever the tile layout, L2->SM pinned at 3.3 TB/s).  Each CTA therefore starts
-  // its reduction at its own rotation of the chunk and tap order; the sum is order-independent up to fp32 rounding.
   const int ncc = cc_end - cc_begin;
+  // HALO: groups never straddle a channel chunk (they share its patch); per-tap: groups run over the flattened
+  // (chunk, tap) item list.
+  const int G = P.group;
+  const int nitems = HALO ? taps : ncc * taps;
+  const int ngroups = (nitems + G - 1) / G;
+  // De-synchronise the CTAs: every CTA walks the same weight tiles, and when all 148 SMs ask the L2 for the SAME lines
+  // at the same moment the few slices that hold them serialise the requests.  Each CTA therefore starts its reduction
+  // at its own rotation of the chunk and group order; the sum is order-independent up to fp32 rounding.
   const unsigned rot_seed = blockIdx.x * 2654435761u + blockIdx.y * 40503u;
-  const int rot_c = has_work ? (int)((rot_seed >> 8) % (unsigned)ncc) : 0;
-  const int rot_t = (int)((rot_seed >> 4) % (unsigned)taps);
+  const int rot_c = (HALO && has_work) ? (int)((rot_seed >> 8) % (unsigned)ncc) : 0;
+  const int rot_g = has_work ? (int)((rot_seed >> 4) % (unsigned)ngroups) : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -249,99 +274,122 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer ============================================
-    if (lane == 0 && has_work) {
+    // The whole warp walks the loop and ONE elected lane issues: in a converged warp the copy operands live in
+    // uniform registers; under `if (lane == 0)` the compiler wraps every UTMALDG in a per-lane waterfall loop.
+    if (has_work) {
       int s = 0, ph = 0, pa = 0, pha = 0;
-      for (int ci = 0; ci < ncc; ++ci) {
-        const int cc = cc_begin + (ci + rot_c) % ncc;
-        if (P.halo) {
+      const int nouter = HALO ? ncc : 1;
+      for (int ci = 0; ci < nouter; ++ci) {
+        int cc = cc_begin + (ci + rot_c) % ncc;
+        if (HALO) {
           mbar_wait(emptya_bar(pa), pha ^ 1, P.error_flag, 1);
-          mbar_expect_tx(fulla_bar(pa), P.patch_bytes * nops);
-          tma_load_4d(patch_addr(pa, 0), &tmA, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
-          if (nops == 2) tma_load_4d(patch_addr(pa, 1), &tmAlo, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
+          if (elect_one()) {
+            mbar_expect_tx(fulla_bar(pa), P.patch_tx * nops);
+            tma_load_4d(patch_addr(pa, 0), &tmA, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
+            if (nops == 2) tma_load_4d(patch_addr(pa, 1), &tmAlo, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
+          }
           pa ^= 1;
           if (pa == 0) pha ^= 1;
         }
-        for (int ti = 0; ti < taps; ++ti) {
-          const int tap = (ti + rot_t) % taps;
+        int g = rot_g;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          const int item0 = g * G, nt = min(G, nitems - item0);
           mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 2);
-          mbar_expect_tx(full_bar(s), stage_bytes);
-          if (!P.halo) {
-            const int dy = tap / P.ks, dx = tap % P.ks;
-            tma_load_4d(stage_a(s, 0), &tmA, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
-            if (nops == 2) tma_load_4d(stage_a(s, 1), &tmAlo, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), (uint32_t)nt * item_bytes);
+            uint32_t dst = slots_base + (uint32_t)s * slot_bytes;
+            int tap = HALO ? item0 : item0 % taps;
+            if (!HALO) cc = cc_begin + item0 / taps;
+            for (int j = 0; j < nt; ++j) {
+              if (!HALO) {
+                const int dy = tap / P.ks, dx = tap - dy * P.ks;
+                tma_load_4d(dst, &tmA, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+                if (nops == 2) tma_load_4d(dst + P.a_stage_bytes, &tmAlo, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+              }
+              // the weight tile of (channel chunk, tap, N block) is ONE contiguous, pre-swizzled run of bn*128 bytes
+              const size_t woff = ((size_t)(cc * taps + tap) * P.rows_pad + n0) * 128u;
+              bulk_load_1d(dst + b_off, P.wp + woff, P.b_stage_bytes, full_bar(s));
+              if (nops == 2) bulk_load_1d(dst + b_off + P.b_stage_bytes, P.wp_lo + woff, P.b_stage_bytes, full_bar(s));
+              dst += item_bytes;
+              if (++tap == taps) { tap = 0; if (!HALO) ++cc; }
+            }
           }
-          // the weight tile of (channel chunk, tap, N block) is ONE contiguous, pre-swizzled run of bn*128 bytes
-          const size_t woff = ((size_t)(cc * taps + tap) * P.rows_pad + n0) * 128u;
-          bulk_load_1d(stage_b(s, 0), P.wp + woff, P.b_stage_bytes, full_bar(s));
-          if (nops == 2) bulk_load_1d(stage_b(s, 1), P.wp_lo + woff, P.b_stage_bytes, full_bar(s));
+          if (++g == ngroups) g = 0;
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ==============================================
-    // One thread feeds the tensor core, so the loop is kept lean: descriptors are (constant high word | start
-    // address), advanced by adding 2 (= 32 bytes >> 4) per K step.
-    // tf32x3 issues TWO MMAs per K step instead of three: B_hi and B_lo of a stage are adjacent in shared memory,
-    // so A_hi x [B_hi ; B_lo] is one N = 2*bn instruction (TMEM columns [0, 2bn)) and A_lo x B_hi a second one
-    // (columns [2bn, 3bn)); the epilogue adds the three column ranges.  Same math time, 22 % fewer operand bytes
-    // read from shared memory (the N = 64 tf32 tile is shared-memory-read bound: DESIGN.md 3.2).
-    if (lane == 0 && has_work) {
+    // The warp stays converged and one ELECTED lane issues: descriptors and the instruction descriptor sit in uniform
+    // registers and an MMA costs one issue slot.  (r01 SASS of the `if (lane == 0)` form: ~25 instructions incl. R2UR
+    // round trips and a waterfall loop per UTCHMMA, ~130 clk each.)  Descriptors are (constant high word | start
+    // address >> 4), advanced by adding 2 (= 32 bytes >> 4) per K step.
+    // The x3 precisions issue TWO MMAs per K step instead of three: B_hi and B_lo of an item are adjacent in shared
+    // memory, so A_hi x [B_hi ; B_lo] is one N = 2*bn instruction (TMEM columns [0, 2bn)) and A_lo x B_hi a second one
+    // (columns [2bn, 3bn)); the epilogue adds the three column ranges.
+    if (has_work) {
       int s = 0, ph = 0, pa = 0, pha = 0;
       uint32_t acc = 0;
-      const uint32_t sbo_a = P.halo ? PATCH_PITCH * 128u : 1024u;
+      const uint32_t sbo_a = HALO ? (uint32_t)P.pitch * 128u : 1024u;
       const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       auto lo_of = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
       auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
       const uint32_t tm_d2 = tmem_base + 2u * (uint32_t)P.bn;
-      const bool bf16 = P.bf16 != 0;
-      for (int ci = 0; ci < ncc; ++ci) {
-        if (P.halo) {
+      const uint32_t item_step = item_bytes >> 4, alo_step = (HALO ? P.patch_bytes : P.a_stage_bytes) >> 4;
+      const int nouter = HALO ? ncc : 1;
+      for (int ci = 0; ci < nouter; ++ci) {
+        uint32_t pbase = 0;
+        if (HALO) {
           mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
-          tc_fence_after();
+          pbase = lo_of(patch_addr(pa, 0));
         }
-        int dy = rot_t / P.ks, dx = rot_t % P.ks;   // same rotated tap order as the producer
-        for (int ti = 0; ti < taps; ++ti) {
+        int g = rot_g;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          const int item0 = g * G, nt = min(G, nitems - item0);
           mbar_wait(full_bar(s), ph, P.error_flag, 4);
           tc_fence_after();
-          uint32_t la_hi, la_lo;
-          if (P.halo) {
-            // Measured on B200 (profiles/r01_conv_probe.txt): the SWIZZLE_128B XOR is a pure function of the
-            // shared-memory ADDRESS bits, exactly like the TMA write, so a 128-B-shifted start keeps base_offset 0.
-            const uint32_t shift = (uint32_t)(dy * PATCH_PITCH + dx) * 128u;
-            la_hi = lo_of(patch_addr(pa, 0) + shift);
-            la_lo = lo_of(patch_addr(pa, 1) + shift);
-            if (++dx == P.ks) { dx = 0; if (++dy == P.ks) dy = 0; }
-          } else {
-            la_hi = lo_of(stage_a(s, 0));
-            la_lo = lo_of(stage_a(s, 1));
-          }
-          const uint32_t lb = lo_of(stage_b(s, 0));
-          if (nops == 2) {
+          // descriptor arithmetic stays in converged code (uniform datapath); only the MMAs sit under the election
+          uint32_t it = lo_of(slots_base + (uint32_t)s * slot_bytes);   // item 0 of the slot
+          int dy = 0, dx = 0;
+          if (HALO) { dy = item0 / P.ks; dx = item0 - dy * P.ks; }
+          for (int j = 0; j < nt; ++j) {
+            // HALO: the SWIZZLE_128B XOR is a pure function of the shared-memory ADDRESS bits (measured on B200,
+            // profiles/r01_conv_probe.txt), exactly like the TMA write, so a 128-B-shifted start keeps base_offset 0
+            // and the 8-row groups may sit at any multiple of 128 B (SBO = patch pitch).
+            const uint32_t la = HALO ? pbase + (uint32_t)(dy * P.pitch + dx) * 8u : it;
+            const uint32_t lb = it + (b_off >> 4);
+            if (elect_one()) {
+              if (nops == 2) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // one UMMA_K (8 tf32 / 16 bf16) = 32 bytes inside the 128-byte swizzle row
-              umma(bf16, tm_d2, desc(hi_a, la_lo + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);       // A_lo x B_hi
-              umma(bf16, tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, acc);  // A_hi x [B_hi;B_lo]
-              acc = 1u;
-            }
-          } else {
+                for (int k = 0; k < 4; ++k) {  // one UMMA_K (8 tf32 / 16 bf16) = 32 bytes inside the 128-byte swizzle row
+                  const uint32_t a1 = k ? 1u : acc;
+                  umma_k<BF16>(tm_d2, desc(hi_a, la + alo_step + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, a1);   // A_lo x B_hi
+                  umma_k<BF16>(tmem_base, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, a1);         // A_hi x [B_hi;B_lo]
+                }
+              } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma(bf16, tmem_base, desc(hi_a, la_hi + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, acc);
-              acc = 1u;
+                for (int k = 0; k < 4; ++k)
+                  umma_k<BF16>(tmem_base, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, k ? 1u : acc);
+              }
             }
+            acc = 1u;
+            it += item_step;
+            if (HALO) { if (++dx == P.ks) { dx = 0; ++dy; } }
           }
-          umma_commit(empty_bar(s));  // frees this stage when the MMAs above have read it
+          if (elect_one()) umma_commit(empty_bar(s));  // frees this slot when the MMAs above have read it
+          acc = 1u;
+          if (++g == ngroups) g = 0;
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
-        if (P.halo) {
-          umma_commit(emptya_bar(pa));
+        if (HALO) {
+          if (elect_one()) umma_commit(emptya_bar(pa));
           pa ^= 1;
           if (pa == 0) pha ^= 1;
         }
       }
-      umma_commit(tmemfull_bar);
+      if (elect_one()) umma_commit(tmemfull_bar);
     }
   } else if (has_work) {
     // ===================================== epilogue ================================================
@@ -443,6 +491,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lb
   return d;
 }
 
+template <bool BF16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -482,55 +531,65 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0 && has_work) {
+    if (has_work) {   // converged warp, one elected lane issues (see conv_igemm_kernel)
       int s = 0, ph = 0;
       // CTAs that share a pixel split walk the same tiles: start each at its own rotation (L2 hot-spot avoidance)
       const int nt = t_end - t_begin;
       const int rot = (int)((blockIdx.x * 2654435761u + blockIdx.y * 40503u) >> 8) % nt;
+      int t = t_begin + rot;
       for (int ti = 0; ti < nt; ++ti) {
-        const int t = t_begin + (ti + rot) % nt;
         const int tx = t % P.tiles_x, ty = (t / P.tiles_x) % P.tiles_y, b = t / (P.tiles_x * P.tiles_y);
         const int x0 = tx * TILE_W, y0 = ty * P.th;
         mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 6);
-        mbar_expect_tx(full_bar(s), stage_bytes);
-        for (int j = 0; j < P.mblks; ++j) tma_load_4d(stage_x(s, j), &tmX, full_bar(s), ci0 + P.blk_ch * j, x0 - P.pad, y0 - P.pad, b);
-        for (int i = 0; i < nblk_n; ++i) tma_load_4d(stage_g(s, i), &tmG, full_bar(s), n0 + P.blk_ch * i, x0, y0, b);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          for (int j = 0; j < P.mblks; ++j) tma_load_4d(stage_x(s, j), &tmX, full_bar(s), ci0 + P.blk_ch * j, x0 - P.pad, y0 - P.pad, b);
+          for (int i = 0; i < nblk_n; ++i) tma_load_4d(stage_g(s, i), &tmG, full_bar(s), n0 + P.blk_ch * i, x0, y0, b);
+        }
+        if (++t == t_end) t = t_begin;
         if (++s == P.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work) {
       int s = 0, ph = 0;
       uint32_t acc = 0;
+      // descriptor = constant high word | (start address >> 4); BF16: plain SWIZZLE_128B (layout 2), one MMA per PAIR
+      // of tile rows (K = 16 pixels = two 8-row groups; patch rows 2048 B apart, dZ rows 1024 B).  TF32: layout 1
+      // (SWIZZLE_128B_BASE32B), one MMA per tile row (K = 8 pixels = two 4-row groups 512 B apart).
+      const uint32_t layout = BF16 ? 2u : 1u;
+      const uint32_t sbo_a = BF16 ? PATCH_PITCH * 128u : 512u, sbo_b = BF16 ? 1024u : 512u;
+      const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+      const uint32_t hi_b = ((sbo_b >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+      const uint32_t lbo_a = ((P.patch_bytes >> 4) & 0x3FFFu) << 16, lbo_b = ((P.gblk_bytes >> 4) & 0x3FFFu) << 16;
+      auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+      constexpr int KSTEP = BF16 ? 2 : 1;   // tile rows per MMA
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(full_bar(s), ph, P.error_flag, 7);
         tc_fence_after();
-        for (int tt = 0; tt < ntap; ++tt) {
-          const int tap = tap0 + tt, dy = tap / P.ks, dx = tap % P.ks;
-          const uint32_t d_t = tmem_base + (uint32_t)(tt * P.acc_stride);
-          if (P.bf16) {
-            // one MMA per PAIR of tile rows: K = 16 pixels = two 8-row groups (patch rows are 2048 B apart, dZ rows 1024 B)
-            for (int kk = 0; kk < P.th; kk += 2) {
-              const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
-              const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
-              umma_bf16(d_t, make_smem_desc_mn(a, P.patch_bytes, PATCH_PITCH * 128u, 2u), make_smem_desc_mn(bb, P.gblk_bytes, 1024u, 2u),
-                        P.idesc, (kk == 0) ? acc : 1u);
+        if (elect_one()) {
+          const uint32_t xa = (stage_x(s, 0) >> 4) | lbo_a, ga = (stage_g(s, 0) >> 4) | lbo_b;
+          int dy = tap0 / P.ks, dx = tap0 % P.ks;
+          uint32_t d_t = tmem_base;
+          for (int tt = 0; tt < ntap; ++tt) {
+            uint32_t la = xa + (uint32_t)(dy * PATCH_PITCH + dx) * 8u;   // 128 B per patch pixel >> 4
+            uint32_t lb = ga;
+            uint32_t a1 = acc;
+            for (int kk = 0; kk < P.th; kk += KSTEP) {
+              umma_k<BF16>(d_t, desc(hi_a, la), desc(hi_b, lb), P.idesc, a1);
+              a1 = 1u;
+              la += (uint32_t)(KSTEP * PATCH_PITCH * 8);
+              lb += (uint32_t)(KSTEP * 64);
             }
-          } else {
-            for (int kk = 0; kk < P.th; ++kk) {  // one MMA per tile row: K = 8 pixels
-              const uint32_t a = stage_x(s, 0) + (uint32_t)((kk + dy) * PATCH_PITCH + dx) * 128u;
-              const uint32_t bb = stage_g(s, 0) + (uint32_t)kk * 1024u;
-              const uint64_t da = P.swap_lbo_sbo ? make_smem_desc_mn(a, 512u, P.patch_bytes) : make_smem_desc_mn(a, P.patch_bytes, 512u);
-              const uint64_t db = P.swap_lbo_sbo ? make_smem_desc_mn(bb, 512u, P.gblk_bytes) : make_smem_desc_mn(bb, P.gblk_bytes, 512u);
-              umma_tf32(d_t, da, db, P.idesc, (kk == 0) ? acc : 1u);
-            }
+            d_t += (uint32_t)P.acc_stride;
+            if (++dx == P.ks) { dx = 0; ++dy; }
           }
+          umma_commit(empty_bar(s));
         }
         acc = 1u;
-        umma_commit(empty_bar(s));
         if (++s == P.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(tmemfull_bar);
+      if (elect_one()) umma_commit(tmemfull_bar);
     }
   } else if (has_work) {
     mbar_wait_warp_backoff(tmemfull_bar, 0, P.error_flag, 8);
@@ -743,7 +802,10 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   P.cchunks = (d->cin + kc - 1) / kc;
   P.a_stage_bytes = TILE_W * TILE_ROWS * 128u;
   P.b_stage_bytes = (uint32_t)bn * 128u;
-  P.patch_bytes = (uint32_t)PATCH_PITCH * (P.th + d->ksize - 1) * 128u;
+  // exact patch pitch: the MMA descriptor takes any 128-byte multiple as the 8-row-group stride (SBO)
+  P.pitch = (d->debug_flags & 64) ? PATCH_PITCH : TILE_W + d->ksize - 1;
+  P.patch_tx = (uint32_t)P.pitch * (P.th + d->ksize - 1) * 128u;
+  P.patch_bytes = (P.patch_tx + 1023u) & ~1023u;
   P.tmem_cols = pow2_cols(P.nsplit == 3 ? 3 * bn : bn);
   // instruction descriptor: fp32 accumulate, A/B format 2 = TF32 (kind::tf32) or 1 = BF16 (kind::f16), K-major, M = 128
   const uint32_t fmt = bf16 ? 1u : 2u;
@@ -752,13 +814,23 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   P.bias = bias; P.out = y; P.error_flag = error_flag;
 
   const uint32_t patch_region = P.halo ? 2u * nops * P.patch_bytes : 0u;
-  const uint32_t stage_bytes = (P.halo ? 0u : nops * P.a_stage_bytes) + nops * P.b_stage_bytes;
+  const uint32_t item_bytes = (P.halo ? 0u : nops * P.a_stage_bytes) + nops * P.b_stage_bytes;
   const uint32_t budget = 227u * 1024u - 1024u /*alignment slack*/ - 512u /*barriers*/;
-  PN_REQUIRE(patch_region + 2 * stage_bytes <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d: tile does not fit in shared memory");
-  int stages = (int)((budget - patch_region) / stage_bytes);
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  P.stages = stages;
-  const size_t smem = 1024 + patch_region + (size_t)stages * stage_bytes + 512;
+  PN_REQUIRE(patch_region + 2 * item_bytes <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d: tile does not fit in shared memory");
+  // Items per slot: amortise the ~100-cycle wait/commit hand-off over >= 16 MMAs (x3: 8 MMAs per item, x1: 4), but
+  // keep at least three slots in flight so that a slot's refill (TMA latency) hides behind the other slots' MMAs.
+  {
+    const int total_items = (P.halo ? 1 : P.cchunks) * d->ksize * d->ksize;
+    const int fit = (int)((budget - patch_region) / item_bytes);
+    int group = (P.nsplit == 3) ? 2 : 4;
+    if (d->debug_flags & 128) group = 1;
+    while (group > 1 && (fit / group < 3 || group > total_items)) --group;
+    int stages = fit / group;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    P.group = group;
+    P.stages = stages;
+  }
+  const size_t smem = 1024 + patch_region + (size_t)P.stages * P.group * item_bytes + 512;
 
   // tensor maps
   alignas(64) CUtensorMap tmA, tmAlo;
@@ -767,7 +839,7 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
     const uint64_t strides[3] = {(uint64_t)d->cin * esize, (uint64_t)d->width * d->cin * esize,
                                  (uint64_t)d->height * d->width * d->cin * esize};
     uint32_t box[4];
-    if (P.halo) { box[0] = kc; box[1] = PATCH_PITCH; box[2] = P.th + d->ksize - 1; box[3] = 1; }
+    if (P.halo) { box[0] = kc; box[1] = (uint32_t)P.pitch; box[2] = P.th + d->ksize - 1; box[3] = 1; }
     else        { box[0] = kc; box[1] = TILE_W;      box[2] = P.th;                box[3] = P.nb; }
     int rc = make_map(&tmA, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
@@ -787,9 +859,25 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
     P.ksplits = ks;
     if (ks > 1) PN_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)d->batch * d->height * d->width * d->cout, stream));
   }
-  PN_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(P.tiles_x * P.tiles_y * bgroups, (d->cout + bn - 1) / bn, P.ksplits);
-  conv_igemm_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmAlo, P);
+  auto launch = [&](auto kern) -> int {
+    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NTHREADS, smem, stream>>>(tmA, tmAlo, P);
+    return 0;
+  };
+  int lrc;
+  const int variant = (P.bf16 ? 4 : 0) | (P.nsplit == 3 ? 2 : 0) | (P.halo ? 1 : 0);
+  switch (variant) {
+    case 0: lrc = launch(conv_igemm_kernel<false, false, false>); break;
+    case 1: lrc = launch(conv_igemm_kernel<false, false, true>); break;
+    case 2: lrc = launch(conv_igemm_kernel<false, true, false>); break;
+    case 3: lrc = launch(conv_igemm_kernel<false, true, true>); break;
+    case 4: lrc = launch(conv_igemm_kernel<true, false, false>); break;
+    case 5: lrc = launch(conv_igemm_kernel<true, false, true>); break;
+    case 6: lrc = launch(conv_igemm_kernel<true, true, false>); break;
+    default: lrc = launch(conv_igemm_kernel<true, true, true>); break;
+  }
+  if (lrc) return lrc;
   count_launch();
   return check_launch("conv_igemm_kernel");
 }
@@ -877,9 +965,14 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* g, float
     int rc = make_map(&tmG, g, 4, dims, strides, box, sw, bf16);
     if (rc) return rc;
   }
-  PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(mblocks, P.tap_groups * nblocks, psplits);
-  conv_wgrad_kernel<<<grid, NTHREADS, smem, stream>>>(tmX, tmG, P);
+  if (P.bf16) {
+    PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_wgrad_kernel<true><<<grid, NTHREADS, smem, stream>>>(tmX, tmG, P);
+  } else {
+    PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_wgrad_kernel<false><<<grid, NTHREADS, smem, stream>>>(tmX, tmG, P);
+  }
   count_launch();
   return check_launch("conv_wgrad_kernel");
 }

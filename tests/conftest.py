@@ -13,7 +13,18 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 # the CPU oracle runs small ops: dozens of OpenMP threads only add spin-wait overhead, and the GPU box reports
 # 128 logical CPUs while its cgroup grants 16 (cpu.max)
-torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+def _usable_cpus():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+torch.set_num_threads(max(1, min(16, _usable_cpus())))
 
 
 def pytest_configure(config):

@@ -13,13 +13,13 @@ dev = torch.device("cuda:0")
 lib = _lib.lib()
 
 
-def bench(tag, B, H, W, Cin, Cout, k, prec, mode, iters=5):
+def bench(tag, B, H, W, Cin, Cout, k, prec, mode, iters=5, dbg=0):
     x = torch.rand(B, H, W, Cin, device=dev) - 0.5
     w = (torch.rand(Cout, Cin, k, k, device=dev) - 0.5) * 0.01
     wp, wlo = PF._pack_weight(w, False, prec)
     xh, xl = PF._operands(x, prec)
     y = torch.empty(B, H, W, Cout, device=dev)
-    d = ConvDesc(B, H, W, Cin, Cout, k, prec, mode, 0)
+    d = ConvDesc(B, H, W, Cin, Cout, k, prec, mode, dbg)
 
     def run():
         _lib.check(lib.pn_conv2d_forward(ctypes.byref(d), _lib.ptr(xh), PF._p(xl), _lib.ptr(wp), PF._p(wlo), None, _lib.ptr(y),
@@ -38,13 +38,16 @@ def bench(tag, B, H, W, Cin, Cout, k, prec, mode, iters=5):
     tiles = B * ((H + 15) // 16) * ((W + 7) // 8) * ((Cout + 127) // 128)
     stages = ((Cin + kc - 1) // kc) * k * k
     waves = -(-tiles // 148)
-    clk_per_stage = ms * 1e-3 * 1.84e9 / (waves * stages)
+    clk_per_stage = ms * 1e-3 * 1.965e9 / (waves * stages)
     print("%-44s %8.3f ms  %7.1f TFLOP/s  tiles %5d waves %3d stages/CTA %5d  ~%6.0f clk/stage" % (
         tag, ms, flops / ms / 1e9, tiles, waves, stages, clk_per_stage), flush=True)
 
 
 B3, B1, T3, T1 = PF.PRECISION_BF16X3, PF.PRECISION_BF16X1, PF.PRECISION_TF32X3, PF.PRECISION_TF32X1
 bench("pack1 bf16x3 halo", 4, 96, 320, 2048, 64, 5, B3, 2)
+bench("pack1 bf16x3 halo  group 1", 4, 96, 320, 2048, 64, 5, B3, 2, dbg=128)
+bench("pack1 bf16x3 halo  pitch 16", 4, 96, 320, 2048, 64, 5, B3, 2, dbg=64)
+bench("pack1 bf16x1 halo  group 1", 4, 96, 320, 2048, 64, 5, B1, 2, dbg=128)
 bench("pack1 bf16x3 per-tap", 4, 96, 320, 2048, 64, 5, B3, 1)
 bench("pack1 bf16x1 halo", 4, 96, 320, 2048, 64, 5, B1, 2)
 bench("pack1 tf32x1 halo", 4, 96, 320, 2048, 64, 5, T1, 2)
