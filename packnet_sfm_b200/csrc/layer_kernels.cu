@@ -332,6 +332,314 @@ __global__ void __launch_bounds__(256) stencil_wgrad_kernel(const StencilBwdPara
 }
 
 // ---------------------------------------------------------------------------------------------------
+// feature stencil, register-tiled (D % 8 == 0): the production path
+// ---------------------------------------------------------------------------------------------------
+// The kernels above spend one or two shared-memory reads per FMA (weights and neighbours both come from shared
+// memory), i.e. they run at the LDS rate, ~1/8 of the fp32 pipe (r01 step breakdown: 14.6 of 58 ms).  Here a thread
+// owns a THREAD TILE of 8 consecutive depths of one pixel (x 8 features forward, x 2 rows backward, x 2 features
+// for the weight gradient): a neighbour column is fetched as 10 floats (two LDS.128 + two LDS.32) and reused by
+// 24..192 FMAs, weights sit in registers or arrive as broadcast LDS.128.  Shared bytes per FMA drop from ~8 to <= 1.1.
+//   staged layout: cell (r, c) of a tile holds depths [0, D) at s[(r*NC + c)*PITCH + 4 + d], PITCH = D + 4; the 4 front
+//   floats are zero (index 3 is depth -1) and depth D of a cell is the (zero) front pad of the next cell; lanes map
+//   to consecutive cells, so with PITCH = 4 (mod 32) words the LDS.128 of a quarter-warp hit 8 different bank groups.
+constexpr int SPAD = 4;
+
+// rows [h0, h0+nr) x cols [w0, w0+nc) of a LOW-resolution H x W grid into the staged layout; pixels outside the grid
+// are zero.  DIRECT: element d of pixel (hh, ww) is src[((b*H + hh)*W + ww)*pixstride + chan0 + d] (float4 loads).
+// S2D (space-to-depth gather): element d comes from the 2x pixel (2hh + i, 2ww + j), ij = d & 3, channel chan0 + (d >> 2).
+template <bool S2D>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int b, int H, int W, int pixstride, int chan0, int D,
+                                           int h0, int nr, int w0, int nc, float* __restrict__ s) {
+  const int PITCH = D + SPAD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ncell = nr * nc;
+  for (int cell = warp; cell < ncell; cell += nwarps) {
+    const int c = cell % nc, r = cell / nc;
+    const int hh = h0 + r, ww = w0 + c;
+    const bool inside = (hh >= 0) && (hh < H) && (ww >= 0) && (ww < W);
+    float* col = s + (size_t)cell * PITCH;
+    if (lane == 0) *reinterpret_cast<float4*>(col) = z4;
+    float4* dst = reinterpret_cast<float4*>(col + SPAD);
+    if (S2D) {
+      const size_t rowstride = (size_t)2 * W * pixstride;
+      const float* p00 = src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + chan0;
+      for (int q = lane; q < (D >> 2); q += 32) {
+        float4 v = z4;
+        if (inside) {
+          v.x = __ldg(p00 + q); v.y = __ldg(p00 + pixstride + q);
+          v.z = __ldg(p00 + rowstride + q); v.w = __ldg(p00 + rowstride + pixstride + q);
+        }
+        dst[q] = v;
+      }
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + chan0);
+      for (int q = lane; q < (D >> 2); q += 32) dst[q] = inside ? __ldg(p + q) : z4;
+    }
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<float4*>(s + (size_t)ncell * PITCH) = z4;   // depth D of the last cell
+}
+
+// the 10 staged floats around depths [d0, d0+8) of one cell: vv[j] = depth d0 - 1 + j
+__device__ __forceinline__ void load_col10(const float* __restrict__ col, float vv[10]) {
+  const float4 a = *reinterpret_cast<const float4*>(col);
+  const float4 c = *reinterpret_cast<const float4*>(col + 4);
+  vv[0] = col[-1];
+  vv[1] = a.x; vv[2] = a.y; vv[3] = a.z; vv[4] = a.w;
+  vv[5] = c.x; vv[6] = c.y; vv[7] = c.z; vv[8] = c.w;
+  vv[9] = col[8];
+}
+
+// forward.  smem: s_v[3][tw+2][PITCH] + 4, s_w[27][8], s_b[8]
+template <bool PACK>
+__global__ void __launch_bounds__(256, 2) stencil_fwd8_kernel(const StencilParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
+  float* s_v = sm;
+  float* s_w = sm + 3 * TWP * PITCH + 4;
+  const int w0 = blockIdx.x * P.tw, h = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 224; i += blockDim.x) {
+    if (i < 216) { const int t = i >> 3, f = i & 7; s_w[i] = __ldg(P.w3 + f * 27 + t); }
+    else s_w[i] = __ldg(P.b3 + (i - 216));
+  }
+  stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+  __syncthreads();
+  const int ntiles = P.tw * (D >> 3);
+  for (int it = threadIdx.x; it < ntiles; it += blockDim.x) {
+    const int pw = it % P.tw, d0 = (it / P.tw) << 3;
+    const int w = w0 + pw;
+    if (w >= P.W) continue;
+    float acc[8][8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      const float bf = s_w[216 + f];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[f][k] = bf;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        float vv[10];
+        load_col10(s_v + (size_t)(dy * TWP + pw + dx) * PITCH + SPAD + d0, vv);
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+          const int t = (dz * 3 + dy) * 3 + dx;
+          const float4 wa = *reinterpret_cast<const float4*>(s_w + t * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(s_w + t * 8 + 4);
+          const float wf[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int f = 0; f < 8; ++f)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[f][k] = fmaf(wf[f], vv[k + dz], acc[f][k]);
+        }
+      }
+    if (PACK) {
+      const size_t o = (((size_t)b * P.H + h) * P.W + w) * P.out_cstride + P.out_coffset + d0;
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        float4* dst = reinterpret_cast<float4*>(P.out + o + (size_t)f * D);
+        dst[0] = make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
+        dst[1] = make_float4(acc[f][4], acc[f][5], acc[f][6], acc[f][7]);
+        if (P.out_lo) {
+          float4* dl = reinterpret_cast<float4*>(P.out_lo + o + (size_t)f * D);
+          dl[0] = make_float4(acc[f][0] - tf32_trunc(acc[f][0]), acc[f][1] - tf32_trunc(acc[f][1]),
+                              acc[f][2] - tf32_trunc(acc[f][2]), acc[f][3] - tf32_trunc(acc[f][3]));
+          dl[1] = make_float4(acc[f][4] - tf32_trunc(acc[f][4]), acc[f][5] - tf32_trunc(acc[f][5]),
+                              acc[f][6] - tf32_trunc(acc[f][6]), acc[f][7] - tf32_trunc(acc[f][7]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int v = f * D + d0 + k, co = v >> 2, i = (v >> 1) & 1, j = v & 1;
+          const size_t o = (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.out_cstride + P.out_coffset + co;
+          P.out[o] = acc[f][k];
+          if (P.out_lo) P.out_lo[o] = acc[f][k] - tf32_trunc(acc[f][k]);
+        }
+    }
+  }
+}
+
+// data gradient:  gin[d][h][w] = sum_f sum_{dz,dy,dx} W[f][dz][dy][dx] * g[f][d-dz+1][h-dy+1][w-dx+1]
+// One CTA owns TH rows x tw columns; feature planes of g are staged one at a time WITH their halo ((TH+2) x (tw+2) cells)
+// and a thread tile is 2 rows x 1 column x 8 depths (16 accumulators, up to MAXT tiles per thread), so the 4 x 3 staged
+// cells around it feed 432 FMAs.  smem: s_g[(TH+2)][(tw+2)][PITCH] + 4 (reused as the output transpose buffer), s_w[216]
+struct StencilBwd8Params {
+  StencilBwdParams p;
+  int th;   // rows per CTA (even)
+};
+
+template <bool PACK, int MAXT>
+__global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Params Q) {
+  const StencilBwdParams& P = Q.p;
+  extern __shared__ __align__(16) float sm[];
+  const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2, TH = Q.th;
+  float* s_g = sm;
+  float* s_w = sm + (TH + 2) * TWP * PITCH + 4;
+  const int w0 = blockIdx.x * P.tw, h0 = blockIdx.y * TH, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 216; i += blockDim.x) s_w[i] = __ldg(P.w3 + i);
+  const int ntiles = (TH >> 1) * P.tw * (D >> 3);
+  float acc[MAXT][2][8];
+#pragma unroll
+  for (int m = 0; m < MAXT; ++m)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[m][rr][k] = 0.0f;
+  for (int f = 0; f < 8; ++f) {
+    __syncthreads();   // the previous plane is consumed (and s_w is visible)
+    if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+    else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+    __syncthreads();
+    float wr[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) wr[t] = s_w[f * 27 + t];
+#pragma unroll
+    for (int m = 0; m < MAXT; ++m) {
+      const int it = threadIdx.x + m * 256;
+      if (it < ntiles) {
+        const int pw = it % P.tw, rest = it / P.tw;
+        const int r0 = (rest % (TH >> 1)) << 1, d0 = (rest / (TH >> 1)) << 3;
+#pragma unroll
+        for (int gr = 0; gr < 4; ++gr)
+#pragma unroll
+          for (int gc = 0; gc < 3; ++gc) {
+            float gg[10];   // gg[j] = g depth d0 - 1 + j of staged cell (r0 + gr, pw + gc)
+            load_col10(s_g + (size_t)((r0 + gr) * TWP + pw + gc) * PITCH + SPAD + d0, gg);
+            const int dx = 2 - gc;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int dy = rr + 2 - gr;     // staged row r0 + gr is output row (r0 + rr) - dy + 1 (+1 halo)
+              if (dy >= 0 && dy <= 2) {
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                  const float wv = wr[(dz * 3 + dy) * 3 + dx];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) acc[m][rr][k] = fmaf(wv, gg[k - dz + 2], acc[m][rr][k]);
+                }
+              }
+            }
+          }
+      }
+    }
+  }
+  // transpose through shared memory so that the stores run along the channels of one pixel
+  __syncthreads();
+  float* s_out = s_g;   // [TH][tw][D]
+#pragma unroll
+  for (int m = 0; m < MAXT; ++m) {
+    const int it = threadIdx.x + m * 256;
+    if (it < ntiles) {
+      const int pw = it % P.tw, rest = it / P.tw;
+      const int r0 = (rest % (TH >> 1)) << 1, d0 = (rest / (TH >> 1)) << 3;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        float4* dst = reinterpret_cast<float4*>(s_out + ((size_t)(r0 + rr) * P.tw + pw) * D + d0);
+        dst[0] = make_float4(acc[m][rr][0], acc[m][rr][1], acc[m][rr][2], acc[m][rr][3]);
+        dst[1] = make_float4(acc[m][rr][4], acc[m][rr][5], acc[m][rr][6], acc[m][rr][7]);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int ncombo = TH * P.tw * (PACK ? 4 : 1);
+    for (int cb = warp; cb < ncombo; cb += nwarps) {
+      const int ij = PACK ? (cb & 3) : 0, cell = PACK ? (cb >> 2) : cb;
+      const int pw = cell % P.tw, r = cell / P.tw;
+      const int w = w0 + pw, h = h0 + r;
+      if (w >= P.W || h >= P.H) continue;
+      const float* srcp = s_out + (size_t)cell * D;
+      if (PACK) {
+        const int i = ij >> 1, j = ij & 1;
+        float* dst = P.gin + (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.C;
+        for (int c = lane; c < P.C; c += 32) dst[c] = srcp[4 * c + ij];
+      } else {
+        float* dst = P.gin + (((size_t)b * P.H + h) * P.W + w) * P.C;
+        for (int d = lane; d < D; d += 32) dst[d] = srcp[d];
+      }
+    }
+  }
+}
+
+// weight / bias gradient.  Warp (fp, half): feature pair {2fp, 2fp+1}, half of the thread tiles; 54 + 2 partial sums in
+// registers over the whole persistent walk, one warp reduction + atomics at the end.
+// smem: s_v[3][tw+2][PITCH] + 4, s_gc[8][tw][PITCH]
+template <bool PACK>
+__global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
+  float* s_v = sm;
+  float* s_gc = sm + 3 * TWP * PITCH + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fp = warp & 3, half = warp >> 2;
+  float wa[27], wb[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) { wa[t] = 0.0f; wb[t] = 0.0f; }
+  float ba = 0.0f, bb = 0.0f;
+  const int wtiles = (P.W + P.tw - 1) / P.tw;
+  const int nwork = P.B * P.H * wtiles;
+  const int ntiles = P.tw * (D >> 3);
+  for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+    const int wt = work % wtiles, row = work / wtiles;
+    const int b = row / P.H, h = row % P.H, w0 = wt * P.tw;
+    __syncthreads();
+    stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+    for (int f = 0; f < 8; ++f) {
+      if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
+      else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
+    }
+    __syncthreads();
+    const float* gA = s_gc + (size_t)(2 * fp) * P.tw * PITCH + SPAD;
+    const float* gB = gA + (size_t)P.tw * PITCH;
+    for (int it = half * 32 + lane; it < ntiles; it += 64) {
+      const int pw = it % P.tw, d0 = (it / P.tw) << 3;
+      const float4 a0 = *reinterpret_cast<const float4*>(gA + (size_t)pw * PITCH + d0);
+      const float4 a1 = *reinterpret_cast<const float4*>(gA + (size_t)pw * PITCH + d0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(gB + (size_t)pw * PITCH + d0);
+      const float4 b1 = *reinterpret_cast<const float4*>(gB + (size_t)pw * PITCH + d0 + 4);
+      const float ga[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float gb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { ba += ga[k]; bb += gb[k]; }
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          float vv[10];
+          load_col10(s_v + (size_t)(dy * TWP + pw + dx) * PITCH + SPAD + d0, vv);
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz) {
+            const int t = (dz * 3 + dy) * 3 + dx;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              wa[t] = fmaf(ga[k], vv[k + dz], wa[t]);
+              wb[t] = fmaf(gb[k], vv[k + dz], wb[t]);
+            }
+          }
+        }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 28; ++t) {
+    float va = (t < 27) ? wa[t < 27 ? t : 0] : ba;
+    float vb = (t < 27) ? wb[t < 27 ? t : 0] : bb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      va += __shfl_xor_sync(0xffffffffu, va, o);
+      vb += __shfl_xor_sync(0xffffffffu, vb, o);
+    }
+    if (lane == 0) {
+      if (t < 27) { atomicAdd(P.gw3 + (2 * fp) * 27 + t, va); atomicAdd(P.gw3 + (2 * fp + 1) * 27 + t, vb); }
+      else { atomicAdd(P.gb3 + 2 * fp, va); atomicAdd(P.gb3 + 2 * fp + 1, vb); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // GroupNorm(16) + ELU   (NHWC; x may be the sum of two tensors for the residual block, layers01.py:72)
 // ---------------------------------------------------------------------------------------------------
 // stats[b][g] = (sum, sumsq) in double, accumulated atomically into a zeroed buffer
@@ -559,6 +867,26 @@ extern "C" int pn_feature_stencil_forward(int pack, const float* in, const float
   P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
   P.in = in; P.w3 = w3; P.b3 = b3; P.out = out; P.out_lo = out_lo;
   P.out_cstride = out_cstride; P.out_coffset = out_coffset;
+  const bool vec_ok = aligned16(in) && aligned16(out) && (!out_lo || aligned16(out_lo)) && out_cstride % 4 == 0 && out_coffset % 4 == 0;
+  if (P.D % 8 == 0 && vec_ok) {   // register-tiled production path
+    int tw = 32;
+    auto smem_of = [&](int t) { return ((size_t)3 * (t + 2) * (P.D + SPAD) + 4 + 224) * sizeof(float); };
+    while (tw > 1 && (tw * (P.D >> 3) > 512 || smem_of(tw) > 200 * 1024)) tw >>= 1;
+    while (tw > 1 && (tw >> 1) >= P.W) tw >>= 1;
+    PN_REQUIRE(smem_of(tw) <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_forward: depth %d too large", P.D);
+    P.tw = tw;
+    const size_t smem8 = smem_of(tw);
+    dim3 grid8((P.W + tw - 1) / tw, P.H, P.B);
+    if (pack) {
+      PN_CUDA(cudaFuncSetAttribute(stencil_fwd8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      stencil_fwd8_kernel<true><<<grid8, 256, smem8, stream>>>(P);
+    } else {
+      PN_CUDA(cudaFuncSetAttribute(stencil_fwd8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      stencil_fwd8_kernel<false><<<grid8, 256, smem8, stream>>>(P);
+    }
+    count_launch();
+    return check_launch("stencil_fwd8_kernel");
+  }
   P.tw = pick_tw(P.D, P.W, false);
   PN_REQUIRE((size_t)3 * 3 * (P.D + 2) * 4 <= 200 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_forward: depth %d too large", P.D);
   const size_t smem = ((size_t)3 * (P.tw + 2) * (P.D + 2) + 224) * sizeof(float);
@@ -584,10 +912,65 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
   P.in = in; P.g = g; P.w3 = w3; P.gin = gin; P.gw3 = gw3; P.gb3 = gb3;
   P.g_cstride = g_cstride; P.g_coffset = g_coffset;
-  P.tw = pick_tw(P.D, P.W, true, !pack);
-  PN_REQUIRE(P.tw * P.D <= 2048, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large", P.D);
   PN_CUDA(cudaMemsetAsync(gw3, 0, sizeof(float) * 216, stream));
   PN_CUDA(cudaMemsetAsync(gb3, 0, sizeof(float) * 8, stream));
+  const bool vec_ok = aligned16(in) && aligned16(g) && aligned16(gin) && g_cstride % 4 == 0 && g_coffset % 4 == 0;
+  if (P.D % 8 == 0 && vec_ok) {   // register-tiled production path
+    const int PITCH = P.D + SPAD;
+    // data gradient
+    {
+      StencilBwd8Params Q8{};
+      Q8.p = P;
+      int th = (P.H >= 3) ? 4 : 2, tw = 32;
+      auto tiles_of = [&](int t) { return (th >> 1) * t * (P.D >> 3); };
+      auto smem_of = [&](int t) { return ((size_t)(th + 2) * (t + 2) * PITCH + 4 + 216) * sizeof(float); };
+      while (tw > 1 && (tiles_of(tw) > 1024 || smem_of(tw) > 200 * 1024)) tw >>= 1;
+      if (tiles_of(tw) > 1024 || smem_of(tw) > 200 * 1024) { th = 2; tw = 32; while (tw > 1 && (tiles_of(tw) > 1024 || smem_of(tw) > 200 * 1024)) tw >>= 1; }
+      while (tw > 1 && (tw >> 1) >= P.W) tw >>= 1;
+      PN_REQUIRE(tiles_of(tw) <= 1024 && smem_of(tw) <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large", P.D);
+      Q8.p.tw = tw; Q8.th = th;
+      const size_t smem8 = smem_of(tw);
+      const int maxt = (tiles_of(tw) + 255) / 256;
+      dim3 grid8((P.W + tw - 1) / tw, (P.H + th - 1) / th, P.B);
+      auto launch = [&](auto kern) -> int {
+        PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        kern<<<grid8, 256, smem8, stream>>>(Q8);
+        return 0;
+      };
+      int lrc;
+      if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2>) : launch(stencil_bwd8_kernel<true, 4>);
+      else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2>) : launch(stencil_bwd8_kernel<false, 4>);
+      if (lrc) return lrc;
+      count_launch();
+      int rc8 = check_launch("stencil_bwd8_kernel");
+      if (rc8) return rc8;
+    }
+    // weight / bias gradient
+    {
+      StencilBwdParams Q = P;
+      int tw = 32;
+      auto smem_of = [&](int t) { return ((size_t)3 * (t + 2) * PITCH + 4 + (size_t)8 * t * PITCH + 4) * sizeof(float); };
+      while (tw > 1 && (tw * (P.D >> 3) > 2048 || smem_of(tw) > 200 * 1024)) tw >>= 1;
+      while (tw > 1 && (tw >> 1) >= P.W) tw >>= 1;
+      PN_REQUIRE(smem_of(tw) <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large for the weight gradient", P.D);
+      Q.tw = tw;
+      const size_t smem8 = smem_of(tw);
+      const int nwork = Q.B * Q.H * ((Q.W + tw - 1) / tw);
+      int ctas = (smem8 <= 110 * 1024) ? 148 * 2 : 148;
+      if (ctas > nwork) ctas = nwork;
+      if (pack) {
+        PN_CUDA(cudaFuncSetAttribute(stencil_wgrad8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        stencil_wgrad8_kernel<true><<<ctas, 256, smem8, stream>>>(Q);
+      } else {
+        PN_CUDA(cudaFuncSetAttribute(stencil_wgrad8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        stencil_wgrad8_kernel<false><<<ctas, 256, smem8, stream>>>(Q);
+      }
+      count_launch();
+      return check_launch("stencil_wgrad8_kernel");
+    }
+  }
+  P.tw = pick_tw(P.D, P.W, true, !pack);
+  PN_REQUIRE(P.tw * P.D <= 2048, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large", P.D);
   const size_t smem = stencil_smem_bytes(P.D, P.tw, true, !pack);
   PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d needs %zu bytes of shared memory", P.D, smem);
   dim3 grid((P.W + P.tw - 1) / P.tw, P.H, P.B);

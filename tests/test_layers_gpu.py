@@ -88,7 +88,11 @@ def test_conv2d_staging_modes_agree(mode):
 def test_feature_stencils_and_groupnorm():
     from packnet_sfm_b200 import functional as PF
     torch.manual_seed(3)
-    for pack, shape in ((True, (2, 16, 24, 32)), (False, (2, 6, 20, 32)), (True, (1, 12, 8, 512))):
+    shapes = ((True, (2, 16, 24, 32)), (False, (2, 6, 20, 32)), (True, (1, 12, 8, 512)),
+              (True, (1, 10, 14, 8)),       # odd low-res height, ragged width (masked rows / columns)
+              (False, (1, 5, 7, 24)), (False, (2, 9, 33, 128)), (True, (2, 4, 4, 64)),
+              (True, (1, 8, 8, 5)))         # depth 20 is not a multiple of 8: generic kernels
+    for pack, shape in shapes:
         x = (torch.rand(*shape, device=DEV) - 0.5).requires_grad_(True)
         w3 = ((torch.rand(8, 1, 3, 3, 3, device=DEV) - 0.5)).requires_grad_(True)
         b3 = (torch.rand(8, device=DEV) - 0.5).requires_grad_(True)
