@@ -202,6 +202,19 @@ int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, c
 /* out[c] = sum over pixels of g[pixel][c] (conv bias gradient), g dense [pixels, channels]. */
 int pn_channel_sum(const float* g, float* out, size_t pixels, int channels, pn_stream_t stream);
 
+/* Single-channel head convolution Conv2d(C -> 1, 3x3, zero pad 1) of InvDepth
+ * (packnet_sfm/networks/layers/packnet/layers01.py:98-122; the sigmoid / min_depth scaling stays with the caller).
+ * x [B,H,W,C] NHWC fp32 (C % 4 == 0), w_tap_major [9][C] (= weight[0, c, dy, dx] at [(dy*3+dx)*C + c]), y / dy [B,H,W]. */
+int pn_head_conv_forward(const float* x, const float* w_tap_major, const float* bias, float* y, int batch, int height,
+                         int width, int channels, pn_stream_t stream);
+int pn_head_conv_backward(const float* x, const float* dy, const float* w_tap_major, float* dx, float* dw_tap_major,
+                          float* dbias, int batch, int height, int width, int channels, pn_stream_t stream);
+
+/* Diagnostics: per-call device timing of the convolution / stencil entry points (CUDA events around each call).
+ * pn_trace_dump writes "tag<TAB>milliseconds" lines for the calls traced since the last dump and returns their count. */
+void pn_trace_enable(int on);
+int pn_trace_dump(char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

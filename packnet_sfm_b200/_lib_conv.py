@@ -31,8 +31,10 @@ def declare(lib):
     lib.pn_groupnorm_elu_forward.argtypes = [vp, vp, vp, vp, f, vp, vp, vp, i, i, i, i, i, vp]
     lib.pn_groupnorm_elu_backward.argtypes = [vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.pn_channel_sum.argtypes = [vp, vp, sz, i, vp]
+    lib.pn_head_conv_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+    lib.pn_head_conv_backward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
     for name in ("pn_feature_stencil_forward", "pn_feature_stencil_backward", "pn_groupnorm_elu_forward",
-                 "pn_groupnorm_elu_backward", "pn_channel_sum"):
+                 "pn_groupnorm_elu_backward", "pn_channel_sum", "pn_head_conv_forward", "pn_head_conv_backward"):
         getattr(lib, name).restype = c.c_int
     lib.pn_conv2d_wgrad.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]
     lib.pn_conv2d_unpack_weight_grad.argtypes = [vp, vp, i, i, i, i, vp]

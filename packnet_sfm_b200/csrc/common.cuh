@@ -15,6 +15,13 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 // launch accounting behind pn_launch_count()
 void count_launch(int n = 1);
+// device-time trace of one C-ABI call (no-op unless pn_trace_enable(1))
+struct TraceScope {
+  TraceScope(cudaStream_t stream, const char* fmt, ...);
+  ~TraceScope();
+  cudaStream_t stream_;
+  int index_;
+};
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -467,10 +467,11 @@ struct WgradParams {
   int tiles_x, tiles_y, ntiles;   // pixel tiles per image / in total (B * tiles_y * tiles_x)
   int psplits;
   int stages;
-  uint32_t patch_bytes;  // PATCH_PITCH * (th + ks - 1) * 128: one 32-channel block of the X patch
-  uint32_t gblk_bytes;   // 8 * th * 128: one 32-channel block of the dZ tile
+  int pitch;             // pixels per patch row (8 + ks - 1)
+  uint32_t patch_bytes;  // one channel block of the X patch: pitch * (th + ks - 1) * 128 rounded up to 1024
+  uint32_t patch_tx;     // bytes one patch box delivers
+  uint32_t gblk_bytes;   // 8 * th * 128: one channel block of the dZ tile
   uint32_t tmem_cols, idesc;
-  int swap_lbo_sbo;      // bring-up knob
   float* dwp;            // [Cout][taps][kpad]
   unsigned int* error_flag;
 };
@@ -491,20 +492,26 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lb
   return d;
 }
 
-template <bool BF16>
+template <bool BF16, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams P) {
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmGlo, const WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int nops = SPLIT ? 2 : 1;
   const int nblk_n = P.bn / P.blk_ch;
-  const uint32_t stage_bytes = (uint32_t)P.mblks * P.patch_bytes + (uint32_t)nblk_n * P.gblk_bytes;
+  // stage: [X_hi blocks][X_lo blocks][dZ_hi blocks][dZ_lo blocks].  The x3 precisions run the three error-compensated
+  // products X_lo*dZ_hi, X_hi*dZ_lo, X_hi*dZ_hi as three MMAs per K step into the SAME accumulator: one launch, one
+  // epilogue and 4 tile loads where three x1 launches needed 6.
+  const uint32_t x_bytes = (uint32_t)P.mblks * P.patch_bytes, g_bytes = (uint32_t)nblk_n * P.gblk_bytes;
+  const uint32_t stage_bytes = nops * (x_bytes + g_bytes);
   const uint32_t bars_base = smem_base + P.stages * stage_bytes;
   auto full_bar = [&](int s) { return bars_base + 8u * s; };
   auto empty_bar = [&](int s) { return bars_base + 8u * (MAX_STAGES + s); };
   const uint32_t tmemfull_bar = bars_base + 8u * (2 * MAX_STAGES);
   const uint32_t tmem_slot = bars_base + 8u * (2 * MAX_STAGES + 1);
-  auto stage_x = [&](int s, int j) { return smem_base + s * stage_bytes + (uint32_t)j * P.patch_bytes; };
-  auto stage_g = [&](int s, int i) { return smem_base + s * stage_bytes + (uint32_t)P.mblks * P.patch_bytes + (uint32_t)i * P.gblk_bytes; };
+  auto stage_x = [&](int s, int op, int j) { return smem_base + s * stage_bytes + op * x_bytes + (uint32_t)j * P.patch_bytes; };
+  auto stage_g = [&](int s, int op, int i) { return smem_base + s * stage_bytes + nops * x_bytes + op * g_bytes + (uint32_t)i * P.gblk_bytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci0 = blockIdx.x * 128;
@@ -536,15 +543,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // CTAs that share a pixel split walk the same tiles: start each at its own rotation (L2 hot-spot avoidance)
       const int nt = t_end - t_begin;
       const int rot = (int)((blockIdx.x * 2654435761u + blockIdx.y * 40503u) >> 8) % nt;
+      const uint32_t tx_bytes = nops * ((uint32_t)P.mblks * P.patch_tx + g_bytes);
       int t = t_begin + rot;
       for (int ti = 0; ti < nt; ++ti) {
         const int tx = t % P.tiles_x, ty = (t / P.tiles_x) % P.tiles_y, b = t / (P.tiles_x * P.tiles_y);
         const int x0 = tx * TILE_W, y0 = ty * P.th;
         mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 6);
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), stage_bytes);
-          for (int j = 0; j < P.mblks; ++j) tma_load_4d(stage_x(s, j), &tmX, full_bar(s), ci0 + P.blk_ch * j, x0 - P.pad, y0 - P.pad, b);
-          for (int i = 0; i < nblk_n; ++i) tma_load_4d(stage_g(s, i), &tmG, full_bar(s), n0 + P.blk_ch * i, x0, y0, b);
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          for (int j = 0; j < P.mblks; ++j) {
+            tma_load_4d(stage_x(s, 0, j), &tmX, full_bar(s), ci0 + P.blk_ch * j, x0 - P.pad, y0 - P.pad, b);
+            if (SPLIT) tma_load_4d(stage_x(s, 1, j), &tmXlo, full_bar(s), ci0 + P.blk_ch * j, x0 - P.pad, y0 - P.pad, b);
+          }
+          for (int i = 0; i < nblk_n; ++i) {
+            tma_load_4d(stage_g(s, 0, i), &tmG, full_bar(s), n0 + P.blk_ch * i, x0, y0, b);
+            if (SPLIT) tma_load_4d(stage_g(s, 1, i), &tmGlo, full_bar(s), n0 + P.blk_ch * i, x0, y0, b);
+          }
         }
         if (++t == t_end) t = t_begin;
         if (++s == P.stages) { s = 0; ph ^= 1; }
@@ -555,37 +569,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       int s = 0, ph = 0;
       uint32_t acc = 0;
       // descriptor = constant high word | (start address >> 4); BF16: plain SWIZZLE_128B (layout 2), one MMA per PAIR
-      // of tile rows (K = 16 pixels = two 8-row groups; patch rows 2048 B apart, dZ rows 1024 B).  TF32: layout 1
+      // of tile rows (K = 16 pixels = two 8-row groups; patch rows pitch*128 B apart, dZ rows 1024 B).  TF32: layout 1
       // (SWIZZLE_128B_BASE32B), one MMA per tile row (K = 8 pixels = two 4-row groups 512 B apart).
       const uint32_t layout = BF16 ? 2u : 1u;
-      const uint32_t sbo_a = BF16 ? PATCH_PITCH * 128u : 512u, sbo_b = BF16 ? 1024u : 512u;
+      const uint32_t sbo_a = BF16 ? (uint32_t)P.pitch * 128u : 512u, sbo_b = BF16 ? 1024u : 512u;
       const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
       const uint32_t hi_b = ((sbo_b >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
       const uint32_t lbo_a = ((P.patch_bytes >> 4) & 0x3FFFu) << 16, lbo_b = ((P.gblk_bytes >> 4) & 0x3FFFu) << 16;
       auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
       constexpr int KSTEP = BF16 ? 2 : 1;   // tile rows per MMA
+      const uint32_t xlo_off = x_bytes >> 4, glo_off = g_bytes >> 4;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(full_bar(s), ph, P.error_flag, 7);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t xa = (stage_x(s, 0) >> 4) | lbo_a, ga = (stage_g(s, 0) >> 4) | lbo_b;
-          int dy = tap0 / P.ks, dx = tap0 % P.ks;
-          uint32_t d_t = tmem_base;
-          for (int tt = 0; tt < ntap; ++tt) {
-            uint32_t la = xa + (uint32_t)(dy * PATCH_PITCH + dx) * 8u;   // 128 B per patch pixel >> 4
-            uint32_t lb = ga;
-            uint32_t a1 = acc;
+        const uint32_t xa = (stage_x(s, 0, 0) >> 4) | lbo_a, ga = (stage_g(s, 0, 0) >> 4) | lbo_b;
+        int dy = tap0 / P.ks, dx = tap0 % P.ks;
+        uint32_t d_t = tmem_base;
+        for (int tt = 0; tt < ntap; ++tt) {
+          const uint32_t la0 = xa + (uint32_t)(dy * P.pitch + dx) * 8u;   // 128 B per patch pixel >> 4
+          if (elect_one()) {
+            uint32_t la = la0, lb = ga, a1 = acc;
             for (int kk = 0; kk < P.th; kk += KSTEP) {
-              umma_k<BF16>(d_t, desc(hi_a, la), desc(hi_b, lb), P.idesc, a1);
+              if (SPLIT) {   // small terms first
+                umma_k<BF16>(d_t, desc(hi_a, la + xlo_off), desc(hi_b, lb), P.idesc, a1);
+                umma_k<BF16>(d_t, desc(hi_a, la), desc(hi_b, lb + glo_off), P.idesc, 1u);
+                umma_k<BF16>(d_t, desc(hi_a, la), desc(hi_b, lb), P.idesc, 1u);
+              } else {
+                umma_k<BF16>(d_t, desc(hi_a, la), desc(hi_b, lb), P.idesc, a1);
+              }
               a1 = 1u;
-              la += (uint32_t)(KSTEP * PATCH_PITCH * 8);
+              la += (uint32_t)(KSTEP * P.pitch * 8);
               lb += (uint32_t)(KSTEP * 64);
             }
-            d_t += (uint32_t)P.acc_stride;
-            if (++dx == P.ks) { dx = 0; ++dy; }
           }
-          umma_commit(empty_bar(s));
+          d_t += (uint32_t)P.acc_stride;
+          if (++dx == P.ks) { dx = 0; ++dy; }
         }
+        if (elect_one()) umma_commit(empty_bar(s));
         acc = 1u;
         if (++s == P.stages) { s = 0; ph ^= 1; }
       }
@@ -883,12 +903,12 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
 }
 
 // x [B,H,W,Cin], g [B,H,W,Cout] (NHWC; fp32 or bf16) -> dwp [Cout][k*k][kpad(Cin)] fp32, ACCUMULATED (caller zeroes it)
-static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* g, float* dwp, unsigned int* error_flag,
-                      cudaStream_t stream) {
+static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* x_lo, const void* g, const void* g_lo, float* dwp,
+                      unsigned int* error_flag, cudaStream_t stream) {
   PN_REQUIRE(d && x && g && dwp, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
   PN_REQUIRE(d->ksize >= 1 && d->ksize <= 7 && (d->ksize & 1), PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: ksize %d", d->ksize);
-  const bool bf16 = is_bf16(d->precision);
-  const int esize = bf16 ? 2 : 4, blk_ch = bf16 ? 64 : 32;
+  const bool bf16 = is_bf16(d->precision), split = is_split(d->precision);
+  const int esize = bf16 ? 2 : 4, blk_ch = bf16 ? 64 : 32, nops = split ? 2 : 1;
   PN_REQUIRE(d->cin % (16 / esize) == 0 && d->cout % (16 / esize) == 0, PN_ERR_UNSUPPORTED,
              "pn_conv2d_wgrad: Cin/Cout must be multiples of %d", 16 / esize);
   PN_REQUIRE(aligned16(x) && aligned16(g) && aligned16(dwp), PN_ERR_ALIGNMENT, "pn_conv2d_wgrad: alignment");
@@ -906,19 +926,22 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* g, float
   if (d->debug_flags & 2) tg = 1;
   P.tg = tg;
   P.tap_groups = (taps + tg - 1) / tg;
-  // pixel tile height: as tall as shared memory allows with >= 2 stages (X-patch blocks + dZ blocks per stage);
-  // bf16 consumes tile rows in pairs (K = 16 pixels per MMA), so its height is even
+  P.pitch = TILE_W + d->ksize - 1;
+  // pixel tile height: as tall as shared memory allows with >= 2 stages (X-patch blocks + dZ blocks per stage, hi and lo
+  // for the x3 precisions); bf16 consumes tile rows in pairs (K = 16 pixels per MMA), so its height is even
   const uint32_t budget = 227u * 1024u - 1024u - 512u;
   int th = TILE_ROWS;
   while (th > 2 && th / 2 >= d->height) th /= 2;
   if (!bf16 && d->height < th) th = d->height;
+  auto patch_of = [&](int t) { return ((uint32_t)P.pitch * (t + d->ksize - 1) * 128u + 1023u) & ~1023u; };
   auto stage_bytes_of = [&](int t) {
-    return (uint32_t)P.mblks * PATCH_PITCH * (t + d->ksize - 1) * 128u + (uint32_t)(bn / blk_ch) * 8u * t * 128u;
+    return (uint32_t)nops * ((uint32_t)P.mblks * patch_of(t) + (uint32_t)(bn / blk_ch) * 8u * t * 128u);
   };
   while (th > (bf16 ? 2 : 1) && 2u * stage_bytes_of(th) > budget) th = bf16 ? th / 2 : (th + 1) / 2;
   PN_REQUIRE(stage_bytes_of(th) <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d_wgrad: tile does not fit in shared memory");
   P.th = th;
-  P.patch_bytes = (uint32_t)PATCH_PITCH * (th + d->ksize - 1) * 128u;
+  P.patch_tx = (uint32_t)P.pitch * (th + d->ksize - 1) * 128u;
+  P.patch_bytes = patch_of(th);
   P.gblk_bytes = 8u * th * 128u;
   const uint32_t stage_bytes = stage_bytes_of(th);
   int stages = (int)(budget / stage_bytes);
@@ -942,19 +965,19 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* g, float
   // fp32 accumulate, M=128, N=bn, A and B MN-major (bits 15, 16); formats 2 = TF32 / 1 = BF16
   const uint32_t fmt = bf16 ? 1u : 2u;
   P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  P.swap_lbo_sbo = (d->debug_flags & 4) ? 1 : 0;   // bring-up knob
-  if (d->debug_flags & 8) P.idesc &= ~((1u << 15) | (1u << 16));   // bring-up: K-major interpretation of both
   P.dwp = dwp; P.error_flag = error_flag;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
   const CUtensorMapSwizzle sw = bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 
-  alignas(64) CUtensorMap tmX, tmG;
+  alignas(64) CUtensorMap tmX, tmXlo, tmG, tmGlo;
   {
     const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->width, (uint64_t)d->height, (uint64_t)d->batch};
     const uint64_t strides[3] = {(uint64_t)d->cin * esize, (uint64_t)d->width * d->cin * esize,
                                  (uint64_t)d->height * d->width * d->cin * esize};
-    const uint32_t box[4] = {(uint32_t)blk_ch, PATCH_PITCH, (uint32_t)(th + d->ksize - 1), 1};
+    const uint32_t box[4] = {(uint32_t)blk_ch, (uint32_t)P.pitch, (uint32_t)(th + d->ksize - 1), 1};
     int rc = make_map(&tmX, x, 4, dims, strides, box, sw, bf16);
+    if (rc) return rc;
+    rc = make_map(&tmXlo, x_lo ? x_lo : x, 4, dims, strides, box, sw, bf16);
     if (rc) return rc;
   }
   {
@@ -964,15 +987,19 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* g, float
     const uint32_t box[4] = {(uint32_t)blk_ch, TILE_W, (uint32_t)th, 1};
     int rc = make_map(&tmG, g, 4, dims, strides, box, sw, bf16);
     if (rc) return rc;
+    rc = make_map(&tmGlo, g_lo ? g_lo : g, 4, dims, strides, box, sw, bf16);
+    if (rc) return rc;
   }
   dim3 grid(mblocks, P.tap_groups * nblocks, psplits);
-  if (P.bf16) {
-    PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_wgrad_kernel<true><<<grid, NTHREADS, smem, stream>>>(tmX, tmG, P);
-  } else {
-    PN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_wgrad_kernel<false><<<grid, NTHREADS, smem, stream>>>(tmX, tmG, P);
-  }
+  auto launch = [&](auto kern) -> int {
+    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NTHREADS, smem, stream>>>(tmX, tmXlo, tmG, tmGlo, P);
+    return 0;
+  };
+  int lrc;
+  if (bf16) lrc = split ? launch(conv_wgrad_kernel<true, true>) : launch(conv_wgrad_kernel<true, false>);
+  else      lrc = split ? launch(conv_wgrad_kernel<false, true>) : launch(conv_wgrad_kernel<false, false>);
+  if (lrc) return lrc;
   count_launch();
   return check_launch("conv_wgrad_kernel");
 }
@@ -985,6 +1012,9 @@ using namespace pn;
 extern "C" int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const void* x_lo, const void* w_packed,
                                  const void* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
                                  pn_stream_t stream) {
+  TraceScope ts(reinterpret_cast<cudaStream_t>(stream), "conv_igemm B%d H%d W%d Cin%d Cout%d k%d prec%d", desc ? desc->batch : 0,
+                desc ? desc->height : 0, desc ? desc->width : 0, desc ? desc->cin : 0, desc ? desc->cout : 0, desc ? desc->ksize : 0,
+                desc ? desc->precision : 0);
   return conv::conv_forward(desc, x, x_lo, w_packed, w_packed_lo, bias, y, error_flag, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1044,17 +1074,13 @@ extern "C" int pn_conv2d_wgrad(const pn_conv_desc* desc, const void* x, const vo
                                float* dw_packed, uint32_t* error_flag, pn_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PN_REQUIRE(desc && dw_packed, PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: null argument");
+  TraceScope ts(stream, "conv_wgrad B%d H%d W%d Cin%d Cout%d k%d prec%d", desc->batch, desc->height, desc->width, desc->cin,
+                desc->cout, desc->ksize, desc->precision);
   const bool split = desc->precision == PN_PRECISION_TF32X3 || desc->precision == PN_PRECISION_BF16X3;
   PN_REQUIRE(!split || (x_lo && g_lo), PN_ERR_BAD_ARGUMENT, "pn_conv2d_wgrad: the x3 precisions need the residual operands");
   const size_t n = (size_t)desc->cout * desc->ksize * desc->ksize * conv::kpad_of(desc->cin, desc->precision);
   PN_CUDA(cudaMemsetAsync(dw_packed, 0, sizeof(float) * n, stream));
-  if (split) {   // error-compensated: small terms first
-    int rc = conv::conv_wgrad(desc, x_lo, g, dw_packed, error_flag, stream);
-    if (rc) return rc;
-    rc = conv::conv_wgrad(desc, x, g_lo, dw_packed, error_flag, stream);
-    if (rc) return rc;
-  }
-  return conv::conv_wgrad(desc, x, g, dw_packed, error_flag, stream);
+  return conv::conv_wgrad(desc, x, x_lo, g, g_lo, dw_packed, error_flag, stream);
 }
 
 extern "C" int pn_conv2d_wgrad_packed_elems(int cout, int cin, int ksize, int precision, size_t* elems) {

@@ -832,6 +832,144 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
+// single-channel head convolution: Conv2d(C -> 1, 3x3, zero pad 1) of InvDepth (layers01.py:98-122)
+//   One output channel is HBM-bound fp32 work (read x once), not a GEMM: x [B,H,W,C] NHWC, w [9][C], y [B,H,W].
+// ---------------------------------------------------------------------------------------------------
+struct HeadParams {
+  int B, H, W, C, tw;      // tw x 8 output pixels per tile
+  const float* x;
+  const float* w;          // [9][C]  (tap-major)
+  const float* bias;       // [1]
+  const float* dy;         // [B,H,W]
+  float* y;                // [B,H,W]
+  float* dx;               // [B,H,W,C]
+  float* dw;               // [9][C] accumulated
+  float* db;               // [1] accumulated
+};
+
+// smem: s_x[(8+2)][(tw+2)][C+4], s_w[9][C]
+__global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = P.C, PITCH = C + SPAD, TWP = P.tw + 2;
+  float* s_x = sm;
+  float* s_w = sm + 10 * TWP * PITCH + 4;
+  const int w0 = blockIdx.x * P.tw, h0 = blockIdx.y * 8, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = __ldg(P.w + i);
+  stage_tile<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
+  __syncthreads();
+  for (int it = threadIdx.x; it < 8 * P.tw; it += blockDim.x) {
+    const int pw = it % P.tw, r = it / P.tw;
+    const int w = w0 + pw, h = h0 + r;
+    if (w >= P.W || h >= P.H) continue;
+    float acc = __ldg(P.bias);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4* xp = reinterpret_cast<const float4*>(s_x + (size_t)((r + dy) * TWP + pw + dx) * PITCH + SPAD);
+        const float4* wp = reinterpret_cast<const float4*>(s_w + (dy * 3 + dx) * C);
+        for (int q = 0; q < (C >> 2); ++q) {
+          const float4 a = xp[q], ww = wp[q];
+          acc = fmaf(a.x, ww.x, acc); acc = fmaf(a.y, ww.y, acc); acc = fmaf(a.z, ww.z, acc); acc = fmaf(a.w, ww.w, acc);
+        }
+      }
+    P.y[((size_t)b * P.H + h) * P.W + w] = acc;
+  }
+}
+
+// data gradient: dx[p][c] = sum_tap w[tap][c] * dy[p - tap + 1].  One thread per (pixel, channel quad).
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const HeadParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = P.C, TWP = P.tw + 2;
+  float* s_dy = sm;                 // [10][tw+2]
+  float* s_w = sm + ((10 * TWP + 3) & ~3);
+  const int w0 = blockIdx.x * P.tw, h0 = blockIdx.y * 8, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = __ldg(P.w + i);
+  for (int i = threadIdx.x; i < 10 * TWP; i += blockDim.x) {
+    const int c = i % TWP, r = i / TWP;
+    const int hh = h0 - 1 + r, ww = w0 - 1 + c;
+    s_dy[i] = (hh >= 0 && hh < P.H && ww >= 0 && ww < P.W) ? __ldg(P.dy + ((size_t)b * P.H + hh) * P.W + ww) : 0.0f;
+  }
+  __syncthreads();
+  const int c4n = C >> 2;
+  for (int it = threadIdx.x; it < 8 * P.tw * c4n; it += blockDim.x) {
+    const int q = it % c4n, pix = it / c4n;
+    const int pw = pix % P.tw, r = pix / P.tw;
+    const int w = w0 + pw, h = h0 + r;
+    if (w >= P.W || h >= P.H) continue;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float g = s_dy[(r + 2 - dy) * TWP + pw + 2 - dx];
+        const float4 ww = *reinterpret_cast<const float4*>(s_w + (dy * 3 + dx) * C + 4 * q);
+        a.x = fmaf(g, ww.x, a.x); a.y = fmaf(g, ww.y, a.y); a.z = fmaf(g, ww.z, a.z); a.w = fmaf(g, ww.w, a.w);
+      }
+    *reinterpret_cast<float4*>(P.dx + (((size_t)b * P.H + h) * P.W + w) * C + 4 * q) = a;
+  }
+}
+
+// weight / bias gradient: dw[tap][c] = sum_p x[p + tap - 1][c] * dy[p].  Persistent CTAs; thread <-> (tap, channel quad)
+// with its partial sums in registers over the whole walk (MAXQ combos per thread), atomics once at the end.
+template <int MAXQ>
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const HeadParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = P.C, PITCH = C + SPAD, TWP = P.tw + 2;
+  float* s_x = sm;
+  float* s_dy = sm + 10 * TWP * PITCH + 4;   // [8][tw]
+  const int c4n = C >> 2, ncombo = 9 * c4n;
+  float4 acc[MAXQ];
+#pragma unroll
+  for (int m = 0; m < MAXQ; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float bsum = 0.0f;
+  const int tiles_x = (P.W + P.tw - 1) / P.tw, tiles_y = (P.H + 7) / 8;
+  const int nwork = P.B * tiles_y * tiles_x;
+  for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+    const int tx = work % tiles_x, ty = (work / tiles_x) % tiles_y, b = work / (tiles_x * tiles_y);
+    const int w0 = tx * P.tw, h0 = ty * 8;
+    __syncthreads();
+    stage_tile<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
+    for (int i = threadIdx.x; i < 8 * P.tw; i += blockDim.x) {
+      const int pw = i % P.tw, r = i / P.tw;
+      const int hh = h0 + r, ww = w0 + pw;
+      const float g = (hh < P.H && ww < P.W) ? __ldg(P.dy + ((size_t)b * P.H + hh) * P.W + ww) : 0.0f;
+      s_dy[i] = g;
+      bsum += g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MAXQ; ++m) {
+      const int cb = threadIdx.x + m * 256;
+      if (cb < ncombo) {
+        const int q = cb % c4n, tap = cb / c4n;
+        const int dy = tap / 3, dx = tap - 3 * dy;
+        float4 a = acc[m];
+        for (int r = 0; r < 8; ++r)
+          for (int pw = 0; pw < P.tw; ++pw) {
+            const float g = s_dy[r * P.tw + pw];
+            const float4 xv = *reinterpret_cast<const float4*>(s_x + (size_t)((r + dy) * TWP + pw + dx) * PITCH + SPAD + 4 * q);
+            a.x = fmaf(g, xv.x, a.x); a.y = fmaf(g, xv.y, a.y); a.z = fmaf(g, xv.z, a.z); a.w = fmaf(g, xv.w, a.w);
+          }
+        acc[m] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MAXQ; ++m) {
+    const int cb = threadIdx.x + m * 256;
+    if (cb < ncombo) {
+      const int q = cb % c4n, tap = cb / c4n;
+      float* d = P.dw + tap * C + 4 * q;
+      atomicAdd(d + 0, acc[m].x); atomicAdd(d + 1, acc[m].y); atomicAdd(d + 2, acc[m].z); atomicAdd(d + 3, acc[m].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(P.db, bsum);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static size_t stencil_smem_bytes(int D, int tw, bool bwd, bool unpack_bwd) {
@@ -863,6 +1001,7 @@ extern "C" int pn_feature_stencil_forward(int pack, const float* in, const float
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PN_REQUIRE(in && w3 && b3 && out && batch > 0 && h_low > 0 && w_low > 0 && channels > 0, PN_ERR_BAD_ARGUMENT,
              "pn_feature_stencil_forward: bad argument");
+  TraceScope ts(stream, "stencil_fwd pack%d B%d H%d W%d C%d", pack, batch, h_low, w_low, channels);
   StencilParams P{};
   P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
   P.in = in; P.w3 = w3; P.b3 = b3; P.out = out; P.out_lo = out_lo;
@@ -908,6 +1047,7 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PN_REQUIRE(in && g && w3 && gin && gw3 && gb3 && batch > 0 && h_low > 0 && w_low > 0 && channels > 0, PN_ERR_BAD_ARGUMENT,
              "pn_feature_stencil_backward: bad argument");
+  TraceScope ts(stream, "stencil_bwd pack%d B%d H%d W%d C%d", pack, batch, h_low, w_low, channels);
   StencilBwdParams P{};
   P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
   P.in = in; P.g = g; P.w3 = w3; P.gin = gin; P.gw3 = gw3; P.gb3 = gb3;
@@ -1069,4 +1209,70 @@ extern "C" int pn_channel_sum(const float* g, float* out, size_t pixels, int cha
   channel_sum_kernel<<<(int)((pixels + ppc - 1) / ppc), 256, 0, stream>>>(g, pixels, channels, ppc, out);
   count_launch();
   return check_launch("channel_sum_kernel");
+}
+
+static int head_tile_w(int C, int W) {
+  int tw = 32;
+  while (tw > 4 && ((size_t)10 * (tw + 2) * (C + SPAD) + 4 + (size_t)9 * C + 8 * tw) * sizeof(float) > 100 * 1024) tw >>= 1;
+  while (tw > 4 && (tw >> 1) >= W) tw >>= 1;
+  return tw;
+}
+
+// y[b,h,w] = bias + sum_{tap,c} x[b, h+dy-1, w+dx-1, c] * w[tap][c]      (Conv2d(C->1, 3x3, pad 1): layers01.py:110-116)
+extern "C" int pn_head_conv_forward(const float* x, const float* w_tap_major, const float* bias, float* y, int batch, int height,
+                                    int width, int channels, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(x && w_tap_major && bias && y && batch > 0 && height > 0 && width > 0 && channels > 0 && channels % 4 == 0,
+             PN_ERR_BAD_ARGUMENT, "pn_head_conv_forward: bad argument (channels must be a multiple of 4)");
+  PN_REQUIRE(aligned16(x) && aligned16(w_tap_major), PN_ERR_ALIGNMENT, "pn_head_conv_forward: pointers must be 16-byte aligned");
+  HeadParams P{};
+  P.B = batch; P.H = height; P.W = width; P.C = channels; P.x = x; P.w = w_tap_major; P.bias = bias; P.y = y;
+  P.tw = head_tile_w(channels, width);
+  const size_t smem = ((size_t)10 * (P.tw + 2) * (channels + SPAD) + 4 + (size_t)9 * channels) * sizeof(float);
+  PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_head_conv_forward: %d channels need %zu bytes of shared memory", channels, smem);
+  PN_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((width + P.tw - 1) / P.tw, (height + 7) / 8, batch);
+  head_fwd_kernel<<<grid, 256, smem, stream>>>(P);
+  count_launch();
+  return check_launch("head_fwd_kernel");
+}
+
+// dx [B,H,W,C], dw [9][C], db [1] from dy [B,H,W]
+extern "C" int pn_head_conv_backward(const float* x, const float* dy, const float* w_tap_major, float* dx, float* dw_tap_major,
+                                     float* dbias, int batch, int height, int width, int channels, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(x && dy && w_tap_major && dx && dw_tap_major && dbias && batch > 0 && height > 0 && width > 0 && channels > 0 &&
+                 channels % 4 == 0, PN_ERR_BAD_ARGUMENT, "pn_head_conv_backward: bad argument");
+  PN_REQUIRE(aligned16(x) && aligned16(w_tap_major) && aligned16(dx), PN_ERR_ALIGNMENT, "pn_head_conv_backward: pointers must be 16-byte aligned");
+  PN_REQUIRE(9 * (channels / 4) <= 4 * 256, PN_ERR_UNSUPPORTED, "pn_head_conv_backward: %d channels (<= 452)", channels);
+  HeadParams P{};
+  P.B = batch; P.H = height; P.W = width; P.C = channels; P.x = x; P.w = w_tap_major; P.dy = dy; P.dx = dx; P.dw = dw_tap_major;
+  P.db = dbias;
+  P.tw = head_tile_w(channels, width);
+  {
+    const size_t smem = ((size_t)((10 * (P.tw + 2) + 3) & ~3) + (size_t)9 * channels) * sizeof(float);
+    dim3 grid((width + P.tw - 1) / P.tw, (height + 7) / 8, batch);
+    PN_CUDA(cudaFuncSetAttribute(head_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_dgrad_kernel<<<grid, 256, smem, stream>>>(P);
+    count_launch();
+    int rc = check_launch("head_dgrad_kernel");
+    if (rc) return rc;
+  }
+  PN_CUDA(cudaMemsetAsync(dw_tap_major, 0, sizeof(float) * 9 * channels, stream));
+  PN_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float), stream));
+  const size_t smem = ((size_t)10 * (P.tw + 2) * (channels + SPAD) + 4 + (size_t)8 * P.tw) * sizeof(float);
+  PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_head_conv_backward: %d channels need %zu bytes of shared memory", channels, smem);
+  const int nwork = batch * ((height + 7) / 8) * ((width + P.tw - 1) / P.tw);
+  int ctas = 148 * 2;
+  if (ctas > nwork) ctas = nwork;
+  const int maxq = (9 * (channels / 4) + 255) / 256;
+  auto launch = [&](auto kern) -> int {
+    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ctas, 256, smem, stream>>>(P);
+    return 0;
+  };
+  int lrc = (maxq <= 1) ? launch(head_wgrad_kernel<1>) : (maxq <= 2) ? launch(head_wgrad_kernel<2>) : launch(head_wgrad_kernel<4>);
+  if (lrc) return lrc;
+  count_launch();
+  return check_launch("head_wgrad_kernel");
 }

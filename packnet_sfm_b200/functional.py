@@ -250,6 +250,39 @@ class _FeatureStencil(torch.autograd.Function):
         return gin, gw3.view(8, 1, 3, 3, 3), gb3, None
 
 
+class _HeadConv(torch.autograd.Function):
+    """Conv2d(C -> 1, 3x3, pad 1) on an NHWC map (InvDepth.conv1, layers01.py:110-116)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _lib.require_cuda(x, weight, bias)
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        wt = weight.detach().reshape(C, 9).t().contiguous()          # [9][C] tap-major
+        y = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().pn_head_conv_forward(_lib.ptr(x), _lib.ptr(wt), _lib.ptr(bias.detach().contiguous()), _lib.ptr(y),
+                                                   B, H, W, C, _stream()), "pn_head_conv_forward")
+        ctx.save_for_backward(x, wt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wt = ctx.saved_tensors
+        B, H, W, C = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty(9, C, dtype=torch.float32, device=x.device)
+        db = torch.empty(1, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().pn_head_conv_backward(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(wt), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db),
+                                                    B, H, W, C, _stream()), "pn_head_conv_backward")
+        return dx, dw.t().reshape(1, C, 3, 3), db
+
+
+def head_conv(x, weight, bias):
+    """[B,H,W,C] NHWC, weight [1,C,3,3], bias [1] -> [B,H,W]"""
+    return _HeadConv.apply(x, weight, bias)
+
+
 def pack_features(x, w3, b3):
     """[B,2h,2w,C] -> [B,h,w,32C]"""
     return _FeatureStencil.apply(x, w3, b3, True)

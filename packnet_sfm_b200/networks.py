@@ -77,7 +77,7 @@ def ResidualBlock(in_channels, out_channels, num_blocks, stride, dropout=None):
 
 class InvDepth(nn.Module):
     """Inverse depth head (layers01.py:98-122): pad 1 -> Conv2d(C->1, 3x3) -> sigmoid / min_depth.
-    One output channel is not tensor-core work; it runs as PyTorch host code on the NHWC map."""
+    One output channel is HBM-bound fp32 work, not a GEMM: pn_head_conv_* (exact fp32 FMAs)."""
 
     def __init__(self, in_channels, out_channels=1, min_depth=0.5):
         super().__init__()
@@ -85,9 +85,11 @@ class InvDepth(nn.Module):
         self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1)
 
     def forward(self, x):
-        # x: NHWC storage viewed as NCHW channels_last (no copy); keep cuDNN in fp32 unless tf32x1 was asked for
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=PF.get_precision() == PF.PRECISION_TF32X1):
-            y = F.conv2d(x.permute(0, 3, 1, 2), self.conv1.weight, self.conv1.bias, padding=1)
+        if x.shape[3] % 4 == 0 and self.conv1.out_channels == 1:
+            y = PF.head_conv(x, self.conv1.weight, self.conv1.bias).unsqueeze(1)
+        else:   # odd channel counts (never in PackNet01): cuDNN on the NHWC storage viewed as channels_last
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=PF.get_precision() == PF.PRECISION_TF32X1):
+                y = F.conv2d(x.permute(0, 3, 1, 2), self.conv1.weight, self.conv1.bias, padding=1)
         return torch.sigmoid(y) / self.min_depth          # [B,1,H,W] (NCHW == NHWC for one channel)
 
 

@@ -137,6 +137,26 @@ def _load_block(module, sd):
     return module.to(DEV)
 
 
+def test_head_conv_matches_fp64_conv2d():
+    """Conv2d(C->1, 3x3, pad 1) of InvDepth (layers01.py:110-116): exact-fp32 kernel vs float64 F.conv2d."""
+    from packnet_sfm_b200 import functional as PF
+    torch.manual_seed(11)
+    for B, H, W, C in ((2, 24, 40, 64), (1, 9, 13, 128), (1, 6, 20, 256), (1, 16, 8, 4)):
+        x = (torch.rand(B, H, W, C, device=DEV) - 0.5).requires_grad_(True)
+        w = ((torch.rand(1, C, 3, 3, device=DEV) - 0.5) * 0.2).requires_grad_(True)
+        b = (torch.rand(1, device=DEV) - 0.5).requires_grad_(True)
+        y = PF.head_conv(x, w, b)
+        gy = torch.rand_like(y) - 0.5
+        y.backward(gy)
+        xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=1)[:, 0]
+        yr.backward(gy.double())
+        assert rel_l2(y, yr) < 1e-6
+        assert rel_l2(x.grad, xd.grad) < 1e-6
+        assert rel_l2(w.grad, wd.grad) < 1e-5
+        assert rel_l2(b.grad, bd.grad) < 1e-5
+
+
 BLOCKS = [
     ("pack_k3", lambda N: N.PackLayerConv3d(32, 3), lambda: PO.block_state_dict("pack", 32, k=3, seed=21)),
     ("pack_k5", lambda N: N.PackLayerConv3d(16, 5), lambda: PO.block_state_dict("pack", 16, k=5, seed=22)),
