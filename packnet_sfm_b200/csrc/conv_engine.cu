@@ -468,6 +468,7 @@ struct WgradParams {
   int psplits;
   int stages;
   int pitch;             // pixels per patch row (8 + ks - 1)
+  int pair;              // 1: Cin <= 64 (bf16): M block 1 is the X patch shifted to the NEXT tap -> two taps per accumulator
   uint32_t patch_bytes;  // one channel block of the X patch: pitch * (th + ks - 1) * 128 rounded up to 1024
   uint32_t patch_tx;     // bytes one patch box delivers
   uint32_t gblk_bytes;   // 8 * th * 128: one channel block of the dZ tile
@@ -517,9 +518,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int ci0 = blockIdx.x * 128;
   const int tgi = blockIdx.y % P.tap_groups, nblk = blockIdx.y / P.tap_groups;
   const int n0 = nblk * P.bn;
-  const int tap0 = tgi * P.tg;
   const int taps = P.ks * P.ks;
-  const int ntap = min(P.tg, taps - tap0);
+  const int tap0 = tgi * P.tg * (P.pair ? 2 : 1);   // pair mode: every accumulator holds two taps
+  const int nacc = P.pair ? min(P.tg, (taps - tap0 + 1) >> 1) : min(P.tg, taps - tap0);
   const int per = (P.ntiles + P.psplits - 1) / P.psplits;
   const int t_begin = blockIdx.z * per, t_end = min(P.ntiles, t_begin + per);
   const bool has_work = t_end > t_begin;
@@ -575,7 +576,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t sbo_a = BF16 ? (uint32_t)P.pitch * 128u : 512u, sbo_b = BF16 ? 1024u : 512u;
       const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
       const uint32_t hi_b = ((sbo_b >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
-      const uint32_t lbo_a = ((P.patch_bytes >> 4) & 0x3FFFu) << 16, lbo_b = ((P.gblk_bytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t lbo_a = P.pair ? 0u : ((P.patch_bytes >> 4) & 0x3FFFu) << 16, lbo_b = ((P.gblk_bytes >> 4) & 0x3FFFu) << 16;
+      const int tstep = P.pair ? 2 : 1;
       auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
       constexpr int KSTEP = BF16 ? 2 : 1;   // tile rows per MMA
       const uint32_t xlo_off = x_bytes >> 4, glo_off = g_bytes >> 4;
@@ -585,8 +587,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t xa = (stage_x(s, 0, 0) >> 4) | lbo_a, ga = (stage_g(s, 0, 0) >> 4) | lbo_b;
         int dy = tap0 / P.ks, dx = tap0 % P.ks;
         uint32_t d_t = tmem_base;
-        for (int tt = 0; tt < ntap; ++tt) {
-          const uint32_t la0 = xa + (uint32_t)(dy * P.pitch + dx) * 8u;   // 128 B per patch pixel >> 4
+        for (int tt = 0; tt < nacc; ++tt) {
+          uint32_t la0 = xa + (uint32_t)(dy * P.pitch + dx) * 8u;   // 128 B per patch pixel >> 4
+          // pair mode: M rows 64..127 read the SAME patch one tap further: +1 pixel (128 B), or the start of the next
+          // tap row ((pitch - ks + 1) = 8 pixels, 1024 B) -- the descriptor's M-block stride (LBO) expresses the shift
+          if (P.pair) la0 |= ((dx + 1 < P.ks) ? 8u : 64u) << 16;
           if (elect_one()) {
             uint32_t la = la0, lb = ga, a1 = acc;
             for (int kk = 0; kk < P.th; kk += KSTEP) {
@@ -603,7 +608,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
           }
           d_t += (uint32_t)P.acc_stride;
-          if (++dx == P.ks) { dx = 0; ++dy; }
+          dx += tstep;
+          if (dx >= P.ks) { dx -= P.ks; ++dy; }
         }
         if (elect_one()) umma_commit(empty_bar(s));
         acc = 1u;
@@ -615,11 +621,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     mbar_wait_warp_backoff(tmemfull_bar, 0, P.error_flag, 8);
     tc_fence_after();
     const int q = warp & 3;
-    const int ci = ci0 + q * 32 + lane;
-    const bool valid = ci < P.kpad;
+    // pair mode: accumulator rows 0..63 are tap 2t, rows 64..127 tap 2t + 1, both over input channels 0..63
+    const int ci = P.pair ? ((q & 1) * 32 + lane) : (ci0 + q * 32 + lane);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int t = 0; t < ntap; ++t) {
-      const int tap = tap0 + t;
+    for (int t = 0; t < nacc; ++t) {
+      const int tap = P.pair ? (tap0 + 2 * t + (q >> 1)) : (tap0 + t);
+      const bool valid = (ci < P.kpad) && (tap < taps);
       for (int c0 = 0; c0 < P.bn; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)(t * P.acc_stride + c0), v);
@@ -917,6 +924,9 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* x_lo, co
   P.kpad = kpad_of(d->cin, d->precision);
   P.bf16 = bf16 ? 1 : 0; P.blk_ch = blk_ch; P.mblks = 128 / blk_ch;
   const int taps = d->ksize * d->ksize;
+  // few input channels: one 64-channel block would leave half of the M = 128 rows empty -> pair two taps per accumulator
+  P.pair = (bf16 && P.kpad <= 64 && taps > 1 && !(d->debug_flags & 256)) ? 1 : 0;
+  if (P.pair) P.mblks = 1;
   int bn = (d->cout + blk_ch - 1) / blk_ch * blk_ch;
   if (bn > 256) bn = 256;
   P.bn = bn;
@@ -924,8 +934,9 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* x_lo, co
   int tg = 512 / P.acc_stride;
   if (tg > taps) tg = taps;
   if (d->debug_flags & 2) tg = 1;
+  if (P.pair && tg > (taps + 1) / 2) tg = (taps + 1) / 2;
   P.tg = tg;
-  P.tap_groups = (taps + tg - 1) / tg;
+  P.tap_groups = P.pair ? ((taps + 1) / 2 + tg - 1) / tg : (taps + tg - 1) / tg;
   P.pitch = TILE_W + d->ksize - 1;
   // pixel tile height: as tall as shared memory allows with >= 2 stages (X-patch blocks + dZ blocks per stage, hi and lo
   // for the x3 precisions); bf16 consumes tile rows in pairs (K = 16 pixels per MMA), so its height is even
