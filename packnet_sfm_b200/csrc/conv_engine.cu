@@ -33,7 +33,8 @@ namespace conv {
 constexpr int TILE_W = 8;        // pixels per tile row (one 8-row swizzle atom)
 constexpr int TILE_ROWS = 16;    // tile rows x images
 constexpr int PATCH_PITCH = 16;  // pixels per row of the HALO patch (2048 B: keeps 8-row groups 1024-B aligned)
-constexpr int NTHREADS = 192;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int NTHREADS = 192;    // wgrad kernel: warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int NTHREADS_IGEMM = 224;  // forward/dgrad kernel: + warp 6, a SECOND MMA issuer (alternating groups)
 constexpr int MAX_STAGES = 8;
 
 struct KernelParams {
@@ -97,9 +98,20 @@ __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, un
     }
   }
 }
-// the fast path is ONE probe: the watchdog clock reads stay out of the issuer's steady state
+// Waits of the single-warp roles (TMA producer, MMA issuer).  Every lane probes, but the loop condition is a warp VOTE,
+// i.e. provably warp-uniform: the compiler keeps the role's loop state (stage index, phases, descriptor words) in
+// uniform registers across the wait instead of spilling it to vector registers + R2UR per use.  The fast path is one
+// probe; the watchdog clock reads stay out of the steady state.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* error_flag, int who) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, error_flag, who);
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  const long long t0 = clock64();
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      if (error_flag) atomicExch(error_flag, 0xDEAD0000u | (unsigned)who);
+      __threadfence_system();
+      __trap();
+    }
+  }
 }
 // long wait of a whole warp (the epilogue waiting for the accumulator): ONE lane polls, with a sleep between probes, so
 // 128 spinning threads do not hammer the mbarrier unit the TMA producer and the MMA issuer depend on (ncu r01: 74 % of
@@ -208,7 +220,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_b
 // the kernel
 // ---------------------------------------------------------------------------------------------------
 template <bool BF16, bool SPLIT, bool HALO>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_IGEMM, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const KernelParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -224,13 +236,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t slot_bytes = (uint32_t)P.group * item_bytes;
   const uint32_t slots_base = smem_base + patch_region;
   const uint32_t bars_base = slots_base + P.stages * slot_bytes;
-  // barriers: full[stages], empty[stages], full_a[2], empty_a[2], tmem_full ; then the TMEM address word
-  auto full_bar = [&](int s) { return bars_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bars_base + 8u * (MAX_STAGES + s); };
-  auto fulla_bar = [&](int s) { return bars_base + 8u * (2 * MAX_STAGES + s); };
-  auto emptya_bar = [&](int s) { return bars_base + 8u * (2 * MAX_STAGES + 2 + s); };
-  const uint32_t tmemfull_bar = bars_base + 8u * (2 * MAX_STAGES + 4);
-  const uint32_t tmem_slot = bars_base + 8u * (2 * MAX_STAGES + 5);
+  // barriers: full[2][stages], empty[stages], full_a[2], empty_a[2], tmem_full, first ; then the TMEM address word.
+  // A slot has TWO full barriers used on alternate rounds (round = use count of the slot).  Each MMA issuer waits only
+  // on its own groups, and with an odd slot count it meets a slot every OTHER round: on a single barrier it would skip a
+  // phase, and mbarrier waits are by parity -- the phase two steps back reads as "complete" when copies finish out of
+  // order (weights streaming from HBM; measured as a pipeline deadlock on the 16384-channel layers).  With two barriers
+  // every waiter observes every phase of the barrier it waits on.
+  auto full_bar = [&](int s, int round) { return bars_base + 8u * ((round & 1) * MAX_STAGES + s); };
+  auto empty_bar = [&](int s) { return bars_base + 8u * (2 * MAX_STAGES + s); };
+  auto fulla_bar = [&](int s) { return bars_base + 8u * (3 * MAX_STAGES + s); };
+  auto emptya_bar = [&](int s) { return bars_base + 8u * (3 * MAX_STAGES + 2 + s); };
+  const uint32_t tmemfull_bar = bars_base + 8u * (3 * MAX_STAGES + 4);
+  const uint32_t tmem_slot = bars_base + 8u * (3 * MAX_STAGES + 5);
+  const uint32_t first_bar = bars_base + 8u * (3 * MAX_STAGES + 6);
   auto patch_addr = [&](int buf, int op) { return smem_base + (uint32_t)(buf * nops + op) * P.patch_bytes; };
   const uint32_t b_off = HALO ? 0u : nops * P.a_stage_bytes;   // weight tiles inside an item
 
@@ -259,9 +277,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int rot_g = has_work ? (int)((rot_seed >> 4) % (unsigned)ngroups) : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 1); }
-    mbar_init(tmemfull_bar, 1);
+    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s, 0), 1); mbar_init(full_bar(s, 1), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 2); }   // both issuers release a patch
+    mbar_init(tmemfull_bar, 2);                                                                // ... and the accumulator
+    mbar_init(first_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -277,7 +296,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // The whole warp walks the loop and ONE elected lane issues: in a converged warp the copy operands live in
     // uniform registers; under `if (lane == 0)` the compiler wraps every UTMALDG in a per-lane waterfall loop.
     if (has_work) {
-      int s = 0, ph = 0, pa = 0, pha = 0;
+      int s = 0, round = 0, pa = 0, pha = 0;
       const int nouter = HALO ? ncc : 1;
       for (int ci = 0; ci < nouter; ++ci) {
         int cc = cc_begin + (ci + rot_c) % ncc;
@@ -294,33 +313,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int g = rot_g;
         for (int gi = 0; gi < ngroups; ++gi) {
           const int item0 = g * G, nt = min(G, nitems - item0);
-          mbar_wait(empty_bar(s), ph ^ 1, P.error_flag, 2);
+          mbar_wait(empty_bar(s), (round & 1) ^ 1, P.error_flag, 2);
+          const uint32_t fb = full_bar(s, round);
           if (elect_one()) {
-            mbar_expect_tx(full_bar(s), (uint32_t)nt * item_bytes);
+            mbar_expect_tx(fb, (uint32_t)nt * item_bytes);
             uint32_t dst = slots_base + (uint32_t)s * slot_bytes;
             int tap = HALO ? item0 : item0 % taps;
             if (!HALO) cc = cc_begin + item0 / taps;
             for (int j = 0; j < nt; ++j) {
               if (!HALO) {
                 const int dy = tap / P.ks, dx = tap - dy * P.ks;
-                tma_load_4d(dst, &tmA, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
-                if (nops == 2) tma_load_4d(dst + P.a_stage_bytes, &tmAlo, full_bar(s), cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+                tma_load_4d(dst, &tmA, fb, cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
+                if (nops == 2) tma_load_4d(dst + P.a_stage_bytes, &tmAlo, fb, cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
               }
               // the weight tile of (channel chunk, tap, N block) is ONE contiguous, pre-swizzled run of bn*128 bytes
               const size_t woff = ((size_t)(cc * taps + tap) * P.rows_pad + n0) * 128u;
-              bulk_load_1d(dst + b_off, P.wp + woff, P.b_stage_bytes, full_bar(s));
-              if (nops == 2) bulk_load_1d(dst + b_off + P.b_stage_bytes, P.wp_lo + woff, P.b_stage_bytes, full_bar(s));
+              bulk_load_1d(dst + b_off, P.wp + woff, P.b_stage_bytes, fb);
+              if (nops == 2) bulk_load_1d(dst + b_off + P.b_stage_bytes, P.wp_lo + woff, P.b_stage_bytes, fb);
               dst += item_bytes;
               if (++tap == taps) { tap = 0; if (!HALO) ++cc; }
             }
           }
           if (++g == ngroups) g = 0;
-          if (++s == P.stages) { s = 0; ph ^= 1; }
+          if (++s == P.stages) { s = 0; ++round; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer ==============================================
+  } else if (warp == 1 || warp == 6) {
+    // ===================================== MMA issuers =============================================
+    // TWO issuer warps take alternate groups.  tcgen05.mma issue is nearly synchronous (the pipe queues ~2 instructions)
+    // and the wait + descriptor arithmetic + commit of a group costs a single warp 200-400 cycles the tensor pipe spends
+    // idle; with two warps one prepares its group while the other's MMAs run.  MMAs of both warps accumulate into the
+    // same TMEM columns -- measured exact and MMA-bound in tools/ubench_tc3.cu; the only ordering that matters is that
+    // the accumulate=0 MMAs of the very first group enter the pipe first (first_bar).
     // The warp stays converged and one ELECTED lane issues: descriptors and the instruction descriptor sit in uniform
     // registers and an MMA costs one issue slot.  (r01 SASS of the `if (lane == 0)` form: ~25 instructions incl. R2UR
     // round trips and a waterfall loop per UTCHMMA, ~130 clk each.)  Descriptors are (constant high word | start
@@ -329,8 +354,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // memory, so A_hi x [B_hi ; B_lo] is one N = 2*bn instruction (TMEM columns [0, 2bn)) and A_lo x B_hi a second one
     // (columns [2bn, 3bn)); the epilogue adds the three column ranges.
     if (has_work) {
-      int s = 0, ph = 0, pa = 0, pha = 0;
-      uint32_t acc = 0;
+      const int me = (warp == 1) ? 0 : 1;
+      int gcount = 0;   // groups since the start of the tile: issuer `me` owns those with (gcount & 1) == me
+      int s = 0, round = 0, pa = 0, pha = 0;
+      uint32_t acc = me ? 1u : 0u;
       const uint32_t sbo_a = HALO ? (uint32_t)P.pitch * 128u : 1024u;
       const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
@@ -348,7 +375,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int g = rot_g;
         for (int gi = 0; gi < ngroups; ++gi) {
           const int item0 = g * G, nt = min(G, nitems - item0);
-          mbar_wait(full_bar(s), ph, P.error_flag, 4);
+          if ((gcount & 1) == me) {
+          mbar_wait(full_bar(s, round), (round >> 1) & 1, P.error_flag, 4);
+          if (gcount == 1) mbar_wait(first_bar, 0, P.error_flag, 9);
           tc_fence_after();
           // descriptor arithmetic stays in converged code (uniform datapath); only the MMAs sit under the election
           uint32_t it = lo_of(slots_base + (uint32_t)s * slot_bytes);   // item 0 of the slot
@@ -378,10 +407,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             it += item_step;
             if (HALO) { if (++dx == P.ks) { dx = 0; ++dy; } }
           }
-          if (elect_one()) umma_commit(empty_bar(s));  // frees this slot when the MMAs above have read it
+          if (elect_one()) {
+            umma_commit(empty_bar(s));  // frees this slot when the MMAs above have read it
+            if (gcount == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(first_bar) : "memory");
+          }
           acc = 1u;
+          }
+          ++gcount;
           if (++g == ngroups) g = 0;
-          if (++s == P.stages) { s = 0; ph ^= 1; }
+          if (++s == P.stages) { s = 0; ++round; }
         }
         if (HALO) {
           if (elect_one()) umma_commit(emptya_bar(pa));
@@ -391,7 +425,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (elect_one()) umma_commit(tmemfull_bar);
     }
-  } else if (has_work) {
+  } else if (warp >= 2 && warp <= 5 && has_work) {
     // ===================================== epilogue ================================================
     mbar_wait_warp_backoff(tmemfull_bar, 0, P.error_flag, 5);
     tc_fence_after();
@@ -844,14 +878,16 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   const uint32_t item_bytes = (P.halo ? 0u : nops * P.a_stage_bytes) + nops * P.b_stage_bytes;
   const uint32_t budget = 227u * 1024u - 1024u /*alignment slack*/ - 512u /*barriers*/;
   PN_REQUIRE(patch_region + 2 * item_bytes <= budget, PN_ERR_UNSUPPORTED, "pn_conv2d: tile does not fit in shared memory");
-  // Items per slot: amortise the ~100-cycle wait/commit hand-off over >= 16 MMAs (x3: 8 MMAs per item, x1: 4), but
-  // keep at least three slots in flight so that a slot's refill (TMA latency) hides behind the other slots' MMAs.
+  // Items per slot: amortise the wait/commit hand-off over >= 16 MMAs (x3: 8 MMAs per item, x1: 4), but keep at least
+  // three slots in flight so that a slot's refill (TMA latency) hides behind the other slots' MMAs.
+  // (pack1, x3, 6 items fit: 2 x 3 slots 1.64 ms; 1 x 6 1.86 ms; 2 x 2 1.96 ms; 3 x 2 1.94 ms -- r01_conv_bench.)
   {
     const int total_items = (P.halo ? 1 : P.cchunks) * d->ksize * d->ksize;
     const int fit = (int)((budget - patch_region) / item_bytes);
     int group = (P.nsplit == 3) ? 2 : 4;
-    if (d->debug_flags & 128) group = 1;
-    while (group > 1 && (fit / group < 3 || group > total_items)) --group;
+    const int forced = (d->debug_flags >> 8) & 15;   // tuning knob: force the group size
+    if (forced) group = forced;
+    while (group > 1 && (fit / group < (forced ? 2 : 3) || group > total_items)) --group;
     int stages = fit / group;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     P.group = group;
@@ -889,7 +925,7 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   dim3 grid(P.tiles_x * P.tiles_y * bgroups, (d->cout + bn - 1) / bn, P.ksplits);
   auto launch = [&](auto kern) -> int {
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NTHREADS, smem, stream>>>(tmA, tmAlo, P);
+    kern<<<grid, NTHREADS_IGEMM, smem, stream>>>(tmA, tmAlo, P);
     return 0;
   };
   int lrc;

@@ -45,9 +45,14 @@ def bench(tag, B, H, W, Cin, Cout, k, prec, mode, iters=5, dbg=0):
 
 B3, B1, T3, T1 = PF.PRECISION_BF16X3, PF.PRECISION_BF16X1, PF.PRECISION_TF32X3, PF.PRECISION_TF32X1
 bench("pack1 bf16x3 halo", 4, 96, 320, 2048, 64, 5, B3, 2)
-bench("pack1 bf16x3 halo  group 1", 4, 96, 320, 2048, 64, 5, B3, 2, dbg=128)
-bench("pack1 bf16x3 halo  pitch 16", 4, 96, 320, 2048, 64, 5, B3, 2, dbg=64)
-bench("pack1 bf16x1 halo  group 1", 4, 96, 320, 2048, 64, 5, B1, 2, dbg=128)
+for gsz in (1, 2, 3):
+    bench("pack1 bf16x3 halo  group %d" % gsz, 4, 96, 320, 2048, 64, 5, B3, 2, dbg=gsz << 8)
+for gsz in (1, 2, 4, 6):
+    bench("pack1 bf16x1 halo  group %d" % gsz, 4, 96, 320, 2048, 64, 5, B1, 2, dbg=gsz << 8)
+for gsz in (1, 2, 3):
+    bench("k3 256->256 24x80 bf16x3 group %d" % gsz, 4, 24, 80, 256, 256, 3, B3, 0, dbg=gsz << 8)
+bench("pack5 16384->512 6x20 bf16x3", 4, 6, 20, 16384, 512, 3, B3, 0)
+bench("512->512 12x40 bf16x3", 4, 12, 40, 512, 512, 3, B3, 0)
 bench("pack1 bf16x3 per-tap", 4, 96, 320, 2048, 64, 5, B3, 1)
 bench("pack1 bf16x1 halo", 4, 96, 320, 2048, 64, 5, B1, 2)
 bench("pack1 tf32x1 halo", 4, 96, 320, 2048, 64, 5, T1, 2)
