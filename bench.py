@@ -298,8 +298,13 @@ def run_ours(args):
     log("host enqueue of one step: %.1f ms" % enqueue_ms)
     launches0 = _lib.launch_count()
     cpu0 = time.process_time()
+    prof = os.environ.get("PN_CUDA_PROFILER") == "1"   # ncu --profile-from-start off: capture the timed region only
+    if prof:
+        torch.cuda.profiler.start()
     with ClockSampler(local) as clk:
         ms = timed_region(lambda: step(dbatch), args.steps)
+    if prof:
+        torch.cuda.profiler.stop()
     cpu_ms = (time.process_time() - cpu0) * 1e3 / args.steps     # host CPU time (all threads) per step
     launches = _lib.launch_count() - launches0
     log("timed region: %.1f ms/step (host CPU %.1f ms/step), %d library launches" % (ms / args.steps, cpu_ms, launches))

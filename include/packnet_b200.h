@@ -189,15 +189,17 @@ int pn_feature_stencil_backward(int pack, const float* in, const float* g, const
  * GroupNorm(16, eps) + ELU on NHWC maps (layers01.py:31-32,37; with x2 != NULL the input is x + x2, the
  * residual sum of layers01.py:72).  stats: B*16*3 doubles of scratch -- [B,16,2] doubles (sum, sum of squares)
  * followed by [B,16,2] floats (mean, rstd) -- written by the forward and read by the backward.  The output may again be a channel window of a wider buffer.
- * backward scratch `bc`: 2*C*B doubles followed by 2*16*B floats.
+ * backward scratch `bc`: 2*C*B doubles followed by 2*16*B floats.  dx_channel_sum (optional, [C]) receives
+ * sum over pixels of dx = the bias gradient of the convolution that produced x (layers01.py:28), fused into pass 2.
  * ------------------------------------------------------------------------------------------------ */
 int pn_groupnorm_elu_forward(const float* x, const float* x2, const float* gamma, const float* beta, float eps,
                              float* y, float* y_lo, double* stats, int batch, int hw, int channels,
                              int out_cstride, int out_coffset, pn_stream_t stream);
 int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, const float* dy,
                               const float* gamma, float eps, const double* stats, double* bc, float* dx,
-                              float* dx_lo, float* dgamma, float* dbeta, int batch, int hw, int channels,
-                              int y_cstride, int y_coffset, int dy_cstride, int dy_coffset, pn_stream_t stream);
+                              float* dx_lo, float* dgamma, float* dbeta, float* dx_channel_sum, int batch, int hw,
+                              int channels, int y_cstride, int y_coffset, int dy_cstride, int dy_coffset,
+                              pn_stream_t stream);
 
 /* out[c] = sum over pixels of g[pixel][c] (conv bias gradient), g dense [pixels, channels]. */
 int pn_channel_sum(const float* g, float* out, size_t pixels, int channels, pn_stream_t stream);

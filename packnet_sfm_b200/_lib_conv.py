@@ -29,7 +29,7 @@ def declare(lib):
     lib.pn_feature_stencil_forward.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     lib.pn_feature_stencil_backward.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     lib.pn_groupnorm_elu_forward.argtypes = [vp, vp, vp, vp, f, vp, vp, vp, i, i, i, i, i, vp]
-    lib.pn_groupnorm_elu_backward.argtypes = [vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.pn_groupnorm_elu_backward.argtypes = [vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.pn_channel_sum.argtypes = [vp, vp, sz, i, vp]
     lib.pn_head_conv_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.pn_head_conv_backward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]

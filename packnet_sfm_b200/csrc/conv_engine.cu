@@ -33,8 +33,7 @@ namespace conv {
 constexpr int TILE_W = 8;        // pixels per tile row (one 8-row swizzle atom)
 constexpr int TILE_ROWS = 16;    // tile rows x images
 constexpr int PATCH_PITCH = 16;  // pixels per row of the HALO patch (2048 B: keeps 8-row groups 1024-B aligned)
-constexpr int NTHREADS = 192;    // wgrad kernel: warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int NTHREADS_IGEMM = 224;  // forward/dgrad kernel: + warp 6, a SECOND MMA issuer (alternating groups)
+constexpr int NTHREADS_IGEMM = 224;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue, warp 6: second MMA issuer
 constexpr int MAX_STAGES = 8;
 
 struct KernelParams {
@@ -528,7 +527,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lb
 }
 
 template <bool BF16, bool SPLIT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_IGEMM, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
                   const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmGlo, const WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -560,8 +559,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const bool has_work = t_end > t_begin;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmemfull_bar, 1);
+    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 2); }   // two MMA issuers
+    mbar_init(tmemfull_bar, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -599,8 +598,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (++s == P.stages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 6) {
+    // Two issuer warps (see conv_igemm_kernel): warp 1 takes the even accumulators (taps / tap pairs) of every stage,
+    // warp 6 the odd ones.  They never share an accumulator, both observe every phase of every full barrier, and a
+    // stage is released when both have committed.
     if (has_work) {
+      const int me = (warp == 1) ? 0 : 1;
       int s = 0, ph = 0;
       uint32_t acc = 0;
       // descriptor = constant high word | (start address >> 4); BF16: plain SWIZZLE_128B (layout 2), one MMA per PAIR
@@ -621,7 +624,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t xa = (stage_x(s, 0, 0) >> 4) | lbo_a, ga = (stage_g(s, 0, 0) >> 4) | lbo_b;
         int dy = tap0 / P.ks, dx = tap0 % P.ks;
         uint32_t d_t = tmem_base;
-        for (int tt = 0; tt < nacc; ++tt) {
+        if (me) {
+          d_t += (uint32_t)P.acc_stride;
+          dx += tstep;
+          if (dx >= P.ks) { dx -= P.ks; ++dy; }
+        }
+        for (int tt = me; tt < nacc; tt += 2) {
           uint32_t la0 = xa + (uint32_t)(dy * P.pitch + dx) * 8u;   // 128 B per patch pixel >> 4
           // pair mode: M rows 64..127 read the SAME patch one tap further: +1 pixel (128 B), or the start of the next
           // tap row ((pitch - ks + 1) = 8 pixels, 1024 B) -- the descriptor's M-block stride (LBO) expresses the shift
@@ -641,9 +649,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               lb += (uint32_t)(KSTEP * 64);
             }
           }
-          d_t += (uint32_t)P.acc_stride;
-          dx += tstep;
-          if (dx >= P.ks) { dx -= P.ks; ++dy; }
+          d_t += 2u * (uint32_t)P.acc_stride;
+          dx += 2 * tstep;
+          while (dx >= P.ks) { dx -= P.ks; ++dy; }
         }
         if (elect_one()) umma_commit(empty_bar(s));
         acc = 1u;
@@ -651,7 +659,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       if (elect_one()) umma_commit(tmemfull_bar);
     }
-  } else if (has_work) {
+  } else if (warp >= 2 && warp <= 5 && has_work) {
     mbar_wait_warp_backoff(tmemfull_bar, 0, P.error_flag, 8);
     tc_fence_after();
     const int q = warp & 3;
@@ -1040,7 +1048,7 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* x_lo, co
   dim3 grid(mblocks, P.tap_groups * nblocks, psplits);
   auto launch = [&](auto kern) -> int {
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NTHREADS, smem, stream>>>(tmX, tmXlo, tmG, tmGlo, P);
+    kern<<<grid, NTHREADS_IGEMM, smem, stream>>>(tmX, tmXlo, tmG, tmGlo, P);
     return 0;
   };
   int lrc;
@@ -1078,6 +1086,8 @@ extern "C" int pn_conv2d_pack_weight(const float* w_oihw, void* w_packed, void* 
   const int rows = transposed ? cin : cout, k = transposed ? cout : cin;
   const size_t total = conv::packed_weight_elems(rows, k, ksize, precision);
   const int kc = conv::kc_of(precision), rows_pad = conv::rows_pad_of(rows);
+  // (a shared-memory tiled variant with contiguous source runs and 16-byte stores measured 2x SLOWER than this
+  // element-per-thread gather -- 4.0 vs 1.9 ms per step over the 93 packings; profiles/r01_step_kernel_breakdown_final.txt)
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

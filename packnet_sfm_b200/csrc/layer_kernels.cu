@@ -785,6 +785,119 @@ __global__ void __launch_bounds__(256) gn_elu_bwd_apply_kernel(const float* __re
   }
 }
 
+// float4 versions of the two backward passes (all channel strides / offsets multiples of 4): thread <-> (pixel lane,
+// float4 column), one CTA per (pixel range, sample) like gn_stats_kernel.  Pass 2 also accumulates sum_pixels dx per
+// channel -- the bias gradient of the convolution that produced x (layers01.py:28) -- so that no separate reduction
+// pass has to re-read dx.
+__global__ void __launch_bounds__(256) gn_elu_bwd_reduce4_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                                 const float* __restrict__ y, const float* __restrict__ dy, int HW, int C,
+                                                                 int in_cstride, int y_cstride, int y_coffset, int dy_cstride,
+                                                                 int dy_coffset, const float* __restrict__ mr, int pixels_per_cta,
+                                                                 double* __restrict__ bc) {
+  __shared__ float s_red[2 * 1024];
+  const int b = blockIdx.y, cg = C / 16, c4 = C / 4;
+  const int p0 = blockIdx.x * pixels_per_cta, p1 = min(p0 + pixels_per_cta, HW);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.0f;
+  __syncthreads();
+  const int lanes = blockDim.x / c4 > 0 ? blockDim.x / c4 : 1;
+  const int col = threadIdx.x % c4, pl = threadIdx.x / c4;
+  if (pl < lanes) {
+    float mean[4], rstd[4], s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = (col * 4 + k) / cg;
+      mean[k] = __ldg(mr + ((size_t)b * 16 + g) * 2 + 0);
+      rstd[k] = __ldg(mr + ((size_t)b * 16 + g) * 2 + 1);
+    }
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const size_t pix = (size_t)b * HW + p;
+      float4 xv = *reinterpret_cast<const float4*>(x + pix * in_cstride + col * 4);
+      if (x2) {
+        const float4 u = *reinterpret_cast<const float4*>(x2 + pix * in_cstride + col * 4);
+        xv.x += u.x; xv.y += u.y; xv.z += u.z; xv.w += u.w;
+      }
+      const float4 yv = *reinterpret_cast<const float4*>(y + pix * y_cstride + y_coffset + col * 4);
+      const float4 gv = *reinterpret_cast<const float4*>(dy + pix * dy_cstride + dy_coffset + col * 4);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float dz = gs[k] * (ys[k] > 0.0f ? 1.0f : ys[k] + 1.0f);
+        s1[k] += dz;
+        s2[k] += dz * (xs[k] - mean[k]) * rstd[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&s_red[(col * 4 + k) * 2 + 0], s1[k]);
+      atomicAdd(&s_red[(col * 4 + k) * 2 + 1], s2[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(bc + (size_t)b * C * 2 + i, (double)s_red[i]);
+}
+
+__global__ void __launch_bounds__(256) gn_elu_bwd_apply4_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                                const float* __restrict__ y, const float* __restrict__ dy, int HW, int C,
+                                                                int in_cstride, int y_cstride, int y_coffset, int dy_cstride,
+                                                                int dy_coffset, const float* __restrict__ mr,
+                                                                const float* __restrict__ gmeans, const float* __restrict__ gamma,
+                                                                int pixels_per_cta, float* __restrict__ dx, float* __restrict__ dx_lo,
+                                                                float* __restrict__ dsum) {
+  __shared__ float s_red[1024];
+  const int b = blockIdx.y, cg = C / 16, c4 = C / 4;
+  const int p0 = blockIdx.x * pixels_per_cta, p1 = min(p0 + pixels_per_cta, HW);
+  if (dsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_red[i] = 0.0f;
+    __syncthreads();
+  }
+  const int lanes = blockDim.x / c4 > 0 ? blockDim.x / c4 : 1;
+  const int col = threadIdx.x % c4, pl = threadIdx.x / c4;
+  if (pl < lanes) {
+    float mean[4], rstd[4], m1[4], m2[4], gm[4], acc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = col * 4 + k, g = c / cg;
+      mean[k] = __ldg(mr + ((size_t)b * 16 + g) * 2 + 0);
+      rstd[k] = __ldg(mr + ((size_t)b * 16 + g) * 2 + 1);
+      m1[k] = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 0);
+      m2[k] = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 1);
+      gm[k] = __ldg(gamma + c);
+    }
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const size_t pix = (size_t)b * HW + p;
+      float4 xv = *reinterpret_cast<const float4*>(x + pix * in_cstride + col * 4);
+      if (x2) {
+        const float4 u = *reinterpret_cast<const float4*>(x2 + pix * in_cstride + col * 4);
+        xv.x += u.x; xv.y += u.y; xv.z += u.z; xv.w += u.w;
+      }
+      const float4 yv = *reinterpret_cast<const float4*>(y + pix * y_cstride + y_coffset + col * 4);
+      const float4 gv = *reinterpret_cast<const float4*>(dy + pix * dy_cstride + dy_coffset + col * 4);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+      float r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xhat = (xs[k] - mean[k]) * rstd[k];
+        const float dz = gs[k] * (ys[k] > 0.0f ? 1.0f : ys[k] + 1.0f);
+        r[k] = rstd[k] * (gm[k] * dz - m1[k] - xhat * m2[k]);
+        acc[k] += r[k];
+      }
+      const size_t o = pix * C + col * 4;
+      *reinterpret_cast<float4*>(dx + o) = make_float4(r[0], r[1], r[2], r[3]);
+      if (dx_lo)
+        *reinterpret_cast<float4*>(dx_lo + o) = make_float4(r[0] - tf32_trunc(r[0]), r[1] - tf32_trunc(r[1]),
+                                                            r[2] - tf32_trunc(r[2]), r[3] - tf32_trunc(r[3]));
+    }
+    if (dsum) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&s_red[col * 4 + k], acc[k]);
+    }
+  }
+  if (dsum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dsum + i, s_red[i]);
+  }
+}
+
 // dgamma[c] = sum_b bc[b][c][1], dbeta[c] = sum_b bc[b][c][0];
 // gmeans[b][g] = (mean_g(gamma*dz), mean_g(gamma*dz*xhat)) over the (HW * C/16) elements of the group
 __global__ void gn_bwd_finalize_kernel(const double* __restrict__ bc, const float* __restrict__ gamma, int B, int C, double cnt,
@@ -1172,8 +1285,8 @@ extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const f
 
 extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, const float* dy, const float* gamma,
                                          float eps, const double* stats, double* bc, float* dx, float* dx_lo, float* dgamma,
-                                         float* dbeta, int batch, int hw, int channels, int y_cstride, int y_coffset, int dy_cstride,
-                                         int dy_coffset, pn_stream_t stream_) {
+                                         float* dbeta, float* dx_channel_sum, int batch, int hw, int channels, int y_cstride,
+                                         int y_coffset, int dy_cstride, int dy_coffset, pn_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PN_REQUIRE(x && y && dy && gamma && stats && bc && dx && dgamma && dbeta && batch > 0 && hw > 0, PN_ERR_BAD_ARGUMENT,
              "pn_groupnorm_elu_backward: bad argument");
@@ -1183,20 +1296,41 @@ extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const 
   if (ppc < 32) ppc = 32;
   dim3 g1((hw + ppc - 1) / ppc, batch);
   const float* mr = reinterpret_cast<const float*>(stats + (size_t)2 * 16 * batch);
+  // bc holds 2*C*B doubles followed by 2*16*B floats of scratch for the group means
+  float* gmeans = reinterpret_cast<float*>(bc + (size_t)2 * channels * batch);
+  const bool vec = aligned16(x) && (!x2 || aligned16(x2)) && aligned16(y) && aligned16(dy) && aligned16(dx) && (!dx_lo || aligned16(dx_lo)) &&
+                   y_cstride % 4 == 0 && y_coffset % 4 == 0 && dy_cstride % 4 == 0 && dy_coffset % 4 == 0;
+  if (dx_channel_sum) PN_CUDA(cudaMemsetAsync(dx_channel_sum, 0, sizeof(float) * channels, stream));
+  if (vec) {
+    gn_elu_bwd_reduce4_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
+                                                      dy_coffset, mr, ppc, bc);
+    count_launch();
+    gn_bwd_finalize_kernel<<<(batch * 16 + channels + 127) / 128, 128, 0, stream>>>(bc, gamma, batch, channels,
+                                                                                   (double)hw * (channels / 16), gmeans, dgamma, dbeta);
+    count_launch();
+    gn_elu_bwd_apply4_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
+                                                     mr, gmeans, gamma, ppc, dx, dx_lo, dx_channel_sum);
+    count_launch();
+    return check_launch("gn_elu_bwd kernels");
+  }
   gn_elu_bwd_reduce_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
                                                    mr, eps, ppc, bc);
   count_launch();
   const size_t total = (size_t)batch * hw * channels;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  // bc holds 2*C*B doubles followed by 2*16*B floats of scratch for the group means
-  float* gmeans = reinterpret_cast<float*>(bc + (size_t)2 * channels * batch);
   gn_bwd_finalize_kernel<<<(batch * 16 + channels + 127) / 128, 128, 0, stream>>>(bc, gamma, batch, channels,
                                                                                  (double)hw * (channels / 16), gmeans, dgamma, dbeta);
   count_launch();
   gn_elu_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
                                                       dy_coffset, mr, gmeans, gamma, eps, dx, dx_lo, batch);
   count_launch();
+  if (dx_channel_sum) {
+    int ppc2 = (int)(((size_t)batch * hw + 147 * 4) / (148 * 4));
+    if (ppc2 < 64) ppc2 = 64;
+    channel_sum_kernel<<<(int)(((size_t)batch * hw + ppc2 - 1) / ppc2), 256, 0, stream>>>(dx, (size_t)batch * hw, channels, ppc2, dx_channel_sum);
+    count_launch();
+  }
   return check_launch("gn_elu_bwd kernels");
 }
 

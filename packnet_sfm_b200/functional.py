@@ -11,6 +11,7 @@ Precision of the tensor-core GEMMs (include/packnet_b200.h): PRECISION_BF16X3 (d
 split, 16 mantissa bits, meets the 1e-3 depth parity bar at twice the tf32 MMA rate), PRECISION_TF32X3 (22 bits),
 PRECISION_TF32X1 (what cuDNN gives the reference on Ampere+ with PyTorch defaults; fails the parity bar)."""
 import ctypes
+import weakref
 
 import torch
 
@@ -165,14 +166,34 @@ class _Conv2d(torch.autograd.Function):
                        "pn_conv2d_unpack_weight_grad")
             gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = torch.empty(cout, dtype=torch.float32, device=gy.device)
-            _lib.check(lib.pn_channel_sum(_lib.ptr(gy), _lib.ptr(gb), B * H * W, cout, _stream()), "pn_channel_sum")
+            gb = _lookup_channel_sum(gy)
+            if gb is None:
+                gb = torch.empty(cout, dtype=torch.float32, device=gy.device)
+                _lib.check(lib.pn_channel_sum(_lib.ptr(gy), _lib.ptr(gb), B * H * W, cout, _stream()), "pn_channel_sum")
         return gx, gw, gb
 
 
 def conv2d(x, weight, bias=None):
     """x: [B,H,W,C] with C a multiple of channel_align(); weight may have fewer input channels (zero-padded)."""
     return _Conv2d.apply(x, weight, bias)
+
+
+# The GroupNorm backward already reduces its dx over the pixels; the convolution that consumes dx as its output
+# gradient takes its bias gradient from here instead of re-reading the tensor.  An entry is valid only while the
+# producing tensor object is alive (weak reference): then no other tensor can own that storage.
+_channel_sums = []
+
+
+def _remember_channel_sum(dx, dsum):
+    _channel_sums.append((weakref.ref(dx), dx.data_ptr(), tuple(dx.shape), dsum))
+    del _channel_sums[:-8]
+
+
+def _lookup_channel_sum(g):
+    for ref, ptr, shape, dsum in reversed(_channel_sums):
+        if ref() is not None and ptr == g.data_ptr() and shape == tuple(g.shape) and g.is_contiguous():
+            return dsum
+    return None
 
 
 class _GroupNormELU(torch.autograd.Function):
@@ -203,10 +224,13 @@ class _GroupNormELU(torch.autograd.Function):
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
         bc = torch.empty(2 * C * B + 16 * B, dtype=torch.float64, device=x.device)   # doubles + float scratch tail
+        dsum = torch.empty(C, dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().pn_groupnorm_elu_backward(_lib.ptr(x), _p(x2), _lib.ptr(y), _lib.ptr(gy),
                                                         _lib.ptr(gamma.detach().contiguous()), ctx.eps, _lib.ptr(stats),
                                                         _lib.ptr(bc), _lib.ptr(dx), None, _lib.ptr(dgamma), _lib.ptr(dbeta),
-                                                        B, H * W, C, C, 0, C, 0, _stream()), "pn_groupnorm_elu_backward")
+                                                        _lib.ptr(dsum), B, H * W, C, C, 0, C, 0, _stream()),
+                   "pn_groupnorm_elu_backward")
+        _remember_channel_sum(dx, dsum)
         return dx, (dx if x2 is not None else None), dgamma, dbeta, None
 
 
