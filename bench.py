@@ -205,7 +205,12 @@ def time_kernels(args, dev, pk):
     bytes_f, bytes_b = 48 * P_s, 44 * P_s
     res["roofline_loss"] = {"bound": "hbm", "kernel": "loss_tile_kernel fwd+bwd (incl. prep launches)",
                             "achieved": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                            "frac": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9 / pk["hbm_gbs"],
+                            # dram__bytes_read+write of the two launches at the default shape (profiles/r01b_ncu_full_summary.txt)
+                            "traffic": 51321856 if (B, H, W) == (4, 192, 640) else None,
+                            "traffic_source": "ncu --set full, profiles/r01b_ncu_full_summary.txt: every input read once, the "
+                                              "per-scale re-reads the algorithmic figure counts hit L2; the kernel is issue bound "
+                                              "(82 % issue-active)",
                             "fwd_ms": t_f, "bwd_ms": t_b, "algorithmic_bytes": bytes_f + bytes_b, "peak_source": pk["source"]}
     # pack1 convolution (tensor bound): [B,96,320,2048] x [64,2048,5,5]
     h2, w2, cin, cout, k = H // 2, W // 2, 2048, 64, 5
@@ -222,7 +227,11 @@ def time_kernels(args, dev, pk):
     tf32_peak = pk["bf16_tflops"] / (1.0 if PF.is_bf16(prec) else 2.0)
     res["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (pack1 conv2d, %s)" % args.precision,
                        "achieved": flops / (t_c * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                       "frac": flops / (t_c * 1e-3) / 1e12 / tf32_peak, "traffic": None, "ms": t_c,
+                       "frac": flops / (t_c * 1e-3) / 1e12 / tf32_peak,
+                       # dram__bytes_read+write of one launch (profiles/r01b_ncu_full_summary.txt; 1.03 GB algorithmic)
+                       "traffic": 1286109440 if (B, H, W, args.precision) == (4, 192, 640, "bf16x3") else None,
+                       "tensor_pipe_active_pct_ncu": 78.8 if (B, H, W, args.precision) == (4, 192, 640, "bf16x3") else None,
+                       "ms": t_c,
                        "algorithmic_flops": flops,
                        "mma_products_per_flop": 3 if PF.is_split(prec) else 1,
                        "peak_source": pk["source"] + (" cuBLAS bf16" if PF.is_bf16(prec) else
