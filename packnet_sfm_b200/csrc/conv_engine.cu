@@ -48,6 +48,8 @@ struct KernelParams {
   int cchunks;             // ceil(Cin / 32)
   int ksplits;             // split of the channel-chunk loop over blockIdx.z (small maps: fill the 148 SMs)
   int stages;              // pipeline slots
+  int nwork, nblocks;      // work items (pixel tile x N block) walked by the grid, N blocks per pixel tile
+  int nsets, set_cols;     // accumulator sets in TMEM (2: epilogue of tile i overlaps the MMAs of tile i+1) and their column stride
   int group;               // (chunk, tap) items per slot
   int pitch;               // HALO patch: pixels per patch row (8 + k - 1)
   uint32_t patch_tx;       // bytes one patch load delivers (patch_bytes is rounded up to 1024)
@@ -235,7 +237,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t slot_bytes = (uint32_t)P.group * item_bytes;
   const uint32_t slots_base = smem_base + patch_region;
   const uint32_t bars_base = slots_base + P.stages * slot_bytes;
-  // barriers: full[2][stages], empty[stages], full_a[2], empty_a[2], tmem_full, first ; then the TMEM address word.
+  // barriers: full[2][stages], empty[stages], full_a[2], empty_a[2], tmem_full[2], tmem_empty[2], first[2]; TMEM address.
   // A slot has TWO full barriers used on alternate rounds (round = use count of the slot).  Each MMA issuer waits only
   // on its own groups, and with an odd slot count it meets a slot every OTHER round: on a single barrier it would skip a
   // phase, and mbarrier waits are by parity -- the phase two steps back reads as "complete" when copies finish out of
@@ -245,19 +247,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto empty_bar = [&](int s) { return bars_base + 8u * (2 * MAX_STAGES + s); };
   auto fulla_bar = [&](int s) { return bars_base + 8u * (3 * MAX_STAGES + s); };
   auto emptya_bar = [&](int s) { return bars_base + 8u * (3 * MAX_STAGES + 2 + s); };
-  const uint32_t tmemfull_bar = bars_base + 8u * (3 * MAX_STAGES + 4);
-  const uint32_t tmem_slot = bars_base + 8u * (3 * MAX_STAGES + 5);
-  const uint32_t first_bar = bars_base + 8u * (3 * MAX_STAGES + 6);
+  auto tmemfull_bar = [&](int a) { return bars_base + 8u * (3 * MAX_STAGES + 4 + a); };
+  auto tmemempty_bar = [&](int a) { return bars_base + 8u * (3 * MAX_STAGES + 6 + a); };
+  auto first_bar = [&](int a) { return bars_base + 8u * (3 * MAX_STAGES + 8 + a); };
+  const uint32_t tmem_slot = bars_base + 8u * (3 * MAX_STAGES + 10);
   auto patch_addr = [&](int buf, int op) { return smem_base + (uint32_t)(buf * nops + op) * P.patch_bytes; };
   const uint32_t b_off = HALO ? 0u : nops * P.a_stage_bytes;   // weight tiles inside an item
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // tile coordinates
-  const int m = blockIdx.x;
-  const int tx = m % P.tiles_x, ty = (m / P.tiles_x) % P.tiles_y, bg = m / (P.tiles_x * P.tiles_y);
-  const int x0 = tx * TILE_W, y0 = ty * P.th, b0 = bg * P.nb;
-  const int n0 = blockIdx.y * P.bn;
+  // WORK ITEMS are (pixel tile, N block) pairs; a CTA walks work = blockIdx.x, blockIdx.x + gridDim.x, ...  With one
+  // work item per CTA this is the plain tiled kernel (used with the K split of small maps, blockIdx.z); with ~148 CTAs
+  // it is PERSISTENT: barrier setup and the TMEM allocation are paid once, the producer prefetches the next tile while
+  // the epilogue drains the current one, and with two accumulator sets in TMEM (P.nsets) the next tile's MMAs overlap
+  // the epilogue as well.  Short-K layers (64 -> 64, 3x3) spent ~75 % of a tile's life outside the MMA loop.
   const int taps = P.ks * P.ks;
   const int cc_per = (P.cchunks + P.ksplits - 1) / P.ksplits;
   const int cc_begin = blockIdx.z * cc_per, cc_end = min(P.cchunks, cc_begin + cc_per);
@@ -268,18 +271,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int G = P.group;
   const int nitems = HALO ? taps : ncc * taps;
   const int ngroups = (nitems + G - 1) / G;
-  // De-synchronise the CTAs: every CTA walks the same weight tiles, and when all 148 SMs ask the L2 for the SAME lines
-  // at the same moment the few slices that hold them serialise the requests.  Each CTA therefore starts its reduction
-  // at its own rotation of the chunk and group order; the sum is order-independent up to fp32 rounding.
-  const unsigned rot_seed = blockIdx.x * 2654435761u + blockIdx.y * 40503u;
-  const int rot_c = (HALO && has_work) ? (int)((rot_seed >> 8) % (unsigned)ncc) : 0;
-  const int rot_g = has_work ? (int)((rot_seed >> 4) % (unsigned)ngroups) : 0;
+  struct Tile { int x0, y0, b0, n0, rot_c, rot_g; };
+  auto tile_of = [&](int work) {
+    Tile t;
+    const int nblk = work % P.nblocks, m = work / P.nblocks;
+    const int tx = m % P.tiles_x, ty = (m / P.tiles_x) % P.tiles_y, bg = m / (P.tiles_x * P.tiles_y);
+    t.x0 = tx * TILE_W; t.y0 = ty * P.th; t.b0 = bg * P.nb; t.n0 = nblk * P.bn;
+    // De-synchronise the CTAs: every CTA walks the same weight tiles, and when all 148 SMs ask the L2 for the SAME
+    // lines at the same moment the few slices that hold them serialise the requests.  Each tile therefore starts its
+    // reduction at its own rotation of the chunk and group order; the sum is order-independent up to fp32 rounding.
+    const unsigned rot_seed = (unsigned)m * 2654435761u + (unsigned)nblk * 40503u;
+    t.rot_c = (HALO && has_work) ? (int)((rot_seed >> 8) % (unsigned)ncc) : 0;
+    t.rot_g = has_work ? (int)((rot_seed >> 4) % (unsigned)ngroups) : 0;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s, 0), 1); mbar_init(full_bar(s, 1), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 2); }   // both issuers release a patch
-    mbar_init(tmemfull_bar, 2);                                                                // ... and the accumulator
-    mbar_init(first_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(fulla_bar(s), 1);
+      mbar_init(emptya_bar(s), 2);      // both issuers release a patch
+      mbar_init(tmemfull_bar(s), 2);    // ... and hand an accumulator set to the epilogue
+      mbar_init(tmemempty_bar(s), 4);   // the four epilogue warps hand it back
+      mbar_init(first_bar(s), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -297,44 +312,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (has_work) {
       int s = 0, round = 0, pa = 0, pha = 0;
       const int nouter = HALO ? ncc : 1;
-      for (int ci = 0; ci < nouter; ++ci) {
-        int cc = cc_begin + (ci + rot_c) % ncc;
-        if (HALO) {
-          mbar_wait(emptya_bar(pa), pha ^ 1, P.error_flag, 1);
-          if (elect_one()) {
-            mbar_expect_tx(fulla_bar(pa), P.patch_tx * nops);
-            tma_load_4d(patch_addr(pa, 0), &tmA, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
-            if (nops == 2) tma_load_4d(patch_addr(pa, 1), &tmAlo, fulla_bar(pa), cc * P.kc, x0 - P.pad, y0 - P.pad, b0);
-          }
-          pa ^= 1;
-          if (pa == 0) pha ^= 1;
-        }
-        int g = rot_g;
-        for (int gi = 0; gi < ngroups; ++gi) {
-          const int item0 = g * G, nt = min(G, nitems - item0);
-          mbar_wait(empty_bar(s), (round & 1) ^ 1, P.error_flag, 2);
-          const uint32_t fb = full_bar(s, round);
-          if (elect_one()) {
-            mbar_expect_tx(fb, (uint32_t)nt * item_bytes);
-            uint32_t dst = slots_base + (uint32_t)s * slot_bytes;
-            int tap = HALO ? item0 : item0 % taps;
-            if (!HALO) cc = cc_begin + item0 / taps;
-            for (int j = 0; j < nt; ++j) {
-              if (!HALO) {
-                const int dy = tap / P.ks, dx = tap - dy * P.ks;
-                tma_load_4d(dst, &tmA, fb, cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
-                if (nops == 2) tma_load_4d(dst + P.a_stage_bytes, &tmAlo, fb, cc * P.kc, x0 + dx - P.pad, y0 + dy - P.pad, b0);
-              }
-              // the weight tile of (channel chunk, tap, N block) is ONE contiguous, pre-swizzled run of bn*128 bytes
-              const size_t woff = ((size_t)(cc * taps + tap) * P.rows_pad + n0) * 128u;
-              bulk_load_1d(dst + b_off, P.wp + woff, P.b_stage_bytes, fb);
-              if (nops == 2) bulk_load_1d(dst + b_off + P.b_stage_bytes, P.wp_lo + woff, P.b_stage_bytes, fb);
-              dst += item_bytes;
-              if (++tap == taps) { tap = 0; if (!HALO) ++cc; }
+      for (int work = blockIdx.x; work < P.nwork; work += gridDim.x) {
+        const Tile T = tile_of(work);
+        for (int ci = 0; ci < nouter; ++ci) {
+          int cc = cc_begin + (ci + T.rot_c) % ncc;
+          if (HALO) {
+            mbar_wait(emptya_bar(pa), pha ^ 1, P.error_flag, 1);
+            if (elect_one()) {
+              mbar_expect_tx(fulla_bar(pa), P.patch_tx * nops);
+              tma_load_4d(patch_addr(pa, 0), &tmA, fulla_bar(pa), cc * P.kc, T.x0 - P.pad, T.y0 - P.pad, T.b0);
+              if (nops == 2) tma_load_4d(patch_addr(pa, 1), &tmAlo, fulla_bar(pa), cc * P.kc, T.x0 - P.pad, T.y0 - P.pad, T.b0);
             }
+            pa ^= 1;
+            if (pa == 0) pha ^= 1;
           }
-          if (++g == ngroups) g = 0;
-          if (++s == P.stages) { s = 0; ++round; }
+          int g = T.rot_g;
+          for (int gi = 0; gi < ngroups; ++gi) {
+            const int item0 = g * G, nt = min(G, nitems - item0);
+            mbar_wait(empty_bar(s), (round & 1) ^ 1, P.error_flag, 2);
+            const uint32_t fb = full_bar(s, round);
+            if (elect_one()) {
+              mbar_expect_tx(fb, (uint32_t)nt * item_bytes);
+              uint32_t dst = slots_base + (uint32_t)s * slot_bytes;
+              int tap = HALO ? item0 : item0 % taps;
+              if (!HALO) cc = cc_begin + item0 / taps;
+              for (int j = 0; j < nt; ++j) {
+                if (!HALO) {
+                  const int dy = tap / P.ks, dx = tap - dy * P.ks;
+                  tma_load_4d(dst, &tmA, fb, cc * P.kc, T.x0 + dx - P.pad, T.y0 + dy - P.pad, T.b0);
+                  if (nops == 2) tma_load_4d(dst + P.a_stage_bytes, &tmAlo, fb, cc * P.kc, T.x0 + dx - P.pad, T.y0 + dy - P.pad, T.b0);
+                }
+                // the weight tile of (channel chunk, tap, N block) is ONE contiguous, pre-swizzled run of bn*128 bytes
+                const size_t woff = ((size_t)(cc * taps + tap) * P.rows_pad + T.n0) * 128u;
+                bulk_load_1d(dst + b_off, P.wp + woff, P.b_stage_bytes, fb);
+                if (nops == 2) bulk_load_1d(dst + b_off + P.b_stage_bytes, P.wp_lo + woff, P.b_stage_bytes, fb);
+                dst += item_bytes;
+                if (++tap == taps) { tap = 0; if (!HALO) ++cc; }
+              }
+            }
+            if (++g == ngroups) g = 0;
+            if (++s == P.stages) { s = 0; ++round; }
+          }
         }
       }
     }
@@ -344,7 +362,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // and the wait + descriptor arithmetic + commit of a group costs a single warp 200-400 cycles the tensor pipe spends
     // idle; with two warps one prepares its group while the other's MMAs run.  MMAs of both warps accumulate into the
     // same TMEM columns -- measured exact and MMA-bound in tools/ubench_tc3.cu; the only ordering that matters is that
-    // the accumulate=0 MMAs of the very first group enter the pipe first (first_bar).
+    // the accumulate=0 MMAs of a tile's first group enter the pipe first (first_bar).
     // The warp stays converged and one ELECTED lane issues: descriptors and the instruction descriptor sit in uniform
     // registers and an MMA costs one issue slot.  (r01 SASS of the `if (lane == 0)` form: ~25 instructions incl. R2UR
     // round trips and a waterfall loop per UTCHMMA, ~130 clk each.)  Descriptors are (constant high word | start
@@ -354,119 +372,144 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // (columns [2bn, 3bn)); the epilogue adds the three column ranges.
     if (has_work) {
       const int me = (warp == 1) ? 0 : 1;
-      int gcount = 0;   // groups since the start of the tile: issuer `me` owns those with (gcount & 1) == me
+      int gcount = 0;   // groups issued by this CTA so far: issuer `me` owns those with (gcount & 1) == me
       int s = 0, round = 0, pa = 0, pha = 0;
-      uint32_t acc = me ? 1u : 0u;
       const uint32_t sbo_a = HALO ? (uint32_t)P.pitch * 128u : 1024u;
       const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       auto lo_of = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
       auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
-      const uint32_t tm_d2 = tmem_base + 2u * (uint32_t)P.bn;
       const uint32_t item_step = item_bytes >> 4, alo_step = (HALO ? P.patch_bytes : P.a_stage_bytes) >> 4;
       const int nouter = HALO ? ncc : 1;
-      for (int ci = 0; ci < nouter; ++ci) {
-        uint32_t pbase = 0;
-        if (HALO) {
-          mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
-          pbase = lo_of(patch_addr(pa, 0));
-        }
-        int g = rot_g;
-        for (int gi = 0; gi < ngroups; ++gi) {
-          const int item0 = g * G, nt = min(G, nitems - item0);
-          if ((gcount & 1) == me) {
-          mbar_wait(full_bar(s, round), (round >> 1) & 1, P.error_flag, 4);
-          if (gcount == 1) mbar_wait(first_bar, 0, P.error_flag, 9);
+      int iter = 0;
+      for (int work = blockIdx.x; work < P.nwork; work += gridDim.x, ++iter) {
+        const Tile T = tile_of(work);
+        const int aset = iter % P.nsets, use = iter / P.nsets;     // accumulator set of this tile and its use count
+        const uint32_t tm_d = tmem_base + (uint32_t)(aset * P.set_cols);
+        const uint32_t tm_d2 = tm_d + 2u * (uint32_t)P.bn;
+        const bool owner = (gcount & 1) == me;                      // this warp issues the tile's first (accumulate=0) group
+        uint32_t acc = 1u;
+        if (owner) {
+          // the epilogue must have drained this accumulator set (tile iter - nsets) before it is overwritten
+          mbar_wait(tmemempty_bar(aset), (use & 1) ^ 1, P.error_flag, 10);
           tc_fence_after();
-          // descriptor arithmetic stays in converged code (uniform datapath); only the MMAs sit under the election
-          uint32_t it = lo_of(slots_base + (uint32_t)s * slot_bytes);   // item 0 of the slot
-          int dy = 0, dx = 0;
-          if (HALO) { dy = item0 / P.ks; dx = item0 - dy * P.ks; }
-          for (int j = 0; j < nt; ++j) {
-            // HALO: the SWIZZLE_128B XOR is a pure function of the shared-memory ADDRESS bits (measured on B200,
-            // profiles/r01_conv_probe.txt), exactly like the TMA write, so a 128-B-shifted start keeps base_offset 0
-            // and the 8-row groups may sit at any multiple of 128 B (SBO = patch pitch).
-            const uint32_t la = HALO ? pbase + (uint32_t)(dy * P.pitch + dx) * 8u : it;
-            const uint32_t lb = it + (b_off >> 4);
-            if (elect_one()) {
-              if (nops == 2) {
+          acc = 0u;
+        }
+        bool ordered = owner;   // non-owner: wait for the owner's first group before issuing into this set
+        for (int ci = 0; ci < nouter; ++ci) {
+          uint32_t pbase = 0;
+          if (HALO) {
+            mbar_wait(fulla_bar(pa), pha, P.error_flag, 3);
+            pbase = lo_of(patch_addr(pa, 0));
+          }
+          int g = T.rot_g;
+          for (int gi = 0; gi < ngroups; ++gi) {
+            const int item0 = g * G, nt = min(G, nitems - item0);
+            if ((gcount & 1) == me) {
+              mbar_wait(full_bar(s, round), (round >> 1) & 1, P.error_flag, 4);
+              if (!ordered) { mbar_wait(first_bar(aset), use & 1, P.error_flag, 9); ordered = true; }
+              tc_fence_after();
+              // descriptor arithmetic stays in converged code (uniform datapath); only the MMAs sit under the election
+              uint32_t it = lo_of(slots_base + (uint32_t)s * slot_bytes);   // item 0 of the slot
+              int dy = 0, dx = 0;
+              if (HALO) { dy = item0 / P.ks; dx = item0 - dy * P.ks; }
+              for (int j = 0; j < nt; ++j) {
+                // HALO: the SWIZZLE_128B XOR is a pure function of the shared-memory ADDRESS bits (measured on B200,
+                // profiles/r01_conv_probe.txt), exactly like the TMA write, so a 128-B-shifted start keeps base_offset 0
+                // and the 8-row groups may sit at any multiple of 128 B (SBO = patch pitch).
+                const uint32_t la = HALO ? pbase + (uint32_t)(dy * P.pitch + dx) * 8u : it;
+                const uint32_t lb = it + (b_off >> 4);
+                if (elect_one()) {
+                  if (nops == 2) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // one UMMA_K (8 tf32 / 16 bf16) = 32 bytes inside the 128-byte swizzle row
-                  const uint32_t a1 = k ? 1u : acc;
-                  umma_k<BF16>(tm_d2, desc(hi_a, la + alo_step + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, a1);   // A_lo x B_hi
-                  umma_k<BF16>(tmem_base, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, a1);         // A_hi x [B_hi;B_lo]
+                    for (int k = 0; k < 4; ++k) {  // one UMMA_K (8 tf32 / 16 bf16) = 32 bytes inside the 128-byte swizzle row
+                      const uint32_t a1 = k ? 1u : acc;
+                      umma_k<BF16>(tm_d2, desc(hi_a, la + alo_step + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, a1);   // A_lo x B_hi
+                      umma_k<BF16>(tm_d, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, a1);              // A_hi x [B_hi;B_lo]
+                    }
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_k<BF16>(tm_d, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, k ? 1u : acc);
+                  }
                 }
-              } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_k<BF16>(tmem_base, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, k ? 1u : acc);
+                acc = 1u;
+                it += item_step;
+                if (HALO) { if (++dx == P.ks) { dx = 0; ++dy; } }
+              }
+              if (elect_one()) {
+                umma_commit(empty_bar(s));  // frees this slot when the MMAs above have read it
+                if (owner && ci == 0 && gi == 0)
+                  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(first_bar(aset)) : "memory");
               }
             }
-            acc = 1u;
-            it += item_step;
-            if (HALO) { if (++dx == P.ks) { dx = 0; ++dy; } }
+            ++gcount;
+            if (++g == ngroups) g = 0;
+            if (++s == P.stages) { s = 0; ++round; }
           }
-          if (elect_one()) {
-            umma_commit(empty_bar(s));  // frees this slot when the MMAs above have read it
-            if (gcount == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(first_bar) : "memory");
+          if (HALO) {
+            if (elect_one()) umma_commit(emptya_bar(pa));
+            pa ^= 1;
+            if (pa == 0) pha ^= 1;
           }
-          acc = 1u;
-          }
-          ++gcount;
-          if (++g == ngroups) g = 0;
-          if (++s == P.stages) { s = 0; ++round; }
         }
-        if (HALO) {
-          if (elect_one()) umma_commit(emptya_bar(pa));
-          pa ^= 1;
-          if (pa == 0) pha ^= 1;
-        }
+        // a non-owner without any group in this tile still observes the phase of first_bar (no skipped phases)
+        if (!ordered) mbar_wait(first_bar(aset), use & 1, P.error_flag, 11);
+        if (elect_one()) umma_commit(tmemfull_bar(aset));
       }
-      if (elect_one()) umma_commit(tmemfull_bar);
     }
   } else if (warp >= 2 && warp <= 5 && has_work) {
     // ===================================== epilogue ================================================
-    mbar_wait_warp_backoff(tmemfull_bar, 0, P.error_flag, 5);
-    tc_fence_after();
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;     // tile row == TMEM lane
-    const int i = row & 7, g = row >> 3;
-    const int x = x0 + i, y = y0 + (g % P.th), n = b0 + (g / P.th);
-    const bool valid = (x < P.W) && (y < P.H) && (n < P.B);
-    float* orow = P.out + (((size_t)n * P.H + y) * P.W + x) * P.Cout + n0;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < P.bn; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(trow + (uint32_t)c0, v);
-      if (nops == 2) {  // tf32x3: add A_hi*B_lo (columns bn..) and A_lo*B_hi (columns 2bn..)
-        uint32_t u[16], t[16];
-        tmem_ld16(trow + (uint32_t)(P.bn + c0), u);
-        tmem_ld16(trow + (uint32_t)(2 * P.bn + c0), t);
+    const int i = row & 7, gr = row >> 3;
+    int iter = 0;
+    for (int work = blockIdx.x; work < P.nwork; work += gridDim.x, ++iter) {
+      const Tile T = tile_of(work);
+      const int aset = iter % P.nsets, use = iter / P.nsets;
+      mbar_wait_warp_backoff(tmemfull_bar(aset), use & 1, P.error_flag, 5);
+      tc_fence_after();
+      const int x = T.x0 + i, y = T.y0 + (gr % P.th), n = T.b0 + (gr / P.th);
+      const bool valid = (x < P.W) && (y < P.H) && (n < P.B);
+      float* orow = P.out + (((size_t)n * P.H + y) * P.W + x) * P.Cout + T.n0;
+      const uint32_t trow = tmem_base + (uint32_t)(aset * P.set_cols) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < P.bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)c0, v);
+        if (nops == 2) {  // x3: add A_hi*B_lo (columns bn..) and A_lo*B_hi (columns 2bn..)
+          uint32_t u[16], t[16];
+          tmem_ld16(trow + (uint32_t)(P.bn + c0), u);
+          tmem_ld16(trow + (uint32_t)(2 * P.bn + c0), t);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = __float_as_uint((__uint_as_float(u[j]) + __uint_as_float(t[j])) + __uint_as_float(v[j]));
-      }
-      if (valid) {
+          for (int j = 0; j < 16; ++j)
+            v[j] = __float_as_uint((__uint_as_float(u[j]) + __uint_as_float(t[j])) + __uint_as_float(v[j]));
+        }
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const int co = n0 + c0 + j;
-          if (co < P.Cout) {
-            float4 o;
-            o.x = __uint_as_float(v[j + 0]); o.y = __uint_as_float(v[j + 1]);
-            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-            if (P.bias && blockIdx.z == 0) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + co));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (P.ksplits == 1) {
-              *reinterpret_cast<float4*>(orow + c0 + j) = o;
-            } else {  // K-split partial sums meet in the zero-initialised output
-              atomicAdd(orow + c0 + j + 0, o.x); atomicAdd(orow + c0 + j + 1, o.y);
-              atomicAdd(orow + c0 + j + 2, o.z); atomicAdd(orow + c0 + j + 3, o.w);
+          for (int j = 0; j < 16; j += 4) {
+            const int co = T.n0 + c0 + j;
+            if (co < P.Cout) {
+              float4 o;
+              o.x = __uint_as_float(v[j + 0]); o.y = __uint_as_float(v[j + 1]);
+              o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+              if (P.bias && blockIdx.z == 0) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + co));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              }
+              if (P.ksplits == 1) {
+                *reinterpret_cast<float4*>(orow + c0 + j) = o;
+              } else {  // K-split partial sums meet in the zero-initialised output
+                atomicAdd(orow + c0 + j + 0, o.x); atomicAdd(orow + c0 + j + 1, o.y);
+                atomicAdd(orow + c0 + j + 2, o.z); atomicAdd(orow + c0 + j + 3, o.w);
+              }
             }
           }
         }
       }
+      // hand the accumulator set back to the issuers (all tcgen05.ld of this warp have completed: wait::ld in tmem_ld16)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmemempty_bar(aset)) : "memory");
     }
   }
   tc_fence_before();
@@ -875,7 +918,7 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   P.pitch = (d->debug_flags & 64) ? PATCH_PITCH : TILE_W + d->ksize - 1;
   P.patch_tx = (uint32_t)P.pitch * (P.th + d->ksize - 1) * 128u;
   P.patch_bytes = (P.patch_tx + 1023u) & ~1023u;
-  P.tmem_cols = pow2_cols(P.nsplit == 3 ? 3 * bn : bn);
+  P.set_cols = (int)pow2_cols(P.nsplit == 3 ? 3 * bn : bn);
   // instruction descriptor: fp32 accumulate, A/B format 2 = TF32 (kind::tf32) or 1 = BF16 (kind::f16), K-major, M = 128
   const uint32_t fmt = bf16 ? 1u : 2u;
   P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -930,7 +973,14 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
     P.ksplits = ks;
     if (ks > 1) PN_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)d->batch * d->height * d->width * d->cout, stream));
   }
-  dim3 grid(P.tiles_x * P.tiles_y * bgroups, (d->cout + bn - 1) / bn, P.ksplits);
+  // work items and the persistent grid: more than one wave of tiles without a K split -> one CTA per SM walks them,
+  // with two accumulator sets in TMEM when they fit (debug flag 4096 forces one tile per CTA)
+  P.nblocks = (d->cout + bn - 1) / bn;
+  P.nwork = P.tiles_x * P.tiles_y * bgroups * P.nblocks;
+  const bool persistent = (P.ksplits == 1) && (P.nwork > 148) && !(d->debug_flags & 4096);
+  P.nsets = (persistent && 2 * P.set_cols <= 512) ? 2 : 1;
+  P.tmem_cols = pow2_cols(P.nsets * P.set_cols);
+  dim3 grid(persistent ? 148 : P.nwork, 1, P.ksplits);
   auto launch = [&](auto kern) -> int {
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NTHREADS_IGEMM, smem, stream>>>(tmA, tmAlo, P);

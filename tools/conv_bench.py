@@ -45,22 +45,10 @@ def bench(tag, B, H, W, Cin, Cout, k, prec, mode, iters=5, dbg=0):
 
 B3, B1, T3, T1 = PF.PRECISION_BF16X3, PF.PRECISION_BF16X1, PF.PRECISION_TF32X3, PF.PRECISION_TF32X1
 bench("pack1 bf16x3 halo", 4, 96, 320, 2048, 64, 5, B3, 2)
-for gsz in (1, 2, 3):
-    bench("pack1 bf16x3 halo  group %d" % gsz, 4, 96, 320, 2048, 64, 5, B3, 2, dbg=gsz << 8)
-for gsz in (1, 2, 4, 6):
-    bench("pack1 bf16x1 halo  group %d" % gsz, 4, 96, 320, 2048, 64, 5, B1, 2, dbg=gsz << 8)
-for gsz in (1, 2, 3):
-    bench("k3 256->256 24x80 bf16x3 group %d" % gsz, 4, 24, 80, 256, 256, 3, B3, 0, dbg=gsz << 8)
-bench("pack5 16384->512 6x20 bf16x3", 4, 6, 20, 16384, 512, 3, B3, 0)
-bench("512->512 12x40 bf16x3", 4, 12, 40, 512, 512, 3, B3, 0)
-bench("pack1 bf16x3 per-tap", 4, 96, 320, 2048, 64, 5, B3, 1)
-bench("pack1 bf16x1 halo", 4, 96, 320, 2048, 64, 5, B1, 2)
-bench("pack1 tf32x1 halo", 4, 96, 320, 2048, 64, 5, T1, 2)
-bench("pack1-like Cin512 bf16x3 halo", 4, 96, 320, 512, 64, 5, B3, 2)
-bench("pack1-like k3 bf16x3 halo", 4, 96, 320, 2048, 64, 3, B3, 2)
-bench("pack1-like k1 bf16x3", 4, 96, 320, 2048, 64, 1, B3, 1)
-bench("pack1-like Cout128 bf16x3 halo", 4, 96, 320, 2048, 128, 5, B3, 2)
-bench("pack1-like B1 (240 tiles) bf16x3 halo", 1, 96, 320, 2048, 64, 5, B3, 2)
-bench("148 tiles exactly: bf16x3 halo", 1, 16 * 37, 32, 2048, 64, 5, B3, 2)
-bench("conv1-like 64->64 k7 bf16x3", 4, 192, 640, 64, 64, 7, B3, 2)
-bench("res 128->128 k3 48x160 bf16x3", 4, 48, 160, 128, 128, 3, B3, 2)
+for tag, dbg in (("persistent", 0), ("one tile per CTA", 4096)):
+    bench("pack1 bf16x3 halo  %s" % tag, 4, 96, 320, 2048, 64, 5, B3, 2, dbg=dbg)
+    bench("64->64 k3 96x320 bf16x3  %s" % tag, 4, 96, 320, 64, 64, 3, B3, 0, dbg=dbg)
+    bench("64->64 k7 192x640 bf16x3  %s" % tag, 4, 192, 640, 64, 64, 7, B3, 0, dbg=dbg)
+    bench("64->136 k3 192x640 bf16x3  %s" % tag, 4, 192, 640, 64, 136, 3, B3, 0, dbg=dbg)
+    bench("256->256 k3 24x80 bf16x3  %s" % tag, 4, 24, 80, 256, 256, 3, B3, 0, dbg=dbg)
+    bench("64->2048 k5 96x320 bf16x3 (pack1 dgrad)  %s" % tag, 4, 96, 320, 64, 2048, 5, B3, 0, dbg=dbg)
