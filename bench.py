@@ -143,17 +143,27 @@ def cpu_baseline(args, steps):
                       "torch %s CPU fp32" % (args.height, args.width, steps, torch.__version__), "ms_per_step": dt * 1e3}
 
 
+METRIC = "images/sec PackNet01 640x192 self-sup step (fwd+loss+bwd+allreduce+Adam)"
+
+
+def workload_name(H, W, B):
+    return ("PackNet01(1A)+PoseNet+MultiViewPhotometricLoss, synthetic %dx%d 3-frame triplets, batch=%d/GPU, "
+            "4 scales upsampled, Adam lr 2e-4" % (H, W, B))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
     cb = cpu_baseline(args, steps)
-    line = {"impl": "reference", "metric": "images/sec PackNet01 self-sup step (fwd+loss+bwd+Adam)", "value": cb["value"],
+    B, H, W = args.batch, args.height, args.width
+    # same metric / unit / config as the GPU arm; each "step" is a bounded sample of that workload (one image of the batch)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"],
             "unit": "images/sec", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PackNet01+MultiViewPhotometricLoss self-sup step, %dx%d, B=1 sample on CPU"
-                                   % (args.width, args.height)},
+            "config": {"workload": workload_name(H, W, B), "global_batch": B * args.gpus, "parallelism": "dp%d" % args.gpus,
+                       "reference_sample": "B=1 image of the workload per step on the host cores (oracle port of the reference)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -332,12 +342,11 @@ def run_ours(args):
         extra = time_kernels(args, dev, pk) if world == 1 else {}
         log("kernel rooflines done")
         imgs = B * world * args.steps
-        line = {"metric": "images/sec PackNet01 640x192 self-sup step (fwd+loss+bwd+allreduce+Adam)",
+        line = {"metric": METRIC,
                 "value": imgs / (ms * 1e-3), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 (tensor-core GEMMs: %s)" % args.precision, "data": "synthetic",
-                "config": {"workload": "PackNet01(1A)+PoseNet+MultiViewPhotometricLoss, synthetic %dx%d 3-frame triplets, "
-                                       "batch=%d/GPU, 4 scales upsampled, Adam lr 2e-4" % (H, W, B),
+                "config": {"workload": workload_name(H, W, B),
                            "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "no flush between steps: weights (0.5 GB) + activations (GBs) exceed the 126 MB L2",
                            "grad_allreduce_bytes": bucket.nbytes()},
