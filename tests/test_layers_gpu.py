@@ -33,6 +33,8 @@ CONV_CASES = [
     (1, 16, 16, 40, 32, 3),      # ragged K (Cin not a multiple of the 32/64-channel chunk)
     (1, 16, 16, 64, 512, 3),     # several N tiles
     (1, 32, 24, 64, 64, 7),
+    (2, 96, 160, 64, 64, 3),     # 240 work items: persistent tile loop, two accumulator sets in TMEM
+    (2, 64, 96, 32, 256, 3),     # 192 work items over 2 N blocks of 128: persistent, one accumulator set
 ]
 
 
