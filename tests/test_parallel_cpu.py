@@ -61,16 +61,24 @@ def test_flat_bucket_allreduce_equals_full_batch_gradient():
     assert torch.allclose(g0, full, rtol=1e-5, atol=1e-7)
 
 
-def test_flat_bucket_views_survive_zero_grad_and_backward():
+def test_flat_bucket_pack_gathers_fresh_gradients_into_views():
     from packnet_sfm_b200 import parallel
     m = _model()
     b = parallel.FlatBucket(m.parameters())
     for _ in range(2):
         b.zero_grad()
+        assert all(p.grad is None for p in m.parameters())
         m(torch.rand(1, 3, 8, 8)).sum().backward()
+        fresh = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
+        b.pack()
         off = 0
         for p in m.parameters():
             assert p.grad.data_ptr() == b.flat_grad.data_ptr() + 4 * off
             off += p.numel()
+        assert torch.equal(b.flat_grad, fresh)
+    # a parameter that took no part in the backward packs as zeros
+    b.zero_grad()
+    b.pack()
+    assert float(b.flat_grad.abs().sum()) == 0.0
     assert b.nbytes() == 4 * sum(p.numel() for p in m.parameters())
     assert b.allreduce_mean() is None      # no process group: a no-op
