@@ -212,6 +212,30 @@ int pn_head_conv_forward(const float* x, const float* w_tap_major, const float* 
 int pn_head_conv_backward(const float* x, const float* dy, const float* w_tap_major, float* dx, float* dw_tap_major,
                           float* dbias, int batch, int height, int width, int channels, pn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pack-block weight folding (packnet_sfm_b200/folded.py): the Conv3d(1->8, 3x3x3, pad 1) and the Conv2d(8n -> Co, k x k)
+ * of PackLayerConv3d (layers01.py:213-247: conv3d :236-237,:244-246, conv :234,:247) compose into one
+ * Conv2d(n -> Co, (k+2) x (k+2)) of the space-to-depth tensor.  This entry point forms that weight -- and, with a
+ * border window of taps against one face of the Conv3d kernel, the thin weights of the exact frame terms:
+ *   out[co][c''][ea][eb] = sum_{f,dc,dy,dx} W2[co][f][c''-dc+1][ky0+ea-(dy-dy0)][kx0+eb-(dx-dx0)] * W3[f][dc][dy][dx]
+ * over ky in [ky0,ky1), kx in [kx0,kx1), dy in [dy0,dy1), dx in [dx0,dx1); ea < (ky1-ky0)+(dy1-dy0)-1, eb likewise.
+ *   w2  = conv.conv_base.weight [Co, 8n, k, k] read as [Co][8][n][k][k]; w3 = conv3d.weight [8,1,3,3,3]
+ *   out = OIHW [Co][n][EA][EB] with the n channels in the (i, j, c) order of the space-to-depth tensor
+ *         (reference order c'' = 4c + 2i + j  ->  (2i+j)*n/4 + c)
+ * Supported: k = 3 or 5; each window dimension is the whole kernel (with the whole face) or the k/2 border taps
+ * (with a single face).  backward: dw2 window (+)= (overwritten when accumulate == 0), dw3 [8][27] atomically
+ * accumulated (caller zeroes), dS (optional, [Co][8][k][k]) is added to every depth of the dw2 window
+ * (gradient of sum over depth of W2, the Conv3d-bias term).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t cout, n, ksize;
+  int32_t ky0, ky1, kx0, kx1; /* tap window of W2 */
+  int32_t dy0, dy1, dx0, dx1; /* face of W3 */
+} pn_fold_desc;
+int pn_pack_fold_forward(const pn_fold_desc* desc, const float* w2, const float* w3, float* out, pn_stream_t stream);
+int pn_pack_fold_backward(const pn_fold_desc* desc, const float* w2, const float* w3, const float* dout, const float* dS,
+                          float* dw2, float* dw3, int accumulate, pn_stream_t stream);
+
 /* Diagnostics: per-call device timing of the convolution / stencil entry points (CUDA events around each call).
  * pn_trace_dump writes "tag<TAB>milliseconds" lines for the calls traced since the last dump and returns their count. */
 void pn_trace_enable(int on);

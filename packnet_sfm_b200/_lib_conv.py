@@ -16,6 +16,12 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class FoldDesc(ctypes.Structure):
+    _fields_ = [("cout", ctypes.c_int32), ("n", ctypes.c_int32), ("ksize", ctypes.c_int32),
+                ("ky0", ctypes.c_int32), ("ky1", ctypes.c_int32), ("kx0", ctypes.c_int32), ("kx1", ctypes.c_int32),
+                ("dy0", ctypes.c_int32), ("dy1", ctypes.c_int32), ("dx0", ctypes.c_int32), ("dx1", ctypes.c_int32)]
+
+
 def declare(lib):
     c = ctypes
     vp, sz = c.c_void_p, c.c_size_t
@@ -44,4 +50,8 @@ def declare(lib):
     lib.pn_conv2d_wgrad_packed_elems.restype = c.c_int
     for name in ("pn_conv2d_forward", "pn_conv2d_packed_weight_elems", "pn_conv2d_pack_weight", "pn_tf32_residual"):
         getattr(lib, name).restype = c.c_int
+    lib.pn_pack_fold_forward.argtypes = [c.POINTER(FoldDesc), vp, vp, vp, vp]
+    lib.pn_pack_fold_backward.argtypes = [c.POINTER(FoldDesc), vp, vp, vp, vp, vp, vp, i, vp]
+    lib.pn_pack_fold_forward.restype = c.c_int
+    lib.pn_pack_fold_backward.restype = c.c_int
     return lib

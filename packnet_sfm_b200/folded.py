@@ -9,10 +9,10 @@ equals a single Conv2d(n -> Co, (k+2) x (k+2)) of xs whose weight is the FULL co
 
     W_eff[co, c'', ey, ex] = sum_{f, dc, dy, dx}  W2[co, f*n + (c''-dc+1), ey-dy, ex-dx] * W3[f, dc, dy, dx]
 
-(= conv_transpose3d of W2 viewed as [Co, 8, n, k, k] with W3; depth index c'' is clipped to [0, n) exactly as the
+(= conv_transpose3d of W2 viewed as [Co, 8, n, k, k] with W3; the depth index c'' is clipped to [0, n) exactly as the
 Conv3d's zero padding in depth does).  The reduction length drops from 8n*k*k to n*(k+2)^2 -- pack1: 51 200 -> 12 544
 (4.08x fewer MACs), pack2..5: 288C -> 100C (2.88x) -- and the [B, 8n, h, w] intermediate (1.0 GB for pack1 at B=4,
-192x640), its bf16 split and the feature-stencil kernels disappear from the step.
+192x640), its bf16 split and the pack feature-stencil kernels disappear from the step.
 
 What the single convolution gets wrong is the FRAME of width m = k//2: the reference zero-pads T, while the folded
 kernel implicitly continues the Conv3d one pixel outside the map (the ring q at distance 1, where T_full(q) != 0 because
@@ -25,44 +25,20 @@ exactly with thin strips:
         + 4 corner blocks                    (the ring corners are in a row AND a column term: inclusion-exclusion)
         + dB                                 (bias term on the frame: fewer taps of W2 see an in-map T)
 
-All the strip work is O(perimeter) and is expressed here with PyTorch ops (weights folded in fp32 with TF32 off, forward
-and backward); the O(area) convolution runs on the tcgen05 engine (functional.conv2d).  The s2d tensor uses the channel
-order (i, j, c) -- 2C contiguous floats of the NHWC source per half-row -- instead of the reference's (c, i, j); the folded
-weights are permuted accordingly, so no tensor in the reference's channel order is ever materialised.
+The O(area) convolution runs on the tcgen05 engine (functional.conv2d); the nine weight folds (interior, four sides,
+four corners) and their gradients on the fold kernels (csrc/fold_kernels.cu, pn_pack_fold_*); the O(perimeter) strip
+GEMMs are fp32 matmuls (cuBLAS through torch.matmul -- plain library GEMMs on a few hundred pixels; no cuDNN call, so
+PyTorch's default cudnn.allow_tf32=True cannot touch them).  The s2d tensor uses the channel order (i, j, c) -- 2C
+contiguous floats of the NHWC source per half-row -- instead of the reference's (c, i, j); the folded weights are
+permuted accordingly, so no tensor in the reference's channel order is ever materialised.
 
 Status (round 1): algebra verified on the CPU against the reference composition in float64 (tests/test_folded_cpu.py:
-values and all gradients to 1e-12); NOT yet run on the B200 -- PackLayerConv3d uses it only when
-functional.set_pack_fold(True) / PN_PACK_FOLD=1 is given."""
+values and all gradients to 1e-11; the fold kernels' index arithmetic against a line-by-line mirror); NOT yet run on the
+B200 -- PackLayerConv3d uses it only when functional.set_pack_fold(True) / PN_PACK_FOLD=1 is given."""
+import ctypes
+
 import torch
 import torch.nn.functional as F
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# exact-fp32 region: cuDNN may not use TF32 for the weight folds, neither in the forward nor in the backward
-# ---------------------------------------------------------------------------------------------------------------
-class _ExactFP32(torch.autograd.Function):
-    """outs = fn(*args) with TF32 disabled; the backward re-runs fn under the same flags (autograd would otherwise
-    execute the recorded graph outside the context, with PyTorch's default cudnn.allow_tf32=True)."""
-
-    @staticmethod
-    def forward(ctx, fn, *args):
-        ctx.fn = fn
-        ctx.save_for_backward(*args)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            outs = fn(*[a.detach() for a in args])
-        return tuple(outs)
-
-    @staticmethod
-    def backward(ctx, *gouts):
-        need = ctx.needs_input_grad[1:]
-        args = [a.detach().requires_grad_(n) for a, n in zip(ctx.saved_tensors, need)]
-        with torch.enable_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            outs = ctx.fn(*args)
-            pairs = [(o, g) for o, g in zip(outs, gouts) if g is not None and o.requires_grad]
-            wrt = [a for a, n in zip(args, need) if n]
-            grads = torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True) if pairs and wrt else []
-        it = iter(grads)
-        return (None,) + tuple(next(it) if n else None for n in need)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -105,8 +81,24 @@ def space_to_depth_borders(x):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# weight folds
+# the nine weight folds
 # ---------------------------------------------------------------------------------------------------------------
+def fold_windows(k):
+    """(tap window of W2, face of W3) of every fold: name -> ((ky0,ky1),(kx0,kx1),(dy0,dy1),(dx0,dx1)).
+    A ring row above the map is reached by the first m rows of taps and touches the map through the LAST row of the
+    Conv3d kernel (dy = 2); below, by the last m rows through dy = 0; columns alike."""
+    m = k // 2
+    lo, hi, al, f3 = (0, m), (m + 1, k), (0, k), (0, 3)
+    return {"main": (al, al, f3, f3),
+            "top": (lo, al, (2, 3), f3), "bottom": (hi, al, (0, 1), f3),
+            "left": (al, lo, f3, (2, 3)), "right": (al, hi, f3, (0, 1)),
+            "tl": (lo, lo, (2, 3), (2, 3)), "tr": (lo, hi, (2, 3), (0, 1)),
+            "bl": (hi, lo, (0, 1), (2, 3)), "br": (hi, hi, (0, 1), (0, 1))}
+
+
+FOLD_ORDER = ("main", "top", "bottom", "left", "right", "tl", "tr", "bl", "br")
+
+
 def _ct3(w2s, w3s):
     """full convolution of a W2 slab [Co, 8, n, a, b] with a W3 slab [8, 1, 3, c, d] -> [Co, n, a+c-1, b+d-1]
     (depth clipped to [0, n): the Conv3d pads the depth with zeros, those taps never meet data)."""
@@ -119,59 +111,140 @@ def _perm_n(t):
     return t.reshape(co, n // 4, 4, *t.shape[2:]).transpose(1, 2).reshape(co, n, *t.shape[2:])
 
 
+def fold_set_torch(w2, w3):
+    """The nine folds and S = sum over depth of W2 with PyTorch ops (the definition; CPU tests, GPU cross-check)."""
+    co, c8, k, _ = w2.shape
+    w2r = w2.reshape(co, 8, c8 // 8, k, k)
+    out = []
+    for name in FOLD_ORDER:
+        ky, kx, dy, dx = fold_windows(k)[name]
+        out.append(_perm_n(_ct3(w2r[:, :, :, ky[0]:ky[1], kx[0]:kx[1]], w3[:, :, :, dy[0]:dy[1], dx[0]:dx[1]])))
+    return tuple(out) + (w2r.sum(2),)
+
+
+class _FoldSetCUDA(torch.autograd.Function):
+    """fold_set_torch on the fold kernels: nine launches forward; backward = nine launches accumulating into ONE dW2
+    (the interior fold writes every tap, the border folds add into their windows) and one dW3."""
+
+    @staticmethod
+    def forward(ctx, w2, w3):
+        from . import _lib
+        from ._lib_conv import FoldDesc
+        _lib.require_cuda(w2, w3)
+        co, c8, k, _ = w2.shape
+        n = c8 // 8
+        w2c, w3c = w2.detach().contiguous(), w3.detach().contiguous()
+        lib, stream = _lib.lib(), _lib.current_stream()
+        outs = []
+        for name in FOLD_ORDER:
+            ky, kx, dy, dx = fold_windows(k)[name]
+            ea, eb = (ky[1] - ky[0]) + (dy[1] - dy[0]) - 1, (kx[1] - kx[0]) + (dx[1] - dx[0]) - 1
+            o = torch.empty(co, n, ea, eb, dtype=torch.float32, device=w2.device)
+            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1])
+            _lib.check(lib.pn_pack_fold_forward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(o), stream),
+                       "pn_pack_fold_forward(%s)" % name)
+            outs.append(o)
+        S = w2c.view(co, 8, n, k, k).sum(2)
+        ctx.save_for_backward(w2c, w3c)
+        return tuple(outs) + (S,)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from . import _lib
+        from ._lib_conv import FoldDesc
+        w2c, w3c = ctx.saved_tensors
+        co, c8, k, _ = w2c.shape
+        n = c8 // 8
+        lib, stream = _lib.lib(), _lib.current_stream()
+        dw2 = torch.empty_like(w2c)
+        dw3 = torch.zeros(216, dtype=torch.float32, device=w2c.device)
+        gS = grads[-1]
+        first = True
+        for name, g in zip(FOLD_ORDER, grads[:-1]):
+            ky, kx, dy, dx = fold_windows(k)[name]
+            if g is None:
+                if name != "main":
+                    continue
+                ea = k + 2
+                g = torch.zeros(co, n, ea, ea, dtype=torch.float32, device=w2c.device)   # the interior fold owns the overwrite
+            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1])
+            ds = gS.contiguous() if (first and gS is not None) else None
+            _lib.check(lib.pn_pack_fold_backward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(g.contiguous()),
+                                                 _lib.ptr(ds) if ds is not None else None, _lib.ptr(dw2), _lib.ptr(dw3),
+                                                 0 if first else 1, stream), "pn_pack_fold_backward(%s)" % name)
+            first = False
+        return dw2, dw3.view(8, 1, 3, 3, 3)
+
+
+def fold_set(w2, w3):
+    """-> (W_eff, Wtop, Wbottom, Wleft, Wright, Wtl, Wtr, Wbl, Wbr, S); kernels on CUDA tensors, PyTorch ops otherwise
+    (the CPU form exists for the algebra tests only: PackNet01.forward refuses CPU tensors)."""
+    if w2.is_cuda:
+        return _FoldSetCUDA.apply(w2, w3)
+    return fold_set_torch(w2, w3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# frame terms (O(perimeter)): fp32 matmuls on the border rows / columns
+# ---------------------------------------------------------------------------------------------------------------
 def _row_conv(row, wt, m, k):
     """row [B, L, n] (one border row / column of xs, zero beyond both ends), wt [Co, n, m, k+2] ->
     [B, m, L, Co]: out[b, a, l, co] = sum_{n, e} wt[co, n, a, e] * row[b, l + e - (m+1), n]."""
     B, L, n = row.shape
     co = wt.shape[0]
-    wgt = wt.permute(2, 0, 1, 3).reshape(m * co, n, 1, k + 2)
-    o = F.conv2d(row.permute(0, 2, 1).unsqueeze(2), wgt, padding=(0, m + 1))          # [B, m*Co, 1, L]
-    return o.view(B, m, co, L).permute(0, 1, 3, 2)
+    win = F.pad(row, (0, 0, m + 1, m + 1)).unfold(1, k + 2, 1)                          # [B, L, n, k+2]
+    o = win.reshape(B * L, n * (k + 2)) @ wt.permute(1, 3, 2, 0).reshape(n * (k + 2), m * co)
+    return o.view(B, L, m, co).permute(0, 2, 1, 3)
 
 
-def _fold_all(top, bot, left, right, w2, b2, w3, b3):
-    """-> (W_eff [Co, n, k+2, k+2] in (i,j,c) channel order, bias [Co], top / bottom strips [B, m, w, Co],
-    left / right strips [B, h, m, Co]) -- the strips are what must be ADDED to conv(xs, W_eff) + bias."""
-    co, c8, k, _ = w2.shape
-    n = c8 // 8
+_const_cache = {}
+
+
+def _class_consts(k, w, device):
+    """(tap mask [2m+1, k]: which taps of a k-kernel stay inside the map for each border class; column class of
+    every x in [0, w))"""
+    key = (k, w, str(device))
+    if key not in _const_cache:
+        m = k // 2
+        g = 2 * m + 1
+        t = torch.arange(g).view(g, 1)
+        kk = torch.arange(k).view(1, k)
+        mask = ((kk >= m - t) & (kk <= 3 * m - t)).to(torch.float32)
+        cx = torch.cat([torch.arange(m), torch.full((w - 2 * m,), m, dtype=torch.long), torch.arange(m + 1, g)])
+        _const_cache[key] = (mask.to(device), cx.to(device))
+    return _const_cache[key]
+
+
+def frame_strips(top, bot, left, right, folds, b3, k):
+    """-> (beta [Co], top / bottom strips [B, m, w, Co], left / right strips [B, h, m, Co]): what must be ADDED to
+    conv(xs, W_eff) + b2 + beta.  folds = fold_set(w2, w3)."""
+    _, Wt, Wb, Wl, Wr, Wtl, Wtr, Wbl, Wbr, S = folds
+    co = S.shape[0]
     m = k // 2
     B, w, _ = top.shape
     h = left.shape[1]
-    w2r = w2.reshape(co, 8, n, k, k)
-    w_eff = _perm_n(_ct3(w2r, w3))
-    # ---- Conv3d-bias term: conv2d(b3 * 1_map, sum_c' W2) depends on the pixel only through its border class
-    g = 2 * m + 1
-    S = w2r.sum(2)                                                                     # [Co, 8, k, k]
-    bclass = F.conv2d(b3.view(1, 8, 1, 1).expand(1, 8, g, g), S, padding=m)[0]         # [Co, g, g]; [m, m] = interior
-    beta = bclass[:, m, m]
-    dB = (bclass - beta.view(co, 1, 1)).permute(1, 2, 0)                               # [g, g, Co]
-    cx = torch.cat([torch.arange(m), torch.full((w - 2 * m,), m, dtype=torch.long), torch.arange(m + 1, g)]).to(w2.device)
-    lo, hi = slice(0, m), slice(m + 1, k)
-    # ---- ring rows / columns (weights: ky or kx restricted to the taps that reach the ring, W3 to the face that
-    #      still touches the map); every index runs as (m-1-idx) from the border, hence the flips
-    Wt = _perm_n(_ct3(w2r[:, :, :, lo, :], w3[:, :, :, 2:3, :]))                        # [Co, n, m, k+2]
-    Wb = _perm_n(_ct3(w2r[:, :, :, hi, :], w3[:, :, :, 0:1, :]))
-    Wl = _perm_n(_ct3(w2r[:, :, :, :, lo], w3[:, :, :, :, 2:3])).transpose(2, 3)        # [Co, n, m, k+2]
-    Wr = _perm_n(_ct3(w2r[:, :, :, :, hi], w3[:, :, :, :, 0:1])).transpose(2, 3)
+    # ---- Conv3d-bias term conv2d(b3 * 1_map, sum_c' W2): depends on the pixel only through its border class
+    mask, cx = _class_consts(k, w, top.device)
+    mask = mask.to(S.dtype)
+    Sb = torch.einsum("f,ofkl->okl", b3, S)
+    bclass = torch.einsum("tk,okl,ul->tuo", mask, Sb, mask)                            # [g, g, Co]; [m, m] = interior
+    beta = bclass[m, m]
+    dB = bclass - beta
+    # ---- ring rows / columns; every index runs as (m-1-idx) from the border, hence the flips
     top_s = dB[0:m][:, cx].unsqueeze(0) - _row_conv(top, Wt, m, k).flip(1)              # [B, m, w, Co]
     bot_s = dB[m + 1:][:, cx].unsqueeze(0) - _row_conv(bot, Wb, m, k).flip(1)
-    left_s = -_row_conv(left, Wl, m, k).flip(1).permute(0, 2, 1, 3)                     # [B, h, m, Co]
-    right_s = -_row_conv(right, Wr, m, k).flip(1).permute(0, 2, 1, 3)
+    left_s = -_row_conv(left, Wl.transpose(2, 3), m, k).flip(1).permute(0, 2, 1, 3)     # [B, h, m, Co]
+    right_s = -_row_conv(right, Wr.transpose(2, 3), m, k).flip(1).permute(0, 2, 1, 3)
     # bias delta of the side columns on the rows the top / bottom strips do not cover
-    zpad = torch.zeros(m, m, co, dtype=w2.dtype, device=w2.device)
+    zpad = torch.zeros(m, m, co, dtype=S.dtype, device=S.device)
     left_s = left_s + torch.cat([zpad, dB[m, 0:m].unsqueeze(0).expand(h - 2 * m, m, co), zpad]).unsqueeze(0)
     right_s = right_s + torch.cat([zpad, dB[m, m + 1:].unsqueeze(0).expand(h - 2 * m, m, co), zpad]).unsqueeze(0)
     # ---- ring corners: counted by a row term and a column term, give one back
-    def corner(px, ys, xs_, dy, dx):
-        wc = _perm_n(_ct3(w2r[:, :, :, ys, xs_], w3[:, :, :, dy:dy + 1, dx:dx + 1]))    # [Co, n, m, m]
+    def corner(px, wc):
         return torch.einsum("bn,onkl->bklo", px, wc).flip(1, 2)                        # [B, m, m, Co]
-    tl = corner(top[:, 0], lo, lo, 2, 2)
-    tr = corner(top[:, w - 1], lo, hi, 2, 0)
-    bl = corner(bot[:, 0], hi, lo, 0, 2)
-    br = corner(bot[:, w - 1], hi, hi, 0, 0)
-    top_s = top_s + F.pad(tl, (0, 0, 0, w - m)) + F.pad(tr, (0, 0, w - m, 0))
-    bot_s = bot_s + F.pad(bl, (0, 0, 0, w - m)) + F.pad(br, (0, 0, w - m, 0))
-    return w_eff, b2 + beta, top_s, bot_s, left_s, right_s
+    top_s = top_s + F.pad(corner(top[:, 0], Wtl), (0, 0, 0, w - m)) + F.pad(corner(top[:, w - 1], Wtr), (0, 0, w - m, 0))
+    bot_s = bot_s + F.pad(corner(bot[:, 0], Wbl), (0, 0, 0, w - m)) + F.pad(corner(bot[:, w - 1], Wbr), (0, 0, w - m, 0))
+    return beta, top_s, bot_s, left_s, right_s
 
 
 def pack_conv_folded(x, w2, b2, w3, b3, conv):
@@ -183,11 +256,14 @@ def pack_conv_folded(x, w2, b2, w3, b3, conv):
     h, w = H // 2, W // 2
     if c8 != 32 * C or H % 2 or W % 2:
         raise ValueError("pack_conv_folded: weight %s does not match input %s" % (tuple(w2.shape), tuple(x.shape)))
+    if k not in (3, 5):
+        raise ValueError("pack_conv_folded: kernel size %d (the fold kernels cover 3 and 5)" % k)
     if h < 2 * m + 1 or w < 2 * m + 1:
         raise ValueError("pack_conv_folded: packed map %dx%d smaller than the frame of a %dx%d kernel" % (h, w, k, k))
     xs, top, bot, left, right = space_to_depth_borders(x.contiguous())
-    w_eff, bias, top_s, bot_s, left_s, right_s = _ExactFP32.apply(_fold_all, top, bot, left, right, w2, b2, w3, b3)
-    z = conv(xs, w_eff, bias)
+    folds = fold_set(w2, w3)
+    beta, top_s, bot_s, left_s, right_s = frame_strips(top, bot, left, right, folds, b3, k)
+    z = conv(xs, folds[0], b2 + beta)
     z[:, :m] += top_s
     z[:, h - m:] += bot_s
     z[:, :, :m] += left_s

@@ -11,6 +11,7 @@ Precision of the tensor-core GEMMs (include/packnet_b200.h): PRECISION_BF16X3 (d
 split, 16 mantissa bits, meets the 1e-3 depth parity bar at twice the tf32 MMA rate), PRECISION_TF32X3 (22 bits),
 PRECISION_TF32X1 (what cuDNN gives the reference on Ampere+ with PyTorch defaults; fails the parity bar)."""
 import ctypes
+import os
 import weakref
 
 import torch
@@ -18,7 +19,17 @@ import torch
 from . import _lib
 from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3, MODE_AUTO
 
-_state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO}
+_state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": os.environ.get("PN_PACK_FOLD", "0") == "1"}
+
+
+def set_pack_fold(on):
+    """Pack layers as ONE folded convolution of the space-to-depth tensor (packnet_sfm_b200/folded.py) instead of
+    feature stencil + convolution over the 8x-inflated channel count.  Off by default until measured on the B200."""
+    _state["pack_fold"] = bool(on)
+
+
+def pack_fold_enabled():
+    return _state["pack_fold"]
 
 
 def set_precision(p):

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import folded
 from . import functional as PF
 
 
@@ -103,6 +104,12 @@ class PackLayerConv3d(nn.Module):
         self.conv3d = nn.Conv3d(1, d, kernel_size=(3, 3, 3), stride=(1, 1, 1), padding=(1, 1, 1))
 
     def forward(self, x):
+        k = self.conv.kernel_size
+        if PF.pack_fold_enabled() and k in (3, 5) and min(x.shape[1], x.shape[2]) // 2 >= 2 * (k // 2) + 1:
+            # conv3d and conv2d composed into one (k+2)x(k+2) convolution of the space-to-depth tensor + exact frame terms
+            z = folded.pack_conv_folded(x, self.conv.conv_base.weight, self.conv.conv_base.bias, self.conv3d.weight,
+                                        self.conv3d.bias, PF.conv2d)
+            return PF.groupnorm_elu(z, self.conv.normalize.weight, self.conv.normalize.bias, self.conv.normalize.eps)
         feats = PF.pack_features(x, self.conv3d.weight, self.conv3d.bias)
         return self.conv(feats)
 
