@@ -41,6 +41,11 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "tf32x3", "tf32x1"],
                     help="tensor-core GEMM mode; bf16x3 and tf32x3 meet the 1e-3 depth parity bar, tf32x1 does not")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the whole step (fwd+loss+bwd+all-reduce+Adam) in two CUDA graphs (flip / no flip) and replay; "
+                         "experimental until measured on the B200")
+    ap.add_argument("--pack-fold", action="store_true",
+                    help="pack layers as one folded convolution (packnet_sfm_b200/folded.py); experimental until measured")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -274,7 +279,9 @@ def run_ours(args):
     bucket = parallel.FlatBucket(model.parameters())
     groups = [{"name": "Depth", "params": list(model.depth_net.parameters()), "lr": 2e-4},
               {"name": "Pose", "params": list(model.pose_net.parameters()), "lr": 2e-4}]
-    opt = torch.optim.Adam(groups, fused=True)
+    opt = torch.optim.Adam(groups, fused=True, capturable=bool(args.graph))
+    if args.pack_fold:
+        PF.set_pack_fold(True)
     B, H, W = args.batch, args.height, args.width
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)
@@ -308,6 +315,52 @@ def run_ours(args):
         step(dbatch)
         torch.cuda.synchronize()
         log("warm-up step %d: %.1f ms (loss %.5f)" % (i, (time.time() - t_w) * 1e3, float(state["loss"].item())))
+    eager_step = step
+    graph_info = None
+    if args.graph:
+        # Whole-step capture: the only host-side decision of a step is the random left-right flip of the depth
+        # network (SfmModel.py:81-90) -> one graph per outcome, chosen every step by the same random.random() draw.
+        # Gradients are freed before each capture so that the backward allocates them from the graph's pool.
+        flip_prob = model.flip_lr_prob
+        graphs = {}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for fl in (False, True):
+                model.flip_lr_prob = 1.0 if fl else 0.0
+                eager_step(dbatch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        per_graph_launches = 0
+        for fl in (False, True):
+            model.flip_lr_prob = 1.0 if fl else 0.0
+            bucket.zero_grad()
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                out = model(dbatch)
+                out["loss"].backward()
+                bucket.allreduce_mean()
+                opt.step()
+            per_graph_launches = _lib.launch_count() - l0
+            graphs[fl] = (g, out["loss"])
+        model.flip_lr_prob = flip_prob
+        torch.cuda.synchronize()
+        log("captured 2 step graphs (%d library launches each)" % per_graph_launches)
+        graph_info = {"graphs": 2, "library_launches_per_graph": int(per_graph_launches)}
+        replays = [0]
+
+        def step(batch):
+            # `batch` must be the static device batch the graphs were captured on (dbatch); e2e copies into it
+            g, loss_t = graphs[random.random() < flip_prob]
+            g.replay()
+            replays[0] += 1
+            state["loss"] = loss_t
+
+        for _ in range(2):
+            step(dbatch)
+        torch.cuda.synchronize()
+        log("graph replay ok (loss %.5f)" % float(state["loss"].item()))
     # host time to ENQUEUE one step on an idle GPU (no sync inside): step time close to this = launch-bound
     torch.cuda.synchronize()
     t_q = time.perf_counter()
@@ -326,10 +379,20 @@ def run_ours(args):
         torch.cuda.profiler.stop()
     cpu_ms = (time.process_time() - cpu0) * 1e3 / args.steps     # host CPU time (all threads) per step
     launches = _lib.launch_count() - launches0
+    if graph_info is not None:
+        launches = graph_info["library_launches_per_graph"] * args.steps     # replayed kernel nodes of our library
     log("timed region: %.1f ms/step (host CPU %.1f ms/step), %d library launches" % (ms / args.steps, cpu_ms, launches))
 
     def e2e_step():
-        step(to_device(hb, dev))
+        if graph_info is not None:
+            # H2D from pinned memory INTO the static tensors the graphs read
+            dbatch["rgb"].copy_(hb["rgb"], non_blocking=True)
+            for dst, src in zip(dbatch["rgb_context"], hb["rgb_context"]):
+                dst.copy_(src, non_blocking=True)
+            dbatch["intrinsics"].copy_(hb["intrinsics"], non_blocking=True)
+            step(dbatch)
+        else:
+            step(to_device(hb, dev))
         state["loss_host"] = float(state["loss"].item())     # D2H read of the step's result
 
     e2e_step()
@@ -353,7 +416,7 @@ def run_ours(args):
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
-                "loss": state.get("loss_host")}
+                "loss": state.get("loss_host"), "cuda_graph": graph_info, "pack_fold": bool(args.pack_fold)}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)

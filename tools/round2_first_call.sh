@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of round 2: everything written after the round-1 GPU budget ran out, in one gpurun.
+#   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
+# 1) default -m gpu tier (the measured path must still be green)
+# 2) experimental tier: fold kernels, folded pack block, PackNet01 with folded pack layers
+# 3) bench: default / --pack-fold / --graph / both; CUPTI step breakdown with and without the fold
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+O=gpurun_out/r02a
+timeout 1200 python -m pytest tests -m gpu -x -q                                   > ${O}_tests_default.log 2>&1; echo "default tier: $?"
+PN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_folded_gpu.py -m gpu -q  > ${O}_tests_folded.log 2>&1;  echo "folded tier: $?"
+tail -5 ${O}_tests_default.log ${O}_tests_folded.log
+for flags in "" "--pack-fold" "--graph" "--graph --pack-fold"; do
+  tag=$(echo "default $flags" | tr -d ' -' )
+  timeout 600 python bench.py --no-cpu-baseline $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
+  echo "bench [$flags]: $? $(cut -c1-400 ${O}_bench_${tag}.log)"
+done
+timeout 300 python tools/step_profile.py             > ${O}_step_breakdown.txt 2>&1
+timeout 300 python tools/step_profile.py --pack-fold > ${O}_step_breakdown_fold.txt 2>&1
+head -30 ${O}_step_breakdown_fold.txt

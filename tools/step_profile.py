@@ -16,7 +16,9 @@ ap.add_argument("--height", type=int, default=192)
 ap.add_argument("--width", type=int, default=640)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--top", type=int, default=45)
+ap.add_argument("--pack-fold", action="store_true", help="folded pack layers (packnet_sfm_b200/folded.py)")
 a = ap.parse_args()
+PF.set_pack_fold(a.pack_fold)
 
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
