@@ -19,17 +19,23 @@ import torch
 from . import _lib
 from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3, MODE_AUTO
 
-_state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": os.environ.get("PN_PACK_FOLD", "0") == "1"}
+_state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": os.environ.get("PN_PACK_FOLD", "0") == "1",
+          "pack_fold_min_pixels": int(os.environ.get("PN_PACK_FOLD_MIN_PIXELS", "1920"))}
 
 
-def set_pack_fold(on):
+def set_pack_fold(on, min_pixels=None):
     """Pack layers as ONE folded convolution of the space-to-depth tensor (packnet_sfm_b200/folded.py) instead of
-    feature stencil + convolution over the 8x-inflated channel count.  Off by default until measured on the B200."""
+    feature stencil + convolution over the 8x-inflated channel count.  Off by default until measured on the B200.
+    min_pixels: fold only layers whose packed map has at least that many pixels -- on the small maps (pack4: 12x40,
+    pack5: 6x20 at 192x640) the frame is 20-40 % of the map and the layer is bound by streaming its weights, which the
+    fold has to read once more (default 1920 = pack1..pack3 at 192x640)."""
     _state["pack_fold"] = bool(on)
+    if min_pixels is not None:
+        _state["pack_fold_min_pixels"] = int(min_pixels)
 
 
-def pack_fold_enabled():
-    return _state["pack_fold"]
+def pack_fold_enabled(packed_pixels=None):
+    return _state["pack_fold"] and (packed_pixels is None or packed_pixels >= _state["pack_fold_min_pixels"])
 
 
 def set_precision(p):

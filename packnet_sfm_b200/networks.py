@@ -105,7 +105,8 @@ class PackLayerConv3d(nn.Module):
 
     def forward(self, x):
         k = self.conv.kernel_size
-        if PF.pack_fold_enabled() and k in (3, 5) and min(x.shape[1], x.shape[2]) // 2 >= 2 * (k // 2) + 1:
+        h, w = x.shape[1] // 2, x.shape[2] // 2
+        if PF.pack_fold_enabled(h * w) and k in (3, 5) and min(h, w) >= 2 * (k // 2) + 1:
             # conv3d and conv2d composed into one (k+2)x(k+2) convolution of the space-to-depth tensor + exact frame terms
             z = folded.pack_conv_folded(x, self.conv.conv_base.weight, self.conv.conv_base.bias, self.conv3d.weight,
                                         self.conv3d.bias, PF.conv2d)

@@ -88,14 +88,14 @@ def test_folded_pack_block_matches_reference_golden(tag, cin, k, seed):
     mod = N.PackLayerConv3d(cin, k)
     mod.load_state_dict(PO.block_state_dict("pack", cin, k=k, seed=seed), strict=True)
     mod = mod.to(DEV)
-    PF.set_pack_fold(True)
+    PF.set_pack_fold(True, min_pixels=0)
     try:
         x = nhwc(z[tag + "_x"].to(DEV)).requires_grad_(True)
         y = mod(x)
         y.backward(nhwc(z[tag + "_gy"].to(DEV)))
         torch.cuda.synchronize()
     finally:
-        PF.set_pack_fold(False)
+        PF.set_pack_fold(False, min_pixels=1920)
     assert rel_l2(nchw(y).cpu(), z[tag + "_y"]) < 1e-4, rel_l2(nchw(y).cpu(), z[tag + "_y"])
     assert rel_l2(nchw(x.grad).cpu(), z[tag + "_gx"]) < 1e-3
     for name, p in mod.named_parameters():
@@ -111,12 +111,12 @@ def test_packnet01_with_folded_pack_layers_matches_reference_golden():
     net = PackNet01(version="1A")
     net.load_state_dict(PO.packnet01_state_dict(seed=42, randomize_affine=True), strict=True)
     net = net.to(DEV).train()
-    PF.set_pack_fold(True)
+    PF.set_pack_fold(True, min_pixels=0)
     try:
         with torch.no_grad():
             out = net(z["rgb"].to(DEV))["inv_depths"]
     finally:
-        PF.set_pack_fold(False)
+        PF.set_pack_fold(False, min_pixels=1920)
     for i, d in enumerate(out):
         ref = z["disp%d" % (i + 1)]
         rel = ((d.cpu() - ref).abs() / ref.abs()).max().item()
