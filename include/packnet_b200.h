@@ -227,14 +227,51 @@ int pn_head_conv_backward(const float* x, const float* dy, const float* w_tap_ma
  * accumulated (caller zeroes), dS (optional, [Co][8][k][k]) is added to every depth of the dw2 window
  * (gradient of sum over depth of W2, the Conv3d-bias term).
  * ------------------------------------------------------------------------------------------------ */
+enum { PN_FOLD_LAYOUT_OIHW = 0, PN_FOLD_LAYOUT_OHWI = 1 };
 typedef struct {
   int32_t cout, n, ksize;
   int32_t ky0, ky1, kx0, kx1; /* tap window of W2 */
   int32_t dy0, dy1, dx0, dx1; /* face of W3 */
+  int32_t layout;             /* of out / dout: OIHW [Co][n][EA][EB] (for pn_conv2d_pack_weight) or OHWI [Co][EA][EB][n]
+                                 (channels last: the reduction index of the frame GEMMs is contiguous) */
 } pn_fold_desc;
 int pn_pack_fold_forward(const pn_fold_desc* desc, const float* w2, const float* w3, float* out, pn_stream_t stream);
 int pn_pack_fold_backward(const pn_fold_desc* desc, const float* w2, const float* w3, const float* dout, const float* dS,
                           float* dw2, float* dw3, int accumulate, pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame terms of the folded pack block (packnet_sfm_b200/folded.py): the reference zero-pads BETWEEN the Conv3d and
+ * the Conv2d of PackLayerConv3d (layers01.py:28-30,36 inside :247), which the single folded convolution cannot see.
+ * Up to eight thin linear terms repair the frame of width m = k/2 exactly:
+ *   z[b, row(a,l), col(a,l), co] += alpha * sum_{e<KE, nn<n} w[co][a][e][nn] * line[b][l+e-pad][nn]   (+ dB, see below)
+ *   row = r0 + (a / A2) * ra1 + (a % A2) * ra2 + l * rl, col likewise;   a < A, l < L
+ * line: a border row / column of the space-to-depth tensor, [B][L][n] with batch stride line_bstride, zero beyond both
+ * ends; w: folded weight of the term (pn_pack_fold_forward, OHWI), element (co,a,e,nn) at co*w_sco + a*w_sa + e*w_se + nn.
+ * bias_mode 1 adds dB[class(row)][class(col)][co] on every pixel of the term, 2 only on rows in [m, h-m), 0 never;
+ * dB [2m+1][2m+1][Co] is the Conv3d-bias correction per border class (class(p) = p for p < m, m inside,
+ * m+1+(p-(len-m)) for the last m).  All terms run in one launch and accumulate into z with atomics.
+ * backward: dline (atomically accumulated; caller zeroes), dw (overwritten) per term; gdB accumulated (caller zeroes).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* line;
+  const float* w;
+  float* dline;
+  float* dw;
+  int64_t line_bstride, dline_bstride;
+  int64_t w_sco, w_sa, w_se;
+  int32_t L, A, A2, KE, pad;
+  int32_t r0, ra1, ra2, rl;
+  int32_t c0, ca1, ca2, cl;
+  float alpha;
+  int32_t bias_mode;
+} pn_frame_term;
+typedef struct {
+  int32_t batch, height, width; /* of z: the packed map */
+  int32_t cout, n, ksize, num_terms, reserved;
+  pn_frame_term terms[8];
+} pn_frame_desc;
+int pn_pack_frame_forward(const pn_frame_desc* desc, const float* dB, float* z, pn_stream_t stream);
+int pn_pack_frame_backward(const pn_frame_desc* desc, const float* gz, float* gdB, pn_stream_t stream);
 
 /* Diagnostics: per-call device timing of the convolution / stencil entry points (CUDA events around each call).
  * pn_trace_dump writes "tag<TAB>milliseconds" lines for the calls traced since the last dump and returns their count. */

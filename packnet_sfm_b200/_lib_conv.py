@@ -19,7 +19,24 @@ class ConvDesc(ctypes.Structure):
 class FoldDesc(ctypes.Structure):
     _fields_ = [("cout", ctypes.c_int32), ("n", ctypes.c_int32), ("ksize", ctypes.c_int32),
                 ("ky0", ctypes.c_int32), ("ky1", ctypes.c_int32), ("kx0", ctypes.c_int32), ("kx1", ctypes.c_int32),
-                ("dy0", ctypes.c_int32), ("dy1", ctypes.c_int32), ("dx0", ctypes.c_int32), ("dx1", ctypes.c_int32)]
+                ("dy0", ctypes.c_int32), ("dy1", ctypes.c_int32), ("dx0", ctypes.c_int32), ("dx1", ctypes.c_int32),
+                ("layout", ctypes.c_int32)]
+
+
+class FrameTerm(ctypes.Structure):
+    _fields_ = [("line", ctypes.c_void_p), ("w", ctypes.c_void_p), ("dline", ctypes.c_void_p), ("dw", ctypes.c_void_p),
+                ("line_bstride", ctypes.c_int64), ("dline_bstride", ctypes.c_int64),
+                ("w_sco", ctypes.c_int64), ("w_sa", ctypes.c_int64), ("w_se", ctypes.c_int64),
+                ("L", ctypes.c_int32), ("A", ctypes.c_int32), ("A2", ctypes.c_int32), ("KE", ctypes.c_int32), ("pad", ctypes.c_int32),
+                ("r0", ctypes.c_int32), ("ra1", ctypes.c_int32), ("ra2", ctypes.c_int32), ("rl", ctypes.c_int32),
+                ("c0", ctypes.c_int32), ("ca1", ctypes.c_int32), ("ca2", ctypes.c_int32), ("cl", ctypes.c_int32),
+                ("alpha", ctypes.c_float), ("bias_mode", ctypes.c_int32)]
+
+
+class FrameDesc(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("cout", ctypes.c_int32), ("n", ctypes.c_int32), ("ksize", ctypes.c_int32), ("num_terms", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("terms", FrameTerm * 8)]
 
 
 def declare(lib):
@@ -52,6 +69,10 @@ def declare(lib):
         getattr(lib, name).restype = c.c_int
     lib.pn_pack_fold_forward.argtypes = [c.POINTER(FoldDesc), vp, vp, vp, vp]
     lib.pn_pack_fold_backward.argtypes = [c.POINTER(FoldDesc), vp, vp, vp, vp, vp, vp, i, vp]
+    lib.pn_pack_frame_forward.argtypes = [c.POINTER(FrameDesc), vp, vp, vp]
+    lib.pn_pack_frame_backward.argtypes = [c.POINTER(FrameDesc), vp, vp, vp]
+    lib.pn_pack_frame_forward.restype = c.c_int
+    lib.pn_pack_frame_backward.restype = c.c_int
     lib.pn_pack_fold_forward.restype = c.c_int
     lib.pn_pack_fold_backward.restype = c.c_int
     return lib

@@ -31,6 +31,7 @@ struct FoldParams {
   float* dw2;               // backward: [cout][8][n][k][k]; the window is overwritten or accumulated
   float* dw3;               // backward: [8][27], atomically accumulated (the caller zeroes it once per fold set)
   int accumulate;
+  int ohwi;                 // layout of out / dout: 0 = OIHW [cout][n][EA][EB], 1 = OHWI [cout][EA][EB][n] (channels last)
 };
 
 __device__ __forceinline__ int perm_channel(int cpp, int C) { return (cpp & 3) * C + (cpp >> 2); }
@@ -93,9 +94,17 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_fwd_kernel(FoldParams P) {
   const int cbase = c0 >> 2;                                   // first channel c of the block
   int nc = P.C - cbase;
   if (nc > 32) nc = 32;
-  for (int idx = tid; idx < 4 * 32 * E; idx += FOLD_THREADS) {
-    const int qq = idx / (32 * E), r = idx - qq * 32 * E;
-    if (r < nc * E) P.out[((size_t)co * P.n + (size_t)qq * P.C + cbase) * E + r] = stage[idx];
+  if (!P.ohwi) {
+    for (int idx = tid; idx < 4 * 32 * E; idx += FOLD_THREADS) {
+      const int qq = idx / (32 * E), r = idx - qq * 32 * E;
+      if (r < nc * E) P.out[((size_t)co * P.n + (size_t)qq * P.C + cbase) * E + r] = stage[idx];
+    }
+  } else {
+    // channels last: for every patch position the block owns four runs (one per (i,j)) of up to 32 consecutive channels
+    for (int idx = tid; idx < 4 * 32 * E; idx += FOLD_THREADS) {
+      const int c = idx & 31, qq = (idx >> 5) & 3, e = idx >> 7;
+      if (c < nc) P.out[((size_t)co * E + e) * P.n + (size_t)qq * P.C + cbase + c] = stage[(qq * 32 + c) * E + e];
+    }
   }
 }
 
@@ -139,12 +148,14 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_bwd_kernel(FoldParams P) {
     for (int dc = 0; dc < 3; ++dc) {
       const int cpp = cp + dc - 1;
       if (cpp < 0 || cpp >= P.n) continue;
-      const float* d = P.dout + ((size_t)co * P.n + perm_channel(cpp, P.C)) * E;
+      const int pc = perm_channel(cpp, P.C);
+      const float* d = P.ohwi ? P.dout + (size_t)co * E * P.n + pc : P.dout + ((size_t)co * P.n + pc) * E;
+      const size_t es = P.ohwi ? (size_t)P.n : 1;                // stride between patch positions
 #pragma unroll
       for (int ea = 0; ea < EA; ++ea)
 #pragma unroll
         for (int eb = 0; eb < EB; ++eb) {
-          const float dv = __ldg(d + ea * EB + eb);
+          const float dv = __ldg(d + (size_t)(ea * EB + eb) * es);
 #pragma unroll
           for (int dy = 0; dy < DA; ++dy)
 #pragma unroll
@@ -215,6 +226,8 @@ static int dispatch(const pn_fold_desc* d, FoldParams& P, bool backward, cudaStr
              ka, kb, da, db, m);
   P.cout = d->cout; P.n = d->n; P.k = k; P.C = d->n / 4;
   P.ky0 = d->ky0; P.kx0 = d->kx0; P.dy0 = d->dy0; P.dx0 = d->dx0;
+  P.ohwi = d->layout == PN_FOLD_LAYOUT_OHWI ? 1 : 0;
+  PN_REQUIRE(d->layout == PN_FOLD_LAYOUT_OIHW || d->layout == PN_FOLD_LAYOUT_OHWI, PN_ERR_BAD_ARGUMENT, "pn_pack_fold: layout %d", d->layout);
   const bool fa = ka == k, fb = kb == k;
   if (k == 3) {
     if (fa && fb) return launch_fold<3, 3, 3, 3>(P, backward, stream);

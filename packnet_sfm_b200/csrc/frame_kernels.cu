@@ -1,0 +1,333 @@
+// frame_kernels.cu -- the exact frame terms of the folded pack block (packnet_sfm_b200/folded.py), sm_100a.
+//
+// One (k+2)x(k+2) convolution of the space-to-depth tensor reproduces PackLayerConv3d (layers01.py:239-247) except on
+// the frame of width m = k/2, where the reference's zero padding BETWEEN its Conv3d and Conv2d matters.  The repair is
+// a sum of up to eight thin linear terms -- four ring rows / columns and four ring corners -- each of the form
+//
+//     z[b, row(a,l), col(a,l), co] += alpha * sum_{e < KE, nn < n}  w[co][a][e][nn] * line[b][l + e - pad][nn]
+//
+// where `line` is a border row / column of the space-to-depth tensor ([B][L][n], zero beyond both ends), `w` the folded
+// weight of the term (pn_pack_fold_forward, channels-last) and (a, l) -> (row, col) an affine map into the frame; plus
+// the Conv3d-bias correction dB[class(row)][class(col)][co], which depends on a frame pixel only through its border class.
+// These are small fp32 GEMMs (M = B*L <= ~1300 pixels, K = KE*n, N = A*Co) in which every operand is contiguous along
+// one GEMM index; all terms of a layer run in ONE launch (blockIdx.z = term), and the backward is one launch for the
+// border-line gradients, one for the folded-weight gradients and one for the bias-class sums.
+//
+// fp32 FMA on CUDA cores on purpose: the terms are O(perimeter) -- 1.2 GMAC per forward for pack1..3 at B=4, 192x640,
+// against 250 GMAC for the folded convolutions -- and must stay exact fp32 (they carry O(1) of the border pixels).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pn {
+namespace frame {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct Term {
+  const float* line;
+  const float* w;
+  float* dline;
+  float* dw;
+  long long line_bs, dline_bs;      // batch strides (floats)
+  long long w_sco, w_sa, w_se;      // w element (co, a, e, nn) at co*w_sco + a*w_sa + e*w_se + nn
+  int L, A, A2, KE, pad;
+  int r0, ra1, ra2, rl;             // row = r0 + (a / A2) * ra1 + (a % A2) * ra2 + l * rl
+  int c0, ca1, ca2, cl;             // col likewise
+  float alpha;
+  int bias_mode;                    // 0: none, 1: add dB on every pixel of the term, 2: only rows in [m, h - m)
+};
+
+struct Params {
+  int B, h, w, Co, n, m, nterms;
+  Term t[8];
+  const float* dB;                  // [2m+1][2m+1][Co]
+  float* z;                         // forward: [B][h][w][Co], accumulated
+  const float* gz;                  // backward
+  float* gdB;                       // backward: [2m+1][2m+1][Co], atomically accumulated
+};
+
+__device__ __forceinline__ int border_class(int p, int len, int m) { return p < m ? p : (p >= len - m ? p - (len - m) + m + 1 : m); }
+
+__device__ __forceinline__ long long z_offset(const Params& P, const Term& T, int b, int a, int l, int* row, int* col) {
+  const int a1 = a / T.A2, a2 = a - a1 * T.A2;
+  const int r = T.r0 + a1 * T.ra1 + a2 * T.ra2 + l * T.rl;
+  const int c = T.c0 + a1 * T.ca1 + a2 * T.ca2 + l * T.cl;
+  *row = r;
+  *col = c;
+  return (((long long)b * P.h + r) * P.w + c) * P.Co;
+}
+
+// line window element of pixel p = (b, l), reduction index k = (e, nn)
+__device__ __forceinline__ float load_line(const Params& P, const Term& T, int p, int k) {
+  const int b = p / T.L, l = p - b * T.L;
+  const int e = k / P.n, nn = k - e * P.n;
+  const int pos = l + e - T.pad;
+  if (pos < 0 || pos >= T.L) return 0.f;
+  return __ldg(T.line + (long long)b * T.line_bs + (long long)pos * P.n + nn);
+}
+
+// one 64x64 tile of C = A * B with K in steps of 16; la(m, k) / lb(k, n) return 0 outside the problem
+template <bool A_KFAST, bool B_KFAST, class LA, class LB>
+__device__ __forceinline__ void gemm_tile(int K, int m0, int n0, LA la, LB lb, float (&acc)[4][4]) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int t = threadIdx.x;
+  const int ty = t / 16, tx = t % 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / NT; ++i) {
+      const int idx = t + i * NT;
+      const int kk = A_KFAST ? idx % BK : idx / BM;
+      const int mm = A_KFAST ? idx / BK : idx % BM;
+      As[kk][mm] = la(m0 + mm, k0 + kk);
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * BK) / NT; ++i) {
+      const int idx = t + i * NT;
+      const int kk = B_KFAST ? idx % BK : idx / BN;
+      const int nn = B_KFAST ? idx / BK : idx % BN;
+      Bs[kk][nn] = lb(k0 + kk, n0 + nn);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+// forward: M = B*L pixels, N = A*Co columns (a, co), K = KE*n
+__global__ void __launch_bounds__(NT) frame_forward_kernel(const __grid_constant__ Params P) {
+  const Term& T = P.t[blockIdx.z];
+  const int M = P.B * T.L, N = T.A * P.Co, K = T.KE * P.n;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= M || n0 >= N) return;
+  float acc[4][4];
+  gemm_tile<true, true>(
+      K, m0, n0,
+      [&](int p, int k) -> float { return (p < M && k < K) ? load_line(P, T, p, k) : 0.f; },
+      [&](int k, int c) -> float {
+        if (k >= K || c >= N) return 0.f;
+        const int a = c / P.Co, co = c - a * P.Co;
+        const int e = k / P.n, nn = k - e * P.n;
+        return __ldg(T.w + co * T.w_sco + a * T.w_sa + e * T.w_se + nn);
+      },
+      acc);
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  const int g = 2 * P.m + 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = m0 + ty * 4 + i;
+    if (p >= M) continue;
+    const int b = p / T.L, l = p - b * T.L;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= N) continue;
+      const int a = c / P.Co, co = c - a * P.Co;
+      int row, col;
+      const long long off = z_offset(P, T, b, a, l, &row, &col);
+      float v = T.alpha * acc[i][j];
+      if (T.bias_mode == 1 || (T.bias_mode == 2 && row >= P.m && row < P.h - P.m))
+        v += __ldg(P.dB + ((long long)border_class(row, P.h, P.m) * g + border_class(col, P.w, P.m)) * P.Co + co);
+      atomicAdd(P.z + off + co, v);
+    }
+  }
+}
+
+// backward, border lines: dline[b][j][nn] += alpha * sum_{a, e, co} gz[b, row(a,l), col(a,l), co] * w[co][a][e][nn], l = j - e + pad
+// M = B*L pixels j, N = n, K = A*KE*Co with co fastest
+__global__ void __launch_bounds__(NT) frame_backward_line_kernel(const __grid_constant__ Params P) {
+  const Term& T = P.t[blockIdx.z];
+  const int M = P.B * T.L, N = P.n, K = T.A * T.KE * P.Co;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= M || n0 >= N) return;
+  float acc[4][4];
+  gemm_tile<true, false>(
+      K, m0, n0,
+      [&](int p, int k) -> float {
+        if (p >= M || k >= K) return 0.f;
+        const int b = p / T.L, j = p - b * T.L;
+        const int co = k % P.Co, ae = k / P.Co;
+        const int e = ae % T.KE, a = ae / T.KE;
+        const int l = j - e + T.pad;
+        if (l < 0 || l >= T.L) return 0.f;
+        int row, col;
+        return __ldg(P.gz + z_offset(P, T, b, a, l, &row, &col) + co);
+      },
+      [&](int k, int nn) -> float {
+        if (k >= K || nn >= N) return 0.f;
+        const int co = k % P.Co, ae = k / P.Co;
+        const int e = ae % T.KE, a = ae / T.KE;
+        return __ldg(T.w + co * T.w_sco + a * T.w_sa + e * T.w_se + nn);
+      },
+      acc);
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = m0 + ty * 4 + i;
+    if (p >= M) continue;
+    const int b = p / T.L, j = p - b * T.L;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn) {
+      const int nn = n0 + tx * 4 + jn;
+      if (nn < N) atomicAdd(T.dline + (long long)b * T.dline_bs + (long long)j * P.n + nn, T.alpha * acc[i][jn]);
+    }
+  }
+}
+
+// backward, folded weights: dw[co][a][e][nn] = alpha * sum_{b, l} gz[b, row(a,l), col(a,l), co] * line[b][l + e - pad][nn]
+// M = A*Co rows (a, co), N = KE*n columns (e, nn), K = B*L pixels
+__global__ void __launch_bounds__(NT) frame_backward_weight_kernel(const __grid_constant__ Params P) {
+  const Term& T = P.t[blockIdx.z];
+  const int M = T.A * P.Co, N = T.KE * P.n, K = P.B * T.L;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= M || n0 >= N) return;
+  float acc[4][4];
+  gemm_tile<false, false>(
+      K, m0, n0,
+      [&](int r, int p) -> float {
+        if (r >= M || p >= K) return 0.f;
+        const int a = r / P.Co, co = r - a * P.Co;
+        const int b = p / T.L, l = p - b * T.L;
+        int row, col;
+        return __ldg(P.gz + z_offset(P, T, b, a, l, &row, &col) + co);
+      },
+      [&](int p, int c) -> float { return (p < K && c < N) ? load_line(P, T, p, c) : 0.f; },
+      acc);
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= M) continue;
+    const int a = r / P.Co, co = r - a * P.Co;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= N) continue;
+      const int e = c / P.n, nn = c - e * P.n;
+      T.dw[co * T.w_sco + a * T.w_sa + e * T.w_se + nn] = T.alpha * acc[i][j];
+    }
+  }
+}
+
+// backward, bias classes: gdB[class(row)][class(col)][co] += gz[b][row][col][co] over the frame pixels
+__global__ void __launch_bounds__(NT) frame_backward_bias_kernel(const __grid_constant__ Params P) {
+  const int m = P.m, h = P.h, w = P.w;
+  const int F = h * w - (h - 2 * m) * (w - 2 * m);              // frame pixels per sample
+  const long long total = (long long)P.B * F * P.Co;
+  const int g = 2 * m + 1;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    const int co = (int)(i % P.Co);
+    const long long bf = i / P.Co;
+    const int f = (int)(bf % F), b = (int)(bf / F);
+    int row, col;
+    if (f < m * w) { row = f / w; col = f - row * w; }
+    else if (f < 2 * m * w) { const int q = f - m * w; row = h - m + q / w; col = q % w; }
+    else {
+      const int q = f - 2 * m * w;                               // (h - 2m) rows x 2m columns
+      row = m + q / (2 * m);
+      const int cc = q % (2 * m);
+      col = cc < m ? cc : w - 2 * m + cc;
+    }
+    const float v = __ldg(P.gz + (((long long)b * h + row) * w + col) * P.Co + co);
+    atomicAdd(P.gdB + ((long long)border_class(row, h, m) * g + border_class(col, w, m)) * P.Co + co, v);
+  }
+}
+
+static int fill(const pn_frame_desc* d, Params& P) {
+  PN_REQUIRE(d, PN_ERR_BAD_ARGUMENT, "pn_pack_frame: null descriptor");
+  PN_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0 && d->cout > 0 && d->n > 0, PN_ERR_BAD_ARGUMENT, "pn_pack_frame: bad shape");
+  PN_REQUIRE(d->ksize == 3 || d->ksize == 5, PN_ERR_UNSUPPORTED, "pn_pack_frame: ksize %d (3 or 5)", d->ksize);
+  const int m = d->ksize / 2;
+  PN_REQUIRE(d->height >= 2 * m + 1 && d->width >= 2 * m + 1, PN_ERR_UNSUPPORTED, "pn_pack_frame: map %dx%d smaller than the frame",
+             d->height, d->width);
+  PN_REQUIRE(d->num_terms >= 1 && d->num_terms <= 8, PN_ERR_BAD_ARGUMENT, "pn_pack_frame: %d terms (1..8)", d->num_terms);
+  P.B = d->batch; P.h = d->height; P.w = d->width; P.Co = d->cout; P.n = d->n; P.m = m; P.nterms = d->num_terms;
+  for (int i = 0; i < d->num_terms; ++i) {
+    const pn_frame_term& s = d->terms[i];
+    Term& T = P.t[i];
+    PN_REQUIRE(s.line && s.w && s.L > 0 && s.A > 0 && s.A2 > 0 && s.KE > 0, PN_ERR_BAD_ARGUMENT, "pn_pack_frame: term %d incomplete", i);
+    T.line = s.line; T.w = s.w; T.dline = s.dline; T.dw = s.dw;
+    T.line_bs = s.line_bstride; T.dline_bs = s.dline_bstride;
+    T.w_sco = s.w_sco; T.w_sa = s.w_sa; T.w_se = s.w_se;
+    T.L = s.L; T.A = s.A; T.A2 = s.A2; T.KE = s.KE; T.pad = s.pad;
+    T.r0 = s.r0; T.ra1 = s.ra1; T.ra2 = s.ra2; T.rl = s.rl;
+    T.c0 = s.c0; T.ca1 = s.ca1; T.ca2 = s.ca2; T.cl = s.cl;
+    T.alpha = s.alpha; T.bias_mode = s.bias_mode;
+    // the affine map must stay inside the map for every (a, l): check the four extreme combinations
+    for (int ea = 0; ea < 2; ++ea)
+      for (int el = 0; el < 2; ++el) {
+        const int a = ea ? s.A - 1 : 0, l = el ? s.L - 1 : 0;
+        const int a1 = a / s.A2, a2 = a % s.A2;
+        const int r = s.r0 + a1 * s.ra1 + a2 * s.ra2 + l * s.rl, c = s.c0 + a1 * s.ca1 + a2 * s.ca2 + l * s.cl;
+        PN_REQUIRE(r >= 0 && r < d->height && c >= 0 && c < d->width, PN_ERR_BAD_ARGUMENT,
+                   "pn_pack_frame: term %d maps (a=%d, l=%d) to (%d, %d) outside the %dx%d map", i, a, l, r, c, d->height, d->width);
+      }
+  }
+  return 0;
+}
+
+static unsigned cdiv(long long a, int b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace frame
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_pack_frame_forward(const pn_frame_desc* desc, const float* dB, float* z, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  frame::Params P{};
+  if (int rc = frame::fill(desc, P)) return rc;
+  PN_REQUIRE(dB && z, PN_ERR_BAD_ARGUMENT, "pn_pack_frame_forward: null argument");
+  TraceScope ts(stream, "frame_fwd B%d H%d W%d Co%d n%d k%d", P.B, P.h, P.w, P.Co, P.n, desc->ksize);
+  P.dB = dB; P.z = z;
+  long long mmax = 0, nmax = 0;
+  for (int i = 0; i < P.nterms; ++i) {
+    mmax = std::max<long long>(mmax, (long long)P.B * P.t[i].L);
+    nmax = std::max<long long>(nmax, (long long)P.t[i].A * P.Co);
+  }
+  frame::frame_forward_kernel<<<dim3(frame::cdiv(nmax, frame::BN), frame::cdiv(mmax, frame::BM), P.nterms), frame::NT, 0, stream>>>(P);
+  count_launch();
+  return check_launch("frame_forward_kernel");
+}
+
+extern "C" int pn_pack_frame_backward(const pn_frame_desc* desc, const float* gz, float* gdB, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  frame::Params P{};
+  if (int rc = frame::fill(desc, P)) return rc;
+  PN_REQUIRE(gz && gdB, PN_ERR_BAD_ARGUMENT, "pn_pack_frame_backward: null argument");
+  for (int i = 0; i < P.nterms; ++i)
+    PN_REQUIRE(P.t[i].dline && P.t[i].dw, PN_ERR_BAD_ARGUMENT, "pn_pack_frame_backward: term %d has no gradient buffers", i);
+  TraceScope ts(stream, "frame_bwd B%d H%d W%d Co%d n%d k%d", P.B, P.h, P.w, P.Co, P.n, desc->ksize);
+  P.gz = gz; P.gdB = gdB;
+  long long pmax = 0, amax = 0, kmax = 0;
+  for (int i = 0; i < P.nterms; ++i) {
+    pmax = std::max<long long>(pmax, (long long)P.B * P.t[i].L);
+    amax = std::max<long long>(amax, (long long)P.t[i].A * P.Co);
+    kmax = std::max<long long>(kmax, (long long)P.t[i].KE * P.n);
+  }
+  frame::frame_backward_line_kernel<<<dim3(frame::cdiv(P.n, frame::BN), frame::cdiv(pmax, frame::BM), P.nterms), frame::NT, 0, stream>>>(P);
+  frame::frame_backward_weight_kernel<<<dim3(frame::cdiv(kmax, frame::BN), frame::cdiv(amax, frame::BM), P.nterms), frame::NT, 0, stream>>>(P);
+  const int m = P.m;
+  const long long total = (long long)P.B * ((long long)P.h * P.w - (long long)(P.h - 2 * m) * (P.w - 2 * m)) * P.Co;
+  unsigned blocks = frame::cdiv(total, frame::NT);
+  if (blocks > 148u * 8u) blocks = 148u * 8u;
+  frame::frame_backward_bias_kernel<<<blocks, frame::NT, 0, stream>>>(P);
+  count_launch(3);
+  return check_launch("frame_backward kernels");
+}

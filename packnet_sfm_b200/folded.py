@@ -124,7 +124,9 @@ def fold_set_torch(w2, w3):
 
 class _FoldSetCUDA(torch.autograd.Function):
     """fold_set_torch on the fold kernels: nine launches forward; backward = nine launches accumulating into ONE dW2
-    (the interior fold writes every tap, the border folds add into their windows) and one dW3."""
+    (the interior fold writes every tap, the border folds add into their windows) and one dW3.  The interior weight
+    is OIHW (what pn_conv2d_pack_weight takes), the eight frame weights channels-last [Co, EA, EB, n] (the reduction
+    index of the frame GEMMs contiguous)."""
 
     @staticmethod
     def forward(ctx, w2, w3):
@@ -139,8 +141,9 @@ class _FoldSetCUDA(torch.autograd.Function):
         for name in FOLD_ORDER:
             ky, kx, dy, dx = fold_windows(k)[name]
             ea, eb = (ky[1] - ky[0]) + (dy[1] - dy[0]) - 1, (kx[1] - kx[0]) + (dx[1] - dx[0]) - 1
-            o = torch.empty(co, n, ea, eb, dtype=torch.float32, device=w2.device)
-            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1])
+            ohwi = name != "main"
+            o = torch.empty((co, ea, eb, n) if ohwi else (co, n, ea, eb), dtype=torch.float32, device=w2.device)
+            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1], int(ohwi))
             _lib.check(lib.pn_pack_fold_forward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(o), stream),
                        "pn_pack_fold_forward(%s)" % name)
             outs.append(o)
@@ -167,7 +170,7 @@ class _FoldSetCUDA(torch.autograd.Function):
                     continue
                 ea = k + 2
                 g = torch.zeros(co, n, ea, ea, dtype=torch.float32, device=w2c.device)   # the interior fold owns the overwrite
-            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1])
+            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1], int(name != "main"))
             ds = gS.contiguous() if (first and gS is not None) else None
             _lib.check(lib.pn_pack_fold_backward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(g.contiguous()),
                                                  _lib.ptr(ds) if ds is not None else None, _lib.ptr(dw2), _lib.ptr(dw3),
@@ -177,8 +180,9 @@ class _FoldSetCUDA(torch.autograd.Function):
 
 
 def fold_set(w2, w3):
-    """-> (W_eff, Wtop, Wbottom, Wleft, Wright, Wtl, Wtr, Wbl, Wbr, S); kernels on CUDA tensors, PyTorch ops otherwise
-    (the CPU form exists for the algebra tests only: PackNet01.forward refuses CPU tensors)."""
+    """-> (W_eff, Wtop, Wbottom, Wleft, Wright, Wtl, Wtr, Wbl, Wbr, S); kernels on CUDA tensors (frame weights
+    channels-last), PyTorch ops otherwise (all OIHW; the CPU form exists for the algebra tests only: PackNet01.forward
+    refuses CPU tensors)."""
     if w2.is_cuda:
         return _FoldSetCUDA.apply(w2, w3)
     return fold_set_torch(w2, w3)
@@ -215,21 +219,29 @@ def _class_consts(k, w, device):
     return _const_cache[key]
 
 
+def bias_classes(S, b3, k, w, device):
+    """Conv3d-bias term conv2d(b3 * 1_map, sum_c' W2): depends on a pixel only through its border class.
+    -> (beta [Co]: the interior value, dB [2m+1, 2m+1, Co]: class value minus beta)."""
+    m = k // 2
+    mask, _ = _class_consts(k, w, device)
+    mask = mask.to(S.dtype)
+    Sb = torch.einsum("f,ofkl->okl", b3, S)
+    bclass = torch.einsum("tk,okl,ul->tuo", mask, Sb, mask)                            # [g, g, Co]; [m, m] = interior
+    beta = bclass[m, m]
+    return beta, bclass - beta
+
+
 def frame_strips(top, bot, left, right, folds, b3, k):
-    """-> (beta [Co], top / bottom strips [B, m, w, Co], left / right strips [B, h, m, Co]): what must be ADDED to
-    conv(xs, W_eff) + b2 + beta.  folds = fold_set(w2, w3)."""
+    """The frame terms with PyTorch ops (the definition; CPU tests and GPU cross-check of pn_pack_frame_*).
+    -> (beta [Co], top / bottom strips [B, m, w, Co], left / right strips [B, h, m, Co]): what must be ADDED to
+    conv(xs, W_eff) + b2 + beta.  folds = fold_set_torch(w2, w3) (all OIHW)."""
     _, Wt, Wb, Wl, Wr, Wtl, Wtr, Wbl, Wbr, S = folds
     co = S.shape[0]
     m = k // 2
     B, w, _ = top.shape
     h = left.shape[1]
-    # ---- Conv3d-bias term conv2d(b3 * 1_map, sum_c' W2): depends on the pixel only through its border class
-    mask, cx = _class_consts(k, w, top.device)
-    mask = mask.to(S.dtype)
-    Sb = torch.einsum("f,ofkl->okl", b3, S)
-    bclass = torch.einsum("tk,okl,ul->tuo", mask, Sb, mask)                            # [g, g, Co]; [m, m] = interior
-    beta = bclass[m, m]
-    dB = bclass - beta
+    beta, dB = bias_classes(S, b3, k, w, top.device)
+    _, cx = _class_consts(k, w, top.device)
     # ---- ring rows / columns; every index runs as (m-1-idx) from the border, hence the flips
     top_s = dB[0:m][:, cx].unsqueeze(0) - _row_conv(top, Wt, m, k).flip(1)              # [B, m, w, Co]
     bot_s = dB[m + 1:][:, cx].unsqueeze(0) - _row_conv(bot, Wb, m, k).flip(1)
@@ -247,6 +259,95 @@ def frame_strips(top, bot, left, right, folds, b3, k):
     return beta, top_s, bot_s, left_s, right_s
 
 
+def frame_term_specs(h, w, n, k):
+    """The eight frame terms in the vocabulary of pn_pack_frame_* (include/packnet_b200.h): which border line and folded
+    weight a term reads, the strides of the channels-last weight, and the affine map (a, l) -> (row, col) into z.
+    Every index counts from the border inwards as (m-1-idx) -- the flips of frame_strips()."""
+    m = k // 2
+    side = dict(A=m, A2=1, KE=k + 2, pad=m + 1, alpha=-1.0, px=0)
+    rowt = dict(side, L=w, w_sco=m * (k + 2) * n, w_sa=(k + 2) * n, w_se=n, bias_mode=1)      # weight [Co][m][k+2][n]
+    colt = dict(side, L=h, w_sco=(k + 2) * m * n, w_sa=n, w_se=m * n, bias_mode=2)            # weight [Co][k+2][m][n]
+    corn = dict(A=m * m, A2=m, KE=1, pad=0, L=1, alpha=1.0, w_sco=m * m * n, w_sa=n, w_se=0, bias_mode=0)
+    z4 = dict(ra1=0, ra2=0, rl=0, ca1=0, ca2=0, cl=0)
+    return [
+        dict({**z4, **rowt}, name="top", line="top", r0=m - 1, ra1=-1, c0=0, cl=1),
+        dict({**z4, **rowt}, name="bottom", line="bottom", r0=h - 1, ra1=-1, c0=0, cl=1),
+        dict({**z4, **colt}, name="left", line="left", r0=0, rl=1, c0=m - 1, ca1=-1),
+        dict({**z4, **colt}, name="right", line="right", r0=0, rl=1, c0=w - 1, ca1=-1),
+        dict({**z4, **corn}, name="tl", line="top", px=0, r0=m - 1, ra1=-1, c0=m - 1, ca2=-1),
+        dict({**z4, **corn}, name="tr", line="top", px=w - 1, r0=m - 1, ra1=-1, c0=w - 1, ca2=-1),
+        dict({**z4, **corn}, name="bl", line="bottom", px=0, r0=h - 1, ra1=-1, c0=m - 1, ca2=-1),
+        dict({**z4, **corn}, name="br", line="bottom", px=w - 1, r0=h - 1, ra1=-1, c0=w - 1, ca2=-1),
+    ]
+
+
+class _FrameApplyCUDA(torch.autograd.Function):
+    """z += frame terms, in place (one launch); backward: border-line, folded-weight and bias-class gradients
+    (three launches).  weights = the eight channels-last frame folds in FOLD_ORDER[1:]."""
+
+    @staticmethod
+    def _desc(z_shape, n, k, lines, weights, dlines=None, dws=None):
+        from . import _lib
+        from ._lib_conv import FrameDesc
+        B, h, w, co = z_shape
+        d = FrameDesc()
+        d.batch, d.height, d.width, d.cout, d.n, d.ksize = B, h, w, co, n, k
+        specs = frame_term_specs(h, w, n, k)
+        d.num_terms = len(specs)
+        for i, sp in enumerate(specs):
+            t = d.terms[i]
+            line = lines[sp["line"]]
+            off = sp["px"] * n * 4
+            t.line = line.data_ptr() + off
+            t.line_bstride = line.shape[1] * n
+            t.w = weights[sp["name"]].data_ptr()
+            if dlines is not None:
+                t.dline = dlines[sp["line"]].data_ptr() + off
+                t.dline_bstride = line.shape[1] * n
+                t.dw = dws[sp["name"]].data_ptr()
+            for key in ("w_sco", "w_sa", "w_se", "L", "A", "A2", "KE", "pad", "r0", "ra1", "ra2", "rl", "c0", "ca1", "ca2", "cl",
+                        "alpha", "bias_mode"):
+                setattr(t, key, sp[key])
+        return d
+
+    @staticmethod
+    def forward(ctx, z, top, bot, left, right, Wt, Wb, Wl, Wr, Wtl, Wtr, Wbl, Wbr, dB, k):
+        from . import _lib
+        _lib.require_cuda(z, top, dB)
+        n = top.shape[2]
+        lines = {"top": top.contiguous(), "bottom": bot.contiguous(), "left": left.contiguous(), "right": right.contiguous()}
+        weights = dict(zip(FOLD_ORDER[1:], (t.contiguous() for t in (Wt, Wb, Wl, Wr, Wtl, Wtr, Wbl, Wbr))))
+        dBc = dB.detach().contiguous()
+        d = _FrameApplyCUDA._desc(tuple(z.shape), n, k, lines, weights)
+        _lib.check(_lib.lib().pn_pack_frame_forward(ctypes.byref(d), _lib.ptr(dBc), _lib.ptr(z), _lib.current_stream()),
+                   "pn_pack_frame_forward")
+        ctx.mark_dirty(z)
+        ctx.save_for_backward(*lines.values(), *weights.values())
+        ctx.k, ctx.n, ctx.dB_shape = k, n, tuple(dB.shape)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        from . import _lib
+        saved = ctx.saved_tensors
+        lines = dict(zip(("top", "bottom", "left", "right"), saved[:4]))
+        weights = dict(zip(FOLD_ORDER[1:], saved[4:]))
+        gz = gz.contiguous()
+        B, h, w, co = gz.shape
+        n, k = ctx.n, ctx.k
+        flat = torch.zeros(B * (2 * w + 2 * h) * n, dtype=torch.float32, device=gz.device)     # one memset for the four lines
+        o1, o2, o3 = B * w * n, 2 * B * w * n, 2 * B * w * n + B * h * n
+        dlines = {"top": flat[:o1].view(B, w, n), "bottom": flat[o1:o2].view(B, w, n),
+                  "left": flat[o2:o3].view(B, h, n), "right": flat[o3:].view(B, h, n)}
+        dws = {name: torch.empty_like(t) for name, t in weights.items()}
+        gdB = torch.zeros(ctx.dB_shape, dtype=torch.float32, device=gz.device)
+        d = _FrameApplyCUDA._desc((B, h, w, co), n, k, lines, weights, dlines, dws)
+        _lib.check(_lib.lib().pn_pack_frame_backward(ctypes.byref(d), _lib.ptr(gz), _lib.ptr(gdB), _lib.current_stream()),
+                   "pn_pack_frame_backward")
+        return (gz, dlines["top"], dlines["bottom"], dlines["left"], dlines["right"]) + tuple(dws[nm] for nm in FOLD_ORDER[1:]) \
+            + (gdB, None)
+
+
 def pack_conv_folded(x, w2, b2, w3, b3, conv):
     """z = Conv2d(W2, b2)(pad(Conv3d(W3, b3)(packing(x)))) on NHWC maps: x [B,2h,2w,C] -> z [B,h,w,Co].
     `conv(xs, weight, bias)` is the O(area) convolution (functional.conv2d on the GPU)."""
@@ -262,6 +363,10 @@ def pack_conv_folded(x, w2, b2, w3, b3, conv):
         raise ValueError("pack_conv_folded: packed map %dx%d smaller than the frame of a %dx%d kernel" % (h, w, k, k))
     xs, top, bot, left, right = space_to_depth_borders(x.contiguous())
     folds = fold_set(w2, w3)
+    if x.is_cuda:
+        beta, dB = bias_classes(folds[9], b3, k, w, x.device)
+        z = conv(xs, folds[0], b2 + beta)
+        return _FrameApplyCUDA.apply(z, top, bot, left, right, *folds[1:9], dB, k)
     beta, top_s, bot_s, left_s, right_s = frame_strips(top, bot, left, right, folds, b3, k)
     z = conv(xs, folds[0], b2 + beta)
     z[:, :m] += top_s

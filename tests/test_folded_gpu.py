@@ -41,8 +41,10 @@ def test_fold_kernels_match_the_pytorch_definition(case):
     torch.cuda.synchronize()
     w2d, w3d = (t.detach().double().requires_grad_(True) for t in (w2, w3))
     refs = folded.fold_set_torch(w2d, w3d)
-    torch.autograd.backward(refs, [g.double() for g in gs])
+    torch.autograd.backward(refs, [g.double() if i in (0, 9) else g.double().permute(0, 3, 1, 2) for i, g in enumerate(gs)])
     for name, a, b in zip(folded.FOLD_ORDER + ("S",), outs, refs):
+        if name not in ("main", "S"):
+            b = b.permute(0, 2, 3, 1)            # the kernels emit the frame weights channels-last
         assert a.shape == b.shape, name
         assert rel_l2(a, b) < 1e-6, (name, rel_l2(a, b))
     assert rel_l2(w2.grad, w2d.grad) < 1e-6, rel_l2(w2.grad, w2d.grad)
@@ -76,6 +78,37 @@ def test_folded_pack_conv_on_the_engine(case):
     assert rel_l2(w2.grad.cpu(), w2d.grad) < 1e-3, rel_l2(w2.grad.cpu(), w2d.grad)
     assert rel_l2(w3.grad.cpu(), w3d.grad) < 1e-3, rel_l2(w3.grad.cpu(), w3d.grad)
     assert rel_l2(b2.grad.cpu(), b2d.grad) < 1e-5 and rel_l2(b3.grad.cpu(), b3d.grad) < 1e-3
+
+
+@pytest.mark.parametrize("case", [(2, 8, 12, 16, 8, 3), (1, 8, 14, 20, 16, 5), (3, 40, 8, 20, 24, 3)])
+def test_fold_and_frame_kernels_with_a_pytorch_convolution(case):
+    """pn_pack_fold_* and pn_pack_frame_* alone: the O(area) convolution is PyTorch's (fp32, TF32 off), so a failure here
+    is in the fold / frame kernels and one only in test_folded_pack_conv_on_the_engine is in the engine's new shapes."""
+    from packnet_sfm_b200 import folded
+    B, C, H, W, Co, k = case
+    torch.manual_seed(B + C + H + k)
+
+    def conv(xs, w, b):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return F.conv2d(xs.permute(0, 3, 1, 2), w, b, padding=w.shape[-1] // 2).permute(0, 2, 3, 1).contiguous()
+
+    x = (torch.rand(B, H, W, C, device=DEV) - 0.5).requires_grad_(True)
+    w2 = ((torch.rand(Co, 32 * C, k, k, device=DEV) - 0.5) * (2.0 / (32 * C * k * k) ** 0.5)).requires_grad_(True)
+    b2 = (torch.rand(Co, device=DEV) - 0.5).requires_grad_(True)
+    w3 = (torch.rand(8, 1, 3, 3, 3, device=DEV) - 0.5).requires_grad_(True)
+    b3 = (torch.rand(8, device=DEV) - 0.5).requires_grad_(True)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        z = folded.pack_conv_folded(x, w2, b2, w3, b3, conv)
+        gz = torch.rand_like(z) - 0.5
+        z.backward(gz)
+    torch.cuda.synchronize()
+    xd, w2d, b2d, w3d, b3d = (t.detach().double().cpu().requires_grad_(True) for t in (x, w2, b2, w3, b3))
+    t = PO.conv3d_features(PO.packing(xd.permute(0, 3, 1, 2)), w3d, b3d)
+    zr = F.conv2d(F.pad(t, [k // 2] * 4), w2d, b2d).permute(0, 2, 3, 1)
+    zr.backward(gz.double().cpu())
+    for name, a, b in (("z", z, zr), ("gx", x.grad, xd.grad), ("gw2", w2.grad, w2d.grad), ("gb2", b2.grad, b2d.grad),
+                       ("gw3", w3.grad, w3d.grad), ("gb3", b3.grad, b3d.grad)):
+        assert rel_l2(a.detach().cpu(), b.detach()) < 2e-5, (name, rel_l2(a.detach().cpu(), b.detach()))
 
 
 BLOCKS = [("pack_k3", 32, 3, 21), ("pack_k5", 16, 5, 22)]
