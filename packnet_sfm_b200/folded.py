@@ -26,15 +26,19 @@ exactly with thin strips:
         + dB                                 (bias term on the frame: fewer taps of W2 see an in-map T)
 
 The O(area) convolution runs on the tcgen05 engine (functional.conv2d); the nine weight folds (interior, four sides,
-four corners) and their gradients on the fold kernels (csrc/fold_kernels.cu, pn_pack_fold_*); the O(perimeter) strip
-GEMMs are fp32 matmuls (cuBLAS through torch.matmul -- plain library GEMMs on a few hundred pixels; no cuDNN call, so
-PyTorch's default cudnn.allow_tf32=True cannot touch them).  The s2d tensor uses the channel order (i, j, c) -- 2C
-contiguous floats of the NHWC source per half-row -- instead of the reference's (c, i, j); the folded weights are
-permuted accordingly, so no tensor in the reference's channel order is ever materialised.
+four corners) and their gradients on the fold kernels (csrc/fold_kernels.cu, pn_pack_fold_*); the O(perimeter) frame
+terms -- eight small fp32 GEMMs plus the bias classes -- in one launch forward and three backward
+(csrc/frame_kernels.cu, pn_pack_frame_*; exact fp32 FMA, no library call, so neither cuDNN's nor cuBLAS's TF32 switches
+can touch the border pixels).  The s2d tensor uses the channel order (i, j, c) -- 2C contiguous floats of the NHWC source
+per half-row -- instead of the reference's (c, i, j); the folded weights are permuted accordingly, so no tensor in the
+reference's channel order is ever materialised.  frame_strips() / fold_set_torch() state the same terms with PyTorch ops:
+they are the definition the kernels are tested against and what the CPU algebra tests run.
 
 Status (round 1): algebra verified on the CPU against the reference composition in float64 (tests/test_folded_cpu.py:
-values and all gradients to 1e-11; the fold kernels' index arithmetic against a line-by-line mirror); NOT yet run on the
-B200 -- PackLayerConv3d uses it only when functional.set_pack_fold(True) / PN_PACK_FOLD=1 is given."""
+values and all gradients to 1e-11); the kernels' index arithmetic verified against line-by-line Python mirrors
+(tests/test_fold_mirror_cpu.py, tests/test_frame_mirror_cpu.py); NOT yet run on the B200 (the round's GPU budget was
+spent) -- PackLayerConv3d uses it only when functional.set_pack_fold(True) / PN_PACK_FOLD=1 is given, and its GPU tests
+(tests/test_folded_gpu.py) only run with PN_EXPERIMENTAL=1."""
 import ctypes
 
 import torch
@@ -64,15 +68,15 @@ class _SpaceToDepthBorders(torch.autograd.Function):
         if g_xs is None:
             gx6 = torch.zeros(B, h, 2, w, 2, C, dtype=g_top.dtype, device=g_top.device)
         else:
-            gx6 = g_xs.view(B, h, w, 2, 2, C).permute(0, 1, 3, 2, 4, 5).contiguous()     # [B,h,i,w,j,C], fresh tensor
+            gx6 = g_xs.reshape(B, h, w, 2, 2, C).permute(0, 1, 3, 2, 4, 5).contiguous()     # [B,h,i,w,j,C], fresh tensor
         if g_top is not None:
-            gx6[:, 0] += g_top.view(B, w, 2, 2, C).permute(0, 2, 1, 3, 4)
+            gx6[:, 0] += g_top.reshape(B, w, 2, 2, C).permute(0, 2, 1, 3, 4)
         if g_bot is not None:
-            gx6[:, h - 1] += g_bot.view(B, w, 2, 2, C).permute(0, 2, 1, 3, 4)
+            gx6[:, h - 1] += g_bot.reshape(B, w, 2, 2, C).permute(0, 2, 1, 3, 4)
         if g_left is not None:
-            gx6[:, :, :, 0] += g_left.view(B, h, 2, 2, C)
+            gx6[:, :, :, 0] += g_left.reshape(B, h, 2, 2, C)
         if g_right is not None:
-            gx6[:, :, :, w - 1] += g_right.view(B, h, 2, 2, C)
+            gx6[:, :, :, w - 1] += g_right.reshape(B, h, 2, 2, C)
         return gx6.view(B, 2 * h, 2 * w, C)
 
 
@@ -171,19 +175,25 @@ class _FoldSetCUDA(torch.autograd.Function):
                 ea = k + 2
                 g = torch.zeros(co, n, ea, ea, dtype=torch.float32, device=w2c.device)   # the interior fold owns the overwrite
             d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1], int(name != "main"))
+            gc = g.contiguous()                   # named: a temporary would be freed before the call reads it
             ds = gS.contiguous() if (first and gS is not None) else None
-            _lib.check(lib.pn_pack_fold_backward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(g.contiguous()),
+            _lib.check(lib.pn_pack_fold_backward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(gc),
                                                  _lib.ptr(ds) if ds is not None else None, _lib.ptr(dw2), _lib.ptr(dw3),
                                                  0 if first else 1, stream), "pn_pack_fold_backward(%s)" % name)
             first = False
         return dw2, dw3.view(8, 1, 3, 3, 3)
 
 
+def _use_kernels(t):
+    """CUDA tensors take the kernel path (the only one the product runs: PackNet01.forward refuses CPU tensors)."""
+    return t.is_cuda
+
+
 def fold_set(w2, w3):
     """-> (W_eff, Wtop, Wbottom, Wleft, Wright, Wtl, Wtr, Wbl, Wbr, S); kernels on CUDA tensors (frame weights
     channels-last), PyTorch ops otherwise (all OIHW; the CPU form exists for the algebra tests only: PackNet01.forward
     refuses CPU tensors)."""
-    if w2.is_cuda:
+    if _use_kernels(w2):
         return _FoldSetCUDA.apply(w2, w3)
     return fold_set_torch(w2, w3)
 
@@ -363,7 +373,7 @@ def pack_conv_folded(x, w2, b2, w3, b3, conv):
         raise ValueError("pack_conv_folded: packed map %dx%d smaller than the frame of a %dx%d kernel" % (h, w, k, k))
     xs, top, bot, left, right = space_to_depth_borders(x.contiguous())
     folds = fold_set(w2, w3)
-    if x.is_cuda:
+    if _use_kernels(x):
         beta, dB = bias_classes(folds[9], b3, k, w, x.device)
         z = conv(xs, folds[0], b2 + beta)
         return _FrameApplyCUDA.apply(z, top, bot, left, right, *folds[1:9], dB, k)

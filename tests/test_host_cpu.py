@@ -69,3 +69,38 @@ def test_pose_mirror_matches_oracle():
     p = Pose.from_vec(vec, "euler")
     ident = (p @ p.inverse()).mat
     assert torch.allclose(ident, torch.eye(4).repeat(3, 1, 1), atol=1e-6)
+
+
+def test_fold_and_frame_descriptors_reach_the_c_side_intact():
+    """The ctypes mirrors of pn_fold_desc / pn_frame_desc against the C structs: the library's own host-side validation
+    (which runs before any launch) echoes the fields it read in its error text."""
+    from packnet_sfm_b200 import _lib, folded
+    from packnet_sfm_b200._lib_conv import FoldDesc
+    lib = _lib.lib()
+    buf = torch.zeros(64)
+    p = _lib.ptr(buf)
+    # fold: an unsupported window (2 taps of a 3x3 kernel) must be reported with exactly these numbers
+    d = FoldDesc(7, 40, 3, 0, 2, 0, 3, 2, 3, 0, 3, 1)
+    assert lib.pn_pack_fold_forward(ctypes.byref(d), p, p, p, None) == -2
+    assert b"window 2x3 with face 1x3" in lib.pn_last_error_string(), lib.pn_last_error_string()
+    d = FoldDesc(7, 40, 3, 0, 1, 0, 3, 2, 3, 0, 3, 5)
+    assert lib.pn_pack_fold_forward(ctypes.byref(d), p, p, p, None) == -1
+    assert b"layout 5" in lib.pn_last_error_string(), lib.pn_last_error_string()
+    # frame: the real descriptor builder on CPU tensors; corrupt one field of one term and read it back from the error
+    B, h, w, co, n, k = 2, 9, 11, 4, 8, 5
+    lines = {"top": torch.zeros(B, w, n), "bottom": torch.zeros(B, w, n), "left": torch.zeros(B, h, n), "right": torch.zeros(B, h, n)}
+    shapes = {"top": (co, 2, 7, n), "bottom": (co, 2, 7, n), "left": (co, 7, 2, n), "right": (co, 7, 2, n),
+              "tl": (co, 2, 2, n), "tr": (co, 2, 2, n), "bl": (co, 2, 2, n), "br": (co, 2, 2, n)}
+    weights = {name: torch.zeros(s) for name, s in shapes.items()}
+    fd = folded._FrameApplyCUDA._desc((B, h, w, co), n, k, lines, weights)
+    assert fd.num_terms == 8 and fd.terms[3].L == h and fd.terms[0].w_sa == 7 * n and fd.terms[2].w_se == 2 * n
+    fd.terms[6].c0 = w + 5                                        # term 6 = "bl": col = c0 - a2
+    z = torch.zeros(B, h, w, co)
+    dB = torch.zeros(5, 5, co)
+    rc = lib.pn_pack_frame_forward(ctypes.byref(fd), _lib.ptr(dB), _lib.ptr(z), None)
+    msg = lib.pn_last_error_string()
+    assert rc == -1 and b"term 6 maps (a=0, l=0) to (8, 16) outside the 9x11 map" in msg, (rc, msg)
+    # an intact descriptor passes the validation of all eight terms; without a GPU the launch itself then fails (> 0)
+    fd = folded._FrameApplyCUDA._desc((B, h, w, co), n, k, lines, weights)
+    if not torch.cuda.is_available():
+        assert lib.pn_pack_frame_forward(ctypes.byref(fd), _lib.ptr(dB), _lib.ptr(z), None) > 0
