@@ -1,6 +1,13 @@
 // common.cuh -- shared host/device helpers of libpacknet_b200 (error reporting, launch accounting).
 #pragma once
+#ifdef PN_EMULATE
+// host build of the plain SIMT kernels for the CPU test tier (tests/emu/cuda_emu.h); never part of the product library
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+// kernel launch, spelled as a macro so that the emulated host build can run the same dispatch code
+#define PN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
 
 #include <cstdint>
 #include <cstdio>

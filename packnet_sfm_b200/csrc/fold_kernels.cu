@@ -202,11 +202,11 @@ template <int KA, int KB, int DA, int DB>
 static int launch_fold(const FoldParams& P, bool backward, cudaStream_t stream) {
   const int nblk = (P.n + FOLD_THREADS - 1) / FOLD_THREADS;
   if (backward) {
-    fold_bwd_kernel<KA, KB, DA, DB><<<dim3(nblk, 8, P.cout), FOLD_THREADS, 0, stream>>>(P);
+    PN_LAUNCH((fold_bwd_kernel<KA, KB, DA, DB>), dim3(nblk, 8, P.cout), FOLD_THREADS, 0, stream, P);
     count_launch();
     return check_launch("fold_bwd_kernel");
   }
-  fold_fwd_kernel<KA, KB, DA, DB><<<dim3(nblk, P.cout), FOLD_THREADS, 0, stream>>>(P);
+  PN_LAUNCH((fold_fwd_kernel<KA, KB, DA, DB>), dim3(nblk, P.cout), FOLD_THREADS, 0, stream, P);
   count_launch();
   return check_launch("fold_fwd_kernel");
 }

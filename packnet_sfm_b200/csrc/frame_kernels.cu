@@ -301,7 +301,7 @@ extern "C" int pn_pack_frame_forward(const pn_frame_desc* desc, const float* dB,
     mmax = std::max<long long>(mmax, (long long)P.B * P.t[i].L);
     nmax = std::max<long long>(nmax, (long long)P.t[i].A * P.Co);
   }
-  frame::frame_forward_kernel<<<dim3(frame::cdiv(nmax, frame::BN), frame::cdiv(mmax, frame::BM), P.nterms), frame::NT, 0, stream>>>(P);
+  PN_LAUNCH(frame::frame_forward_kernel, dim3(frame::cdiv(nmax, frame::BN), frame::cdiv(mmax, frame::BM), P.nterms), frame::NT, 0, stream, P);
   count_launch();
   return check_launch("frame_forward_kernel");
 }
@@ -321,13 +321,13 @@ extern "C" int pn_pack_frame_backward(const pn_frame_desc* desc, const float* gz
     amax = std::max<long long>(amax, (long long)P.t[i].A * P.Co);
     kmax = std::max<long long>(kmax, (long long)P.t[i].KE * P.n);
   }
-  frame::frame_backward_line_kernel<<<dim3(frame::cdiv(P.n, frame::BN), frame::cdiv(pmax, frame::BM), P.nterms), frame::NT, 0, stream>>>(P);
-  frame::frame_backward_weight_kernel<<<dim3(frame::cdiv(kmax, frame::BN), frame::cdiv(amax, frame::BM), P.nterms), frame::NT, 0, stream>>>(P);
+  PN_LAUNCH(frame::frame_backward_line_kernel, dim3(frame::cdiv(P.n, frame::BN), frame::cdiv(pmax, frame::BM), P.nterms), frame::NT, 0, stream, P);
+  PN_LAUNCH(frame::frame_backward_weight_kernel, dim3(frame::cdiv(kmax, frame::BN), frame::cdiv(amax, frame::BM), P.nterms), frame::NT, 0, stream, P);
   const int m = P.m;
   const long long total = (long long)P.B * ((long long)P.h * P.w - (long long)(P.h - 2 * m) * (P.w - 2 * m)) * P.Co;
   unsigned blocks = frame::cdiv(total, frame::NT);
   if (blocks > 148u * 8u) blocks = 148u * 8u;
-  frame::frame_backward_bias_kernel<<<blocks, frame::NT, 0, stream>>>(P);
+  PN_LAUNCH(frame::frame_backward_bias_kernel, blocks, frame::NT, 0, stream, P);
   count_launch(3);
   return check_launch("frame_backward kernels");
 }

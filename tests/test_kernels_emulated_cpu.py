@@ -1,0 +1,160 @@
+"""The fold and frame kernels executed on the CPU tier FROM THEIR REAL SOURCE: packnet_sfm_b200/csrc/fold_kernels.cu and
+frame_kernels.cu compiled for the host with g++ -DPN_EMULATE against tests/emu/cuda_emu.h (one OS thread per CUDA thread,
+std::barrier for __syncthreads, per-warp exchange for the shuffles) behind the same C-ABI entry points, then driven by
+the real Python glue of packnet_sfm_b200/folded.py.  Checked against the reference composition
+packing -> Conv3d -> pad -> Conv2d (layers01.py:239-247): values and every gradient.
+
+This pins the kernels' index arithmetic, staging, synchronisation placement and host-side dispatch before they ever see
+a GPU; performance and the tcgen05 convolution itself remain GPU-tier matters (tests/test_folded_gpu.py)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import packnet_oracle as PO
+from packnet_sfm_b200 import _lib, _lib_conv, folded
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+SO = os.path.join(EMU, "_build", "libpacknet_emu.so")
+SOURCES = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_emu.h"),
+           os.path.join(ROOT, "packnet_sfm_b200", "csrc", "fold_kernels.cu"),
+           os.path.join(ROOT, "packnet_sfm_b200", "csrc", "frame_kernels.cu"),
+           os.path.join(ROOT, "packnet_sfm_b200", "csrc", "common.cuh"), os.path.join(ROOT, "include", "packnet_b200.h")]
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SOURCES):
+        cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-DPN_EMULATE", "-x", "c++", "-Wno-unknown-pragmas",
+               "-I", EMU, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "packnet_sfm_b200", "csrc"),
+               SOURCES[0], "-o", SO]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+    lib = ctypes.CDLL(SO)
+    _lib_conv_declare_fold_frame(lib)
+    return lib
+
+
+def _lib_conv_declare_fold_frame(lib):
+    c = ctypes
+    vp = c.c_void_p
+    lib.pn_pack_fold_forward.argtypes = [c.POINTER(_lib_conv.FoldDesc), vp, vp, vp, vp]
+    lib.pn_pack_fold_backward.argtypes = [c.POINTER(_lib_conv.FoldDesc), vp, vp, vp, vp, vp, vp, c.c_int, vp]
+    lib.pn_pack_frame_forward.argtypes = [c.POINTER(_lib_conv.FrameDesc), vp, vp, vp]
+    lib.pn_pack_frame_backward.argtypes = [c.POINTER(_lib_conv.FrameDesc), vp, vp, vp]
+    for n in ("pn_pack_fold_forward", "pn_pack_fold_backward", "pn_pack_frame_forward", "pn_pack_frame_backward"):
+        getattr(lib, n).restype = c.c_int
+    lib.pn_last_error_string.restype = c.c_char_p
+
+
+@pytest.fixture
+def kernel_path(emu_lib, monkeypatch):
+    monkeypatch.setattr(_lib, "lib", lambda: emu_lib)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "current_stream", lambda: None)
+    monkeypatch.setattr(folded, "_use_kernels", lambda t: True)
+    return emu_lib
+
+
+def rel(a, b):
+    return float((a.detach().double() - b.detach().double()).abs().max() / b.detach().double().abs().max())
+
+
+@pytest.mark.parametrize("co,C,k", [(2, 2, 3), (1, 33, 3), (1, 3, 5)])
+def test_fold_kernels_emulated(kernel_path, co, C, k):
+    """nine windows, both layouts, multi-block depth (n > 128), dS, accumulate, the dW3 warp/shared/global reduction"""
+    n = 4 * C
+    g = torch.Generator().manual_seed(co + C + k)
+    w2 = (torch.rand(co, 8 * n, k, k, generator=g) - 0.5).requires_grad_(True)
+    w3 = (torch.rand(8, 1, 3, 3, 3, generator=g) - 0.5).requires_grad_(True)
+    outs = folded.fold_set(w2, w3)
+    gs = [torch.rand(o.shape, generator=g) - 0.5 for o in outs]
+    torch.autograd.backward(outs, gs)
+    w2d, w3d = (t.detach().double().requires_grad_(True) for t in (w2, w3))
+    refs = folded.fold_set_torch(w2d, w3d)
+    torch.autograd.backward(refs, [x.double() if i in (0, 9) else x.double().permute(0, 3, 1, 2) for i, x in enumerate(gs)])
+    for i, (name, a, b) in enumerate(zip(folded.FOLD_ORDER + ("S",), outs, refs)):
+        if i not in (0, 9):
+            b = b.permute(0, 2, 3, 1)
+        assert a.shape == b.shape and rel(a, b) < 1e-5, (name, rel(a, b))
+    assert rel(w2.grad, w2d.grad) < 1e-5 and rel(w3.grad, w3d.grad) < 1e-5, (rel(w2.grad, w2d.grad), rel(w3.grad, w3d.grad))
+
+
+def _conv_nhwc(x, w, b):
+    return F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=w.shape[-1] // 2).permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("case", [(2, 2, 8, 12, 3, 3), (1, 2, 10, 12, 2, 5)])
+def test_folded_pack_block_with_emulated_kernels(kernel_path, case):
+    """the whole kernel path of pack_conv_folded (PyTorch convolution for the O(area) part): folds, all eight frame terms,
+    bias classes, both backward chains"""
+    B, C, H, W, Co, k = case
+    g = torch.Generator().manual_seed(B + C + H + k)
+    x = (torch.rand(B, H, W, C, generator=g) - 0.5).requires_grad_(True)
+    w2 = ((torch.rand(Co, 32 * C, k, k, generator=g) - 0.5) * 0.2).requires_grad_(True)
+    b2 = (torch.rand(Co, generator=g) - 0.5).requires_grad_(True)
+    w3 = (torch.rand(8, 1, 3, 3, 3, generator=g) - 0.5).requires_grad_(True)
+    b3 = (torch.rand(8, generator=g) - 0.5).requires_grad_(True)
+    z = folded.pack_conv_folded(x, w2, b2, w3, b3, _conv_nhwc)
+    gz = torch.rand(z.shape, generator=g) - 0.5
+    z.backward(gz)
+    xd, w2d, b2d, w3d, b3d = (t.detach().double().requires_grad_(True) for t in (x, w2, b2, w3, b3))
+    t = PO.conv3d_features(PO.packing(xd.permute(0, 3, 1, 2)), w3d, b3d)
+    zr = F.conv2d(F.pad(t, [k // 2] * 4), w2d, b2d).permute(0, 2, 3, 1)
+    zr.backward(gz.double())
+    for name, a, b in (("z", z, zr), ("gx", x.grad, xd.grad), ("gw2", w2.grad, w2d.grad), ("gb2", b2.grad, b2d.grad),
+                       ("gw3", w3.grad, w3d.grad), ("gb3", b3.grad, b3d.grad)):
+        assert rel(a, b) < 3e-5, (name, rel(a, b))
+
+
+@pytest.mark.parametrize("case", [(2, 17, 4, 35, 66, 3), (1, 3, 5, 70, 5, 5)])
+def test_frame_kernels_emulated_with_several_tiles(kernel_path, case):
+    """pn_pack_frame_* alone (folds from the PyTorch definition): more than one 64-wide tile in every GEMM dimension --
+    pixels (B*w = 70), output columns (A*Co = 66), channels (n = 68) -- and ragged last tiles, against frame_strips."""
+    B, C, h, w, Co, k = case
+    n, m = 4 * C, k // 2
+    g = torch.Generator().manual_seed(B + C + h + k)
+    xs = torch.rand(B, h, w, n, generator=g) - 0.5
+    lines = [xs[:, 0].clone(), xs[:, h - 1].clone(), xs[:, :, 0].clone(), xs[:, :, w - 1].clone()]
+    w2 = (torch.rand(Co, 8 * n, k, k, generator=g) - 0.5) * 0.2
+    w3 = torch.rand(8, 1, 3, 3, 3, generator=g) - 0.5
+    b3 = torch.rand(8, generator=g) - 0.5
+    folds = folded.fold_set_torch(w2, w3)
+    gz = torch.rand(B, h, w, Co, generator=g) - 0.5
+    # kernel path
+    la = [t.clone().requires_grad_(True) for t in lines]
+    wa = [f.permute(0, 2, 3, 1).contiguous().requires_grad_(True) for f in folds[1:9]]
+    _, dB = folded.bias_classes(folds[9], b3, k, w, "cpu")
+    dBa = dB.clone().requires_grad_(True)
+    z0 = torch.zeros(B, h, w, Co).requires_grad_(True)
+    z = folded._FrameApplyCUDA.apply(z0 * 1.0, *la, *wa, dBa, k)
+    z.backward(gz)
+    # definition
+    lb = [t.clone().double().requires_grad_(True) for t in lines]
+    fb = [f.double().clone().requires_grad_(True) for f in folds]
+    b3b = b3.double().requires_grad_(True)
+    _, ts, bs, ls, rs = folded.frame_strips(*lb, fb, b3b, k)
+    zr = torch.zeros(B, h, w, Co, dtype=torch.float64)
+    zr[:, :m] += ts
+    zr[:, h - m:] += bs
+    zr[:, :, :m] += ls
+    zr[:, :, w - m:] += rs
+    (zr * gz.double()).sum().backward()
+    assert rel(z, zr) < 1e-5, rel(z, zr)
+    for a, b in zip(la, lb):
+        assert rel(a.grad, b.grad) < 1e-5, rel(a.grad, b.grad)
+    for name, a, b in zip(folded.FOLD_ORDER[1:], wa, fb[1:9]):
+        assert rel(a.grad, b.grad.permute(0, 2, 3, 1)) < 1e-5, (name, rel(a.grad, b.grad.permute(0, 2, 3, 1)))
+    # bias classes: gradient of the class table = sum of gz over the pixels of each class
+    from kernel_mirrors import border_class
+    want = torch.zeros_like(dBa)
+    for row in range(h):
+        for col in range(w):
+            if row < m or row >= h - m or col < m or col >= w - m:
+                want[border_class(row, h, m), border_class(col, w, m)] += gz[:, row, col].sum(0)
+    assert rel(dBa.grad, want) < 1e-5
