@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 // kernel launch, spelled as a macro so that the emulated host build can run the same dispatch code
 #define PN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// the dynamic shared memory of a kernel (16-byte aligned)
+#define PN_DYNAMIC_SHARED(type, name) extern __shared__ __align__(16) type name[]
+#define PN_DYNAMIC_SHARED_PLAIN(type, name) extern __shared__ type name[]
 #endif
 
 #include <cstdint>

@@ -83,7 +83,7 @@ __device__ __forceinline__ void stage_volume(const float* __restrict__ in, int b
 // smem: s_v[3][tw+2][D+2] (zero padded in all three dims), s_w[8*27 + 8]
 template <bool PACK>
 __global__ void __launch_bounds__(256) stencil_fwd_kernel(const StencilParams P) {
-  extern __shared__ float sm[];
+  PN_DYNAMIC_SHARED_PLAIN(float, sm);
   const int D = P.D, DP = D + 2, TWP = P.tw + 2;
   float* s_v = sm;
   float* s_w = sm + 3 * TWP * DP;
@@ -158,7 +158,7 @@ __device__ __forceinline__ float load_gout(const StencilBwdParams& P, int b, int
 //       s_w[216], s_red[256]
 template <bool PACK>
 __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams P) {
-  extern __shared__ float sm[];
+  PN_DYNAMIC_SHARED_PLAIN(float, sm);
   const int D = P.D, DP = D + 2, TWP = P.tw + 2;
   float* s_v = sm;
   float* s_g = s_v + 3 * TWP * DP;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) stencil_bwd_kernel(const StencilBwdParams
 // smem: s_v[3][tw+2][D+2] (forward input with halo), s_gc[8][tw][D] (g at the tile's pixels, all 8 features)
 template <bool PACK>
 __global__ void __launch_bounds__(256) stencil_wgrad_kernel(const StencilBwdParams P) {
-  extern __shared__ float sm[];
+  PN_DYNAMIC_SHARED_PLAIN(float, sm);
   const int D = P.D, DP = D + 2, TWP = P.tw + 2;
   float* s_v = sm;
   float* s_gc = s_v + 3 * TWP * DP;
@@ -393,7 +393,7 @@ __device__ __forceinline__ void load_col10(const float* __restrict__ col, float 
 // forward.  smem: s_v[3][tw+2][PITCH] + 4, s_w[27][8], s_b[8]
 template <bool PACK>
 __global__ void __launch_bounds__(256, 2) stencil_fwd8_kernel(const StencilParams P) {
-  extern __shared__ __align__(16) float sm[];
+  PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
   float* s_v = sm;
   float* s_w = sm + 3 * TWP * PITCH + 4;
@@ -475,7 +475,7 @@ struct StencilBwd8Params {
 template <bool PACK, int MAXT>
 __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Params Q) {
   const StencilBwdParams& P = Q.p;
-  extern __shared__ __align__(16) float sm[];
+  PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2, TH = Q.th;
   float* s_g = sm;
   float* s_w = sm + (TH + 2) * TWP * PITCH + 4;
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
 // smem: s_v[3][tw+2][PITCH] + 4, s_gc[8][tw][PITCH]
 template <bool PACK>
 __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdParams P) {
-  extern __shared__ __align__(16) float sm[];
+  PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
   float* s_v = sm;
   float* s_gc = sm + 3 * TWP * PITCH + 4;
@@ -962,7 +962,7 @@ struct HeadParams {
 
 // smem: s_x[(8+2)][(tw+2)][C+4], s_w[9][C]
 __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams P) {
-  extern __shared__ __align__(16) float sm[];
+  PN_DYNAMIC_SHARED(float, sm);
   const int C = P.C, PITCH = C + SPAD, TWP = P.tw + 2;
   float* s_x = sm;
   float* s_w = sm + 10 * TWP * PITCH + 4;
@@ -992,7 +992,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams P) {
 
 // data gradient: dx[p][c] = sum_tap w[tap][c] * dy[p - tap + 1].  One thread per (pixel, channel quad).
 __global__ void __launch_bounds__(256) head_dgrad_kernel(const HeadParams P) {
-  extern __shared__ __align__(16) float sm[];
+  PN_DYNAMIC_SHARED(float, sm);
   const int C = P.C, TWP = P.tw + 2;
   float* s_dy = sm;                 // [10][tw+2]
   float* s_w = sm + ((10 * TWP + 3) & ~3);
@@ -1027,7 +1027,7 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const HeadParams P) {
 // with its partial sums in registers over the whole walk (MAXQ combos per thread), atomics once at the end.
 template <int MAXQ>
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const HeadParams P) {
-  extern __shared__ __align__(16) float sm[];
+  PN_DYNAMIC_SHARED(float, sm);
   const int C = P.C, PITCH = C + SPAD, TWP = P.tw + 2;
   float* s_x = sm;
   float* s_dy = sm + 10 * TWP * PITCH + 4;   // [8][tw]
@@ -1131,10 +1131,10 @@ extern "C" int pn_feature_stencil_forward(int pack, const float* in, const float
     dim3 grid8((P.W + tw - 1) / tw, P.H, P.B);
     if (pack) {
       PN_CUDA(cudaFuncSetAttribute(stencil_fwd8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      stencil_fwd8_kernel<true><<<grid8, 256, smem8, stream>>>(P);
+      PN_LAUNCH((stencil_fwd8_kernel<true>), grid8, 256, smem8, stream, P);
     } else {
       PN_CUDA(cudaFuncSetAttribute(stencil_fwd8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      stencil_fwd8_kernel<false><<<grid8, 256, smem8, stream>>>(P);
+      PN_LAUNCH((stencil_fwd8_kernel<false>), grid8, 256, smem8, stream, P);
     }
     count_launch();
     return check_launch("stencil_fwd8_kernel");
@@ -1145,10 +1145,10 @@ extern "C" int pn_feature_stencil_forward(int pack, const float* in, const float
   dim3 grid((P.W + P.tw - 1) / P.tw, P.H, P.B);
   if (pack) {
     PN_CUDA(cudaFuncSetAttribute(stencil_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stencil_fwd_kernel<true><<<grid, 256, smem, stream>>>(P);
+    PN_LAUNCH((stencil_fwd_kernel<true>), grid, 256, smem, stream, P);
   } else {
     PN_CUDA(cudaFuncSetAttribute(stencil_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stencil_fwd_kernel<false><<<grid, 256, smem, stream>>>(P);
+    PN_LAUNCH((stencil_fwd_kernel<false>), grid, 256, smem, stream, P);
   }
   count_launch();
   return check_launch("stencil_fwd_kernel");
@@ -1187,7 +1187,7 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
       dim3 grid8((P.W + tw - 1) / tw, (P.H + th - 1) / th, P.B);
       auto launch = [&](auto kern) -> int {
         PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-        kern<<<grid8, 256, smem8, stream>>>(Q8);
+        PN_LAUNCH(kern, grid8, 256, smem8, stream, Q8);
         return 0;
       };
       int lrc;
@@ -1213,10 +1213,10 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
       if (ctas > nwork) ctas = nwork;
       if (pack) {
         PN_CUDA(cudaFuncSetAttribute(stencil_wgrad8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-        stencil_wgrad8_kernel<true><<<ctas, 256, smem8, stream>>>(Q);
+        PN_LAUNCH((stencil_wgrad8_kernel<true>), ctas, 256, smem8, stream, Q);
       } else {
         PN_CUDA(cudaFuncSetAttribute(stencil_wgrad8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-        stencil_wgrad8_kernel<false><<<ctas, 256, smem8, stream>>>(Q);
+        PN_LAUNCH((stencil_wgrad8_kernel<false>), ctas, 256, smem8, stream, Q);
       }
       count_launch();
       return check_launch("stencil_wgrad8_kernel");
@@ -1229,10 +1229,10 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   dim3 grid((P.W + P.tw - 1) / P.tw, P.H, P.B);
   if (pack) {
     PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stencil_bwd_kernel<true><<<grid, 256, smem, stream>>>(P);
+    PN_LAUNCH((stencil_bwd_kernel<true>), grid, 256, smem, stream, P);
   } else {
     PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stencil_bwd_kernel<false><<<grid, 256, smem, stream>>>(P);
+    PN_LAUNCH((stencil_bwd_kernel<false>), grid, 256, smem, stream, P);
   }
   count_launch();
   int rc = check_launch("stencil_bwd_kernel");
@@ -1248,10 +1248,10 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   if (ctas > 148 * 2) ctas = 148 * 2;
   if (pack) {
     PN_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-    stencil_wgrad_kernel<true><<<ctas, 256, smem_w, stream>>>(Q);
+    PN_LAUNCH((stencil_wgrad_kernel<true>), ctas, 256, smem_w, stream, Q);
   } else {
     PN_CUDA(cudaFuncSetAttribute(stencil_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-    stencil_wgrad_kernel<false><<<ctas, 256, smem_w, stream>>>(Q);
+    PN_LAUNCH((stencil_wgrad_kernel<false>), ctas, 256, smem_w, stream, Q);
   }
   count_launch();
   return check_launch("stencil_wgrad_kernel");
@@ -1269,15 +1269,15 @@ extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const f
   int ppc = (hw + 147) / 148;
   if (ppc < 32) ppc = 32;
   dim3 g1((hw + ppc - 1) / ppc, batch);
-  gn_stats_kernel<<<g1, 256, 0, stream>>>(x, x2, hw, channels, channels, ppc, stats);
+  PN_LAUNCH(gn_stats_kernel, g1, 256, 0, stream, x, x2, hw, channels, channels, ppc, stats);
   count_launch();
   float* mr = reinterpret_cast<float*>(stats + (size_t)2 * 16 * batch);   // (mean, rstd) floats behind the doubles
-  gn_finalize_stats_kernel<<<(16 * batch + 127) / 128, 128, 0, stream>>>(stats, mr, 16 * batch, (double)hw * (channels / 16), eps);
+  PN_LAUNCH(gn_finalize_stats_kernel, (16 * batch + 127) / 128, 128, 0, stream, stats, mr, 16 * batch, (double)hw * (channels / 16), eps);
   count_launch();
   const size_t total = (size_t)batch * hw * (channels / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_elu_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, hw, channels, channels, mr, gamma, beta, eps, y, y_lo, out_cstride,
+  PN_LAUNCH(gn_elu_apply_kernel, blocks, 256, 0, stream, x, x2, hw, channels, channels, mr, gamma, beta, eps, y, y_lo, out_cstride,
                                                   out_coffset, batch);
   count_launch();
   return check_launch("gn_elu_apply_kernel");
@@ -1302,33 +1302,33 @@ extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const 
                    y_cstride % 4 == 0 && y_coffset % 4 == 0 && dy_cstride % 4 == 0 && dy_coffset % 4 == 0;
   if (dx_channel_sum) PN_CUDA(cudaMemsetAsync(dx_channel_sum, 0, sizeof(float) * channels, stream));
   if (vec) {
-    gn_elu_bwd_reduce4_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
+    PN_LAUNCH(gn_elu_bwd_reduce4_kernel, g1, 256, 0, stream, x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
                                                       dy_coffset, mr, ppc, bc);
     count_launch();
-    gn_bwd_finalize_kernel<<<(batch * 16 + channels + 127) / 128, 128, 0, stream>>>(bc, gamma, batch, channels,
+    PN_LAUNCH(gn_bwd_finalize_kernel, (batch * 16 + channels + 127) / 128, 128, 0, stream, bc, gamma, batch, channels,
                                                                                    (double)hw * (channels / 16), gmeans, dgamma, dbeta);
     count_launch();
-    gn_elu_bwd_apply4_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
+    PN_LAUNCH(gn_elu_bwd_apply4_kernel, g1, 256, 0, stream, x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
                                                      mr, gmeans, gamma, ppc, dx, dx_lo, dx_channel_sum);
     count_launch();
     return check_launch("gn_elu_bwd kernels");
   }
-  gn_elu_bwd_reduce_kernel<<<g1, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
+  PN_LAUNCH(gn_elu_bwd_reduce_kernel, g1, 256, 0, stream, x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
                                                    mr, eps, ppc, bc);
   count_launch();
   const size_t total = (size_t)batch * hw * channels;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_bwd_finalize_kernel<<<(batch * 16 + channels + 127) / 128, 128, 0, stream>>>(bc, gamma, batch, channels,
+  PN_LAUNCH(gn_bwd_finalize_kernel, (batch * 16 + channels + 127) / 128, 128, 0, stream, bc, gamma, batch, channels,
                                                                                  (double)hw * (channels / 16), gmeans, dgamma, dbeta);
   count_launch();
-  gn_elu_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
+  PN_LAUNCH(gn_elu_bwd_apply_kernel, blocks, 256, 0, stream, x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
                                                       dy_coffset, mr, gmeans, gamma, eps, dx, dx_lo, batch);
   count_launch();
   if (dx_channel_sum) {
     int ppc2 = (int)(((size_t)batch * hw + 147 * 4) / (148 * 4));
     if (ppc2 < 64) ppc2 = 64;
-    channel_sum_kernel<<<(int)(((size_t)batch * hw + ppc2 - 1) / ppc2), 256, 0, stream>>>(dx, (size_t)batch * hw, channels, ppc2, dx_channel_sum);
+    PN_LAUNCH(channel_sum_kernel, (int)(((size_t)batch * hw + ppc2 - 1) / ppc2), 256, 0, stream, dx, (size_t)batch * hw, channels, ppc2, dx_channel_sum);
     count_launch();
   }
   return check_launch("gn_elu_bwd kernels");
@@ -1340,7 +1340,7 @@ extern "C" int pn_channel_sum(const float* g, float* out, size_t pixels, int cha
   PN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * channels, stream));
   int ppc = (int)((pixels + 147 * 4) / (148 * 4));
   if (ppc < 64) ppc = 64;
-  channel_sum_kernel<<<(int)((pixels + ppc - 1) / ppc), 256, 0, stream>>>(g, pixels, channels, ppc, out);
+  PN_LAUNCH(channel_sum_kernel, (int)((pixels + ppc - 1) / ppc), 256, 0, stream, g, pixels, channels, ppc, out);
   count_launch();
   return check_launch("channel_sum_kernel");
 }
@@ -1366,7 +1366,7 @@ extern "C" int pn_head_conv_forward(const float* x, const float* w_tap_major, co
   PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_head_conv_forward: %d channels need %zu bytes of shared memory", channels, smem);
   PN_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((width + P.tw - 1) / P.tw, (height + 7) / 8, batch);
-  head_fwd_kernel<<<grid, 256, smem, stream>>>(P);
+  PN_LAUNCH(head_fwd_kernel, grid, 256, smem, stream, P);
   count_launch();
   return check_launch("head_fwd_kernel");
 }
@@ -1387,7 +1387,7 @@ extern "C" int pn_head_conv_backward(const float* x, const float* dy, const floa
     const size_t smem = ((size_t)((10 * (P.tw + 2) + 3) & ~3) + (size_t)9 * channels) * sizeof(float);
     dim3 grid((width + P.tw - 1) / P.tw, (height + 7) / 8, batch);
     PN_CUDA(cudaFuncSetAttribute(head_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_dgrad_kernel<<<grid, 256, smem, stream>>>(P);
+    PN_LAUNCH(head_dgrad_kernel, grid, 256, smem, stream, P);
     count_launch();
     int rc = check_launch("head_dgrad_kernel");
     if (rc) return rc;
@@ -1402,7 +1402,7 @@ extern "C" int pn_head_conv_backward(const float* x, const float* dy, const floa
   const int maxq = (9 * (channels / 4) + 255) / 256;
   auto launch = [&](auto kern) -> int {
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ctas, 256, smem, stream>>>(P);
+    PN_LAUNCH(kern, ctas, 256, smem, stream, P);
     return 0;
   };
   int lrc = (maxq <= 1) ? launch(head_wgrad_kernel<1>) : (maxq <= 2) ? launch(head_wgrad_kernel<2>) : launch(head_wgrad_kernel<4>);

@@ -292,7 +292,7 @@ template <int N, bool MIN, bool GRAD>
 __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
   using G = TileGeom<GRAD>;
   constexpr int HALO = G::HALO, RW = G::RW, RP = G::RP;
-  extern __shared__ __align__(16) float smem[];
+  PN_DYNAMIC_SHARED(float, smem);
   float* s_inv = smem;
   float* s_tgt = s_inv + RP;            // [3][RP]
   float* s_ref = s_tgt + 3 * RP;        // [N][3][RP]
@@ -792,7 +792,7 @@ static int launch_tiles(const Params& P, dim3 grid, cudaStream_t stream) {
   const size_t smem = tile_smem_floats<N, GRAD>() * sizeof(float);
   auto kern = loss_tile_kernel<N, MIN, GRAD>;
   PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, NT, smem, stream>>>(P);
+  PN_LAUNCH(kern, grid, NT, smem, stream, P);
   count_launch();
   return check_launch("loss_tile_kernel");
 }
@@ -871,11 +871,11 @@ static int setup(const pn_loss_desc* d, const float* image, const float* const* 
     const ScaleParams& S = P.sc[i];
     const long long total = 3LL * d->batch * S.h * S.w;
     const int blocks = (int)((total + 255) / 256);
-    resize_bilinear_ac_kernel<<<blocks, 256, 0, stream>>>(image, reinterpret_cast<float*>(base + ws.resized_img[i]),
+    PN_LAUNCH(resize_bilinear_ac_kernel, blocks, 256, 0, stream, image, reinterpret_cast<float*>(base + ws.resized_img[i]),
                                                           3 * d->batch, d->height, d->width, S.h, S.w);
     count_launch();
     for (int j = 0; j < d->num_context; ++j) {
-      resize_bilinear_ac_kernel<<<blocks, 256, 0, stream>>>(context[j], reinterpret_cast<float*>(base + ws.resized_ctx[i][j]),
+      PN_LAUNCH(resize_bilinear_ac_kernel, blocks, 256, 0, stream, context[j], reinterpret_cast<float*>(base + ws.resized_ctx[i][j]),
                                                             3 * d->batch, d->height, d->width, S.h, S.w);
       count_launch();
     }
@@ -890,7 +890,7 @@ static int setup(const pn_loss_desc* d, const float* image, const float* const* 
   int chunks = (d->height * d->width + 256 * 16 - 1) / (256 * 16);
   if (chunks < 1) chunks = 1;
   if (chunks > 64) chunks = 64;
-  loss_prep_kernel<<<dim3(chunks, d->num_scales * d->batch), 256, 0, stream>>>(Q);
+  PN_LAUNCH(loss_prep_kernel, dim3(chunks, d->num_scales * d->batch), 256, 0, stream, Q);
   count_launch();
   return check_launch("loss_prep_kernel");
 }
@@ -975,10 +975,10 @@ extern "C" int pn_loss_warp_indices(const pn_loss_desc* desc, int scale, const f
   Q.K = K; Q.ref_K = ref_K; Q.poses[0] = pose;
   Q.cams = reinterpret_cast<float*>(base + ws.cams);
   Q.invsum = reinterpret_cast<double*>(base + ws.invsum);
-  loss_prep_kernel<<<dim3(1, one.batch), 256, 0, stream>>>(Q);
+  PN_LAUNCH(loss_prep_kernel, dim3(1, one.batch), 256, 0, stream, Q);
   count_launch();
   const int total = one.batch * one.scale_h[0] * one.scale_w[0];
-  warp_indices_kernel<<<(total + 255) / 256, 256, 0, stream>>>(inv_depth, Q.cams, CAM_STRIDE_BASE + 12, one.batch,
+  PN_LAUNCH(warp_indices_kernel, (total + 255) / 256, 256, 0, stream, inv_depth, Q.cams, CAM_STRIDE_BASE + 12, one.batch,
                                                               one.scale_h[0], one.scale_w[0], tap_xy, coord_xy);
   count_launch();
   return check_launch("warp_indices_kernel");
@@ -990,7 +990,7 @@ extern "C" int pn_resize_bilinear_ac(const float* src, float* dst, int batch, in
   PN_REQUIRE(src && dst && batch > 0 && channels > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0,
              PN_ERR_BAD_ARGUMENT, "pn_resize_bilinear_ac: bad argument");
   const long long total = (long long)batch * channels * h_out * w_out;
-  resize_bilinear_ac_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, dst, batch * channels, h_in, w_in, h_out,
+  PN_LAUNCH(resize_bilinear_ac_kernel, (int)((total + 255) / 256), 256, 0, stream, src, dst, batch * channels, h_in, w_in, h_out,
                                                                             w_out);
   count_launch();
   return check_launch("resize_bilinear_ac_kernel");
