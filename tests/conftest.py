@@ -56,3 +56,49 @@ def golden():
 def rel_l2(a, b):
     a, b = a.double(), b.double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host emulation of the plain SIMT kernels (tests/emu/): the product's .cu sources compiled with g++ -DPN_EMULATE
+# ---------------------------------------------------------------------------------------------------------------
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(EMU_DIR, "_build", "libpacknet_emu.so")
+
+
+def _emu_sources():
+    csrc = os.path.join(ROOT, "packnet_sfm_b200", "csrc")
+    return [os.path.join(EMU_DIR, "emu_kernels.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
+            os.path.join(ROOT, "include", "packnet_b200.h")] + \
+           [os.path.join(csrc, f) for f in ("common.cuh", "fold_kernels.cu", "frame_kernels.cu", "layer_kernels.cu", "loss_kernels.cu")]
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    """libpacknet_emu.so: fold / frame / layer / loss kernels from their real source, built for the host
+    (-ffp-contract=off: every float operation rounds once, as the __f*_rn chains of the loss kernel require)."""
+    import ctypes
+    import subprocess
+    from packnet_sfm_b200 import _lib, _lib_conv
+    src = _emu_sources()
+    os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(f) > os.path.getmtime(EMU_SO) for f in src):
+        cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-DPN_EMULATE", "-x", "c++",
+               "-Wno-unknown-pragmas", "-I", EMU_DIR, "-I", os.path.join(ROOT, "include"),
+               "-I", os.path.join(ROOT, "packnet_sfm_b200", "csrc"), src[0], "-o", EMU_SO]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+    lib = ctypes.CDLL(EMU_SO)
+    _lib._declare(lib)
+    _lib_conv.declare(lib)
+    return lib
+
+
+@pytest.fixture
+def emulated_kernels(emu_lib, monkeypatch):
+    """Route the product's Python layer (packnet_sfm_b200._lib) to the emulated library; CPU tensors pass as device memory."""
+    from packnet_sfm_b200 import _lib, folded
+    monkeypatch.setattr(_lib, "lib", lambda: emu_lib)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "current_stream", lambda: None)
+    monkeypatch.setattr(folded, "_use_kernels", lambda t: True)
+    return emu_lib

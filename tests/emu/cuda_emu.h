@@ -6,8 +6,11 @@
 // (tests/test_kernels_emulated_cpu.py).  It checks index arithmetic, staging, synchronisation placement and the host-side
 // dispatch; it says nothing about performance, memory-model subtleties or tcgen05/TMA code (not used by these kernels).
 #pragma once
+#include <algorithm>
 #include <barrier>
+#include <cfloat>
 #include <cmath>
+#include <cstring>
 #include <cstddef>
 #include <cstdint>
 #include <functional>
@@ -24,7 +27,20 @@ struct dim3 {
 typedef struct CUstream_st* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <class K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+
+struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct alignas(8) float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+struct alignas(8) uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+using std::max;
+using std::min;
 
 #define __global__
 #define __device__
@@ -33,12 +49,22 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static
+#define __align__(n) alignas(n)
+// IEEE single operations with one rounding each: the host build is compiled with -ffp-contract=off
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline void __threadfence() {}
 
 namespace cuda_emu {
 struct BlockCtx {
   std::barrier<>* bar;
-  float (*warp_buf)[32];
+  double (*warp_buf)[32];
   std::barrier<>** warp_bar;
+  void* dyn_smem;
 };
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_gridDim, t_blockDim;
@@ -53,17 +79,17 @@ inline std::mutex g_atomic_mu;
 
 inline void __syncthreads() { cuda_emu::t_ctx.bar->arrive_and_wait(); }
 template <class T> inline T __ldg(const T* p) { return *p; }
-inline float atomicAdd(float* p, float v) {
+template <class T> inline T atomicAdd(T* p, T v) {
   std::lock_guard<std::mutex> lk(cuda_emu::g_atomic_mu);
-  const float old = *p;
+  const T old = *p;
   *p = old + v;
   return old;
 }
-inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   const unsigned tid = cuda_emu::t_threadIdx.x, warp = tid / 32, lane = tid % 32;
-  cuda_emu::t_ctx.warp_buf[warp][lane] = v;
+  cuda_emu::t_ctx.warp_buf[warp][lane] = (double)v;
   cuda_emu::t_ctx.warp_bar[warp]->arrive_and_wait();
-  const float r = cuda_emu::t_ctx.warp_buf[warp][lane ^ (unsigned)lane_mask];
+  const T r = (T)cuda_emu::t_ctx.warp_buf[warp][lane ^ (unsigned)lane_mask];
   cuda_emu::t_ctx.warp_bar[warp]->arrive_and_wait();
   return r;
 }
@@ -71,8 +97,9 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
 namespace cuda_emu {
 // run `kernel(args...)` for every block of `grid` with `block.x` threads (1-D blocks only)
 template <class K, class... Args>
-void launch(K kernel, dim3 grid, dim3 block, Args... args) {
+void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
   const unsigned nt = block.x, nwarps = (nt + 31) / 32;
+  std::vector<float4> dyn((smem_bytes + 15) / 16 + 1);
   std::barrier<> bar((std::ptrdiff_t)nt);
   std::vector<std::unique_ptr<std::barrier<>>> wbars;
   std::vector<std::barrier<>*> wptr;
@@ -81,11 +108,11 @@ void launch(K kernel, dim3 grid, dim3 block, Args... args) {
     wbars.emplace_back(new std::barrier<>((std::ptrdiff_t)lanes));
     wptr.push_back(wbars.back().get());
   }
-  std::vector<float[32]> wbuf(nwarps);
+  std::vector<double[32]> wbuf(nwarps);
   auto worker = [&](unsigned tid) {
     t_blockDim = block;
     t_gridDim = grid;
-    t_ctx = BlockCtx{&bar, wbuf.data(), wptr.data()};
+    t_ctx = BlockCtx{&bar, wbuf.data(), wptr.data(), dyn.data()};
     for (unsigned bz = 0; bz < grid.z; ++bz)
       for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -101,4 +128,6 @@ void launch(K kernel, dim3 grid, dim3 block, Args... args) {
 }
 }  // namespace cuda_emu
 
-#define PN_LAUNCH(kernel, grid, block, smem, stream, ...) cuda_emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+#define PN_LAUNCH(kernel, grid, block, smem, stream, ...) cuda_emu::launch(kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+#define PN_DYNAMIC_SHARED(type, name) type* name = reinterpret_cast<type*>(cuda_emu::t_ctx.dyn_smem)
+#define PN_DYNAMIC_SHARED_PLAIN(type, name) type* name = reinterpret_cast<type*>(cuda_emu::t_ctx.dyn_smem)

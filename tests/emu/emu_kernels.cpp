@@ -24,3 +24,26 @@ extern "C" const char* pn_last_error_string(void) { return pn::g_err; }
 
 #include "../../packnet_sfm_b200/csrc/fold_kernels.cu"
 #include "../../packnet_sfm_b200/csrc/frame_kernels.cu"
+#include "../../packnet_sfm_b200/csrc/layer_kernels.cu"
+#include "../../packnet_sfm_b200/csrc/loss_kernels.cu"
+
+// The tcgen05 / TMA convolution engine has no host emulation (tensor-core instructions): its entry points exist so that
+// the ctypes declarations of packnet_sfm_b200/_lib_conv.py resolve, and refuse to run.
+#define PN_EMU_UNSUPPORTED(name, ...)                                              \
+  extern "C" int name(__VA_ARGS__) {                                               \
+    pn::set_error(#name ": the tensor-core engine is not part of the host emulation"); \
+    return PN_ERR_UNSUPPORTED;                                                     \
+  }
+PN_EMU_UNSUPPORTED(pn_conv2d_forward, const pn_conv_desc*, const void*, const void*, const void*, const void*, const float*, float*,
+                   uint32_t*, pn_stream_t)
+PN_EMU_UNSUPPORTED(pn_conv2d_packed_weight_elems, int, int, int, int, int, size_t*)
+PN_EMU_UNSUPPORTED(pn_conv2d_pack_weight, const float*, void*, void*, int, int, int, int, int, pn_stream_t)
+PN_EMU_UNSUPPORTED(pn_conv2d_wgrad, const pn_conv_desc*, const void*, const void*, const void*, const void*, float*, uint32_t*, pn_stream_t)
+PN_EMU_UNSUPPORTED(pn_conv2d_wgrad_packed_elems, int, int, int, int, size_t*)
+PN_EMU_UNSUPPORTED(pn_conv2d_unpack_weight_grad, const float*, float*, int, int, int, int, pn_stream_t)
+PN_EMU_UNSUPPORTED(pn_tf32_residual, const float*, float*, size_t, pn_stream_t)
+PN_EMU_UNSUPPORTED(pn_split_bf16, const float*, void*, void*, size_t, pn_stream_t)
+extern "C" int pn_version(void) { return 100; }
+extern "C" uint64_t pn_launch_count(void) { return 0; }
+extern "C" void pn_trace_enable(int) {}
+extern "C" int pn_trace_dump(char*, size_t) { return 0; }

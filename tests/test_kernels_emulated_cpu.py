@@ -6,59 +6,17 @@ packing -> Conv3d -> pad -> Conv2d (layers01.py:239-247): values and every gradi
 
 This pins the kernels' index arithmetic, staging, synchronisation placement and host-side dispatch before they ever see
 a GPU; performance and the tcgen05 convolution itself remain GPU-tier matters (tests/test_folded_gpu.py)."""
-import ctypes
-import os
-import subprocess
-
 import pytest
 import torch
 import torch.nn.functional as F
 
 from oracle import packnet_oracle as PO
-from packnet_sfm_b200 import _lib, _lib_conv, folded
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU = os.path.join(ROOT, "tests", "emu")
-SO = os.path.join(EMU, "_build", "libpacknet_emu.so")
-SOURCES = [os.path.join(EMU, "emu_kernels.cpp"), os.path.join(EMU, "cuda_emu.h"),
-           os.path.join(ROOT, "packnet_sfm_b200", "csrc", "fold_kernels.cu"),
-           os.path.join(ROOT, "packnet_sfm_b200", "csrc", "frame_kernels.cu"),
-           os.path.join(ROOT, "packnet_sfm_b200", "csrc", "common.cuh"), os.path.join(ROOT, "include", "packnet_b200.h")]
-
-
-@pytest.fixture(scope="module")
-def emu_lib():
-    os.makedirs(os.path.dirname(SO), exist_ok=True)
-    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SOURCES):
-        cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-DPN_EMULATE", "-x", "c++", "-Wno-unknown-pragmas",
-               "-I", EMU, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "packnet_sfm_b200", "csrc"),
-               SOURCES[0], "-o", SO]
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        assert r.returncode == 0, r.stdout
-    lib = ctypes.CDLL(SO)
-    _lib_conv_declare_fold_frame(lib)
-    return lib
-
-
-def _lib_conv_declare_fold_frame(lib):
-    c = ctypes
-    vp = c.c_void_p
-    lib.pn_pack_fold_forward.argtypes = [c.POINTER(_lib_conv.FoldDesc), vp, vp, vp, vp]
-    lib.pn_pack_fold_backward.argtypes = [c.POINTER(_lib_conv.FoldDesc), vp, vp, vp, vp, vp, vp, c.c_int, vp]
-    lib.pn_pack_frame_forward.argtypes = [c.POINTER(_lib_conv.FrameDesc), vp, vp, vp]
-    lib.pn_pack_frame_backward.argtypes = [c.POINTER(_lib_conv.FrameDesc), vp, vp, vp]
-    for n in ("pn_pack_fold_forward", "pn_pack_fold_backward", "pn_pack_frame_forward", "pn_pack_frame_backward"):
-        getattr(lib, n).restype = c.c_int
-    lib.pn_last_error_string.restype = c.c_char_p
+from packnet_sfm_b200 import folded
 
 
 @pytest.fixture
-def kernel_path(emu_lib, monkeypatch):
-    monkeypatch.setattr(_lib, "lib", lambda: emu_lib)
-    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
-    monkeypatch.setattr(_lib, "current_stream", lambda: None)
-    monkeypatch.setattr(folded, "_use_kernels", lambda t: True)
-    return emu_lib
+def kernel_path(emulated_kernels):
+    return emulated_kernels
 
 
 def rel(a, b):

@@ -1,0 +1,156 @@
+"""CPU-tier execution of the product's plain SIMT kernels FROM THEIR REAL SOURCE (tests/emu/: csrc/loss_kernels.cu and
+csrc/layer_kernels.cu compiled for the host, one OS thread per CUDA thread), called through the product's own Python
+layer (packnet_sfm_b200.losses / functional) and checked against the golden vectors of the live reference and the
+oracle -- the same assertions the GPU tier makes (tests/test_loss_gpu.py, tests/test_layers_gpu.py) at sizes the
+emulation finishes in seconds.  The host build rounds every float operation once (-ffp-contract=off) where nvcc may fuse
+multiply-adds, so values agree to rounding; the warp-index chain is written with explicit __f*_rn intrinsics and must be
+BIT-exact here as on the GPU.  The tcgen05 convolution engine has no emulation and stays a GPU-tier matter."""
+import ast
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_l2
+from oracle import loss_oracle as LO
+from oracle import packnet_oracle as PO
+
+LOSS_TOL = 1e-3     # north_star bar; the emulated kernel is in fact ~1e-7 from the reference
+GRAD_TOL = 1e-3
+
+
+def _field_close(got, want, tag):
+    """as tests/test_loss_gpu.py: a handful of kink pixels (ties of the per-pixel min, |.|, tap boundaries) may differ"""
+    got, want = got.detach().double(), want.detach().double()
+    err = (got - want).abs()
+    scale = float(want.abs().max()) + 1e-30
+    outlier = err > 1e-3 * scale
+    inl = ~outlier
+    rel = float((err[inl] ** 2).sum().sqrt() / ((want[inl] ** 2).sum().sqrt() + 1e-30))
+    assert float(outlier.double().mean()) <= max(1e-3, 12.0 / err.numel()), tag
+    assert rel < GRAD_TOL, (tag, rel)
+
+
+@pytest.mark.parametrize("case", ["loss_fullres", "loss_multires", "loss_mean_noautomask", "loss_bigmotion", "loss_progressive"])
+def test_emulated_loss_kernel_matches_reference_golden(emulated_kernels, case):
+    from packnet_sfm_b200.geometry import Pose
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    z = load_golden(case)
+    meta = ast.literal_eval(str(z["meta"]))
+    n = meta["num_scales"]
+    inv = [z["inv%d" % i].clone().requires_grad_(True) for i in range(n)]
+    mats = [z["pose%d" % j].clone().requires_grad_(True) for j in range(2)]
+    out = MultiViewPhotometricLoss(**meta)(z["rgb"], [z["ctx0"], z["ctx1"]], inv, z["K"], z["K"], [Pose(m) for m in mats])
+    out["loss"].backward()
+    ref, got = float(z["loss"]), float(out["loss"].item())
+    assert abs(got - ref) <= 1e-5 * abs(ref), (got, ref)
+    assert abs(float(out["metrics"]["photometric_loss"]) - float(z["photometric_loss"])) <= 1e-5 * abs(ref)
+    assert abs(float(out["metrics"]["smoothness_loss"]) - float(z["smoothness_loss"])) <= 1e-4 * abs(float(z["smoothness_loss"])) + 1e-9
+    for i, d in enumerate(inv):
+        g = z["ginv%d" % i]
+        if d.grad is None:
+            assert float(g.abs().max()) == 0.0
+            continue
+        _field_close(d.grad, g, ("ginv", i))
+    for j, m in enumerate(mats):
+        assert rel_l2(m.grad, z["gpose%d" % j]) < 2e-2
+        assert float(m.grad[:, 3, :].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", ["loss_fullres", "loss_bigmotion"])
+def test_emulated_warp_tap_indices_bit_exact(emulated_kernels, case):
+    from packnet_sfm_b200.losses import warp_tap_indices
+    z = load_golden(case)
+    for j in range(2):
+        taps, coords = warp_tap_indices(z["inv0"], z["K"], z["K"], z["pose%d" % j])
+        idx, ocoords = LO.warp_tap_indices(z["inv0"], z["K"], z["K"], z["pose%d" % j])
+        assert np.array_equal(coords.numpy().view(np.int32), ocoords.view(np.int32)), "float coordinates differ bitwise"
+        assert np.array_equal(taps.numpy(), idx)
+
+
+def test_emulated_loss_kernel_ragged_tiles_against_oracle(emulated_kernels):
+    """35x70 is not a multiple of the 32x16 tile: masked rows / columns, partial halos"""
+    from packnet_sfm_b200 import synthetic
+    from packnet_sfm_b200.geometry import Pose
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    B, H, W = 1, 35, 70
+    fr = synthetic.make_frames(B, H, W, seed=135)
+    inv = synthetic.make_inv_depths(B, H, W, seed=235, full_res=True)
+    vec = synthetic.make_pose_vecs(B, seed=335)
+    mats = [LO.pose_from_vec(vec[:, j]) for j in range(2)]
+    cfg = dict(num_scales=4, ssim_loss_weight=0.85, smooth_loss_weight=0.001, photometric_reduce_op="min", clip_loss=0.0,
+               automask_loss=True)
+    inv_d = [d.clone().requires_grad_(True) for d in inv]
+    mats_d = [m.clone().requires_grad_(True) for m in mats]
+    K = fr["intrinsics"]
+    out = MultiViewPhotometricLoss(**cfg)(fr["rgb"], fr["rgb_context"], inv_d, K, K, [Pose(m) for m in mats_d])
+    out["loss"].backward()
+    inv_c = [d.clone().requires_grad_(True) for d in inv]
+    mats_c = [m.clone().requires_grad_(True) for m in mats]
+    ref = LO.multiview_photometric_loss(fr["rgb"], fr["rgb_context"], inv_c, K, K, mats_c)
+    ref["loss"].backward()
+    assert abs(float(out["loss"].item()) - float(ref["loss"].item())) <= 1e-5 * abs(float(ref["loss"].item()))
+    for i, (a, b) in enumerate(zip(inv_d, inv_c)):
+        _field_close(a.grad, b.grad, ("ginv", i))
+    for a, b in zip(mats_d, mats_c):
+        assert rel_l2(a.grad, b.grad) < 2e-2
+
+
+def test_emulated_feature_stencils(emulated_kernels):
+    """Conv3d(1->8) feature stencils fused with space-to-depth / depth-to-space: the register-tiled 8-depth kernels, the
+    generic kernels (depth not a multiple of 8), masked rows / columns"""
+    from packnet_sfm_b200 import functional as PF
+    torch.manual_seed(3)
+    for pack, shape in ((True, (1, 8, 12, 8)), (False, (1, 5, 7, 24)), (True, (1, 6, 10, 5)), (False, (2, 3, 4, 16))):
+        x = (torch.rand(*shape) - 0.5).requires_grad_(True)
+        w3 = (torch.rand(8, 1, 3, 3, 3) - 0.5).requires_grad_(True)
+        b3 = (torch.rand(8) - 0.5).requires_grad_(True)
+        y = PF.pack_features(x, w3, b3) if pack else PF.unpack_features(x, w3, b3)
+        gy = torch.rand_like(y) - 0.5
+        y.backward(gy)
+        xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w3, b3))
+        xn = xd.permute(0, 3, 1, 2)
+        if pack:
+            yr = PO.conv3d_features(PO.packing(xn), wd, bd).permute(0, 2, 3, 1)
+        else:
+            yr = F.pixel_shuffle(PO.conv3d_features(xn, wd, bd), 2).permute(0, 2, 3, 1)
+        yr.backward(gy.double())
+        assert rel_l2(y, yr) < 1e-6, (pack, shape)
+        assert rel_l2(x.grad, xd.grad) < 1e-5 and rel_l2(w3.grad, wd.grad) < 1e-4 and rel_l2(b3.grad, bd.grad) < 1e-4, (pack, shape)
+
+
+def test_emulated_groupnorm_elu_and_head_conv(emulated_kernels):
+    from packnet_sfm_b200 import functional as PF
+    torch.manual_seed(4)
+    for C in (16, 64):
+        x = (torch.rand(2, 6, 10, C) * 2 - 0.7).requires_grad_(True)
+        x2 = (torch.rand(2, 6, 10, C) - 0.5).requires_grad_(True)
+        g = (torch.rand(C) + 0.5).requires_grad_(True)
+        bt = (torch.rand(C) - 0.5).requires_grad_(True)
+        for second in (None, x2):
+            for t in (x, x2, g, bt):
+                t.grad = None
+            y = PF.groupnorm_elu(x, g, bt, 1e-5, x2=second)
+            gy = torch.rand_like(y) - 0.5
+            y.backward(gy)
+            xd, x2d, gd, bd = (t.detach().double().requires_grad_(True) for t in (x, x2, g, bt))
+            inp = xd if second is None else xd + x2d
+            yr = F.elu(F.group_norm(inp.permute(0, 3, 1, 2), 16, gd, bd, 1e-5)).permute(0, 2, 3, 1)
+            yr.backward(gy.double())
+            assert rel_l2(y, yr) < 1e-6
+            assert rel_l2(x.grad, xd.grad) < 1e-5 and rel_l2(g.grad, gd.grad) < 1e-5 and rel_l2(bt.grad, bd.grad) < 1e-5
+            if second is not None:
+                assert rel_l2(x2.grad, x2d.grad) < 1e-5
+    for B, H, W, C in ((1, 9, 13, 16), (2, 6, 20, 8)):
+        x = (torch.rand(B, H, W, C) - 0.5).requires_grad_(True)
+        w = ((torch.rand(1, C, 3, 3) - 0.5) * 0.2).requires_grad_(True)
+        b = (torch.rand(1) - 0.5).requires_grad_(True)
+        y = PF.head_conv(x, w, b)
+        gy = torch.rand_like(y) - 0.5
+        y.backward(gy)
+        xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=1)[:, 0]
+        yr.backward(gy.double())
+        assert rel_l2(y, yr) < 1e-6 and rel_l2(x.grad, xd.grad) < 1e-6
+        assert rel_l2(w.grad, wd.grad) < 1e-5 and rel_l2(b.grad, bd.grad) < 1e-5
