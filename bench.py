@@ -240,6 +240,26 @@ def time_kernels(args, dev, pk):
         t_c = timed(lambda: PF._conv_raw(xh, xlo, wp, wlo, None, cout, k, prec), iters=5)
     flops = 2.0 * B * h2 * w2 * cout * cin * k * k
     tf32_peak = pk["bf16_tflops"] / (1.0 if PF.is_bf16(prec) else 2.0)
+    if PF.pack_fold_enabled(h2 * w2):
+        # the same pack1 block evaluated as ONE folded 7x7 convolution of the space-to-depth tensor (folded.py): the nine
+        # weight folds + space-to-depth + operand split + weight packing + conv_igemm + frame terms, i.e. everything the
+        # forward of the block launches between its input x [B,H,W,64] and the GroupNorm.  Algorithmic FLOPs stay the
+        # reference's (Conv2d over the 8x-inflated channel count), the Conv3d stencil's 5.6 GFLOP not counted.
+        from packnet_sfm_b200 import folded
+        x1 = torch.rand(B, H, W, 64, device=dev) - 0.5
+        w3 = torch.rand(8, 1, 3, 3, 3, device=dev) - 0.5
+        b3, b2 = torch.rand(8, device=dev) - 0.5, torch.rand(cout, device=dev) - 0.5
+        with torch.no_grad():
+            for _ in range(2):
+                folded.pack_conv_folded(x1, w, b2, w3, b3, PF.conv2d)
+            t_fold = timed(lambda: folded.pack_conv_folded(x1, w, b2, w3, b3, PF.conv2d), iters=5)
+        res["roofline_pack1_folded"] = {"bound": "tensor", "kernel": "pack1 block forward, folded: fold + s2d + split + pack + "
+                                        "conv_igemm 7x7 (n=256 -> 64) + frame terms (%s)" % args.precision,
+                                        "achieved": flops / (t_fold * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                                        "frac": flops / (t_fold * 1e-3) / 1e12 / tf32_peak, "traffic": None, "ms": t_fold,
+                                        "algorithmic_flops": flops, "executed_mac_ratio": 12544.0 / 51200.0,
+                                        "note": "achieved counts the REFERENCE formulation's FLOPs; the folded convolution executes "
+                                                "12544/51200 of them (x3 bf16 products)"}
     res["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (pack1 conv2d, %s)" % args.precision,
                        "achieved": flops / (t_c * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                        "frac": flops / (t_c * 1e-3) / 1e12 / tf32_peak,
