@@ -154,3 +154,45 @@ def test_emulated_groupnorm_elu_and_head_conv(emulated_kernels):
         yr.backward(gy.double())
         assert rel_l2(y, yr) < 1e-6 and rel_l2(x.grad, xd.grad) < 1e-6
         assert rel_l2(w.grad, wd.grad) < 1e-5 and rel_l2(b.grad, bd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,N,full_res,kw", [
+    (1, 16, 32, 1, True, {}),                                  # one context frame
+    (1, 16, 32, 3, True, {}),                                  # three (the reference's configs use two)
+    (2, 8, 8, 2, True, {}),                                    # a map smaller than one 32x16 tile
+    (1, 20, 40, 2, True, {"smooth_loss_weight": 0.0}),
+    (1, 20, 40, 2, True, {"num_scales": 2}),
+    (1, 32, 64, 2, False, {"photometric_reduce_op": "mean", "automask_loss": False}),   # multi-resolution scales + mean
+], ids=["N1", "N3", "tiny", "nosmooth", "2scales", "multires_mean"])
+def test_emulated_loss_kernel_configurations_against_oracle(emulated_kernels, B, H, W, N, full_res, kw):
+    """template instantiations and switches the golden vectors do not reach (context count, scale count, reductions)"""
+    from packnet_sfm_b200 import synthetic
+    from packnet_sfm_b200.geometry import Pose
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    fr = synthetic.make_frames(B, H, W, seed=100 + N)
+    ctx = list(fr["rgb_context"])
+    while len(ctx) < N:
+        ctx.append(torch.roll(fr["rgb"], 2 + len(ctx), 3) * 0.9 + 0.05)
+    ctx = ctx[:N]
+    inv = synthetic.make_inv_depths(B, H, W, seed=200 + N, full_res=full_res)
+    g = torch.Generator().manual_seed(N)
+    scale = torch.tensor([0.2, 0.2, 0.2, 0.02, 0.02, 0.02])
+    mats = [LO.pose_from_vec((torch.rand(B, 6, generator=g) - 0.5) * scale) for _ in range(N)]
+    cfg = dict(num_scales=4, ssim_loss_weight=0.85, smooth_loss_weight=0.001, photometric_reduce_op="min", clip_loss=0.0,
+               automask_loss=True)
+    cfg.update(kw)
+    K = fr["intrinsics"]
+    inv_d = [d.clone().requires_grad_(True) for d in inv]
+    mats_d = [m.clone().requires_grad_(True) for m in mats]
+    out = MultiViewPhotometricLoss(**cfg)(fr["rgb"], ctx, inv_d, K, K, [Pose(m) for m in mats_d])
+    out["loss"].backward()
+    inv_c = [d.clone().requires_grad_(True) for d in inv]
+    mats_c = [m.clone().requires_grad_(True) for m in mats]
+    okw = {k: v for k, v in cfg.items() if k != "clip_loss"}
+    ref = LO.multiview_photometric_loss(fr["rgb"], ctx, inv_c, K, K, mats_c, **okw)
+    ref["loss"].backward()
+    assert abs(float(out["loss"].item()) - float(ref["loss"].item())) <= 1e-5 * abs(float(ref["loss"].item()))
+    for i in range(cfg["num_scales"]):
+        _field_close(inv_d[i].grad, inv_c[i].grad, ("ginv", i))
+    for a, b in zip(mats_d, mats_c):
+        assert rel_l2(a.grad, b.grad) < 2e-2
