@@ -897,6 +897,12 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   // tile rows: tall tiles for big maps, batch folding for small ones
   P.th = TILE_ROWS;
   while (P.th > 1 && P.th / 2 >= d->height) P.th /= 2;
+  {
+    // tuning knob (debug_flags bits 16..19): force the tile height to 1, 2, 4 or 8 rows -- e.g. 4 rows x 2 images on a
+    // 12-row map fills every MMA row where the default 8-row tile leaves a quarter empty (but gives up halo staging)
+    const int forced_th = (d->debug_flags >> 16) & 15;
+    if (forced_th == 1 || forced_th == 2 || forced_th == 4 || forced_th == 8) P.th = forced_th;
+  }
   P.nb = TILE_ROWS / P.th;
   P.halo = (d->mode == PN_CONV_MODE_HALO) || (d->mode == PN_CONV_MODE_AUTO && P.nb == 1 && d->ksize > 1);
   if (d->mode == PN_CONV_MODE_PER_TAP) P.halo = 0;

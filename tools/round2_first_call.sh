@@ -18,3 +18,4 @@ done
 timeout 300 python tools/step_profile.py             > ${O}_step_breakdown.txt 2>&1
 timeout 300 python tools/step_profile.py --pack-fold > ${O}_step_breakdown_fold.txt 2>&1
 head -30 ${O}_step_breakdown_fold.txt
+timeout 600 python tools/conv_sweep.py > ${O}_conv_sweep.txt 2>&1; tail -5 ${O}_conv_sweep.txt
