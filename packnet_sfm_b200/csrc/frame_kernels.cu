@@ -49,8 +49,17 @@ struct Params {
 
 __device__ __forceinline__ int border_class(int p, int len, int m) { return p < m ? p : (p >= len - m ? p - (len - m) + m + 1 : m); }
 
+
+// (a / A2, a % A2) without a division for the two cases that occur (A2 = 1: sides, A2 = m = 2: corners of a 5x5 kernel)
+__device__ __forceinline__ void split_a(int a, int A2, int* a1, int* a2) {
+  if (A2 == 1) { *a1 = a; *a2 = 0; }
+  else if (A2 == 2) { *a1 = a >> 1; *a2 = a & 1; }
+  else { *a1 = a / A2; *a2 = a - *a1 * A2; }
+}
+
 __device__ __forceinline__ long long z_offset(const Params& P, const Term& T, int b, int a, int l, int* row, int* col) {
-  const int a1 = a / T.A2, a2 = a - a1 * T.A2;
+  int a1, a2;
+  split_a(a, T.A2, &a1, &a2);
   const int r = T.r0 + a1 * T.ra1 + a2 * T.ra2 + l * T.rl;
   const int c = T.c0 + a1 * T.ca1 + a2 * T.ca2 + l * T.cl;
   *row = r;
@@ -58,74 +67,103 @@ __device__ __forceinline__ long long z_offset(const Params& P, const Term& T, in
   return (((long long)b * P.h + r) * P.w + c) * P.Co;
 }
 
-// line window element of pixel p = (b, l), reduction index k = (e, nn)
-__device__ __forceinline__ float load_line(const Params& P, const Term& T, int p, int k) {
-  const int b = p / T.L, l = p - b * T.L;
-  const int e = k / P.n, nn = k - e * P.n;
-  const int pos = l + e - T.pad;
-  if (pos < 0 || pos >= T.L) return 0.f;
-  return __ldg(T.line + (long long)b * T.line_bs + (long long)pos * P.n + nn);
-}
-
-// one 64x64 tile of C = A * B with K in steps of 16; la(m, k) / lb(k, n) return 0 outside the problem
-template <bool A_KFAST, bool B_KFAST, class LA, class LB>
-__device__ __forceinline__ void gemm_tile(int K, int m0, int n0, LA la, LB lb, float (&acc)[4][4]) {
+// One 64x64 tile of C = A * B.  The reduction index is a triple (k2, k1, k0) with k0 the contiguous one, walked in steps
+// of BK: the loaders never divide -- a thread decomposes ITS rows / columns once (ra / rb -> context) and receives the
+// reduction triple ready-made.  A_KFAST / B_KFAST: whether consecutive threads of the tile load run along k0 (the operand
+// is contiguous in the reduction index) or along the row / column index.
+template <bool A_KFAST, bool B_KFAST, class RA, class LA, class RB, class LB>
+__device__ __forceinline__ void gemm_tile(int K2, int K1, int K0, int m0, int n0, RA ra, LA la, RB rb, LB lb, float (&acc)[4][4]) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int t = threadIdx.x;
   const int ty = t / 16, tx = t % 16;
+  constexpr int LD = (BM * BK) / NT;                     // 4 loads per thread and operand
+  // fixed per-thread assignment of the tile loads
+  int a_kk[LD], a_mm[LD], b_kk[LD], b_nn[LD];
+#pragma unroll
+  for (int i = 0; i < LD; ++i) {
+    const int idx = t + i * NT;
+    a_kk[i] = A_KFAST ? idx % BK : idx / BM;
+    a_mm[i] = A_KFAST ? idx / BK : idx % BM;
+    b_kk[i] = B_KFAST ? idx % BK : idx / BN;
+    b_nn[i] = B_KFAST ? idx / BK : idx % BN;
+  }
+  auto ca0 = ra(m0 + a_mm[0]);
+  decltype(ca0) ca[LD] = {ca0, ra(m0 + a_mm[1]), ra(m0 + a_mm[2]), ra(m0 + a_mm[3])};
+  auto cb0 = rb(n0 + b_nn[0]);
+  decltype(cb0) cb[LD] = {cb0, rb(n0 + b_nn[1]), rb(n0 + b_nn[2]), rb(n0 + b_nn[3])};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  for (int k2 = 0; k2 < K2; ++k2)
+    for (int k1 = 0; k1 < K1; ++k1)
+      for (int kb = 0; kb < K0; kb += BK) {
 #pragma unroll
-    for (int i = 0; i < (BM * BK) / NT; ++i) {
-      const int idx = t + i * NT;
-      const int kk = A_KFAST ? idx % BK : idx / BM;
-      const int mm = A_KFAST ? idx / BK : idx % BM;
-      As[kk][mm] = la(m0 + mm, k0 + kk);
-    }
+        for (int i = 0; i < LD; ++i) {
+          const int k0 = kb + a_kk[i];
+          As[a_kk[i]][a_mm[i]] = (k0 < K0) ? la(ca[i], k2, k1, k0) : 0.f;
+        }
 #pragma unroll
-    for (int i = 0; i < (BN * BK) / NT; ++i) {
-      const int idx = t + i * NT;
-      const int kk = B_KFAST ? idx % BK : idx / BN;
-      const int nn = B_KFAST ? idx / BK : idx % BN;
-      Bs[kk][nn] = lb(k0 + kk, n0 + nn);
-    }
-    __syncthreads();
+        for (int i = 0; i < LD; ++i) {
+          const int k0 = kb + b_kk[i];
+          Bs[b_kk[i]][b_nn[i]] = (k0 < K0) ? lb(cb[i], k2, k1, k0) : 0.f;
+        }
+        __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      float a[4], b[4];
+        for (int kk = 0; kk < BK; ++kk) {
+          float a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+          for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+          for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
 }
 
-// forward: M = B*L pixels, N = A*Co columns (a, co), K = KE*n
+struct PixelCtx { int valid, b, l; };                    // a row of the border line: pixel l of sample b
+struct WeightColCtx { int valid, a, co; long long off; };  // an output column (a, co) and its offset co*w_sco + a*w_sa
+struct ChannelCtx { int valid, nn; };
+struct WindowCtx { int valid, e, nn; };                  // a column (e, nn) of the line window
+
+__device__ __forceinline__ PixelCtx pixel_ctx(const Term& T, int M, int p) {
+  PixelCtx c;
+  c.valid = p < M;
+  c.b = c.valid ? p / T.L : 0;
+  c.l = p - c.b * T.L;
+  return c;
+}
+__device__ __forceinline__ WeightColCtx weight_col_ctx(const Params& P, const Term& T, int N, int c) {
+  WeightColCtx w;
+  w.valid = c < N;
+  w.a = w.valid ? c / P.Co : 0;
+  w.co = c - w.a * P.Co;
+  w.off = (long long)w.co * T.w_sco + (long long)w.a * T.w_sa;
+  return w;
+}
+__device__ __forceinline__ float line_at(const Params& P, const Term& T, int b, int pos, int nn) {
+  if (pos < 0 || pos >= T.L) return 0.f;
+  return __ldg(T.line + (long long)b * T.line_bs + (long long)pos * P.n + nn);
+}
+
+// forward: M = B*L pixels, N = A*Co columns (a, co), reduction (e, nn)
 __global__ void __launch_bounds__(NT) frame_forward_kernel(const __grid_constant__ Params P) {
   const Term& T = P.t[blockIdx.z];
-  const int M = P.B * T.L, N = T.A * P.Co, K = T.KE * P.n;
+  const int M = P.B * T.L, N = T.A * P.Co;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= M || n0 >= N) return;
   float acc[4][4];
   gemm_tile<true, true>(
-      K, m0, n0,
-      [&](int p, int k) -> float { return (p < M && k < K) ? load_line(P, T, p, k) : 0.f; },
-      [&](int k, int c) -> float {
-        if (k >= K || c >= N) return 0.f;
-        const int a = c / P.Co, co = c - a * P.Co;
-        const int e = k / P.n, nn = k - e * P.n;
-        return __ldg(T.w + co * T.w_sco + a * T.w_sa + e * T.w_se + nn);
-      },
+      1, T.KE, P.n, m0, n0,
+      [&](int p) { return pixel_ctx(T, M, p); },
+      [&](const PixelCtx& c, int, int e, int nn) -> float { return c.valid ? line_at(P, T, c.b, c.l + e - T.pad, nn) : 0.f; },
+      [&](int c) { return weight_col_ctx(P, T, N, c); },
+      [&](const WeightColCtx& c, int, int e, int nn) -> float { return c.valid ? __ldg(T.w + c.off + (long long)e * T.w_se + nn) : 0.f; },
       acc);
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
   const int g = 2 * P.m + 1;
@@ -150,30 +188,25 @@ __global__ void __launch_bounds__(NT) frame_forward_kernel(const __grid_constant
 }
 
 // backward, border lines: dline[b][j][nn] += alpha * sum_{a, e, co} gz[b, row(a,l), col(a,l), co] * w[co][a][e][nn], l = j - e + pad
-// M = B*L pixels j, N = n, K = A*KE*Co with co fastest
+// M = B*L pixels j, N = n, reduction (a, e, co)
 __global__ void __launch_bounds__(NT) frame_backward_line_kernel(const __grid_constant__ Params P) {
   const Term& T = P.t[blockIdx.z];
-  const int M = P.B * T.L, N = P.n, K = T.A * T.KE * P.Co;
+  const int M = P.B * T.L, N = P.n;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= M || n0 >= N) return;
   float acc[4][4];
   gemm_tile<true, false>(
-      K, m0, n0,
-      [&](int p, int k) -> float {
-        if (p >= M || k >= K) return 0.f;
-        const int b = p / T.L, j = p - b * T.L;
-        const int co = k % P.Co, ae = k / P.Co;
-        const int e = ae % T.KE, a = ae / T.KE;
-        const int l = j - e + T.pad;
-        if (l < 0 || l >= T.L) return 0.f;
+      T.A, T.KE, P.Co, m0, n0,
+      [&](int p) { return pixel_ctx(T, M, p); },
+      [&](const PixelCtx& c, int a, int e, int co) -> float {
+        const int l = c.l - e + T.pad;
+        if (!c.valid || l < 0 || l >= T.L) return 0.f;
         int row, col;
-        return __ldg(P.gz + z_offset(P, T, b, a, l, &row, &col) + co);
+        return __ldg(P.gz + z_offset(P, T, c.b, a, l, &row, &col) + co);
       },
-      [&](int k, int nn) -> float {
-        if (k >= K || nn >= N) return 0.f;
-        const int co = k % P.Co, ae = k / P.Co;
-        const int e = ae % T.KE, a = ae / T.KE;
-        return __ldg(T.w + co * T.w_sco + a * T.w_sa + e * T.w_se + nn);
+      [&](int nn) { ChannelCtx c; c.valid = nn < N; c.nn = nn; return c; },
+      [&](const ChannelCtx& c, int a, int e, int co) -> float {
+        return c.valid ? __ldg(T.w + (long long)co * T.w_sco + (long long)a * T.w_sa + (long long)e * T.w_se + c.nn) : 0.f;
       },
       acc);
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
@@ -191,23 +224,29 @@ __global__ void __launch_bounds__(NT) frame_backward_line_kernel(const __grid_co
 }
 
 // backward, folded weights: dw[co][a][e][nn] = alpha * sum_{b, l} gz[b, row(a,l), col(a,l), co] * line[b][l + e - pad][nn]
-// M = A*Co rows (a, co), N = KE*n columns (e, nn), K = B*L pixels
+// M = A*Co rows (a, co), N = KE*n columns (e, nn), reduction (b, l)
 __global__ void __launch_bounds__(NT) frame_backward_weight_kernel(const __grid_constant__ Params P) {
   const Term& T = P.t[blockIdx.z];
-  const int M = T.A * P.Co, N = T.KE * P.n, K = P.B * T.L;
+  const int M = T.A * P.Co, N = T.KE * P.n;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= M || n0 >= N) return;
   float acc[4][4];
   gemm_tile<false, false>(
-      K, m0, n0,
-      [&](int r, int p) -> float {
-        if (r >= M || p >= K) return 0.f;
-        const int a = r / P.Co, co = r - a * P.Co;
-        const int b = p / T.L, l = p - b * T.L;
+      1, P.B, T.L, m0, n0,
+      [&](int r) { return weight_col_ctx(P, T, M, r); },
+      [&](const WeightColCtx& c, int, int b, int l) -> float {
+        if (!c.valid) return 0.f;
         int row, col;
-        return __ldg(P.gz + z_offset(P, T, b, a, l, &row, &col) + co);
+        return __ldg(P.gz + z_offset(P, T, b, c.a, l, &row, &col) + c.co);
       },
-      [&](int p, int c) -> float { return (p < K && c < N) ? load_line(P, T, p, c) : 0.f; },
+      [&](int c) {
+        WindowCtx w;
+        w.valid = c < N;
+        w.e = w.valid ? c / P.n : 0;
+        w.nn = c - w.e * P.n;
+        return w;
+      },
+      [&](const WindowCtx& c, int, int b, int l) -> float { return c.valid ? line_at(P, T, b, l + c.e - T.pad, c.nn) : 0.f; },
       acc);
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
 #pragma unroll
@@ -220,7 +259,7 @@ __global__ void __launch_bounds__(NT) frame_backward_weight_kernel(const __grid_
       const int c = n0 + tx * 4 + j;
       if (c >= N) continue;
       const int e = c / P.n, nn = c - e * P.n;
-      T.dw[co * T.w_sco + a * T.w_sa + e * T.w_se + nn] = T.alpha * acc[i][j];
+      T.dw[(long long)co * T.w_sco + (long long)a * T.w_sa + (long long)e * T.w_se + nn] = T.alpha * acc[i][j];
     }
   }
 }
