@@ -1,9 +1,9 @@
 """Line-by-line Python mirrors of the fold and frame kernels (packnet_sfm_b200/csrc/fold_kernels.cu, frame_kernels.cu):
 thread -> element maps, shared-memory staging, store indices, loaders and the (a, l) -> (row, col) maps, restated with flat
 arrays exactly as the kernels index them.  TEST INFRASTRUCTURE: the kernels only run on the GPU tier; the mirrors pin their
-index arithmetic on the CPU tier (tests/test_fold_mirror_cpu.py, tests/test_frame_mirror_cpu.py) and, as MirrorLib, stand
-in for the shared library so that the real Python glue of folded.py runs end to end on the CPU
-(tests/test_folded_glue_cpu.py).  Keep in step with the .cu files."""
+index arithmetic on the CPU tier (tests/test_fold_mirror_cpu.py, tests/test_frame_mirror_cpu.py) in plain Python, next to
+the host emulation that executes the real sources (tests/emu/, tests/test_kernels_emulated_cpu.py).  The frame mirror states
+the reduction as one flat index; the kernel walks the same index space as nested loops."""
 import numpy as np
 
 T = 128
@@ -192,95 +192,3 @@ def frame_backward(terms, B, h, w, Co, n, m, gz, gdB):
                 col = cc if cc < m else w - 2*m + cc
             for co in range(Co):
                 gdB[(border_class(row, h, m)*g + border_class(col, w, m))*Co + co] += gz[((b*h + row)*w + col)*Co + co]
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# a stand-in for libpacknet_b200.so that runs the mirrors on CPU tensors: lets the CPU tier drive the REAL Python
-# glue (ctypes descriptors, pointer offsets, autograd functions) of packnet_sfm_b200/folded.py end to end
-# ---------------------------------------------------------------------------------------------------------------
-import ctypes
-
-
-def _arr(ptr, count):
-    if ptr is None:
-        return None
-    addr = ptr.value if hasattr(ptr, "value") else int(ptr)
-    if not addr:
-        return None
-    return np.ctypeslib.as_array(ctypes.cast(addr, ctypes.POINTER(ctypes.c_float)), shape=(int(count),))
-
-
-class MirrorLib:
-    """pn_pack_fold_* / pn_pack_frame_* with the C-ABI signatures of include/packnet_b200.h, computed by the mirrors."""
-
-    def __init__(self):
-        self.calls = []
-
-    @staticmethod
-    def _fold_dims(d):
-        ka, kb, da, db = d.ky1 - d.ky0, d.kx1 - d.kx0, d.dy1 - d.dy0, d.dx1 - d.dx0
-        return (ka + da - 1) * (kb + db - 1)
-
-    def pn_pack_fold_forward(self, dref, w2, w3, out, stream):
-        d = dref._obj
-        E = self._fold_dims(d)
-        self.calls.append("fold_fwd")
-        w2a, w3a, outa = _arr(w2, d.cout * 8 * d.n * d.ksize ** 2), _arr(w3, 216), _arr(out, d.cout * d.n * E)
-        r = fwd(w2a.astype(np.float64), w3a.astype(np.float64), d.cout, d.n, d.ksize, d.ky0, d.ky1, d.kx0, d.kx1, d.dy0, d.dy1,
-                d.dx0, d.dx1, d.layout)
-        outa[:] = r.reshape(-1)
-        return 0
-
-    def pn_pack_fold_backward(self, dref, w2, w3, dout, dS, dw2, dw3, accumulate, stream):
-        d = dref._obj
-        E = self._fold_dims(d)
-        self.calls.append("fold_bwd")
-        nw2 = d.cout * 8 * d.n * d.ksize ** 2
-        w2a, w3a, da = _arr(w2, nw2), _arr(w3, 216), _arr(dout, d.cout * d.n * E)
-        dSa = _arr(dS, d.cout * 8 * d.ksize ** 2)
-        dw2a, dw3a = _arr(dw2, nw2), _arr(dw3, 216)
-        t2, t3 = dw2a.astype(np.float64), dw3a.astype(np.float64)     # the kernel touches only the fold's tap window of dw2
-        bwd(w2a.astype(np.float64), w3a.astype(np.float64), da.astype(np.float64), None if dSa is None else dSa.astype(np.float64),
-            t2, t3, accumulate, d.cout, d.n, d.ksize, d.ky0, d.ky1, d.kx0, d.kx1, d.dy0, d.dy1, d.dx0, d.dx1, d.layout)
-        dw2a[:] = t2
-        dw3a[:] = t3
-        return 0
-
-    @staticmethod
-    def _terms(d, with_grads):
-        terms = []
-        for i in range(d.num_terms):
-            t = d.terms[i]
-            T = {k: getattr(t, k) for k in ("L", "A", "A2", "KE", "pad", "r0", "ra1", "ra2", "rl", "c0", "ca1", "ca2", "cl",
-                                            "alpha", "bias_mode", "w_sco", "w_sa", "w_se")}
-            T["line_bs"], T["dline_bs"] = t.line_bstride, t.dline_bstride
-            T["line"] = _arr(t.line, (d.batch - 1) * t.line_bstride + t.L * d.n)
-            T["w"] = _arr(t.w, d.cout * t.w_sco)
-            if with_grads:
-                T["dline"] = _arr(t.dline, (d.batch - 1) * t.dline_bstride + t.L * d.n)
-                T["dw"] = _arr(t.dw, d.cout * t.w_sco)
-            terms.append(T)
-        return terms
-
-    def pn_pack_frame_forward(self, dref, dB, z, stream):
-        d = dref._obj
-        m = d.ksize // 2
-        self.calls.append("frame_fwd")
-        g = 2 * m + 1
-        za = _arr(z, d.batch * d.height * d.width * d.cout)
-        z64 = za.astype(np.float64)
-        frame_forward(self._terms(d, False), d.batch, d.height, d.width, d.cout, d.n, m, _arr(dB, g * g * d.cout).astype(np.float64), z64)
-        za[:] = z64
-        return 0
-
-    def pn_pack_frame_backward(self, dref, gz, gdB, stream):
-        d = dref._obj
-        m = d.ksize // 2
-        self.calls.append("frame_bwd")
-        g = 2 * m + 1
-        frame_backward(self._terms(d, True), d.batch, d.height, d.width, d.cout, d.n, m,
-                       _arr(gz, d.batch * d.height * d.width * d.cout), _arr(gdB, g * g * d.cout))
-        return 0
-
-    def pn_last_error_string(self):
-        return b"mirror"
