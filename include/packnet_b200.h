@@ -238,6 +238,14 @@ typedef struct {
 int pn_pack_fold_forward(const pn_fold_desc* desc, const float* w2, const float* w3, float* out, pn_stream_t stream);
 int pn_pack_fold_backward(const pn_fold_desc* desc, const float* w2, const float* w3, const float* dout, const float* dS,
                           float* dw2, float* dw3, int accumulate, pn_stream_t stream);
+/* All nine folds of one pack layer in one call.  outs / douts: host arrays of 9 device pointers in the order
+ * main, top, bottom, left, right, tl, tr, bl, br (main OIHW [Co][n][k+2][k+2]; top/bottom [Co][m][k+2][n],
+ * left/right [Co][k+2][m][n], corners [Co][m][m][n], m = k/2: OHWI).  backward: douts[0] mandatory (it overwrites dw2,
+ * with dS added), NULL entries among the others are skipped; dw3 [8][27] is accumulated (caller zeroes). */
+int pn_pack_fold_set_forward(int cout, int n, int ksize, const float* w2, const float* w3, float* const* outs,
+                             pn_stream_t stream);
+int pn_pack_fold_set_backward(int cout, int n, int ksize, const float* w2, const float* w3, const float* const* douts,
+                              const float* dS, float* dw2, float* dw3, pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Frame terms of the folded pack block (packnet_sfm_b200/folded.py): the reference zero-pads BETWEEN the Conv3d and

@@ -73,6 +73,10 @@ def declare(lib):
     lib.pn_pack_frame_backward.argtypes = [c.POINTER(FrameDesc), vp, vp, vp]
     lib.pn_pack_frame_forward.restype = c.c_int
     lib.pn_pack_frame_backward.restype = c.c_int
+    lib.pn_pack_fold_set_forward.argtypes = [i, i, i, vp, vp, c.POINTER(vp), vp]
+    lib.pn_pack_fold_set_backward.argtypes = [i, i, i, vp, vp, c.POINTER(vp), vp, vp, vp, vp]
+    lib.pn_pack_fold_set_forward.restype = c.c_int
+    lib.pn_pack_fold_set_backward.restype = c.c_int
     lib.pn_pack_fold_forward.restype = c.c_int
     lib.pn_pack_fold_backward.restype = c.c_int
     return lib

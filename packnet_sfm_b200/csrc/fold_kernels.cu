@@ -264,3 +264,49 @@ extern "C" int pn_pack_fold_backward(const pn_fold_desc* desc, const float* w2, 
   P.w2 = w2; P.w3 = w3; P.dout = dout; P.dS = dS; P.dw2 = dw2; P.dw3 = dw3; P.accumulate = accumulate;
   return fold::dispatch(desc, P, true, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// The nine folds of one pack layer in ONE call (interior, four sides, four corners -- the window table of
+// packnet_sfm_b200/folded.py::fold_windows): saves the Python -> C round trips of the per-window entry points.
+// outs / douts [9]: order main, top, bottom, left, right, tl, tr, bl, br; main OIHW, the others OHWI.
+namespace pn {
+namespace fold {
+static void window_of(int which, int k, pn_fold_desc* d) {
+  const int m = k / 2;
+  struct R { int a0, a1; };
+  const R lo{0, m}, hi{m + 1, k}, al{0, k}, f3{0, 3}, last{2, 3}, first{0, 1};
+  const R ky[9] = {al, lo, hi, al, al, lo, lo, hi, hi};
+  const R kx[9] = {al, al, al, lo, hi, lo, hi, lo, hi};
+  const R dy[9] = {f3, last, first, f3, f3, last, last, first, first};
+  const R dx[9] = {f3, f3, f3, last, first, last, first, last, first};
+  d->ky0 = ky[which].a0; d->ky1 = ky[which].a1; d->kx0 = kx[which].a0; d->kx1 = kx[which].a1;
+  d->dy0 = dy[which].a0; d->dy1 = dy[which].a1; d->dx0 = dx[which].a0; d->dx1 = dx[which].a1;
+  d->layout = which == 0 ? PN_FOLD_LAYOUT_OIHW : PN_FOLD_LAYOUT_OHWI;
+}
+}  // namespace fold
+}  // namespace pn
+
+extern "C" int pn_pack_fold_set_forward(int cout, int n, int ksize, const float* w2, const float* w3, float* const* outs,
+                                        pn_stream_t stream) {
+  PN_REQUIRE(w2 && w3 && outs, PN_ERR_BAD_ARGUMENT, "pn_pack_fold_set_forward: null argument");
+  for (int i = 0; i < 9; ++i) {
+    pn_fold_desc d{};
+    d.cout = cout; d.n = n; d.ksize = ksize;
+    fold::window_of(i, ksize, &d);
+    if (int rc = pn_pack_fold_forward(&d, w2, w3, outs[i], stream)) return rc;
+  }
+  return PN_OK;
+}
+
+extern "C" int pn_pack_fold_set_backward(int cout, int n, int ksize, const float* w2, const float* w3, const float* const* douts,
+                                         const float* dS, float* dw2, float* dw3, pn_stream_t stream) {
+  PN_REQUIRE(w2 && w3 && douts && douts[0] && dw2 && dw3, PN_ERR_BAD_ARGUMENT,
+             "pn_pack_fold_set_backward: null argument (the interior gradient douts[0] is mandatory: it overwrites dw2)");
+  for (int i = 0; i < 9; ++i) {
+    if (!douts[i]) continue;
+    pn_fold_desc d{};
+    d.cout = cout; d.n = n; d.ksize = ksize;
+    fold::window_of(i, ksize, &d);
+    if (int rc = pn_pack_fold_backward(&d, w2, w3, douts[i], i == 0 ? dS : nullptr, dw2, dw3, i == 0 ? 0 : 1, stream)) return rc;
+  }
+  return PN_OK;
+}

@@ -127,30 +127,25 @@ def fold_set_torch(w2, w3):
 
 
 class _FoldSetCUDA(torch.autograd.Function):
-    """fold_set_torch on the fold kernels: nine launches forward; backward = nine launches accumulating into ONE dW2
-    (the interior fold writes every tap, the border folds add into their windows) and one dW3.  The interior weight
-    is OIHW (what pn_conv2d_pack_weight takes), the eight frame weights channels-last [Co, EA, EB, n] (the reduction
-    index of the frame GEMMs contiguous)."""
+    """fold_set_torch on the fold kernels, one C call each way (pn_pack_fold_set_forward / _backward: nine launches;
+    the backward accumulates all nine gradients into ONE dW2 -- the interior fold writes every tap, the border folds add
+    into their windows -- and one dW3).  The interior weight is OIHW (what pn_conv2d_pack_weight takes), the eight frame
+    weights channels-last [Co, EA, EB, n] (the reduction index of the frame GEMMs contiguous)."""
 
     @staticmethod
     def forward(ctx, w2, w3):
         from . import _lib
-        from ._lib_conv import FoldDesc
         _lib.require_cuda(w2, w3)
         co, c8, k, _ = w2.shape
         n = c8 // 8
+        m = k // 2
         w2c, w3c = w2.detach().contiguous(), w3.detach().contiguous()
-        lib, stream = _lib.lib(), _lib.current_stream()
-        outs = []
-        for name in FOLD_ORDER:
-            ky, kx, dy, dx = fold_windows(k)[name]
-            ea, eb = (ky[1] - ky[0]) + (dy[1] - dy[0]) - 1, (kx[1] - kx[0]) + (dx[1] - dx[0]) - 1
-            ohwi = name != "main"
-            o = torch.empty((co, ea, eb, n) if ohwi else (co, n, ea, eb), dtype=torch.float32, device=w2.device)
-            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1], int(ohwi))
-            _lib.check(lib.pn_pack_fold_forward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(o), stream),
-                       "pn_pack_fold_forward(%s)" % name)
-            outs.append(o)
+        dev = w2.device
+        shapes = [(co, n, k + 2, k + 2), (co, m, k + 2, n), (co, m, k + 2, n), (co, k + 2, m, n), (co, k + 2, m, n)] + \
+                 [(co, m, m, n)] * 4
+        outs = [torch.empty(sh, dtype=torch.float32, device=dev) for sh in shapes]
+        _lib.check(_lib.lib().pn_pack_fold_set_forward(co, n, k, _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr_array(outs),
+                                                       _lib.current_stream()), "pn_pack_fold_set_forward")
         S = w2c.view(co, 8, n, k, k).sum(2)
         ctx.save_for_backward(w2c, w3c)
         return tuple(outs) + (S,)
@@ -158,29 +153,21 @@ class _FoldSetCUDA(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         from . import _lib
-        from ._lib_conv import FoldDesc
         w2c, w3c = ctx.saved_tensors
         co, c8, k, _ = w2c.shape
         n = c8 // 8
-        lib, stream = _lib.lib(), _lib.current_stream()
+        dev = w2c.device
         dw2 = torch.empty_like(w2c)
-        dw3 = torch.zeros(216, dtype=torch.float32, device=w2c.device)
-        gS = grads[-1]
-        first = True
-        for name, g in zip(FOLD_ORDER, grads[:-1]):
-            ky, kx, dy, dx = fold_windows(k)[name]
-            if g is None:
-                if name != "main":
-                    continue
-                ea = k + 2
-                g = torch.zeros(co, n, ea, ea, dtype=torch.float32, device=w2c.device)   # the interior fold owns the overwrite
-            d = FoldDesc(co, n, k, ky[0], ky[1], kx[0], kx[1], dy[0], dy[1], dx[0], dx[1], int(name != "main"))
-            gc = g.contiguous()                   # named: a temporary would be freed before the call reads it
-            ds = gS.contiguous() if (first and gS is not None) else None
-            _lib.check(lib.pn_pack_fold_backward(ctypes.byref(d), _lib.ptr(w2c), _lib.ptr(w3c), _lib.ptr(gc),
-                                                 _lib.ptr(ds) if ds is not None else None, _lib.ptr(dw2), _lib.ptr(dw3),
-                                                 0 if first else 1, stream), "pn_pack_fold_backward(%s)" % name)
-            first = False
+        dw3 = torch.zeros(216, dtype=torch.float32, device=dev)
+        gs = [None if g is None else g.contiguous() for g in grads]      # named: the pointers must outlive the call
+        if gs[0] is None:
+            gs[0] = torch.zeros(co, n, k + 2, k + 2, dtype=torch.float32, device=dev)   # the interior fold owns the overwrite
+        arr = (ctypes.c_void_p * 9)()
+        for i in range(9):
+            arr[i] = None if gs[i] is None else gs[i].data_ptr()
+        _lib.check(_lib.lib().pn_pack_fold_set_backward(co, n, k, _lib.ptr(w2c), _lib.ptr(w3c), arr,
+                                                        None if gs[9] is None else _lib.ptr(gs[9]), _lib.ptr(dw2), _lib.ptr(dw3),
+                                                        _lib.current_stream()), "pn_pack_fold_set_backward")
         return dw2, dw3.view(8, 1, 3, 3, 3)
 
 
@@ -216,7 +203,7 @@ _const_cache = {}
 
 def _class_consts(k, w, device):
     """(tap mask [2m+1, k]: which taps of a k-kernel stay inside the map for each border class; column class of
-    every x in [0, w))"""
+    every x in [0, w); the outer product of the tap mask with itself as a [(2m+1)^2, k*k] matrix)"""
     key = (k, w, str(device))
     if key not in _const_cache:
         m = k // 2
@@ -225,18 +212,21 @@ def _class_consts(k, w, device):
         kk = torch.arange(k).view(1, k)
         mask = ((kk >= m - t) & (kk <= 3 * m - t)).to(torch.float32)
         cx = torch.cat([torch.arange(m), torch.full((w - 2 * m,), m, dtype=torch.long), torch.arange(m + 1, g)])
-        _const_cache[key] = (mask.to(device), cx.to(device))
+        mask2 = (mask.view(g, 1, k, 1) * mask.view(1, g, 1, k)).reshape(g * g, k * k)   # [(t,u), (ky,kx)]
+        _const_cache[key] = (mask.to(device), cx.to(device), mask2.to(device))
     return _const_cache[key]
 
 
 def bias_classes(S, b3, k, w, device):
     """Conv3d-bias term conv2d(b3 * 1_map, sum_c' W2): depends on a pixel only through its border class.
-    -> (beta [Co]: the interior value, dB [2m+1, 2m+1, Co]: class value minus beta)."""
+    -> (beta [Co]: the interior value, dB [2m+1, 2m+1, Co]: class value minus beta).  Two small matmuls:
+    Sb[co, tap] = sum_f b3[f] S[co, f, tap];  bclass[(t,u), co] = sum_tap mask[t, ky] mask[u, kx] Sb[co, tap]."""
     m = k // 2
-    mask, _ = _class_consts(k, w, device)
-    mask = mask.to(S.dtype)
-    Sb = torch.einsum("f,ofkl->okl", b3, S)
-    bclass = torch.einsum("tk,okl,ul->tuo", mask, Sb, mask)                            # [g, g, Co]; [m, m] = interior
+    g = 2 * m + 1
+    co = S.shape[0]
+    mask2 = _class_consts(k, w, device)[2].to(S.dtype)
+    Sb = torch.matmul(b3, S.reshape(co, 8, k * k))                                    # [Co, k*k]
+    bclass = torch.matmul(mask2, Sb.t()).view(g, g, co)                               # [m, m] = interior
     beta = bclass[m, m]
     return beta, bclass - beta
 
@@ -251,7 +241,7 @@ def frame_strips(top, bot, left, right, folds, b3, k):
     B, w, _ = top.shape
     h = left.shape[1]
     beta, dB = bias_classes(S, b3, k, w, top.device)
-    _, cx = _class_consts(k, w, top.device)
+    cx = _class_consts(k, w, top.device)[1]
     # ---- ring rows / columns; every index runs as (m-1-idx) from the border, hence the flips
     top_s = dB[0:m][:, cx].unsqueeze(0) - _row_conv(top, Wt, m, k).flip(1)              # [B, m, w, Co]
     bot_s = dB[m + 1:][:, cx].unsqueeze(0) - _row_conv(bot, Wb, m, k).flip(1)
@@ -295,29 +285,40 @@ class _FrameApplyCUDA(torch.autograd.Function):
     """z += frame terms, in place (one launch); backward: border-line, folded-weight and bias-class gradients
     (three launches).  weights = the eight channels-last frame folds in FOLD_ORDER[1:]."""
 
+    _templates = {}
+
     @staticmethod
     def _desc(z_shape, n, k, lines, weights, dlines=None, dws=None):
-        from . import _lib
+        """pn_frame_desc for this call: the shape-dependent part (term table, strides, maps) is built once per shape and
+        copied; only the pointers change from call to call."""
         from ._lib_conv import FrameDesc
-        B, h, w, co = z_shape
-        d = FrameDesc()
-        d.batch, d.height, d.width, d.cout, d.n, d.ksize = B, h, w, co, n, k
-        specs = frame_term_specs(h, w, n, k)
-        d.num_terms = len(specs)
-        for i, sp in enumerate(specs):
+        key = (tuple(z_shape), n, k)
+        tpl = _FrameApplyCUDA._templates.get(key)
+        if tpl is None:
+            B, h, w, co = z_shape
+            d = FrameDesc()
+            d.batch, d.height, d.width, d.cout, d.n, d.ksize = B, h, w, co, n, k
+            specs = frame_term_specs(h, w, n, k)
+            d.num_terms = len(specs)
+            where = []
+            for i, sp in enumerate(specs):
+                t = d.terms[i]
+                lfull = w if sp["line"] in ("top", "bottom") else h
+                t.line_bstride = t.dline_bstride = lfull * n
+                for f in ("w_sco", "w_sa", "w_se", "L", "A", "A2", "KE", "pad", "r0", "ra1", "ra2", "rl", "c0", "ca1", "ca2", "cl",
+                          "alpha", "bias_mode"):
+                    setattr(t, f, sp[f])
+                where.append((sp["line"], sp["px"] * n * 4, sp["name"]))
+            tpl = (d, where)
+            _FrameApplyCUDA._templates[key] = tpl
+        d = FrameDesc.from_buffer_copy(tpl[0])
+        for i, (line, off, name) in enumerate(tpl[1]):
             t = d.terms[i]
-            line = lines[sp["line"]]
-            off = sp["px"] * n * 4
-            t.line = line.data_ptr() + off
-            t.line_bstride = line.shape[1] * n
-            t.w = weights[sp["name"]].data_ptr()
+            t.line = lines[line].data_ptr() + off
+            t.w = weights[name].data_ptr()
             if dlines is not None:
-                t.dline = dlines[sp["line"]].data_ptr() + off
-                t.dline_bstride = line.shape[1] * n
-                t.dw = dws[sp["name"]].data_ptr()
-            for key in ("w_sco", "w_sa", "w_se", "L", "A", "A2", "KE", "pad", "r0", "ra1", "ra2", "rl", "c0", "ca1", "ca2", "cl",
-                        "alpha", "bias_mode"):
-                setattr(t, key, sp[key])
+                t.dline = dlines[line].data_ptr() + off
+                t.dw = dws[name].data_ptr()
         return d
 
     @staticmethod
