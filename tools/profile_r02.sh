@@ -10,5 +10,5 @@ PN_CUDA_PROFILER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --pack-fold > gpurun_out/${TAG}_fold_launches_bench.log 2>&1
 # --set full of the folded pack1 block: the 7x7 convolution (fprop, dgrad), its weight gradient, the fold and frame kernels
 ncu --set full --clock-control none --import-source on -k regex:"conv_igemm_kernel|conv_wgrad_kernel|fold_fwd_kernel|fold_bwd_kernel|frame_" \
-    -s 30 -c 30 -f -o gpurun_out/${TAG}_folded_pack1 python tools/folded_only.py > gpurun_out/${TAG}_folded_ncu.log 2>&1
+    -s 50 -c 25 -f -o gpurun_out/${TAG}_folded_pack1 python tools/folded_only.py > gpurun_out/${TAG}_folded_ncu.log 2>&1
 ls -la gpurun_out | tail -8
