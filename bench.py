@@ -48,6 +48,8 @@ def parse():
                     help="pack layers as one folded convolution (packnet_sfm_b200/folded.py); experimental until measured")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-staged-probe", action="store_true",
+                    help="skip the isolated child runs of the staged (not yet default) variants that the N=1 run appends as `staged`")
     return ap.parse_args()
 
 
@@ -274,6 +276,46 @@ def time_kernels(args, dev, pk):
     return res
 
 
+def staged_probe(args):
+    """Measure the STAGED variants of the step (folded pack layers, whole-step CUDA graph) in isolated
+    child processes, after every CUDA call of this process is done.  They are off by default because they were written
+    after the round-1 GPU budget was spent; each child runs this same script with the variant's flags for a few steps
+    and its JSON line (or its failure) is recorded under `staged` -- the headline `value` never depends on them, and a
+    child that faults or hangs (killed at the timeout) cannot take this process's result with it."""
+    out = {}
+    if os.environ.get("PN_NO_STAGED_PROBE") == "1":
+        return out
+    deadline = time.time() + 300.0
+    base = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
+            "--no-staged-probe", "--batch", str(args.batch), "--height", str(args.height), "--width", str(args.width),
+            "--precision", args.precision]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    for tag, flags in (("pack_fold", ["--pack-fold"]), ("cuda_graph", ["--graph"]), ("pack_fold+cuda_graph", ["--pack-fold", "--graph"])):
+        left = deadline - time.time()
+        if left < 45.0:
+            out[tag] = {"skipped": "probe time budget used up"}
+            continue
+        t0 = time.time()
+        try:
+            r = subprocess.run(base + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=min(120.0, left), env=env)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and lines:
+                j = json.loads(lines[-1])
+                out[tag] = {k: j.get(k) for k in ("value", "ms_per_step", "loss", "gpu_launches", "host_enqueue_ms_per_step", "cuda_graph",
+                                                  "pack_fold", "roofline_pack1_folded")}
+                out[tag]["e2e_value"] = (j.get("e2e") or {}).get("value")
+            else:
+                out[tag] = {"failed": "exit code %d" % r.returncode, "stderr_tail": r.stderr[-600:]}
+        except subprocess.TimeoutExpired:
+            out[tag] = {"failed": "timeout"}
+        except Exception as e:    # a probe must never cost the main result
+            out[tag] = {"failed": repr(e)[:300]}
+        log("staged probe %s: %.0f s -> %s" % (tag, time.time() - t0, json.dumps(out[tag])[:200]))
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from packnet_sfm_b200 import _lib, functional as PF, parallel
@@ -440,6 +482,9 @@ def run_ours(args):
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)
+        if world == 1 and not args.no_staged_probe:
+            torch.cuda.synchronize()          # nothing of this process touches the GPU after this point
+            line["staged"] = staged_probe(args)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
