@@ -196,3 +196,19 @@ def test_emulated_loss_kernel_configurations_against_oracle(emulated_kernels, B,
         _field_close(inv_d[i].grad, inv_c[i].grad, ("ginv", i))
     for a, b in zip(mats_d, mats_c):
         assert rel_l2(a.grad, b.grad) < 2e-2
+
+
+def test_emulated_packnet01_forward_matches_reference_golden():
+    """tests/emu/packnet01_emulated.py: the product's PackNet01 (networks.py) with every SIMT kernel from its real source
+    under the emulation and PyTorch's conv2d in place of the tcgen05 engine, against the golden depth maps of the live
+    reference.  Runs as a script in its own process (it swaps functional.conv2d and lifts the CUDA-only guard)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import __graft_entry__ as ge
+    ge._build_kernel_emulation()
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "packnet01_emulated.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=500)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "disp4 max-rel" in r.stdout
