@@ -69,6 +69,7 @@ struct BlockCtx {
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_gridDim, t_blockDim;
 inline thread_local BlockCtx t_ctx;
+inline thread_local unsigned t_shfl_count = 0;
 inline std::mutex g_atomic_mu;
 }  // namespace cuda_emu
 
@@ -85,13 +86,16 @@ template <class T> inline T atomicAdd(T* p, T v) {
   *p = old + v;
   return old;
 }
+// One barrier per shuffle: the exchange buffer is double-buffered by the parity of the thread's shuffle count.  A lane
+// can only reach shuffle n+2 (which reuses buffer n % 2) after the barrier of shuffle n+1, i.e. after every lane has
+// finished reading buffer n % 2.
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   const unsigned tid = cuda_emu::t_threadIdx.x, warp = tid / 32, lane = tid % 32;
-  cuda_emu::t_ctx.warp_buf[warp][lane] = (double)v;
+  const unsigned par = (cuda_emu::t_shfl_count++) & 1u;
+  double(*buf)[32] = cuda_emu::t_ctx.warp_buf + 2 * warp + par;
+  (*buf)[lane] = (double)v;
   cuda_emu::t_ctx.warp_bar[warp]->arrive_and_wait();
-  const T r = (T)cuda_emu::t_ctx.warp_buf[warp][lane ^ (unsigned)lane_mask];
-  cuda_emu::t_ctx.warp_bar[warp]->arrive_and_wait();
-  return r;
+  return (T)(*buf)[lane ^ (unsigned)lane_mask];
 }
 
 namespace cuda_emu {
@@ -108,11 +112,12 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
     wbars.emplace_back(new std::barrier<>((std::ptrdiff_t)lanes));
     wptr.push_back(wbars.back().get());
   }
-  std::vector<double[32]> wbuf(nwarps);
+  std::vector<double[32]> wbuf(2 * nwarps);
   auto worker = [&](unsigned tid) {
     t_blockDim = block;
     t_gridDim = grid;
     t_ctx = BlockCtx{&bar, wbuf.data(), wptr.data(), dyn.data()};
+    t_shfl_count = 0;
     for (unsigned bz = 0; bz < grid.z; ++bz)
       for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
