@@ -296,16 +296,17 @@ def staged_probe(args):
     # folded block on the engine against float64, block and network against the reference's golden vectors)
     t0 = time.time()
     try:
-        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_folded_gpu.py"), "-m", "gpu", "-q",
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_folded_gpu.py"),
+                            os.path.join(ROOT, "tests", "test_graph_gpu.py"), "-m", "gpu", "-q",
                             "-p", "no:cacheprovider"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200.0,
                            env=dict(env, PN_EXPERIMENTAL="1"), cwd=ROOT)
         tail = [ln for ln in r.stdout.splitlines() if ln.strip()][-6:]
-        out["tests_folded_gpu"] = {"exit_code": r.returncode, "summary": tail[-1] if tail else "", "tail": tail}
+        out["tests_experimental_gpu"] = {"exit_code": r.returncode, "summary": tail[-1] if tail else "", "tail": tail}
     except subprocess.TimeoutExpired:
-        out["tests_folded_gpu"] = {"failed": "timeout"}
+        out["tests_experimental_gpu"] = {"failed": "timeout"}
     except Exception as e:
-        out["tests_folded_gpu"] = {"failed": repr(e)[:300]}
-    log("staged probe tests: %.0f s -> %s" % (time.time() - t0, json.dumps(out["tests_folded_gpu"])[:300]))
+        out["tests_experimental_gpu"] = {"failed": repr(e)[:300]}
+    log("staged probe tests: %.0f s -> %s" % (time.time() - t0, json.dumps(out["tests_experimental_gpu"])[:300]))
     for tag, flags in (("pack_fold", ["--pack-fold"]), ("cuda_graph", ["--graph"]), ("pack_fold+cuda_graph", ["--pack-fold", "--graph"])):
         left = deadline - time.time()
         if left < 45.0:

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 O=gpurun_out/r02a
 timeout 1200 python -m pytest tests -m gpu -x -q                                   > ${O}_tests_default.log 2>&1; echo "default tier: $?"
-PN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_folded_gpu.py -m gpu -q  > ${O}_tests_folded.log 2>&1;  echo "folded tier: $?"
+PN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_folded_gpu.py tests/test_graph_gpu.py -m gpu -q  > ${O}_tests_folded.log 2>&1;  echo "folded tier: $?"
 tail -5 ${O}_tests_default.log ${O}_tests_folded.log
 for flags in "" "--pack-fold" "--graph" "--graph --pack-fold"; do
   tag=$(echo "default $flags" | tr -d ' -' )
