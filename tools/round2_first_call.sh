@@ -12,7 +12,7 @@ PN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_folded_gpu.py tests/te
 tail -5 ${O}_tests_default.log ${O}_tests_folded.log
 for flags in "" "--pack-fold" "--graph" "--graph --pack-fold"; do
   tag=$(echo "default $flags" | tr -d ' -' )
-  timeout 600 python bench.py --no-cpu-baseline $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
+  timeout 600 python bench.py --no-cpu-baseline --no-staged-probe $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
   echo "bench [$flags]: $? $(cut -c1-400 ${O}_bench_${tag}.log)"
 done
 timeout 300 python tools/step_profile.py             > ${O}_step_breakdown.txt 2>&1
