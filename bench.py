@@ -48,8 +48,10 @@ def parse():
                     help="pack layers as one folded convolution (packnet_sfm_b200/folded.py); experimental until measured")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-staged-probe", action="store_true",
-                    help="skip the isolated child runs of the staged (not yet default) variants that the N=1 run appends as `staged`")
+    ap.add_argument("--staged-probe", action="store_true",
+                    help="OPT-IN (also PN_STAGED_PROBE=1): after the N=1 run's own work, run the staged (not yet default) variants in "
+                         "isolated child processes and append their summaries as `staged` (adds up to ~8 minutes)")
+    ap.add_argument("--no-staged-probe", action="store_true", help="accepted for compatibility; the probe is off by default")
     return ap.parse_args()
 
 
@@ -283,8 +285,6 @@ def staged_probe(args):
     and its JSON line (or its failure) is recorded under `staged` -- the headline `value` never depends on them, and a
     child that faults or hangs (killed at the timeout) cannot take this process's result with it."""
     out = {}
-    if os.environ.get("PN_NO_STAGED_PROBE") == "1":
-        return out
     deadline = time.time() + 500.0
     base = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
             "--no-staged-probe", "--batch", str(args.batch), "--height", str(args.height), "--width", str(args.width),
@@ -497,7 +497,7 @@ def run_ours(args):
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)
-        if world == 1 and not args.no_staged_probe:
+        if world == 1 and not args.no_staged_probe and (args.staged_probe or os.environ.get("PN_STAGED_PROBE") == "1"):
             torch.cuda.synchronize()          # nothing of this process touches the GPU after this point
             line["staged"] = staged_probe(args)
         print(json.dumps(line))
