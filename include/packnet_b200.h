@@ -65,7 +65,13 @@ typedef struct {
   float C1, C2;                   /* SSIM constants */
   int32_t reduce_min;             /* 1: photometric_reduce_op='min', 0: 'mean' */
   int32_t automask;               /* 1: add the un-warped candidates (requires reduce_min) */
+  int32_t flags;                  /* PN_LOSS_FLAG_*; 0 = the default tile program */
 } pn_loss_desc;
+
+/* flags: run the grouped-scale tile program (csrc/loss_group_kernel.cuh): one CTA carries a tile through every scale that
+ * shares its image size, so that the target statistics, the un-warped candidates and the edge weights are computed once.
+ * Same inputs, outputs, workspace and semantics; forward and backward may use different values of the flag. */
+#define PN_LOSS_FLAG_GROUPED 1
 
 /* Scratch size for one forward(+backward) pair with this descriptor. */
 int pn_loss_workspace_bytes(const pn_loss_desc* desc, size_t* bytes);

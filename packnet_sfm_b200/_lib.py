@@ -21,8 +21,11 @@ class LossDesc(ctypes.Structure):
         ("scale_h", ctypes.c_int32 * PN_MAX_SCALES), ("scale_w", ctypes.c_int32 * PN_MAX_SCALES),
         ("ssim_loss_weight", ctypes.c_float), ("smooth_loss_weight", ctypes.c_float),
         ("C1", ctypes.c_float), ("C2", ctypes.c_float),
-        ("reduce_min", ctypes.c_int32), ("automask", ctypes.c_int32),
+        ("reduce_min", ctypes.c_int32), ("automask", ctypes.c_int32), ("flags", ctypes.c_int32),
     ]
+
+
+PN_LOSS_FLAG_GROUPED = 1
 
 
 

@@ -1,0 +1,645 @@
+// loss_group_kernel.cuh -- second generation of the fused photometric loss tile program (included by loss_kernels.cu).
+//
+// STAGED (pn_loss_desc.flags & PN_LOSS_FLAG_GROUPED; off by default until it has run on a B200): same mathematics and
+// the same reference call sites as loss_tile_kernel, restructured around what the first kernel's profile showed -- it is
+// instruction-issue bound (82 % issue-active, ~75 warp instructions per pixel and scale), not memory bound:
+//   * one CTA owns a tile for EVERY scale that shares the tile's image size (the default configuration upsamples all
+//     four inverse-depth maps to HxW, SfmModel.py:87-88): the target / context tiles are loaded once, the target's box
+//     statistics, the un-warped (auto-mask) candidates and the smoothness edge weights are computed once and reused by
+//     the 2..4 scales; only the warp and the warped candidates are per scale;
+//   * the 3x3 box sums are separable: a thread owns one column and TWO rows of the 32x16 photometric region, forms the
+//     three-tap row sums of x, x^2, x*y for four rows and combines them into both windows (12 shared loads for two
+//     pixels instead of 18, the products shared);
+//   * the SSIM quotient is evaluated on window SUMS (numerator and denominator scaled by 81^2: no division by nine) with
+//     one fast reciprocal; the candidates' order of comparison is the reference's (first minimum wins);
+//   * forward and backward use the same 34x18 warp region: the forward's core is the 32x16 photometric region, the
+//     backward's core is its 30x14 interior (every core pixel needs the winners of its eight neighbours);
+//   * pose gradients are accumulated over the scales of the group and reduced once, twelve values per context in one
+//     block reduction.
+// The warp coordinate chain (project_point / make_taps / sample3) is shared with loss_tile_kernel: bit-exact taps.
+#pragma once
+
+namespace pn {
+namespace loss {
+
+constexpr int GW = 32, GH = 16;                              // photometric region of a CTA
+constexpr int GNT = 256;                                     // threads: one column x two rows each
+constexpr int GRW = GW + 2, GRH = GH + 2, GRP = GRW * GRH;   // warp region (photometric region + 1)
+constexpr int GPP = GW * GH;
+
+struct GroupParams {
+  int h, w;
+  int tiles_x, tiles_y, tile_base;
+  int ns;                     // scales of this group (same h, w and images)
+  int scale[PN_MAX_SCALES];   // their indices in Params::sc
+};
+
+struct GParams {
+  Params P;
+  int ng;
+  GroupParams g[PN_MAX_SCALES];
+};
+
+template <bool GRAD>
+struct GroupGeom {
+  static constexpr int CO = GRAD ? 1 : 0;          // core origin inside the photometric region
+  static constexpr int CW = GW - 2 * CO;           // core: 32x16 forward, 30x14 backward
+  static constexpr int CH = GH - 2 * CO;
+  static constexpr int SLOTS = (CW * CH + GNT - 1) / GNT;
+};
+
+template <int N, bool GRAD>
+constexpr size_t group_smem_floats() {
+  size_t f = (size_t)GRP * (1 + 3 + 3 * N + 3 * N);  // inv, tgt, ref, warp
+  if (GRAD) f += (size_t)GPP * 10;                    // 9 coefficients + winner id
+  return f + 8 * 12 * N + 16;                         // reduction scratch
+}
+
+// project_point with the two exact simplifications the compiler does not make: x / 2 == x * 0.5 for every float, so the
+// ATen unnormalise step loses its two divisions (same bits, GridSampler.h grid_sampler_unnormalize)
+__device__ __forceinline__ Projection project_point_g(const float* __restrict__ Kref, const float* __restrict__ Rt,
+                                                      float X, float Y, float Zc, float wm1, float hm1) {
+  Projection p;
+  p.X = X; p.Y = Y; p.Zc = Zc;
+  const float wx = __fadd_rn(dot3_rn(Rt + 0, X, Y, Zc), Rt[9]);    // pose.py:84-85
+  const float wy = __fadd_rn(dot3_rn(Rt + 3, X, Y, Zc), Rt[10]);
+  const float wz = __fadd_rn(dot3_rn(Rt + 6, X, Y, Zc), Rt[11]);
+  p.px = dot3_rn(Kref + 0, wx, wy, wz);                            // camera.py:173
+  p.py = dot3_rn(Kref + 3, wx, wy, wz);
+  p.pz = dot3_rn(Kref + 6, wx, wy, wz);
+  p.Z = fmaxf(p.pz, 1e-5f);                                         // camera.py:180
+  const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fdiv_rn(p.px, p.Z)), wm1), 1.0f);  // camera.py:181
+  const float yn = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fdiv_rn(p.py, p.Z)), hm1), 1.0f);  // camera.py:182
+  p.ix = __fmul_rn(__fmul_rn(__fadd_rn(xn, 1.0f), 0.5f), wm1);
+  p.iy = __fmul_rn(__fmul_rn(__fadd_rn(yn, 1.0f), 0.5f), hm1);
+  return p;
+}
+
+// one MUFU.RCP (div.approx carries range scaling the SSIM denominator, >= 81^2*C1*C2 > 0 and < 1e5, does not need)
+__device__ __forceinline__ float fast_rcp(float d) {
+#ifdef PN_EMULATE
+  return 1.0f / d;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+#endif
+}
+
+// sample3 with a 32-bit tap offset from the sample's frame base and pointer steps between the channel planes
+__device__ __forceinline__ void sample3_g(const float* __restrict__ frame, int plane, int w, float ix, float iy,
+                                          const Taps& t, float out[3]) {
+  const float x1f = t.x0f + 1.0f, y1f = t.y0f + 1.0f;
+  const float wnw = (x1f - ix) * (y1f - iy), wne = (ix - t.x0f) * (y1f - iy);
+  const float wsw = (x1f - ix) * (iy - t.y0f), wse = (ix - t.x0f) * (iy - t.y0f);
+  const float* p0 = frame + (t.yi * w + t.xi);  // one index -> address conversion, then pointer steps
+  const float* p1 = p0 + w;
+#pragma unroll
+  for (int c = 0; c < 3; ++c, p0 += plane, p1 += plane) {
+    float acc = 0.0f;
+    if (t.nw) acc += __ldg(p0) * wnw;
+    if (t.ne) acc += __ldg(p0 + 1) * wne;
+    if (t.sw) acc += __ldg(p1) * wsw;
+    if (t.se) acc += __ldg(p1 + 1) * wse;
+    out[c] = acc;
+  }
+}
+
+// three-tap row sums of x, x^2 and x*y for the four rows of a thread, combined into its two 3x3 windows
+__device__ __forceinline__ void plane_sums(const float* __restrict__ src, const int (&ro)[4], const int (&co)[3],
+                                           const float (&yv)[4][3], float (&sx)[2], float (&sxx)[2], float (&sxy)[2],
+                                           float (&xc)[2]) {
+  float hx[4], hxx[4], hxy[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float* row = src + ro[r];
+    const float a = row[co[0]], b = row[co[1]], c = row[co[2]];
+    hx[r] = (a + b) + c;
+    hxx[r] = fmaf(c, c, fmaf(b, b, a * a));
+    hxy[r] = fmaf(c, yv[r][2], fmaf(b, yv[r][1], a * yv[r][0]));
+    if (r == 1) xc[0] = b;
+    if (r == 2) xc[1] = b;
+  }
+  const float mx = hx[1] + hx[2], mxx = hxx[1] + hxx[2], mxy = hxy[1] + hxy[2];
+  sx[0] = mx + hx[0];   sx[1] = mx + hx[3];
+  sxx[0] = mxx + hxx[0]; sxx[1] = mxx + hxx[3];
+  sxy[0] = mxy + hxy[0]; sxy[1] = mxy + hxy[3];
+}
+
+// clamp((1 - SSIM) / 2, 0, 1) from 3x3 window SUMS (multiview_photometric_loss.py:35-53): numerator and denominator of
+// the quotient are both scaled by 81^2, c1 = 81*C1, c2 = 81*C2, sy2 = sy*sy
+__device__ __forceinline__ float ssim_loss_from_sums(float sx, float sxx, float sxy, float sy, float syy, float sy2,
+                                                     float c1, float c2) {
+  const float p = sx * sy;
+  const float A1 = fmaf(2.0f, p, c1);
+  const float A2 = fmaf(-2.0f, p, fmaf(18.0f, sxy, c2));
+  const float q = fmaf(sx, sx, sy2);
+  const float B1 = q + c1;
+  const float B2 = fmaf(9.0f, sxx + syy, c2) - q;
+  const float ssim = (A1 * A2) * fast_rcp(B1 * B2);
+  return __saturatef(fmaf(-0.5f, ssim, 0.5f));
+}
+
+// sum of K per-thread values over the block: result in threads 0..K-1 of warp 0 ... (valid for threadIdx.x < K)
+template <int K>
+__device__ __forceinline__ float block_sum_vec(float (&v)[K], float* red /* >= 8*K floats */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) red[warp * K + i] = v[i];
+  }
+  __syncthreads();
+  float r = 0.0f;
+  if (threadIdx.x < K) {
+#pragma unroll
+    for (int wq = 0; wq < GNT / 32; ++wq) r += red[wq * K + threadIdx.x];
+  }
+  return r;
+}
+
+template <int N, bool MIN, bool GRAD>
+__global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GParams Q) {
+  using GG = GroupGeom<GRAD>;
+  constexpr int CO = GG::CO, CWc = GG::CW, CHc = GG::CH, SLOTS = GG::SLOTS;
+  const Params& P = Q.P;
+  PN_DYNAMIC_SHARED(float, smem);
+  float* s_inv = smem;
+  float* s_tgt = s_inv + GRP;             // [3][GRP]
+  float* s_ref = s_tgt + 3 * GRP;         // [N][3][GRP]  un-warped context (auto-mask)
+  float* s_warp = s_ref + 3 * N * GRP;    // [N][3][GRP]  warped context of the current scale
+  float* s_coef = s_warp + 3 * N * GRP;   // [9][GPP]     (GRAD)
+  float* s_selj = s_coef + (GRAD ? 9 * GPP : 0);  // [GPP] winner context as float (-1: none) (GRAD)
+  float* s_red = s_selj + (GRAD ? GPP : 0);       // [8*12*N + 16]
+
+  // ---- which tile -------------------------------------------------------------------------------
+  int gi = 0;
+#pragma unroll
+  for (int i = 1; i < PN_MAX_SCALES; ++i)
+    if (i < Q.ng && (int)blockIdx.x >= Q.g[i].tile_base) gi = i;
+  const GroupParams& G = Q.g[gi];
+  const int b = blockIdx.y;
+  const int tile = blockIdx.x - G.tile_base;
+  const int cx0 = (tile % G.tiles_x) * CWc, cy0 = (tile / G.tiles_x) * CHc;  // core origin
+  const int px0 = cx0 - CO, py0 = cy0 - CO;                                  // photometric region origin
+  const int rx0 = px0 - 1, ry0 = py0 - 1;                                    // warp region origin
+  const int h = G.h, w = G.w;
+  const size_t plane = (size_t)h * w;
+  const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
+  const int s_first = G.scale[0];
+  const ScaleParams& S0 = P.sc[s_first];
+
+  // the camera block depends on the scale only through (h, w): the group's first scale stands for all of them
+  const int cam_stride = CAM_STRIDE_BASE + 12 * P.N;
+  const float* cam = P.cams + (size_t)(s_first * P.B + b) * cam_stride;
+  __shared__ float s_cam[CAM_STRIDE_BASE + 12 * PN_MAX_CONTEXT];
+  if (threadIdx.x < cam_stride) s_cam[threadIdx.x] = cam[threadIdx.x];
+  const float* Kinv = s_cam;
+  const float* Kref = s_cam + 9;
+
+  const float* img_b = S0.img + (size_t)b * 3 * plane;
+
+  // ---- phase A (once): target and un-warped context tiles ------------------------------------------
+  for (int idx = threadIdx.x; idx < GRP; idx += GNT) {
+    const int i = idx % GRW, j = idx / GRW;
+    const int x = rx0 + i, y = ry0 + j;
+    const bool inside = (x >= 0) && (x < w) && (y >= 0) && (y < h);
+    const size_t o = inside ? (size_t)y * w + x : 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s_tgt[c * GRP + idx] = inside ? __ldg(img_b + c * plane + o) : 0.0f;
+    if (P.automask) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float* ctx_b = S0.ctx[k] + (size_t)b * 3 * plane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_ref[(k * 3 + c) * GRP + idx] = inside ? __ldg(ctx_b + c * plane + o) : 0.0f;
+      }
+    }
+  }
+  __syncthreads();
+
+  const float go = GRAD ? __ldg(P.grad_out) : 1.0f;
+  const float wS = P.ssim_w / 3.0f, wL = (1.0f - P.ssim_w) / 3.0f;  // channel means, :214-216
+  const float c1 = 81.0f * P.C1, c2 = 81.0f * P.C2;
+  const int ncand = P.automask ? 2 * N : N;
+  const float cand_w = MIN ? 1.0f : 1.0f / (float)ncand;               // 'mean': sum of means / len, :242
+
+  // ---- the two photometric pixels of this thread: column `col`, rows 2*rp and 2*rp+1 of the region ----
+  const int col = threadIdx.x & 31, rp = threadIdx.x >> 5;
+  const int tx = px0 + col, ty = py0 + 2 * rp;
+  const bool xin = (tx >= 0) && (tx < w);
+  bool pv[2];  // pixel inside the image
+  pv[0] = xin && (ty >= 0) && (ty < h);
+  pv[1] = xin && (ty + 1 >= 0) && (ty + 1 < h);
+  const bool active = pv[0] || pv[1];
+  bool pcore[2];  // pixel inside the core of this CTA (it contributes to the loss here)
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+    pcore[o] = pv[o] && (col >= CO) && (col < CO + CWc) && (2 * rp + o >= CO) && (2 * rp + o < CO + CHc);
+  int co[3] = {1, 1, 1}, ro[4] = {GRW, GRW, GRW, GRW};
+  if (active) {
+    // reflected window rows / columns (nn.ReflectionPad2d(1)) as offsets into the region; the rows of the two
+    // windows are (r0, r1, r2) and (r1, r2, r3)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) co[d] = reflect_idx(tx + d - 1, w) - rx0;
+    ro[0] = (reflect_idx(ty - 1, h) - ry0) * GRW;
+    ro[1] = (reflect_idx(ty, h) - ry0) * GRW;
+    ro[2] = (reflect_idx(ty + 1, h) - ry0) * GRW;
+    ro[3] = pv[1] ? (reflect_idx(ty + 2, h) - ry0) * GRW : ro[1];
+  }
+
+  // ---- phase B (once): target statistics and the un-warped candidates ---------------------------------
+  float sy[3][2], syy[3][2];
+  float pu[N][2];
+#pragma unroll
+  for (int k = 0; k < N; ++k) pu[k][0] = pu[k][1] = 0.0f;
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float yv[4][3], hy[4], hyy[4];
+      const float* tg = s_tgt + c * GRP;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) yv[r][d] = tg[ro[r] + co[d]];
+        hy[r] = (yv[r][0] + yv[r][1]) + yv[r][2];
+        hyy[r] = fmaf(yv[r][2], yv[r][2], fmaf(yv[r][1], yv[r][1], yv[r][0] * yv[r][0]));
+      }
+      sy[c][0] = (hy[1] + hy[2]) + hy[0];    sy[c][1] = (hy[1] + hy[2]) + hy[3];
+      syy[c][0] = (hyy[1] + hyy[2]) + hyy[0]; syy[c][1] = (hyy[1] + hyy[2]) + hyy[3];
+      if (P.automask) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          float sx[2], sxx[2], sxy[2], xc[2];
+          plane_sums(s_ref + (k * 3 + c) * GRP, ro, co, yv, sx, sxx, sxy, xc);
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const float l = ssim_loss_from_sums(sx[o], sxx[o], sxy[o], sy[c][o], syy[c][o], sy[c][o] * sy[c][o], c1, c2);
+            pu[k][o] += wS * l + wL * fabsf(xc[o] - yv[1 + o][1]);
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sy[c][0] = sy[c][1] = syy[c][0] = syy[c][1] = 0.0f;
+  }
+
+  // ---- (once) edge weights of the smoothness term for the core pixels of this thread -------------------
+  // exp(-mean_c |dI|) towards +x, +y and (backward) from -x, -y (utils/depth.py:176-186)
+  const bool any_smooth = (S0.sx_coef != 0.0f) || (S0.sy_coef != 0.0f);
+  float ewx[SLOTS], ewy[SLOTS], ewxl[GRAD ? SLOTS : 1], ewyu[GRAD ? SLOTS : 1];
+  if (any_smooth) {
+#pragma unroll
+    for (int slot = 0; slot < SLOTS; ++slot) {
+      const int qidx = threadIdx.x + slot * GNT;
+      ewx[slot] = ewy[slot] = 0.0f;
+      if (GRAD) ewxl[slot] = ewyu[slot] = 0.0f;
+      if (qidx >= CWc * CHc) continue;
+      const int qi = qidx % CWc, qj = qidx / CWc;
+      const int x = cx0 + qi, y = cy0 + qj;
+      if (x >= w || y >= h) continue;
+      const int ridx = (qj + CO + 1) * GRW + (qi + CO + 1);
+      float i0[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) i0[c] = s_tgt[c * GRP + ridx];
+      auto edge = [&](int off) {
+        float ad = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ad += fabsf(i0[c] - s_tgt[c * GRP + ridx + off]);
+        return expf(-ad / 3.0f);
+      };
+      if (x + 1 < w) ewx[slot] = edge(1);
+      if (y + 1 < h) ewy[slot] = edge(GRW);
+      if (GRAD) {
+        if (x >= 1) ewxl[slot] = edge(-1);
+        if (y >= 1) ewyu[slot] = edge(-GRW);
+      }
+    }
+  }
+
+  float photo_acc = 0.0f;
+  float dPose[GRAD ? N : 1][12];  // dR (row-major 3x3) then dT, accumulated over the scales of the group
+  if (GRAD) {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) dPose[k][i] = 0.0f;
+  }
+
+  // ============================== per scale ==========================================================
+  for (int js = 0; js < G.ns; ++js) {
+    const int s = G.scale[js];
+    const ScaleParams& S = P.sc[s];
+    const float* inv_b = S.inv + (size_t)b * plane;
+    __syncthreads();  // the previous scale's readers of s_inv / s_warp / s_coef are done
+
+    // ---- warp every context frame over the region -------------------------------------------------
+    for (int idx = threadIdx.x; idx < GRP; idx += GNT) {
+      const int i = idx % GRW, j = idx / GRW;
+      const int x = rx0 + i, y = ry0 + j;
+      const bool inside = (x >= 0) && (x < w) && (y >= 0) && (y < h);
+      const float inv = inside ? __ldg(inv_b + (size_t)y * w + x) : 0.0f;
+      s_inv[idx] = inv;
+      float X = 0.0f, Y = 0.0f, Zc = 0.0f;
+      if (inside) backproject(Kinv, (float)x, (float)y, depth_from_inv(inv), X, Y, Zc);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        float wv[3] = {0.0f, 0.0f, 0.0f};
+        if (inside) {
+          const float* ctx_b = S.ctx[k] + (size_t)b * 3 * plane;
+          const Projection pr = project_point_g(Kref, s_cam + CAM_STRIDE_BASE + 12 * k, X, Y, Zc, wm1, hm1);
+          const Taps t = make_taps(pr.ix, pr.iy, w, h);
+          sample3_g(ctx_b, (int)plane, w, pr.ix, pr.iy, t, wv);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_warp[(k * 3 + c) * GRP + idx] = wv[c];
+      }
+    }
+    __syncthreads();
+
+    // ---- warped candidates, min / mean over the candidates -------------------------------------------
+    float pw[N][2];
+#pragma unroll
+    for (int k = 0; k < N; ++k) pw[k][0] = pw[k][1] = 0.0f;
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float yv[4][3];
+        const float* tg = s_tgt + c * GRP;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) yv[r][d] = tg[ro[r] + co[d]];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          float sx[2], sxx[2], sxy[2], xc[2];
+          plane_sums(s_warp + (k * 3 + c) * GRP, ro, co, yv, sx, sxx, sxy, xc);
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const float l = ssim_loss_from_sums(sx[o], sxx[o], sxy[o], sy[c][o], syy[c][o], sy[c][o] * sy[c][o], c1, c2);
+            pw[k][o] += wS * l + wL * fabsf(xc[o] - yv[1 + o][1]);
+          }
+        }
+      }
+    }
+    int sel[2] = {-1, -1};  // winning candidate in the reference's order [warp0, unwarp0, warp1, unwarp1, ...] (:326-334)
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      if (!pv[o]) continue;
+      float val;
+      if (MIN) {
+        val = FLT_MAX;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          if (pw[k][o] < val) { val = pw[k][o]; sel[o] = 2 * k; }                        // first minimum wins
+          if (P.automask && pu[k][o] < val) { val = pu[k][o]; sel[o] = 2 * k + 1; }
+        }
+        if (sel[o] < 0) { val = pw[0][o]; sel[o] = 0; }  // all-NaN guard
+      } else {
+        val = 0.0f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) val += pw[k][o];
+      }
+      if (pcore[o]) photo_acc += val * cand_w;
+    }
+
+    float ginv_acc[SLOTS];
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) ginv_acc[i] = 0.0f;
+
+    if (GRAD) {
+      // 'mean' treats the contexts one after the other (pass = context); 'min' has one winner per pixel
+      const int passes = MIN ? 1 : N;
+      for (int pass = 0; pass < passes; ++pass) {
+        if (pass > 0) __syncthreads();
+        // ---- SSIM derivative coefficients of the winner (min) / of context `pass` (mean) ----------------
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int pidx = (2 * rp + o) * GW + col;
+          float coef[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) coef[i] = 0.0f;
+          float selj = -1.0f;
+          const int k = MIN ? (((sel[o] >= 0) && !(sel[o] & 1)) ? (sel[o] >> 1) : -1) : pass;
+          if (pv[o] && k >= 0) {
+            selj = (float)k;
+            const float up = go * S.photo_coef * cand_w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float* tg = s_tgt + c * GRP;
+              const float* src = s_warp + (k * 3 + c) * GRP;
+              float sx = 0.0f, sxx = 0.0f, sxy = 0.0f;
+#pragma unroll
+              for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                  const int off = ro[o + a] + co[d];
+                  const float v = src[off];
+                  sx += v; sxx += v * v; sxy += v * tg[off];
+                }
+              const SsimTerms t = ssim_from_sums<true>(sx, sxx, sxy, sy[c][o], syy[c][o], P.C1, P.C2);
+              const float half = (1.0f - t.ssim) * 0.5f;
+              const float g = (half >= 0.0f && half <= 1.0f) ? up * wS * (-0.5f) / 9.0f : 0.0f;
+              coef[c * 3 + 0] = g * t.a;
+              coef[c * 3 + 1] = g * 2.0f * t.b;
+              coef[c * 3 + 2] = g * t.c;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 9; ++i) s_coef[i * GPP + pidx] = coef[i];
+          s_selj[pidx] = selj;
+        }
+        __syncthreads();
+        // ---- gather the SSIM / L1 gradient onto the warped pixel, push it through the sampler ------------
+#pragma unroll
+        for (int slot = 0; slot < SLOTS; ++slot) {
+          const int qidx = threadIdx.x + slot * GNT;
+          if (qidx >= CWc * CHc) continue;
+          const int qi = qidx % CWc, qj = qidx / CWc;
+          const int x = cx0 + qi, y = cy0 + qj;
+          if (x >= w || y >= h) continue;
+          const int ridx = (qj + CO + 1) * GRW + (qi + CO + 1);
+          const float inv = s_inv[ridx];
+          const float depth = depth_from_inv(inv);
+          float X, Y, Zc;
+          backproject(Kinv, (float)x, (float)y, depth, X, Y, Zc);
+          float ddepth = 0.0f;
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            if (!MIN && k != pass) continue;
+            float Gc[3] = {0.0f, 0.0f, 0.0f};
+            float xq[3], yq[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              xq[c] = s_warp[(k * 3 + c) * GRP + ridx];
+              yq[c] = s_tgt[c * GRP + ridx];
+            }
+            bool any = false;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+              const int py = y + dy;
+              if (py < 0 || py >= h) continue;
+              const float my = ((py == 0 && y == 1 && dy == -1) || (py == h - 1 && y == h - 2 && dy == 1)) ? 2.0f : 1.0f;
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                const int px = x + dx;
+                if (px < 0 || px >= w) continue;
+                const float mx = ((px == 0 && x == 1 && dx == -1) || (px == w - 1 && x == w - 2 && dx == 1)) ? 2.0f : 1.0f;
+                const int cidx = (qj + CO + dy) * GW + (qi + CO + dx);
+                if (s_selj[cidx] != (float)k) continue;
+                any = true;
+                const float m = mx * my;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                  Gc[c] += m * (s_coef[(c * 3 + 0) * GPP + cidx] + s_coef[(c * 3 + 1) * GPP + cidx] * xq[c] +
+                                s_coef[(c * 3 + 2) * GPP + cidx] * yq[c]);
+              }
+            }
+            const int cself = (qj + CO) * GW + (qi + CO);
+            if (s_selj[cself] == (float)k) {
+              any = true;
+              const float up = go * S.photo_coef * cand_w * wL;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) Gc[c] += up * sgnf(xq[c] - yq[c]);
+            }
+            if (!any) continue;
+            // d warped / d (ix, iy): grid_sampler_2d backward w.r.t. the grid, in-bounds taps only
+            const float* Rt = s_cam + CAM_STRIDE_BASE + 12 * k;
+            const Projection pr = project_point_g(Kref, Rt, X, Y, Zc, wm1, hm1);
+            const Taps t = make_taps(pr.ix, pr.iy, w, h);
+            const float x1f = t.x0f + 1.0f, y1f = t.y0f + 1.0f;
+            const float* ctx_b = S.ctx[k] + (size_t)b * 3 * plane + (ptrdiff_t)t.yi * w + t.xi;
+            float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float* pc = ctx_b + c * plane;
+              const float g = Gc[c];
+              if (t.nw) { const float v = __ldg(pc);         gix -= v * (y1f - pr.iy) * g; giy -= v * (x1f - pr.ix) * g; }
+              if (t.ne) { const float v = __ldg(pc + 1);     gix += v * (y1f - pr.iy) * g; giy -= v * (pr.ix - t.x0f) * g; }
+              if (t.sw) { const float v = __ldg(pc + w);     gix -= v * (pr.iy - t.y0f) * g; giy += v * (x1f - pr.ix) * g; }
+              if (t.se) { const float v = __ldg(pc + w + 1); gix += v * (pr.iy - t.y0f) * g; giy += v * (pr.ix - t.x0f) * g; }
+            }
+            // ix == px/Z, iy == py/Z up to rounding (camera.py:181-182 then GridSampler unnormalise)
+            const float iZ = 1.0f / pr.Z;
+            const float dPx = gix * iZ, dPy = giy * iZ;
+            const float dPz = (pr.pz >= 1e-5f) ? -(gix * pr.px + giy * pr.py) * iZ * iZ : 0.0f;
+            float dXc[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dXc[i] = Kref[0 + i] * dPx + Kref[3 + i] * dPy + Kref[6 + i] * dPz;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              dPose[k][9 + r] += dXc[r];
+              dPose[k][r * 3 + 0] += dXc[r] * X;
+              dPose[k][r * 3 + 1] += dXc[r] * Y;
+              dPose[k][r * 3 + 2] += dXc[r] * Zc;
+            }
+            const float dX = Rt[0] * dXc[0] + Rt[3] * dXc[1] + Rt[6] * dXc[2];
+            const float dY = Rt[1] * dXc[0] + Rt[4] * dXc[1] + Rt[7] * dXc[2];
+            const float dZ = Rt[2] * dXc[0] + Rt[5] * dXc[1] + Rt[8] * dXc[2];
+            // X = ray * depth with ray = X / depth
+            const float rx = dot3_rn(Kinv + 0, (float)x, (float)y, 1.0f), ry = dot3_rn(Kinv + 3, (float)x, (float)y, 1.0f),
+                        rz = dot3_rn(Kinv + 6, (float)x, (float)y, 1.0f);
+            ddepth += rx * dX + ry * dY + rz * dZ;
+          }
+          if (inv >= 1e-6f) ginv_acc[slot] += -ddepth * depth * depth;  // d(1/clamp(inv)) (depth.py:120)
+        }
+      }
+    }
+
+    // ---- smoothness (utils/depth.py:146-198, multiview_photometric_loss.py:257-283) + gradient writes ----
+    float smooth_acc = 0.0f;
+    const bool do_smooth = (S.sx_coef != 0.0f) || (S.sy_coef != 0.0f);
+    const double isum = P.invsum[s * P.B + b];
+    const float mean = (float)(isum / (double)plane);
+    const float mcl = fmaxf(mean, 1e-6f);
+    const float inv_mcl = 1.0f / mcl;
+    float bs_const = 0.0f;
+    if (GRAD && do_smooth && mean >= 1e-6f)
+      bs_const = -go * (float)(P.smooth_bs[s * P.B + b] / ((double)mcl * (double)plane));
+#pragma unroll
+    for (int slot = 0; slot < SLOTS; ++slot) {
+      const int qidx = threadIdx.x + slot * GNT;
+      if (qidx >= CWc * CHc) continue;
+      const int qi = qidx % CWc, qj = qidx / CWc;
+      const int x = cx0 + qi, y = cy0 + qj;
+      if (x >= w || y >= h) continue;
+      const int ridx = (qj + CO + 1) * GRW + (qi + CO + 1);
+      float gq = 0.0f;
+      if (do_smooth) {
+        // explicit single roundings: an FMA-contracted (d0 - d1) would turn exact ties of the nearest-upsampled
+        // scales into +-1 ulp noise and sign() of noise into a full-size gradient
+        const float d0 = __fmul_rn(s_inv[ridx], inv_mcl);
+        if (x + 1 < w) {
+          const float sx = __fsub_rn(d0, __fmul_rn(s_inv[ridx + 1], inv_mcl)) * ewx[slot];
+          smooth_acc += fabsf(sx) * S.sx_coef;
+          gq += sgnf(sx) * ewx[slot] * S.sx_coef;
+        }
+        if (y + 1 < h) {
+          const float sy_ = __fsub_rn(d0, __fmul_rn(s_inv[ridx + GRW], inv_mcl)) * ewy[slot];
+          smooth_acc += fabsf(sy_) * S.sy_coef;
+          gq += sgnf(sy_) * ewy[slot] * S.sy_coef;
+        }
+        if (GRAD) {
+          if (x >= 1) {
+            const float sx = __fsub_rn(__fmul_rn(s_inv[ridx - 1], inv_mcl), d0) * ewxl[slot];
+            gq -= sgnf(sx) * ewxl[slot] * S.sx_coef;
+          }
+          if (y >= 1) {
+            const float sy_ = __fsub_rn(__fmul_rn(s_inv[ridx - GRW], inv_mcl), d0) * ewyu[slot];
+            gq -= sgnf(sy_) * ewyu[slot] * S.sy_coef;
+          }
+        }
+      }
+      if (GRAD) S.ginv[(size_t)b * plane + (size_t)y * w + x] = ginv_acc[slot] + go * gq * inv_mcl + bs_const;
+    }
+    if (!GRAD && do_smooth) {
+      const float ss = block_sum(smooth_acc, s_red);
+      if (threadIdx.x == 0) atomicAdd(P.smooth_bs + s * P.B + b, (double)ss);
+    }
+  }
+
+  // ---- reductions ----------------------------------------------------------------------------------
+  if (!GRAD) {
+    // every scale of the group has the same photo_coef (same B, h, w, n): one sum, credited to the first scale
+    const float ps = block_sum(photo_acc * S0.photo_coef, s_red);
+    if (threadIdx.x == 0) {
+      atomicAdd(P.photo_sum + s_first, (double)ps);
+      __threadfence();
+      const unsigned int ticket = atomicAdd(P.counter, 1u);
+      if (ticket == (unsigned int)(P.total_tiles * P.B) - 1u) {
+        __threadfence();
+        double photo = 0.0, smooth = 0.0;
+        for (int i = 0; i < P.n; ++i) photo += atomicAdd(P.photo_sum + i, 0.0);
+        for (int i = 0; i < P.n * P.B; ++i) smooth += atomicAdd(P.smooth_bs + i, 0.0);
+        const bool has_smooth = (P.sc[0].sx_coef != 0.0f) || (P.sc[0].sy_coef != 0.0f);
+        const float loss = (float)(photo + smooth);
+        P.out[0] = loss;
+        // reference quirk: `loss += smoothness` is in place on the tensor aliased by the stored
+        // 'photometric_loss' metric (multiview_photometric_loss.py:252,338; loss_base.py:72-74)
+        P.out[1] = has_smooth ? loss : (float)photo;
+        P.out[2] = (float)smooth;
+        P.out[3] = 0.0f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float v = block_sum_vec<12>(dPose[k], s_red);
+      if (threadIdx.x < 12 && v != 0.0f) {
+        const int i = threadIdx.x;
+        float* gp = P.gpose[k] + b * 16;
+        // dPose = [dR row-major 3x3 | dT] -> the 4x4 pose matrix gradient
+        atomicAdd(i < 9 ? gp + (i / 3) * 4 + (i % 3) : gp + (i - 9) * 4 + 3, v);
+      }
+    }
+  }
+}
+
+}  // namespace loss
+}  // namespace pn

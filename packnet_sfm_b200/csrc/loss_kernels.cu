@@ -696,9 +696,19 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
   }
 }
 
+}  // namespace loss
+}  // namespace pn
+
+#include "loss_group_kernel.cuh"   // the grouped-scale tile program (PN_LOSS_FLAG_GROUPED)
+
+namespace pn {
+namespace loss {
+
 // ---------------------------------------------------------------------------------------------------
 // inspection kernel: integer taps and float coordinates from the same device functions
 // ---------------------------------------------------------------------------------------------------
+// (GROUPED: through the grouped-scale program's copy of the coordinate chain, project_point_g)
+template <bool GROUPED>
 __global__ void warp_indices_kernel(const float* __restrict__ inv, const float* __restrict__ cams, int cam_stride,
                                     int B, int h, int w, int32_t* __restrict__ tap, float* __restrict__ coord) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -708,7 +718,8 @@ __global__ void warp_indices_kernel(const float* __restrict__ inv, const float* 
   const float* cam = cams + (size_t)b * cam_stride;
   float X, Y, Zc;
   backproject(cam, (float)x, (float)y, depth_from_inv(inv[idx]), X, Y, Zc);
-  const Projection pr = project_point(cam + 9, cam + CAM_STRIDE_BASE, X, Y, Zc, (float)(w - 1), (float)(h - 1));
+  const Projection pr = GROUPED ? project_point_g(cam + 9, cam + CAM_STRIDE_BASE, X, Y, Zc, (float)(w - 1), (float)(h - 1))
+                                : project_point(cam + 9, cam + CAM_STRIDE_BASE, X, Y, Zc, (float)(w - 1), (float)(h - 1));
   coord[2 * idx + 0] = pr.ix;
   coord[2 * idx + 1] = pr.iy;
   tap[2 * idx + 0] = (int32_t)floorf(fminf(fmaxf(pr.ix, -2.0e9f), 2.0e9f));
@@ -762,6 +773,7 @@ static int validate(const pn_loss_desc* d) {
   PN_REQUIRE(!(d->automask && !d->reduce_min), PN_ERR_BAD_ARGUMENT,
              "pn_loss: automask requires photometric_reduce_op='min' (multiview_photometric_loss.py:112-114)");
   PN_REQUIRE(d->batch <= 65535, PN_ERR_UNSUPPORTED, "pn_loss: batch > 65535");
+  PN_REQUIRE((d->flags & ~PN_LOSS_FLAG_GROUPED) == 0, PN_ERR_BAD_ARGUMENT, "pn_loss: unknown flags 0x%x", d->flags);
   return PN_OK;
 }
 
@@ -802,6 +814,65 @@ static int dispatch_tiles(const pn_loss_desc* d, const Params& P, dim3 grid, cud
 #define PN_CASE(NN)                                                                       \
   case NN:                                                                                \
     return d->reduce_min ? launch_tiles<NN, true, GRAD>(P, grid, stream) : launch_tiles<NN, false, GRAD>(P, grid, stream);
+  switch (d->num_context) {
+    PN_CASE(1)
+    PN_CASE(2)
+    PN_CASE(3)
+    PN_CASE(4)
+  }
+#undef PN_CASE
+  set_error("pn_loss: unsupported num_context %d", d->num_context);
+  return PN_ERR_UNSUPPORTED;
+}
+
+// ---- grouped-scale program: scales with the same size and images share a tile walk -----------------------------
+template <bool GRAD>
+static void make_groups(const Params& P, GParams& Q) {
+  using GG = GroupGeom<GRAD>;
+  Q.P = P;
+  Q.ng = 0;
+  int tile_base = 0;
+  for (int i = 0; i < P.n; ++i) {
+    const ScaleParams& S = P.sc[i];
+    int gi = -1;
+    for (int j = 0; j < Q.ng; ++j)
+      if (Q.g[j].h == S.h && Q.g[j].w == S.w && P.sc[Q.g[j].scale[0]].img == S.img) gi = j;
+    if (gi < 0) {
+      gi = Q.ng++;
+      GroupParams& G = Q.g[gi];
+      G.h = S.h; G.w = S.w; G.ns = 0;
+      G.tiles_x = (S.w + GG::CW - 1) / GG::CW;
+      G.tiles_y = (S.h + GG::CH - 1) / GG::CH;
+    }
+    GroupParams& G = Q.g[gi];
+    G.scale[G.ns++] = i;
+  }
+  for (int j = 0; j < Q.ng; ++j) {
+    Q.g[j].tile_base = tile_base;
+    tile_base += Q.g[j].tiles_x * Q.g[j].tiles_y;
+  }
+  Q.P.total_tiles = tile_base;
+}
+
+template <int N, bool MIN, bool GRAD>
+static int launch_groups(const GParams& Q, int batch, cudaStream_t stream) {
+  const size_t smem = group_smem_floats<N, GRAD>() * sizeof(float);
+  auto kern = loss_group_kernel<N, MIN, GRAD>;
+  PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PN_LAUNCH(kern, dim3(Q.P.total_tiles, batch), GNT, smem, stream, Q);
+  count_launch();
+  return check_launch("loss_group_kernel");
+}
+
+template <bool GRAD>
+static int dispatch_groups(const pn_loss_desc* d, const Params& P, cudaStream_t stream) {
+  PN_REQUIRE(3LL * d->height * d->width < (1LL << 31), PN_ERR_UNSUPPORTED,
+             "pn_loss (grouped): 3*H*W must fit 32-bit tap offsets");
+  GParams Q{};
+  make_groups<GRAD>(P, Q);
+#define PN_CASE(NN)                                                                       \
+  case NN:                                                                                \
+    return d->reduce_min ? launch_groups<NN, true, GRAD>(Q, d->batch, stream) : launch_groups<NN, false, GRAD>(Q, d->batch, stream);
   switch (d->num_context) {
     PN_CASE(1)
     PN_CASE(2)
@@ -922,6 +993,7 @@ extern "C" int pn_loss_forward(const pn_loss_desc* desc, const float* image, con
   if (rc) return rc;
   PN_REQUIRE(out != nullptr, PN_ERR_BAD_ARGUMENT, "pn_loss_forward: null out");
   P.out = out;
+  if (desc->flags & PN_LOSS_FLAG_GROUPED) return dispatch_groups<false>(desc, P, stream);
   return dispatch_tiles<false>(desc, P, dim3(P.total_tiles, desc->batch), stream);
 }
 
@@ -947,6 +1019,7 @@ extern "C" int pn_loss_backward(const pn_loss_desc* desc, const float* image, co
     P.gpose[j] = grad_poses[j];
     PN_CUDA(cudaMemsetAsync(grad_poses[j], 0, sizeof(float) * 16 * desc->batch, stream));
   }
+  if (desc->flags & PN_LOSS_FLAG_GROUPED) return dispatch_groups<true>(desc, P, stream);
   return dispatch_tiles<true>(desc, P, dim3(P.total_tiles, desc->batch), stream);
 }
 
@@ -978,8 +1051,13 @@ extern "C" int pn_loss_warp_indices(const pn_loss_desc* desc, int scale, const f
   PN_LAUNCH(loss_prep_kernel, dim3(1, one.batch), 256, 0, stream, Q);
   count_launch();
   const int total = one.batch * one.scale_h[0] * one.scale_w[0];
-  PN_LAUNCH(warp_indices_kernel, (total + 255) / 256, 256, 0, stream, inv_depth, Q.cams, CAM_STRIDE_BASE + 12, one.batch,
-                                                              one.scale_h[0], one.scale_w[0], tap_xy, coord_xy);
+  if (desc->flags & PN_LOSS_FLAG_GROUPED) {
+    PN_LAUNCH(warp_indices_kernel<true>, (total + 255) / 256, 256, 0, stream, inv_depth, Q.cams, CAM_STRIDE_BASE + 12, one.batch,
+                                                                      one.scale_h[0], one.scale_w[0], tap_xy, coord_xy);
+  } else {
+    PN_LAUNCH(warp_indices_kernel<false>, (total + 255) / 256, 256, 0, stream, inv_depth, Q.cams, CAM_STRIDE_BASE + 12, one.batch,
+                                                                       one.scale_h[0], one.scale_w[0], tap_xy, coord_xy);
+  }
   count_launch();
   return check_launch("warp_indices_kernel");
 }

@@ -6,6 +6,7 @@ The whole forward (warp, SSIM, L1, auto-mask min, smoothness, reduction) is ONE 
 prep kernel; the backward is one more launch of the same tile program (include/packnet_b200.h:
 pn_loss_forward / pn_loss_backward).  Gradients flow to `inv_depths[i]` and `poses[j].mat`."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -51,8 +52,21 @@ class LossBase(nn.Module):
         self._metrics[key] = val.detach()
 
 
+_grouped = os.environ.get("PN_LOSS_GROUPED") == "1"
+
+
+def set_grouped_kernel(on):
+    """Select the grouped-scale tile program (csrc/loss_group_kernel.cuh, PN_LOSS_FLAG_GROUPED) for the descriptors built
+    from now on.  STAGED: off by default until it has been measured on a B200; PN_LOSS_GROUPED=1 sets
+    the initial value.  Returns the previous setting."""
+    global _grouped
+    prev, _grouped = _grouped, bool(on)
+    return prev
+
+
 def _make_desc(B, H, W, num_context, shapes, ssim_w, smooth_w, C1, C2, reduce_min, automask):
     d = _lib.LossDesc()
+    d.flags = _lib.PN_LOSS_FLAG_GROUPED if _grouped else 0
     d.batch, d.height, d.width = B, H, W
     d.num_context, d.num_scales = num_context, len(shapes)
     for i, (h, w) in enumerate(shapes):

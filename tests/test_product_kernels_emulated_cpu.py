@@ -32,8 +32,17 @@ def _field_close(got, want, tag):
     assert rel < GRAD_TOL, (tag, rel)
 
 
+@pytest.fixture(params=[False, True], ids=["tile", "grouped"])
+def loss_program(request):
+    """both generations of the loss tile program: the default one and the grouped-scale one (PN_LOSS_FLAG_GROUPED)"""
+    from packnet_sfm_b200 import losses
+    prev = losses.set_grouped_kernel(request.param)
+    yield request.param
+    losses.set_grouped_kernel(prev)
+
+
 @pytest.mark.parametrize("case", ["loss_fullres", "loss_multires", "loss_mean_noautomask", "loss_bigmotion", "loss_progressive"])
-def test_emulated_loss_kernel_matches_reference_golden(emulated_kernels, case):
+def test_emulated_loss_kernel_matches_reference_golden(emulated_kernels, loss_program, case):
     from packnet_sfm_b200.geometry import Pose
     from packnet_sfm_b200.losses import MultiViewPhotometricLoss
     z = load_golden(case)
@@ -59,7 +68,7 @@ def test_emulated_loss_kernel_matches_reference_golden(emulated_kernels, case):
 
 
 @pytest.mark.parametrize("case", ["loss_fullres", "loss_bigmotion"])
-def test_emulated_warp_tap_indices_bit_exact(emulated_kernels, case):
+def test_emulated_warp_tap_indices_bit_exact(emulated_kernels, loss_program, case):
     from packnet_sfm_b200.losses import warp_tap_indices
     z = load_golden(case)
     for j in range(2):
@@ -69,7 +78,7 @@ def test_emulated_warp_tap_indices_bit_exact(emulated_kernels, case):
         assert np.array_equal(taps.numpy(), idx)
 
 
-def test_emulated_loss_kernel_ragged_tiles_against_oracle(emulated_kernels):
+def test_emulated_loss_kernel_ragged_tiles_against_oracle(emulated_kernels, loss_program):
     """35x70 is not a multiple of the 32x16 tile: masked rows / columns, partial halos"""
     from packnet_sfm_b200 import synthetic
     from packnet_sfm_b200.geometry import Pose
