@@ -46,6 +46,8 @@ def parse():
                          "experimental until measured on the B200")
     ap.add_argument("--pack-fold", action="store_true",
                     help="pack layers as one folded convolution (packnet_sfm_b200/folded.py); experimental until measured")
+    ap.add_argument("--loss-grouped", action="store_true",
+                    help="STAGED (DESIGN.md 7.5): the grouped-scale loss tile program (PN_LOSS_FLAG_GROUPED) instead of the default one")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged-probe", action="store_true",
@@ -222,11 +224,13 @@ def time_kernels(args, dev, pk):
     t_b = timed(bwd)
     P_s = B * H * W * 4
     bytes_f, bytes_b = 48 * P_s, 44 * P_s
-    res["roofline_loss"] = {"bound": "hbm", "kernel": "loss_tile_kernel fwd+bwd (incl. prep launches)",
+    from packnet_sfm_b200 import losses as _losses
+    grouped = bool(_losses._grouped)
+    res["roofline_loss"] = {"bound": "hbm", "kernel": ("loss_group_kernel" if grouped else "loss_tile_kernel") + " fwd+bwd (incl. prep launches)",
                             "achieved": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9 / pk["hbm_gbs"],
                             # dram__bytes_read+write of the two launches at the default shape (profiles/r01b_ncu_full_summary.txt)
-                            "traffic": 51321856 if (B, H, W) == (4, 192, 640) else None,
+                            "traffic": 51321856 if (B, H, W) == (4, 192, 640) and not grouped else None,
                             "traffic_source": "ncu --set full, profiles/r01b_ncu_full_summary.txt: every input read once, the "
                                               "per-scale re-reads the algorithmic figure counts hit L2; the kernel is issue bound "
                                               "(82 % issue-active)",
@@ -307,7 +311,8 @@ def staged_probe(args):
     except Exception as e:
         out["tests_experimental_gpu"] = {"failed": repr(e)[:300]}
     log("staged probe tests: %.0f s -> %s" % (time.time() - t0, json.dumps(out["tests_experimental_gpu"])[:300]))
-    for tag, flags in (("pack_fold", ["--pack-fold"]), ("cuda_graph", ["--graph"]), ("pack_fold+cuda_graph", ["--pack-fold", "--graph"])):
+    for tag, flags in (("pack_fold", ["--pack-fold"]), ("cuda_graph", ["--graph"]), ("pack_fold+cuda_graph", ["--pack-fold", "--graph"]),
+                       ("loss_grouped", ["--loss-grouped"])):
         left = deadline - time.time()
         if left < 45.0:
             out[tag] = {"skipped": "probe time budget used up"}
@@ -319,7 +324,7 @@ def staged_probe(args):
             if r.returncode == 0 and lines:
                 j = json.loads(lines[-1])
                 out[tag] = {k: j.get(k) for k in ("value", "ms_per_step", "loss", "gpu_launches", "host_enqueue_ms_per_step", "cuda_graph",
-                                                  "pack_fold", "roofline_pack1_folded")}
+                                                  "pack_fold", "roofline_pack1_folded", "loss_grouped", "roofline_loss")}
                 out[tag]["e2e_value"] = (j.get("e2e") or {}).get("value")
             else:
                 out[tag] = {"failed": "exit code %d" % r.returncode, "stderr_tail": r.stderr[-600:]}
@@ -359,6 +364,9 @@ def run_ours(args):
     opt = torch.optim.Adam(groups, fused=True, capturable=bool(args.graph))
     if args.pack_fold:
         PF.set_pack_fold(True)
+    if args.loss_grouped:
+        from packnet_sfm_b200 import losses as _losses
+        _losses.set_grouped_kernel(True)
     B, H, W = args.batch, args.height, args.width
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)
@@ -493,7 +501,8 @@ def run_ours(args):
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
-                "loss": state.get("loss_host"), "cuda_graph": graph_info, "pack_fold": bool(args.pack_fold)}
+                "loss": state.get("loss_host"), "cuda_graph": graph_info, "pack_fold": bool(args.pack_fold),
+                "loss_grouped": bool(args.loss_grouped)}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)

@@ -9,7 +9,21 @@ import torch
 from conftest import load_golden, rel_l2
 from oracle import loss_oracle as LO
 
+import os
+
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["tile", "grouped"])
+def loss_program(request):
+    """Every test of this file runs on the default tile program; with PN_EXPERIMENTAL=1 also on the staged grouped-scale
+    program (csrc/loss_group_kernel.cuh, PN_LOSS_FLAG_GROUPED) -- same assertions."""
+    from packnet_sfm_b200 import losses
+    if request.param == "grouped" and os.environ.get("PN_EXPERIMENTAL") != "1":
+        pytest.skip("staged grouped-scale loss program: set PN_EXPERIMENTAL=1")
+    prev = losses.set_grouped_kernel(request.param == "grouped")
+    yield request.param
+    losses.set_grouped_kernel(prev)
 
 LOSS_TOL = 1e-3        # north_star: photometric loss within 1e-3 relative fp32
 GRAD_TOL = 1e-3        # gradient fields: relative L2 over the inlier pixels

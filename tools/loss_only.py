@@ -23,3 +23,39 @@ for _ in range(3):
     torch.autograd.grad(out["loss"], inv + mats)
 torch.cuda.synchronize()
 print("loss", float(out["loss"]))
+
+# CUDA-event timing of the forward and the backward call (L2 flushed before each), for the tile-vs-grouped comparison:
+#   python tools/loss_only.py ; PN_LOSS_GROUPED=1 python tools/loss_only.py
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, iters=20):
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+state = {}
+
+
+def fwd():
+    state["o"] = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats])
+
+
+def bwd():
+    torch.autograd.grad(state["o"]["loss"], inv + mats, retain_graph=True)
+
+
+fwd()
+t_f, t_b = timed(fwd), timed(bwd)
+P_s = B * H * W * 4
+print("program %s: fwd %.4f ms (%.0f GB/s algorithmic), bwd %.4f ms (%.0f GB/s algorithmic)" % (
+    "grouped" if os.environ.get("PN_LOSS_GROUPED") == "1" else "tile", t_f, 48 * P_s / t_f / 1e6, t_b, 44 * P_s / t_b / 1e6))

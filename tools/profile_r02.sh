@@ -12,3 +12,7 @@ PN_CUDA_PROFILER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum
 ncu --set full --clock-control none --import-source on -k regex:"conv_igemm_kernel|conv_wgrad_kernel|fold_fwd_kernel|fold_bwd_kernel|frame_" \
     -s 50 -c 25 -f -o gpurun_out/${TAG}_folded_pack1 python tools/folded_only.py > gpurun_out/${TAG}_folded_ncu.log 2>&1
 ls -la gpurun_out | tail -8
+# --set full of the grouped-scale loss program (forward + backward launches of the third iteration)
+PN_LOSS_GROUPED=1 ncu --set full --clock-control none --import-source on -k regex:"loss_group_kernel" \
+    -s 4 -c 2 -f -o gpurun_out/${TAG}_loss_grouped python tools/loss_only.py > gpurun_out/${TAG}_loss_grouped_ncu.log 2>&1
+ls -la gpurun_out | tail -4

@@ -2,15 +2,18 @@
 # First GPU call of round 2: everything written after the round-1 GPU budget ran out, in one gpurun.
 #   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
 # 1) default -m gpu tier (the measured path must still be green)
-# 2) experimental tier: fold kernels, folded pack block, PackNet01 with folded pack layers
+# 2) experimental tier: fold kernels, folded pack block, PackNet01 with folded pack layers; the grouped-scale loss program
 # 3) bench: default / --pack-fold / --graph / both; CUPTI step breakdown with and without the fold
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 O=gpurun_out/r02a
 timeout 1200 python -m pytest tests -m gpu -x -q                                   > ${O}_tests_default.log 2>&1; echo "default tier: $?"
 PN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_folded_gpu.py tests/test_graph_gpu.py -m gpu -q  > ${O}_tests_folded.log 2>&1;  echo "folded tier: $?"
-tail -5 ${O}_tests_default.log ${O}_tests_folded.log
-for flags in "" "--pack-fold" "--graph" "--graph --pack-fold"; do
+PN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_loss_gpu.py -m gpu -q -k grouped > ${O}_tests_loss_grouped.log 2>&1;  echo "grouped loss tier: $?"
+tail -5 ${O}_tests_default.log ${O}_tests_folded.log ${O}_tests_loss_grouped.log
+timeout 300 python tools/loss_only.py > ${O}_loss_only_tile.txt 2>&1; PN_LOSS_GROUPED=1 timeout 300 python tools/loss_only.py > ${O}_loss_only_grouped.txt 2>&1
+tail -3 ${O}_loss_only_tile.txt ${O}_loss_only_grouped.txt
+for flags in "" "--loss-grouped" "--pack-fold" "--graph" "--graph --pack-fold --loss-grouped"; do
   tag=$(echo "default $flags" | tr -d ' -' )
   timeout 600 python bench.py --no-cpu-baseline --no-staged-probe $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
   echo "bench [$flags]: $? $(cut -c1-400 ${O}_bench_${tag}.log)"
@@ -19,3 +22,6 @@ timeout 300 python tools/step_profile.py             > ${O}_step_breakdown.txt 2
 timeout 300 python tools/step_profile.py --pack-fold > ${O}_step_breakdown_fold.txt 2>&1
 head -30 ${O}_step_breakdown_fold.txt
 timeout 600 python tools/conv_sweep.py > ${O}_conv_sweep.txt 2>&1; tail -5 ${O}_conv_sweep.txt
+# BASELINE configs[2] shape on one GPU (B=2, 384x1280): never run on the B200 in round 1
+timeout 600 python bench.py --no-cpu-baseline --height 384 --width 1280 --batch 2 > ${O}_bench_384x1280.log 2> ${O}_bench_384x1280.err
+echo "bench [384x1280 B=2]: $? $(cut -c1-300 ${O}_bench_384x1280.log)"
