@@ -1,0 +1,50 @@
+"""The loss tile programs at the BENCH image size (192x640, default loss settings, four upsampled scales) under the host
+emulation against the oracle -- the tile walks at the real dimensions (fwd 20x12 tiles of 32x16; grouped backward 22x14 tiles
+of 30x14 with ragged last row / column).  TEST INFRASTRUCTURE, a script (minutes): python tests/emu/loss_fullsize_emulated.py
+[grouped|tile] [B]"""
+import ctypes, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import torch
+from conftest import rel_l2
+from packnet_sfm_b200 import _lib, _lib_conv, synthetic, losses
+lib = ctypes.CDLL(os.path.join(ROOT, 'tests', 'emu', '_build', 'libpacknet_emu.so'))
+_lib._declare(lib); _lib_conv.declare(lib)
+_lib.lib = lambda: lib; _lib.require_cuda = lambda *a: None; _lib.current_stream = lambda: None
+from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+from packnet_sfm_b200.geometry import Pose
+from packnet_sfm_b200.models import YACS_LOSS_DEFAULTS
+from oracle import loss_oracle as LO
+
+program = sys.argv[1] if len(sys.argv) > 1 else "grouped"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+H, W = 192, 640
+losses.set_grouped_kernel(program == "grouped")
+fr = synthetic.make_frames(B, H, W, seed=5)
+inv = synthetic.make_inv_depths(B, H, W, seed=6)
+vec = synthetic.make_pose_vecs(B, seed=7)
+mats = [LO.pose_from_vec(vec[:, j]) for j in range(2)]
+K = fr["intrinsics"]
+inv_d = [d.clone().requires_grad_(True) for d in inv]; mats_d = [m.clone().requires_grad_(True) for m in mats]
+t0 = time.time()
+out = MultiViewPhotometricLoss(**YACS_LOSS_DEFAULTS)(fr["rgb"], fr["rgb_context"], inv_d, K, K, [Pose(m) for m in mats_d])
+out["loss"].backward()
+t1 = time.time()
+inv_c = [d.clone().requires_grad_(True) for d in inv]; mats_c = [m.clone().requires_grad_(True) for m in mats]
+cfg = {k: v for k, v in YACS_LOSS_DEFAULTS.items() if k in ("num_scales", "ssim_loss_weight", "smooth_loss_weight", "photometric_reduce_op", "automask_loss", "C1", "C2")}
+ref = LO.multiview_photometric_loss(fr["rgb"], fr["rgb_context"], inv_c, K, K, mats_c, **cfg)
+ref["loss"].backward()
+a, b = float(out["loss"].item()), float(ref["loss"].item())
+print("program %s B=%d %dx%d: emulated %.1f s; loss %.8f oracle %.8f rel %.2e" % (program, B, H, W, t1 - t0, a, b, abs(a - b) / abs(b)))
+ok = abs(a - b) <= 1e-5 * abs(b)
+for i, (x, y) in enumerate(zip(inv_d, inv_c)):
+    err = (x.grad.double() - y.grad.double()).abs(); sc = float(y.grad.abs().max()) + 1e-30
+    outl = err > 1e-3 * sc
+    rel = float((err[~outl] ** 2).sum().sqrt() / ((y.grad.double()[~outl] ** 2).sum().sqrt() + 1e-30))
+    print("  ginv%d: outlier fraction %.2e, inlier rel_l2 %.2e" % (i, float(outl.double().mean()), rel))
+    ok = ok and float(outl.double().mean()) <= 1e-3 and rel < 1e-3
+for j, (x, y) in enumerate(zip(mats_d, mats_c)):
+    r = rel_l2(x.grad, y.grad)
+    print("  gpose%d: rel_l2 %.2e" % (j, r))
+    ok = ok and r < 2e-2
+print("OK" if ok else "MISMATCH")
