@@ -28,7 +28,9 @@ def _field_close(got, want, tag):
     outlier = err > 1e-3 * scale
     inl = ~outlier
     rel = float((err[inl] ** 2).sum().sqrt() / ((want[inl] ** 2).sum().sqrt() + 1e-30))
-    assert float(outlier.double().mean()) <= max(1e-3, 12.0 / err.numel()), tag
+    from packnet_sfm_b200 import losses
+    kink = 21.0 if losses._grouped else 12.0     # see tests/test_loss_gpu.py _kink_pixels
+    assert float(outlier.double().mean()) <= max(1e-3, kink / err.numel()), tag
     assert rel < GRAD_TOL, (tag, rel)
 
 
