@@ -32,7 +32,7 @@ out["loss"].backward()
 t1 = time.time()
 inv_c = [d.clone().requires_grad_(True) for d in inv]; mats_c = [m.clone().requires_grad_(True) for m in mats]
 cfg = {k: v for k, v in YACS_LOSS_DEFAULTS.items() if k in ("num_scales", "ssim_loss_weight", "smooth_loss_weight", "photometric_reduce_op", "automask_loss", "C1", "C2")}
-ref = LO.multiview_photometric_loss(fr["rgb"], fr["rgb_context"], inv_c, K, K, mats_c, **cfg)
+ref = LO.multiview_photometric_loss(fr["rgb"], fr["rgb_context"], inv_c, K, K, mats_c, return_maps=True, **cfg)
 ref["loss"].backward()
 a, b = float(out["loss"].item()), float(ref["loss"].item())
 print("program %s B=%d %dx%d: emulated %.1f s; loss %.8f oracle %.8f rel %.2e" % (program, B, H, W, t1 - t0, a, b, abs(a - b) / abs(b)))
@@ -41,7 +41,16 @@ for i, (x, y) in enumerate(zip(inv_d, inv_c)):
     err = (x.grad.double() - y.grad.double()).abs(); sc = float(y.grad.abs().max()) + 1e-30
     outl = err > 1e-3 * sc
     rel = float((err[~outl] ** 2).sum().sqrt() / ((y.grad.double()[~outl] ** 2).sum().sqrt() + 1e-30))
-    print("  ginv%d: outlier fraction %.2e, inlier rel_l2 %.2e" % (i, float(outl.double().mean()), rel))
+    # kink pixels explained by a near-tie of the per-pixel minimum: the two smallest candidates of the oracle closer than the
+    # fp32 noise of the SSIM term (tools/ssim_noise_study.py) somewhere in the pixel's 3x3 neighbourhood
+    cand = torch.cat([m.detach() for m in ref["photometric_maps"][i]], 1)
+    two = cand.topk(2, dim=1, largest=False).values
+    tie = ((two[:, 1:2] - two[:, 0:1]) < 1e-4).float()
+    tie = torch.nn.functional.max_pool2d(tie, 3, 1, 1) > 0
+    unexplained = int((outl & ~tie).sum())
+    print("  ginv%d: outlier fraction %.2e (%d pixels, %d not next to a near-tie), inlier rel_l2 %.2e" % (
+        i, float(outl.double().mean()), int(outl.sum()), unexplained, rel))
+    ok = ok and unexplained <= 2
     ok = ok and float(outl.double().mean()) <= 1e-3 and rel < 1e-3
 for j, (x, y) in enumerate(zip(mats_d, mats_c)):
     r = rel_l2(x.grad, y.grad)
