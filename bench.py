@@ -48,6 +48,8 @@ def parse():
                     help="pack layers as one folded convolution (packnet_sfm_b200/folded.py); experimental until measured")
     ap.add_argument("--loss-grouped", action="store_true",
                     help="STAGED (DESIGN.md 7.5): the grouped-scale loss tile program (PN_LOSS_FLAG_GROUPED) instead of the default one")
+    ap.add_argument("--im2col-first", action="store_true",
+                    help="STAGED (DESIGN.md 7.6): first convolution (3 -> 64, 5x5) as a 1x1 convolution over its im2col tensor")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged-probe", action="store_true",
@@ -367,6 +369,8 @@ def run_ours(args):
     if args.loss_grouped:
         from packnet_sfm_b200 import losses as _losses
         _losses.set_grouped_kernel(True)
+    if args.im2col_first:
+        PF.set_im2col_first(True)
     B, H, W = args.batch, args.height, args.width
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)
@@ -502,7 +506,7 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
                 "loss": state.get("loss_host"), "cuda_graph": graph_info, "pack_fold": bool(args.pack_fold),
-                "loss_grouped": bool(args.loss_grouped)}
+                "loss_grouped": bool(args.loss_grouped), "im2col_first": bool(args.im2col_first)}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)

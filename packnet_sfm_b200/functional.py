@@ -20,7 +20,19 @@ from . import _lib
 from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3, MODE_AUTO
 
 _state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": os.environ.get("PN_PACK_FOLD", "0") == "1",
-          "pack_fold_min_pixels": int(os.environ.get("PN_PACK_FOLD_MIN_PIXELS", "1920"))}
+          "pack_fold_min_pixels": int(os.environ.get("PN_PACK_FOLD_MIN_PIXELS", "1920")),
+          "im2col_first": os.environ.get("PN_IM2COL_FIRST", "0") == "1"}
+
+
+def set_im2col_first(on):
+    """STAGED (off by default): evaluate the network's first convolution (3 -> 64, 5x5) as a 1x1 convolution
+    over its im2col tensor (conv2d_im2col) instead of 25 tap items that each fill 3 of 64 reduction lanes."""
+    prev, _state["im2col_first"] = _state["im2col_first"], bool(on)
+    return prev
+
+
+def im2col_first_enabled():
+    return _state["im2col_first"]
 
 
 def set_pack_fold(on, min_pixels=None):
@@ -193,6 +205,33 @@ class _Conv2d(torch.autograd.Function):
 def conv2d(x, weight, bias=None):
     """x: [B,H,W,C] with C a multiple of channel_align(); weight may have fewer input channels (zero-padded)."""
     return _Conv2d.apply(x, weight, bias)
+
+
+def conv2d_im2col(x, weight, bias=None, conv=None, align=None):
+    """The same convolution (stride 1, zero pad k//2, nn.Conv2d + ConstantPad2d of layers01.py:28-30,36) for a layer with
+    FEW input channels, evaluated as ONE 1x1 convolution over the im2col tensor [B,H,W,align(Cin*k*k)].
+
+    The tensor-core engine walks (tap, 64-channel chunk) items; with Cin = 3 every one of the 25 taps of PackNet01's first
+    layer is a full-width MMA over 3 useful reduction lanes (measured 0.45 ms forward + 0.35 ms weight gradient at 28 and
+    36 TFLOP/s, profiles/r01_layer_table.txt).  The im2col tensor has 75 -> 80 channels = two chunks of one 1x1 tap:
+    12.5x fewer MMA cycles for one extra 157 MB copy.  x: [B,H,W,C>=Cin] NHWC (only the first Cin channels are read);
+    `conv` is the convolution callable (default: this module's tensor-core conv2d; the CPU tests pass a PyTorch one)."""
+    import torch.nn.functional as F
+    conv = conv2d if conv is None else conv
+    align = channel_align() if align is None else align
+    B, H, W, _ = x.shape
+    cout, cin, k, _ = weight.shape
+    m = k // 2
+    xp = F.pad(x[..., :cin], (0, 0, m, m, m, m))              # zero frame of k//2 pixels around the map
+    patches = xp.unfold(1, k, 1).unfold(2, k, 1)                 # [B,H,W,cin,k,k] view: (c, ky, kx) as in weight[co]
+    K = cin * k * k
+    Kp = (K + align - 1) // align * align
+    col = torch.empty(B, H, W, Kp, dtype=x.dtype, device=x.device)
+    col[..., :K].view(B, H, W, cin, k, k).copy_(patches)
+    if Kp > K:
+        col[..., K:].zero_()
+    w2 = F.pad(weight.reshape(cout, K), (0, Kp - K)).view(cout, Kp, 1, 1)
+    return conv(col, w2, bias)
 
 
 # The GroupNorm backward already reduces its dx over the pixels; the convolution that consumes dx as its output

@@ -222,7 +222,13 @@ class PackNet01(nn.Module):
         # NCHW image -> NHWC, zero-padded to the operand's channel multiple (TMA row pitch)
         cpad = PF.channel_align() - 3
         x_in = torch.cat([rgb.permute(0, 2, 3, 1), torch.zeros(B, H, W, cpad, dtype=rgb.dtype, device=rgb.device)], -1)
-        x = self.pre_calc(x_in.contiguous())
+        if PF.im2col_first_enabled():
+            # staged: the 3 -> 64 5x5 layer as one 1x1 convolution over its im2col tensor (functional.conv2d_im2col)
+            pc = self.pre_calc
+            z = PF.conv2d_im2col(rgb.permute(0, 2, 3, 1), pc.conv_base.weight, pc.conv_base.bias)
+            x = PF.groupnorm_elu(z, pc.normalize.weight, pc.normalize.bias, pc.normalize.eps)
+        else:
+            x = self.pre_calc(x_in.contiguous())
 
         x1 = self.conv1(x)
         x1p = self.pack1(x1)

@@ -10,10 +10,11 @@ O=gpurun_out/r02a
 timeout 1200 python -m pytest tests -m gpu -x -q                                   > ${O}_tests_default.log 2>&1; echo "default tier: $?"
 PN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_folded_gpu.py tests/test_graph_gpu.py -m gpu -q  > ${O}_tests_folded.log 2>&1;  echo "folded tier: $?"
 PN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_loss_gpu.py -m gpu -q -k grouped > ${O}_tests_loss_grouped.log 2>&1;  echo "grouped loss tier: $?"
+PN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_recompose_gpu.py -m gpu -q -s > ${O}_tests_recompose.log 2>&1;  echo "recompose tier: $?"; tail -3 ${O}_tests_recompose.log
 tail -5 ${O}_tests_default.log ${O}_tests_folded.log ${O}_tests_loss_grouped.log
 timeout 300 python tools/loss_only.py > ${O}_loss_only_tile.txt 2>&1; PN_LOSS_GROUPED=1 timeout 300 python tools/loss_only.py > ${O}_loss_only_grouped.txt 2>&1
 tail -3 ${O}_loss_only_tile.txt ${O}_loss_only_grouped.txt
-for flags in "" "--loss-grouped" "--pack-fold" "--graph" "--graph --pack-fold --loss-grouped"; do
+for flags in "" "--loss-grouped" "--im2col-first" "--pack-fold" "--graph" "--graph --pack-fold --loss-grouped --im2col-first"; do
   tag=$(echo "default $flags" | tr -d ' -' )
   timeout 600 python bench.py --no-cpu-baseline --no-staged-probe $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
   echo "bench [$flags]: $? $(cut -c1-400 ${O}_bench_${tag}.log)"
