@@ -16,7 +16,8 @@
 //     backward's core is its 30x14 interior (every core pixel needs the winners of its eight neighbours);
 //   * pose gradients are accumulated over the scales of the group and reduced once, twelve values per context in one
 //     block reduction.
-// The warp coordinate chain (project_point / make_taps / sample3) is shared with loss_tile_kernel: bit-exact taps.
+// The warp coordinate chain is loss_tile_kernel's (backproject / make_taps) with project_point_g / sample3_g below: the same
+// IEEE operations in the same order minus two exact simplifications -- bit-exact taps (pn_loss_warp_indices honours the flag).
 #pragma once
 
 namespace pn {
@@ -140,7 +141,7 @@ __device__ __forceinline__ float ssim_loss_from_sums(float sx, float sxx, float 
   return __saturatef(fmaf(-0.5f, ssim, 0.5f));
 }
 
-// sum of K per-thread values over the block: result in threads 0..K-1 of warp 0 ... (valid for threadIdx.x < K)
+// sums of K per-thread values over the block: thread i < K returns the i-th sum (other threads return 0)
 template <int K>
 __device__ __forceinline__ float block_sum_vec(float (&v)[K], float* red /* >= 8*K floats */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
