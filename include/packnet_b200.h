@@ -44,6 +44,11 @@ int pn_version(void);
 const char* pn_last_error_string(void);
 /* Number of kernel launches this library has enqueued so far (process-wide, monotonic). */
 uint64_t pn_launch_count(void);
+/* Process-wide tuning switches for STAGED kernel variants (same results; each is off until measured on a B200).
+ *   PN_TUNE_STAGE_FLAT (0/1, initial value from the environment variable PN_STAGE_FLAT): the feature-stencil and head-convolution
+ *   kernels stage their input tiles with all threads of the CTA (stage_tile_flat) instead of one cell per warp iteration. */
+#define PN_TUNE_STAGE_FLAT 1
+int pn_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Photometric view-synthesis loss

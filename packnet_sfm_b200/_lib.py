@@ -26,6 +26,7 @@ class LossDesc(ctypes.Structure):
 
 
 PN_LOSS_FLAG_GROUPED = 1
+PN_TUNE_STAGE_FLAT = 1
 
 
 
@@ -36,6 +37,8 @@ def _declare(lib):
     lib.pn_version.restype = c.c_int
     lib.pn_last_error_string.restype = c.c_char_p
     lib.pn_launch_count.restype = c.c_uint64
+    lib.pn_set_tuning.argtypes = [c.c_int, c.c_int]
+    lib.pn_set_tuning.restype = c.c_int
     lib.pn_loss_workspace_bytes.argtypes = [c.POINTER(LossDesc), c.POINTER(sz)]
     lib.pn_loss_forward.argtypes = [c.POINTER(LossDesc), fp, c.POINTER(vp), c.POINTER(vp), fp, fp, c.POINTER(vp), fp,
                                     vp, sz, vp]
@@ -71,6 +74,11 @@ def check(rc, what):
     if rc != 0:
         msg = lib().pn_last_error_string().decode("utf-8", "replace")
         raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def set_tuning(key, value):
+    """Process-wide switch of a STAGED kernel variant (include/packnet_b200.h pn_set_tuning)."""
+    check(lib().pn_set_tuning(int(key), int(value)), "pn_set_tuning")
 
 
 def launch_count():

@@ -11,7 +11,9 @@
 //     and their backward (data gradient, conv3d weight/bias gradient).
 //   * GroupNorm(16) + ELU (layers01.py:31-32,37 / :61-62,72): statistics pass + fused apply pass, and backward.
 //   * tf32 residual outputs (x - trunc_tf32(x)) are emitted by the producers for the tf32x3 GEMM path.
+#include <atomic>
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -379,6 +381,43 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int b,
   }
   if (threadIdx.x == 0) *reinterpret_cast<float4*>(s + (size_t)ncell * PITCH) = z4;   // depth D of the last cell
 }
+
+// STAGED variant of stage_tile for the head convolution kernels (pn_set_tuning(PN_TUNE_STAGE_FLAT, 1); off by default until
+// measured on a B200; the default instantiations compile exactly as before): the same
+// shared-memory image, but the (cell, float4) items are spread over ALL threads of the CTA and unrolled, instead of one
+// cell per warp iteration.  With D = 64 the original keeps 16 of 32 lanes busy and issues one dependent 256-byte load per
+// warp iteration: the head convolution stages 340 cells = 43 serial round trips to DRAM per warp, which is what its
+// 0.22 ms at 192x640 (126 MB: 17 us at the HBM rate) amounts to; the unpack stencils (D = 32) keep 8 lanes busy.
+template <bool S2D>
+__device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, int b, int H, int W, int pixstride, int chan0, int D,
+                                                int h0, int nr, int w0, int nc, float* __restrict__ s) {
+  const int PITCH = D + SPAD, dq = D >> 2;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ncell = nr * nc, total = ncell * dq;
+#pragma unroll 4
+  for (int it = threadIdx.x; it < total; it += blockDim.x) {
+    const int q = it % dq, cell = it / dq;
+    const int c = cell % nc, r = cell / nc;
+    const int hh = h0 + r, ww = w0 + c;
+    const bool inside = (hh >= 0) && (hh < H) && (ww >= 0) && (ww < W);
+    float* col = s + (size_t)cell * PITCH;
+    if (q == 0) *reinterpret_cast<float4*>(col) = z4;
+    float4 v = z4;
+    if (inside) {
+      if (S2D) {
+        const size_t rowstride = (size_t)2 * W * pixstride;
+        const float* p00 = src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + chan0;
+        v.x = __ldg(p00 + q); v.y = __ldg(p00 + pixstride + q);
+        v.z = __ldg(p00 + rowstride + q); v.w = __ldg(p00 + rowstride + pixstride + q);
+      } else {
+        v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + chan0) + q);
+      }
+    }
+    reinterpret_cast<float4*>(col + SPAD)[q] = v;
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<float4*>(s + (size_t)ncell * PITCH) = z4;   // depth D of the last cell
+}
+
 
 // the 10 staged floats around depths [d0, d0+8) of one cell: vv[j] = depth d0 - 1 + j
 __device__ __forceinline__ void load_col10(const float* __restrict__ col, float vv[10]) {
@@ -961,6 +1000,7 @@ struct HeadParams {
 };
 
 // smem: s_x[(8+2)][(tw+2)][C+4], s_w[9][C]
+template <bool FLAT>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams P) {
   PN_DYNAMIC_SHARED(float, sm);
   const int C = P.C, PITCH = C + SPAD, TWP = P.tw + 2;
@@ -968,7 +1008,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams P) {
   float* s_w = sm + 10 * TWP * PITCH + 4;
   const int w0 = blockIdx.x * P.tw, h0 = blockIdx.y * 8, b = blockIdx.z;
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = __ldg(P.w + i);
-  stage_tile<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
+  if (FLAT) stage_tile_flat<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
+  else stage_tile<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
   __syncthreads();
   for (int it = threadIdx.x; it < 8 * P.tw; it += blockDim.x) {
     const int pw = it % P.tw, r = it / P.tw;
@@ -1025,7 +1066,7 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const HeadParams P) {
 
 // weight / bias gradient: dw[tap][c] = sum_p x[p + tap - 1][c] * dy[p].  Persistent CTAs; thread <-> (tap, channel quad)
 // with its partial sums in registers over the whole walk (MAXQ combos per thread), atomics once at the end.
-template <int MAXQ>
+template <int MAXQ, bool FLAT>
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const HeadParams P) {
   PN_DYNAMIC_SHARED(float, sm);
   const int C = P.C, PITCH = C + SPAD, TWP = P.tw + 2;
@@ -1042,7 +1083,8 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const HeadParams P) {
     const int tx = work % tiles_x, ty = (work / tiles_x) % tiles_y, b = work / (tiles_x * tiles_y);
     const int w0 = tx * P.tw, h0 = ty * 8;
     __syncthreads();
-    stage_tile<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
+    if (FLAT) stage_tile_flat<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
+  else stage_tile<false>(P.x, b, P.H, P.W, C, 0, C, h0 - 1, 10, w0 - 1, TWP, s_x);
     for (int i = threadIdx.x; i < 8 * P.tw; i += blockDim.x) {
       const int pw = i % P.tw, r = i / P.tw;
       const int hh = h0 + r, ww = w0 + pw;
@@ -1085,6 +1127,18 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const HeadParams P) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+// process-wide tuning switch behind pn_set_tuning(PN_TUNE_STAGE_FLAT, v): -1 = not set yet -> environment PN_STAGE_FLAT
+static std::atomic<int> g_stage_flat{-1};
+static int stage_flat() {
+  int v = g_stage_flat.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("PN_STAGE_FLAT");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_stage_flat.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 static size_t stencil_smem_bytes(int D, int tw, bool bwd, bool unpack_bwd) {
   size_t f = (size_t)(bwd ? 2 : 1) * 3 * (tw + 2) * (D + 2) + 224;
   if (bwd) f += 216 + 8 * 28 + 32;
@@ -1334,6 +1388,13 @@ extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const 
   return check_launch("gn_elu_bwd kernels");
 }
 
+extern "C" int pn_set_tuning(int key, int value) {
+  PN_REQUIRE(key == PN_TUNE_STAGE_FLAT && (value == 0 || value == 1), PN_ERR_BAD_ARGUMENT, "pn_set_tuning: unknown key %d / value %d", key,
+             value);
+  g_stage_flat.store(value, std::memory_order_relaxed);
+  return PN_OK;
+}
+
 extern "C" int pn_channel_sum(const float* g, float* out, size_t pixels, int channels, pn_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PN_REQUIRE(g && out && pixels > 0 && channels > 0 && channels <= 1024, PN_ERR_BAD_ARGUMENT, "pn_channel_sum: bad argument");
@@ -1364,9 +1425,14 @@ extern "C" int pn_head_conv_forward(const float* x, const float* w_tap_major, co
   P.tw = head_tile_w(channels, width);
   const size_t smem = ((size_t)10 * (P.tw + 2) * (channels + SPAD) + 4 + (size_t)9 * channels) * sizeof(float);
   PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_head_conv_forward: %d channels need %zu bytes of shared memory", channels, smem);
-  PN_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((width + P.tw - 1) / P.tw, (height + 7) / 8, batch);
-  PN_LAUNCH(head_fwd_kernel, grid, 256, smem, stream, P);
+  if (stage_flat()) {
+    PN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PN_LAUNCH(head_fwd_kernel<true>, grid, 256, smem, stream, P);
+  } else {
+    PN_CUDA(cudaFuncSetAttribute(head_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PN_LAUNCH(head_fwd_kernel<false>, grid, 256, smem, stream, P);
+  }
   count_launch();
   return check_launch("head_fwd_kernel");
 }
@@ -1405,7 +1471,11 @@ extern "C" int pn_head_conv_backward(const float* x, const float* dy, const floa
     PN_LAUNCH(kern, ctas, 256, smem, stream, P);
     return 0;
   };
-  int lrc = (maxq <= 1) ? launch(head_wgrad_kernel<1>) : (maxq <= 2) ? launch(head_wgrad_kernel<2>) : launch(head_wgrad_kernel<4>);
+  int lrc;
+  if (stage_flat())
+    lrc = (maxq <= 1) ? launch(head_wgrad_kernel<1, true>) : (maxq <= 2) ? launch(head_wgrad_kernel<2, true>) : launch(head_wgrad_kernel<4, true>);
+  else
+    lrc = (maxq <= 1) ? launch(head_wgrad_kernel<1, false>) : (maxq <= 2) ? launch(head_wgrad_kernel<2, false>) : launch(head_wgrad_kernel<4, false>);
   if (lrc) return lrc;
   count_launch();
   return check_launch("head_wgrad_kernel");

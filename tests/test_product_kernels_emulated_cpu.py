@@ -153,18 +153,30 @@ def test_emulated_groupnorm_elu_and_head_conv(emulated_kernels):
             assert rel_l2(x.grad, xd.grad) < 1e-5 and rel_l2(g.grad, gd.grad) < 1e-5 and rel_l2(bt.grad, bd.grad) < 1e-5
             if second is not None:
                 assert rel_l2(x2.grad, x2d.grad) < 1e-5
-    for B, H, W, C in ((1, 9, 13, 16), (2, 6, 20, 8)):
-        x = (torch.rand(B, H, W, C) - 0.5).requires_grad_(True)
-        w = ((torch.rand(1, C, 3, 3) - 0.5) * 0.2).requires_grad_(True)
-        b = (torch.rand(1) - 0.5).requires_grad_(True)
-        y = PF.head_conv(x, w, b)
-        gy = torch.rand_like(y) - 0.5
-        y.backward(gy)
-        xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
-        yr = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=1)[:, 0]
-        yr.backward(gy.double())
-        assert rel_l2(y, yr) < 1e-6 and rel_l2(x.grad, xd.grad) < 1e-6
-        assert rel_l2(w.grad, wd.grad) < 1e-5 and rel_l2(b.grad, bd.grad) < 1e-5
+    from packnet_sfm_b200 import _lib
+    results = {}
+    for flat in (0, 1):      # 1: the staged all-threads tile staging of the head kernels (pn_set_tuning PN_TUNE_STAGE_FLAT)
+        _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, flat)
+        try:
+            torch.manual_seed(5)
+            for B, H, W, C in ((1, 9, 13, 16), (2, 6, 20, 8), (1, 17, 40, 64)):
+                x = (torch.rand(B, H, W, C) - 0.5).requires_grad_(True)
+                w = ((torch.rand(1, C, 3, 3) - 0.5) * 0.2).requires_grad_(True)
+                b = (torch.rand(1) - 0.5).requires_grad_(True)
+                y = PF.head_conv(x, w, b)
+                gy = torch.rand_like(y) - 0.5
+                y.backward(gy)
+                xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+                yr = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=1)[:, 0]
+                yr.backward(gy.double())
+                assert rel_l2(y, yr) < 1e-6 and rel_l2(x.grad, xd.grad) < 1e-6
+                assert rel_l2(w.grad, wd.grad) < 1e-5 and rel_l2(b.grad, bd.grad) < 1e-5
+                results.setdefault((B, H, W, C), []).append((y.detach().clone(), w.grad.clone()))
+        finally:
+            _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 0)
+    for (y0, w0), (y1, w1) in results.values():
+        assert torch.equal(y0, y1)      # the same shared-memory image -> the forward is bit-identical
+        assert rel_l2(w1, w0) < 1e-6    # weight gradient: atomics, order may differ
 
 
 @pytest.mark.parametrize("B,H,W,N,full_res,kw", [

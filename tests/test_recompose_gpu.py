@@ -53,3 +53,35 @@ def test_packnet01_with_im2col_first_layer_matches_reference_golden():
         rel = ((d.cpu() - ref).abs() / ref.abs()).max().item()
         print("im2col disp%d max-rel %.3e" % (i + 1, rel))
         assert rel < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(4, 192, 640, 64), (2, 24, 80, 256), (1, 9, 13, 16)])
+def test_head_conv_flat_staging_matches_default(shape):
+    """pn_set_tuning(PN_TUNE_STAGE_FLAT): the head kernels stage their tiles with all threads; the shared-memory image is
+    the same, so the forward must be bit-identical and the weight gradient equal up to the order of its atomics."""
+    from packnet_sfm_b200 import _lib, functional as PF
+    B, H, W, C = shape
+    g = torch.Generator().manual_seed(C)
+    x = (torch.rand(B, H, W, C, generator=g) - 0.5).to(DEV)
+    w = ((torch.rand(1, C, 3, 3, generator=g) - 0.5) * 0.2).to(DEV)
+    b = (torch.rand(1, generator=g) - 0.5).to(DEV)
+    gy = None
+    res = []
+    for flat in (0, 1):
+        _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, flat)
+        try:
+            xs, ws, bs = (t.clone().requires_grad_(True) for t in (x, w, b))
+            y = PF.head_conv(xs, ws, bs)
+            if gy is None:
+                gy = torch.rand(y.shape, generator=g).to(DEV) - 0.5
+            y.backward(gy)
+            torch.cuda.synchronize()
+            res.append((y.detach().cpu(), xs.grad.cpu(), ws.grad.cpu(), bs.grad.cpu()))
+        finally:
+            _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 0)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert rel_l2(res[1][2], res[0][2]) < 1e-5 and rel_l2(res[1][3], res[0][3]) < 1e-5
+    xd, wd, bd = x.cpu().double(), w.cpu().double().requires_grad_(True), b.cpu().double()
+    yr = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=1)[:, 0]
+    yr.backward(gy.cpu().double())
+    assert rel_l2(res[1][0], yr.detach()) < 1e-5 and rel_l2(res[1][2], wd.grad) < 1e-4
