@@ -382,7 +382,7 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int b,
   if (threadIdx.x == 0) *reinterpret_cast<float4*>(s + (size_t)ncell * PITCH) = z4;   // depth D of the last cell
 }
 
-// STAGED variant of stage_tile for the head convolution kernels (pn_set_tuning(PN_TUNE_STAGE_FLAT, 1); off by default until
+// STAGED variant of stage_tile for the head convolution and register-tiled feature-stencil kernels (pn_set_tuning(PN_TUNE_STAGE_FLAT, 1); off by default until
 // measured on a B200; the default instantiations compile exactly as before): the same
 // shared-memory image, but the (cell, float4) items are spread over ALL threads of the CTA and unrolled, instead of one
 // cell per warp iteration.  With D = 64 the original keeps 16 of 32 lanes busy and issues one dependent 256-byte load per
@@ -430,7 +430,7 @@ __device__ __forceinline__ void load_col10(const float* __restrict__ col, float 
 }
 
 // forward.  smem: s_v[3][tw+2][PITCH] + 4, s_w[27][8], s_b[8]
-template <bool PACK>
+template <bool PACK, bool FLAT = false>
 __global__ void __launch_bounds__(256, 2) stencil_fwd8_kernel(const StencilParams P) {
   PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(256, 2) stencil_fwd8_kernel(const StencilParam
     if (i < 216) { const int t = i >> 3, f = i & 7; s_w[i] = __ldg(P.w3 + f * 27 + t); }
     else s_w[i] = __ldg(P.b3 + (i - 216));
   }
-  stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+  if (FLAT) stage_tile_flat<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+  else      stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
   __syncthreads();
   const int ntiles = P.tw * (D >> 3);
   for (int it = threadIdx.x; it < ntiles; it += blockDim.x) {
@@ -511,7 +512,7 @@ struct StencilBwd8Params {
   int th;   // rows per CTA (even)
 };
 
-template <bool PACK, int MAXT>
+template <bool PACK, int MAXT, bool FLAT = false>
 __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Params Q) {
   const StencilBwdParams& P = Q.p;
   PN_DYNAMIC_SHARED(float, sm);
@@ -530,8 +531,13 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
       for (int k = 0; k < 8; ++k) acc[m][rr][k] = 0.0f;
   for (int f = 0; f < 8; ++f) {
     __syncthreads();   // the previous plane is consumed (and s_w is visible)
-    if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
-    else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+    if (FLAT) {
+      if (PACK) stage_tile_flat<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+      else      stage_tile_flat<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+    } else {
+      if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+      else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+    }
     __syncthreads();
     float wr[27];
 #pragma unroll
@@ -607,7 +613,7 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
 // weight / bias gradient.  Warp (fp, half): feature pair {2fp, 2fp+1}, half of the thread tiles; 54 + 2 partial sums in
 // registers over the whole persistent walk, one warp reduction + atomics at the end.
 // smem: s_v[3][tw+2][PITCH] + 4, s_gc[8][tw][PITCH]
-template <bool PACK>
+template <bool PACK, bool FLAT = false>
 __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdParams P) {
   PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
@@ -626,10 +632,16 @@ __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdPar
     const int wt = work % wtiles, row = work / wtiles;
     const int b = row / P.H, h = row % P.H, w0 = wt * P.tw;
     __syncthreads();
-    stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+    if (FLAT) stage_tile_flat<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+    else      stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
     for (int f = 0; f < 8; ++f) {
-      if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
-      else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
+      if (FLAT) {
+        if (PACK) stage_tile_flat<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
+        else      stage_tile_flat<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
+      } else {
+        if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
+        else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
+      }
     }
     __syncthreads();
     const float* gA = s_gc + (size_t)(2 * fp) * P.tw * PITCH + SPAD;
@@ -1183,13 +1195,15 @@ extern "C" int pn_feature_stencil_forward(int pack, const float* in, const float
     P.tw = tw;
     const size_t smem8 = smem_of(tw);
     dim3 grid8((P.W + tw - 1) / tw, P.H, P.B);
-    if (pack) {
-      PN_CUDA(cudaFuncSetAttribute(stencil_fwd8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      PN_LAUNCH((stencil_fwd8_kernel<true>), grid8, 256, smem8, stream, P);
-    } else {
-      PN_CUDA(cudaFuncSetAttribute(stencil_fwd8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      PN_LAUNCH((stencil_fwd8_kernel<false>), grid8, 256, smem8, stream, P);
-    }
+    auto launch8 = [&](auto kern) -> int {
+      PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      PN_LAUNCH(kern, grid8, 256, smem8, stream, P);
+      return 0;
+    };
+    const bool flat = stage_flat() != 0;   // staged all-threads tile staging (pn_set_tuning)
+    const int lrc8 = pack ? (flat ? launch8(stencil_fwd8_kernel<true, true>) : launch8(stencil_fwd8_kernel<true>))
+                          : (flat ? launch8(stencil_fwd8_kernel<false, true>) : launch8(stencil_fwd8_kernel<false>));
+    if (lrc8) return lrc8;
     count_launch();
     return check_launch("stencil_fwd8_kernel");
   }
@@ -1245,8 +1259,13 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
         return 0;
       };
       int lrc;
-      if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2>) : launch(stencil_bwd8_kernel<true, 4>);
-      else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2>) : launch(stencil_bwd8_kernel<false, 4>);
+      if (stage_flat()) {
+        if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2, true>) : launch(stencil_bwd8_kernel<true, 4, true>);
+        else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2, true>) : launch(stencil_bwd8_kernel<false, 4, true>);
+      } else {
+        if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2>) : launch(stencil_bwd8_kernel<true, 4>);
+        else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2>) : launch(stencil_bwd8_kernel<false, 4>);
+      }
       if (lrc) return lrc;
       count_launch();
       int rc8 = check_launch("stencil_bwd8_kernel");
@@ -1265,13 +1284,15 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
       const int nwork = Q.B * Q.H * ((Q.W + tw - 1) / tw);
       int ctas = (smem8 <= 110 * 1024) ? 148 * 2 : 148;
       if (ctas > nwork) ctas = nwork;
-      if (pack) {
-        PN_CUDA(cudaFuncSetAttribute(stencil_wgrad8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-        PN_LAUNCH((stencil_wgrad8_kernel<true>), ctas, 256, smem8, stream, Q);
-      } else {
-        PN_CUDA(cudaFuncSetAttribute(stencil_wgrad8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-        PN_LAUNCH((stencil_wgrad8_kernel<false>), ctas, 256, smem8, stream, Q);
-      }
+      auto launchw = [&](auto kern) -> int {
+        PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        PN_LAUNCH(kern, ctas, 256, smem8, stream, Q);
+        return 0;
+      };
+      const bool flat = stage_flat() != 0;
+      const int lrcw = pack ? (flat ? launchw(stencil_wgrad8_kernel<true, true>) : launchw(stencil_wgrad8_kernel<true>))
+                            : (flat ? launchw(stencil_wgrad8_kernel<false, true>) : launchw(stencil_wgrad8_kernel<false>));
+      if (lrcw) return lrcw;
       count_launch();
       return check_launch("stencil_wgrad8_kernel");
     }

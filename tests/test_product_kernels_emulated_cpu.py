@@ -108,12 +108,23 @@ def test_emulated_loss_kernel_ragged_tiles_against_oracle(emulated_kernels, loss
         assert rel_l2(a.grad, b.grad) < 2e-2
 
 
-def test_emulated_feature_stencils(emulated_kernels):
+@pytest.mark.parametrize("flat", [0, 1], ids=["stage_tile", "stage_tile_flat"])
+def test_emulated_feature_stencils(emulated_kernels, flat):
     """Conv3d(1->8) feature stencils fused with space-to-depth / depth-to-space: the register-tiled 8-depth kernels, the
-    generic kernels (depth not a multiple of 8), masked rows / columns"""
-    from packnet_sfm_b200 import functional as PF
+    generic kernels (depth not a multiple of 8), masked rows / columns; flat=1: the staged all-threads tile staging
+    (pn_set_tuning PN_TUNE_STAGE_FLAT) of the register-tiled kernels"""
+    from packnet_sfm_b200 import _lib, functional as PF
+    _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, flat)
+    try:
+        _feature_stencil_cases(PF)
+    finally:
+        _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 0)
+
+
+def _feature_stencil_cases(PF):
     torch.manual_seed(3)
-    for pack, shape in ((True, (1, 8, 12, 8)), (False, (1, 5, 7, 24)), (True, (1, 6, 10, 5)), (False, (2, 3, 4, 16))):
+    for pack, shape in ((True, (1, 8, 12, 8)), (False, (1, 5, 7, 24)), (True, (1, 6, 10, 5)), (False, (2, 3, 4, 16)),
+                        (False, (1, 4, 37, 32)), (True, (1, 6, 70, 16))):     # several w tiles, D = 32 / 64
         x = (torch.rand(*shape) - 0.5).requires_grad_(True)
         w3 = (torch.rand(8, 1, 3, 3, 3) - 0.5).requires_grad_(True)
         b3 = (torch.rand(8) - 0.5).requires_grad_(True)

@@ -85,3 +85,32 @@ def test_head_conv_flat_staging_matches_default(shape):
     yr = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=1)[:, 0]
     yr.backward(gy.cpu().double())
     assert rel_l2(res[1][0], yr.detach()) < 1e-5 and rel_l2(res[1][2], wd.grad) < 1e-4
+
+
+@pytest.mark.parametrize("pack,shape", [(True, (4, 192, 640, 64)), (False, (4, 96, 320, 32)), (False, (4, 12, 40, 256)),
+                                        (True, (2, 24, 80, 128)), (False, (1, 5, 7, 24))])
+def test_feature_stencils_flat_staging_matches_default(pack, shape):
+    """pn_set_tuning(PN_TUNE_STAGE_FLAT) for the register-tiled feature stencils: same shared-memory image -> forward and
+    input gradient bit-identical, weight / bias gradients equal up to the order of their atomics."""
+    from packnet_sfm_b200 import _lib, functional as PF
+    g = torch.Generator().manual_seed(shape[3])
+    x = (torch.rand(*shape, generator=g) - 0.5).to(DEV)
+    w3 = (torch.rand(8, 1, 3, 3, 3, generator=g) - 0.5).to(DEV)
+    b3 = (torch.rand(8, generator=g) - 0.5).to(DEV)
+    gy = None
+    res = []
+    for flat in (0, 1):
+        _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, flat)
+        try:
+            xs, ws, bs = (t.clone().requires_grad_(True) for t in (x, w3, b3))
+            y = PF.pack_features(xs, ws, bs) if pack else PF.unpack_features(xs, ws, bs)
+            if gy is None:
+                gy = (torch.rand(y.shape, generator=g) - 0.5).to(DEV)
+            y.backward(gy)
+            torch.cuda.synchronize()
+            res.append((y.detach().cpu(), xs.grad.cpu(), ws.grad.cpu(), bs.grad.cpu()))
+            del y, xs
+        finally:
+            _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 0)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert rel_l2(res[1][2], res[0][2]) < 1e-5 and rel_l2(res[1][3], res[0][3]) < 1e-5
