@@ -46,8 +46,11 @@ const char* pn_last_error_string(void);
 uint64_t pn_launch_count(void);
 /* Process-wide tuning switches for STAGED kernel variants (same results; each is off until measured on a B200).
  *   PN_TUNE_STAGE_FLAT (0/1, initial value from the environment variable PN_STAGE_FLAT): the feature-stencil and head-convolution
- *   kernels stage their input tiles with all threads of the CTA (stage_tile_flat) instead of one cell per warp iteration. */
+ *   kernels stage their input tiles with all threads of the CTA (stage_tile_flat) instead of one cell per warp iteration.
+ *   PN_TUNE_GN_TREE (0/1, environment PN_GN_TREE): the GroupNorm statistics kernel reduces its per-thread partial sums with warp
+ *   shuffles before one shared atomic per (warp, group) instead of eight fp64 shared atomics per thread. */
 #define PN_TUNE_STAGE_FLAT 1
+#define PN_TUNE_GN_TREE 2
 int pn_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@ class LossDesc(ctypes.Structure):
 
 PN_LOSS_FLAG_GROUPED = 1
 PN_TUNE_STAGE_FLAT = 1
+PN_TUNE_GN_TREE = 2
 
 
 

@@ -694,6 +694,11 @@ __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdPar
 // GroupNorm(16) + ELU   (NHWC; x may be the sum of two tensors for the residual block, layers01.py:72)
 // ---------------------------------------------------------------------------------------------------
 // stats[b][g] = (sum, sumsq) in double, accumulated atomically into a zeroed buffer
+// TREE (staged, pn_set_tuning(PN_TUNE_GN_TREE, 1)): the per-thread partial sums meet in the block through warp shuffles
+// (lanes of the same float4 column, then the columns of a group) before ONE shared atomic per (warp, group), instead of
+// 8 double-precision shared atomics per thread on 32 addresses -- shared fp64 atomics are compare-and-swap loops, and 16
+// lanes of every warp collide on each address.
+template <bool TREE>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ x2, int HW, int C,
                                                        int in_cstride, int pixels_per_cta, double* __restrict__ stats) {
   __shared__ double s_sum[16], s_sq[16];
@@ -719,11 +724,37 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
     }
+    const int gw_ = cg >> 2;   // float4 columns per group
+    if (!(TREE && (cg & 3) == 0 && (gw_ & (gw_ - 1)) == 0 && gw_ <= 32 && (c4 & (c4 - 1)) == 0)) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int g = (col * 4 + k) / cg;
-      atomicAdd(&s_sum[g], (double)s[k]);
-      atomicAdd(&s_sq[g], (double)q[k]);
+      for (int k = 0; k < 4; ++k) {
+        const int g = (col * 4 + k) / cg;
+        atomicAdd(&s_sum[g], (double)s[k]);
+        atomicAdd(&s_sq[g], (double)q[k]);
+      }
+    }
+  }
+  if (TREE) {
+    const int gw = cg >> 2;
+    if ((cg & 3) == 0 && (gw & (gw - 1)) == 0 && gw <= 32 && (c4 & (c4 - 1)) == 0) {   // uniform over the block
+      // a float4 column lies inside one group (cg % 4 == 0); idle pixel lanes contribute zeros
+      double ds = (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3];
+      double dq = (double)q[0] + (double)q[1] + (double)q[2] + (double)q[3];
+      for (int o = 16; o >= c4; o >>= 1) {          // the same column in the other pixel lanes of this warp (c4 < 32)
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      }
+      for (int o = 1; o < gw; o <<= 1) {            // the other columns of the group (consecutive lanes)
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      }
+      const int lane = threadIdx.x & 31;
+      const bool leader = ((lane & (gw - 1)) == 0) && (c4 >= 32 || lane < c4) && (pl < lanes);
+      if (leader) {
+        const int g = (col * 4) / cg;
+        atomicAdd(&s_sum[g], ds);
+        atomicAdd(&s_sq[g], dq);
+      }
     }
   }
   __syncthreads();
@@ -1151,6 +1182,17 @@ static int stage_flat() {
   return v;
 }
 
+static std::atomic<int> g_gn_tree{-1};
+static int gn_tree() {
+  int v = g_gn_tree.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("PN_GN_TREE");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_gn_tree.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 static size_t stencil_smem_bytes(int D, int tw, bool bwd, bool unpack_bwd) {
   size_t f = (size_t)(bwd ? 2 : 1) * 3 * (tw + 2) * (D + 2) + 224;
   if (bwd) f += 216 + 8 * 28 + 32;
@@ -1344,7 +1386,11 @@ extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const f
   int ppc = (hw + 147) / 148;
   if (ppc < 32) ppc = 32;
   dim3 g1((hw + ppc - 1) / ppc, batch);
-  PN_LAUNCH(gn_stats_kernel, g1, 256, 0, stream, x, x2, hw, channels, channels, ppc, stats);
+  if (gn_tree()) {
+    PN_LAUNCH(gn_stats_kernel<true>, g1, 256, 0, stream, x, x2, hw, channels, channels, ppc, stats);
+  } else {
+    PN_LAUNCH(gn_stats_kernel<false>, g1, 256, 0, stream, x, x2, hw, channels, channels, ppc, stats);
+  }
   count_launch();
   float* mr = reinterpret_cast<float*>(stats + (size_t)2 * 16 * batch);   // (mean, rstd) floats behind the doubles
   PN_LAUNCH(gn_finalize_stats_kernel, (16 * batch + 127) / 128, 128, 0, stream, stats, mr, 16 * batch, (double)hw * (channels / 16), eps);
@@ -1410,9 +1456,9 @@ extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const 
 }
 
 extern "C" int pn_set_tuning(int key, int value) {
-  PN_REQUIRE(key == PN_TUNE_STAGE_FLAT && (value == 0 || value == 1), PN_ERR_BAD_ARGUMENT, "pn_set_tuning: unknown key %d / value %d", key,
-             value);
-  g_stage_flat.store(value, std::memory_order_relaxed);
+  PN_REQUIRE((key == PN_TUNE_STAGE_FLAT || key == PN_TUNE_GN_TREE) && (value == 0 || value == 1), PN_ERR_BAD_ARGUMENT,
+             "pn_set_tuning: unknown key %d / value %d", key, value);
+  (key == PN_TUNE_STAGE_FLAT ? g_stage_flat : g_gn_tree).store(value, std::memory_order_relaxed);
   return PN_OK;
 }
 

@@ -143,9 +143,12 @@ def _feature_stencil_cases(PF):
 
 
 def test_emulated_groupnorm_elu_and_head_conv(emulated_kernels):
-    from packnet_sfm_b200 import functional as PF
+    from packnet_sfm_b200 import _lib, functional as PF
     torch.manual_seed(4)
-    for C in (16, 64):
+    # (C, tree): tree = the staged shuffle reduction of the statistics kernel (pn_set_tuning PN_TUNE_GN_TREE): one float4
+    # column per group (64), two (128), four columns over two warps per pixel (256); 16 and 32 fall back to the atomics
+    for C, tree in ((16, 0), (64, 0), (16, 1), (32, 1), (64, 1), (128, 1), (256, 1)):
+        _lib.set_tuning(_lib.PN_TUNE_GN_TREE, tree)
         x = (torch.rand(2, 6, 10, C) * 2 - 0.7).requires_grad_(True)
         x2 = (torch.rand(2, 6, 10, C) - 0.5).requires_grad_(True)
         g = (torch.rand(C) + 0.5).requires_grad_(True)
@@ -164,7 +167,7 @@ def test_emulated_groupnorm_elu_and_head_conv(emulated_kernels):
             assert rel_l2(x.grad, xd.grad) < 1e-5 and rel_l2(g.grad, gd.grad) < 1e-5 and rel_l2(bt.grad, bd.grad) < 1e-5
             if second is not None:
                 assert rel_l2(x2.grad, x2d.grad) < 1e-5
-    from packnet_sfm_b200 import _lib
+    _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 0)
     results = {}
     for flat in (0, 1):      # 1: the staged all-threads tile staging of the head kernels (pn_set_tuning PN_TUNE_STAGE_FLAT)
         _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, flat)

@@ -114,3 +114,25 @@ def test_feature_stencils_flat_staging_matches_default(pack, shape):
             _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 0)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     assert rel_l2(res[1][2], res[0][2]) < 1e-5 and rel_l2(res[1][3], res[0][3]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(4, 192, 640, 64), (4, 48, 160, 128), (4, 12, 40, 512), (2, 6, 10, 32)])
+def test_groupnorm_tree_statistics_match_default(shape):
+    """pn_set_tuning(PN_TUNE_GN_TREE): shuffle reduction of the GroupNorm statistics instead of fp64 shared atomics per
+    thread -- the same sums in another order (double accumulation): outputs equal to rounding, and against float64."""
+    from packnet_sfm_b200 import _lib, functional as PF
+    B, H, W, C = shape
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.rand(B, H, W, C, generator=g) * 2 - 0.7).to(DEV)
+    gm, bt = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.rand(C, generator=g) - 0.5).to(DEV)
+    res = []
+    for tree in (0, 1):
+        _lib.set_tuning(_lib.PN_TUNE_GN_TREE, tree)
+        try:
+            res.append(PF.groupnorm_elu(x, gm, bt, 1e-5).cpu())
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 0)
+    assert rel_l2(res[1], res[0]) < 1e-6
+    yr = F.elu(F.group_norm(x.cpu().double().permute(0, 3, 1, 2), 16, gm.cpu().double(), bt.cpu().double(), 1e-5)).permute(0, 2, 3, 1)
+    assert rel_l2(res[1], yr) < 1e-5
