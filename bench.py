@@ -54,6 +54,8 @@ def parse():
                     help="STAGED (DESIGN.md 7.7): all-threads tile staging in the head convolution kernels (pn_set_tuning)")
     ap.add_argument("--gn-tree", action="store_true",
                     help="STAGED (DESIGN.md 7.7): shuffle reduction in the GroupNorm statistics kernel (pn_set_tuning)")
+    ap.add_argument("--unpack-tiled", action="store_true",
+                    help="STAGED (DESIGN.md 7.9): weight-gradient re-layout through shared memory")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged-probe", action="store_true",
@@ -379,6 +381,8 @@ def run_ours(args):
         _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 1)
     if args.gn_tree:
         _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
+    if args.unpack_tiled:
+        PF.set_unpack_tiled(True)
     B, H, W = args.batch, args.height, args.width
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)
@@ -514,7 +518,7 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
                 "loss": state.get("loss_host"), "cuda_graph": graph_info, "pack_fold": bool(args.pack_fold),
-                "loss_grouped": bool(args.loss_grouped), "im2col_first": bool(args.im2col_first), "stage_flat": bool(args.stage_flat), "gn_tree": bool(args.gn_tree)}
+                "loss_grouped": bool(args.loss_grouped), "im2col_first": bool(args.im2col_first), "stage_flat": bool(args.stage_flat), "gn_tree": bool(args.gn_tree), "unpack_tiled": bool(args.unpack_tiled)}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)

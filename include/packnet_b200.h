@@ -173,6 +173,10 @@ int pn_conv2d_wgrad(const pn_conv_desc* desc, const void* x, const void* x_lo, c
 int pn_conv2d_wgrad_packed_elems(int cout, int cin, int ksize, int precision, size_t* elems);
 int pn_conv2d_unpack_weight_grad(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, int precision,
                                  pn_stream_t stream);
+/* STAGED alternative of pn_conv2d_unpack_weight_grad (same result, bit for bit): the re-layout through shared memory, one CTA
+ * per (output channel, 128 input channels).  kpad = row pitch of dw_packed in floats = pn_conv2d_wgrad_packed_elems / (cout*k*k). */
+int pn_conv2d_unpack_weight_grad_tiled(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, int kpad,
+                                       pn_stream_t stream);
 
 /* lo[i] = x[i] - trunc_tf32(x[i]) (the bits a tf32 tensor-core operand read drops); n % 4 == 0. */
 int pn_tf32_residual(const float* x, float* lo, size_t n, pn_stream_t stream);

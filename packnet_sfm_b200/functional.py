@@ -21,7 +21,15 @@ from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_T
 
 _state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": os.environ.get("PN_PACK_FOLD", "0") == "1",
           "pack_fold_min_pixels": int(os.environ.get("PN_PACK_FOLD_MIN_PIXELS", "1920")),
-          "im2col_first": os.environ.get("PN_IM2COL_FIRST", "0") == "1"}
+          "im2col_first": os.environ.get("PN_IM2COL_FIRST", "0") == "1",
+          "unpack_tiled": os.environ.get("PN_UNPACK_TILED", "0") == "1"}
+
+
+def set_unpack_tiled(on):
+    """STAGED (off by default): weight-gradient re-layout [Cout][tap][Cin] -> OIHW through shared memory
+    (pn_conv2d_unpack_weight_grad_tiled) instead of the strided element-per-thread gather."""
+    prev, _state["unpack_tiled"] = _state["unpack_tiled"], bool(on)
+    return prev
 
 
 def set_im2col_first(on):
@@ -191,8 +199,13 @@ class _Conv2d(torch.autograd.Function):
             _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
                                            _lib.ptr(dwp), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
             gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=gy.device)
-            _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, precision, _stream()),
-                       "pn_conv2d_unpack_weight_grad")
+            if _state["unpack_tiled"]:
+                _lib.check(lib.pn_conv2d_unpack_weight_grad_tiled(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k,
+                                                                  int(n.value) // (cout * k * k), _stream()),
+                           "pn_conv2d_unpack_weight_grad_tiled")
+            else:
+                _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, precision, _stream()),
+                           "pn_conv2d_unpack_weight_grad")
             gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = _lookup_channel_sum(gy)

@@ -116,3 +116,20 @@ def test_frame_kernels_emulated_with_several_tiles(kernel_path, case):
             if row < m or row >= h - m or col < m or col >= w - m:
                 want[border_class(row, h, m), border_class(col, w, m)] += gz[:, row, col].sum(0)
     assert rel(dBa.grad, want) < 1e-5
+
+
+def test_weight_grad_unpack_tiled_emulated(emulated_kernels):
+    """pn_conv2d_unpack_weight_grad_tiled (staged shared-memory re-layout of the weight gradient) from its real source under
+    the host emulation: dw[co][ci][tap] == dw_packed[co][tap][ci] bit for bit, ragged channel blocks, 1x1 .. 7x7."""
+    import ctypes
+    import torch
+    from packnet_sfm_b200 import _lib
+    lib = _lib.lib()
+    torch.manual_seed(0)
+    for cout, cin, k, kpad in ((3, 5, 3, 8), (2, 130, 3, 192), (4, 64, 1, 64), (1, 200, 5, 256), (2, 9, 7, 64), (1, 257, 3, 320)):
+        dwp = torch.rand(cout, k * k, kpad)
+        out = torch.full((cout, cin, k, k), float("nan"))
+        rc = lib.pn_conv2d_unpack_weight_grad_tiled(_lib.ptr(dwp), _lib.ptr(out), cout, cin, k, kpad, None)
+        assert rc == 0, lib.pn_last_error_string()
+        want = dwp[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, k, k)
+        assert torch.equal(out, want), (cout, cin, k, kpad)

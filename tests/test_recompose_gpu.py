@@ -136,3 +136,23 @@ def test_groupnorm_tree_statistics_match_default(shape):
     assert rel_l2(res[1], res[0]) < 1e-6
     yr = F.elu(F.group_norm(x.cpu().double().permute(0, 3, 1, 2), 16, gm.cpu().double(), bt.cpu().double(), 1e-5)).permute(0, 2, 3, 1)
     assert rel_l2(res[1], yr) < 1e-5
+
+
+@pytest.mark.parametrize("cout,cin,k", [(64, 2048, 5), (512, 16384, 3), (64, 136, 3), (64, 64, 7), (128, 64, 1), (64, 8, 5)])
+def test_weight_grad_unpack_tiled_is_bit_identical(cout, cin, k):
+    """pn_conv2d_unpack_weight_grad_tiled against the default element-per-thread gather on the network's layer shapes."""
+    import ctypes
+    from packnet_sfm_b200 import _lib, functional as PF
+    lib = _lib.lib()
+    n = ctypes.c_size_t(0)
+    prec = PF.get_precision()
+    _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, cin, k, prec, ctypes.byref(n)), "wgrad_packed_elems")
+    dwp = torch.rand(int(n.value), device=DEV)
+    a = torch.empty(cout, cin, k, k, device=DEV)
+    b = torch.full((cout, cin, k, k), float("nan"), device=DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(a), cout, cin, k, prec, st), "unpack")
+    _lib.check(lib.pn_conv2d_unpack_weight_grad_tiled(_lib.ptr(dwp), _lib.ptr(b), cout, cin, k, int(n.value) // (cout * k * k), st),
+               "unpack tiled")
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
