@@ -56,6 +56,9 @@ def parse():
                     help="STAGED (DESIGN.md 7.7): shuffle reduction in the GroupNorm statistics kernel (pn_set_tuning)")
     ap.add_argument("--unpack-tiled", action="store_true",
                     help="STAGED (DESIGN.md 7.9): weight-gradient re-layout through shared memory")
+    ap.add_argument("--staged-all", action="store_true",
+                    help="every staged variant at once (pack fold, grouped loss, im2col first layer, flat staging, GroupNorm tree, "
+                         "tiled unpack) -- not --graph, which is orthogonal")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged-probe", action="store_true",
@@ -345,6 +348,8 @@ def staged_probe(args):
 
 
 def run_ours(args):
+    if args.staged_all:
+        args.pack_fold = args.loss_grouped = args.im2col_first = args.stage_flat = args.gn_tree = args.unpack_tiled = True
     import torch.distributed as dist
     from packnet_sfm_b200 import _lib, functional as PF, parallel
     from packnet_sfm_b200.models import SelfSupModel
