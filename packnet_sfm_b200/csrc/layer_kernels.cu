@@ -384,36 +384,51 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int b,
 
 // STAGED variant of stage_tile for the head convolution and register-tiled feature-stencil kernels (pn_set_tuning(PN_TUNE_STAGE_FLAT, 1); off by default until
 // measured on a B200; the default instantiations compile exactly as before): the same
-// shared-memory image, but the (cell, float4) items are spread over ALL threads of the CTA and unrolled, instead of one
+// shared-memory image, but the (cell, float4) items are spread over ALL threads of the CTA, eight loads in flight per thread
+// (explicit load phase / store phase: left to `#pragma unroll` nvcc keeps each store right behind its load), instead of one
 // cell per warp iteration.  With D = 64 the original keeps 16 of 32 lanes busy and issues one dependent 256-byte load per
 // warp iteration: the head convolution stages 340 cells = 43 serial round trips to DRAM per warp, which is what its
 // 0.22 ms at 192x640 (126 MB: 17 us at the HBM rate) amounts to; the unpack stencils (D = 32) keep 8 lanes busy.
 template <bool S2D>
 __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, int b, int H, int W, int pixstride, int chan0, int D,
                                                 int h0, int nr, int w0, int nc, float* __restrict__ s) {
+  constexpr int U = 8;   // items in flight per thread: all loads of a batch are issued before the first store
   const int PITCH = D + SPAD, dq = D >> 2;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int ncell = nr * nc, total = ncell * dq;
-#pragma unroll 4
-  for (int it = threadIdx.x; it < total; it += blockDim.x) {
-    const int q = it % dq, cell = it / dq;
-    const int c = cell % nc, r = cell / nc;
-    const int hh = h0 + r, ww = w0 + c;
-    const bool inside = (hh >= 0) && (hh < H) && (ww >= 0) && (ww < W);
-    float* col = s + (size_t)cell * PITCH;
-    if (q == 0) *reinterpret_cast<float4*>(col) = z4;
-    float4 v = z4;
-    if (inside) {
-      if (S2D) {
-        const size_t rowstride = (size_t)2 * W * pixstride;
-        const float* p00 = src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + chan0;
-        v.x = __ldg(p00 + q); v.y = __ldg(p00 + pixstride + q);
-        v.z = __ldg(p00 + rowstride + q); v.w = __ldg(p00 + rowstride + pixstride + q);
-      } else {
-        v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + chan0) + q);
+  const int step = (int)blockDim.x;
+  for (int base = threadIdx.x; base < total; base += step * U) {
+    float4 v[U];
+    int off[U];   // shared-memory float offset of the item's float4, -1: no item
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = base + u * step;
+      v[u] = z4;
+      off[u] = -1;
+      if (it < total) {
+        const int q = it % dq, cell = it / dq;
+        const int c = cell % nc, r = cell / nc;
+        const int hh = h0 + r, ww = w0 + c;
+        off[u] = cell * PITCH + SPAD + 4 * q;
+        if ((hh >= 0) && (hh < H) && (ww >= 0) && (ww < W)) {
+          if (S2D) {
+            const size_t rowstride = (size_t)2 * W * pixstride;
+            const float* p00 = src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + chan0;
+            v[u].x = __ldg(p00 + q); v[u].y = __ldg(p00 + pixstride + q);
+            v[u].z = __ldg(p00 + rowstride + q); v[u].w = __ldg(p00 + rowstride + pixstride + q);
+          } else {
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + chan0) + q);
+          }
+        }
       }
     }
-    reinterpret_cast<float4*>(col + SPAD)[q] = v;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (off[u] >= 0) {
+        *reinterpret_cast<float4*>(s + off[u]) = v[u];
+        if (((off[u] - SPAD) % PITCH) == 0) *reinterpret_cast<float4*>(s + off[u] - SPAD) = z4;   // q == 0: the cell's front pad
+      }
+    }
   }
   if (threadIdx.x == 0) *reinterpret_cast<float4*>(s + (size_t)ncell * PITCH) = z4;   // depth D of the last cell
 }
