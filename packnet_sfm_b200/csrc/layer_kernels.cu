@@ -709,7 +709,8 @@ __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdPar
 // GroupNorm(16) + ELU   (NHWC; x may be the sum of two tensors for the residual block, layers01.py:72)
 // ---------------------------------------------------------------------------------------------------
 // stats[b][g] = (sum, sumsq) in double, accumulated atomically into a zeroed buffer
-// TREE (staged, pn_set_tuning(PN_TUNE_GN_TREE, 1)): the per-thread partial sums meet in the block through warp shuffles
+// TREE (staged, pn_set_tuning(PN_TUNE_GN_TREE, 1)): four independent loads per trip of the pixel loop, and the per-thread
+// partial sums meet in the block through warp shuffles
 // (lanes of the same float4 column, then the columns of a group) before ONE shared atomic per (warp, group), instead of
 // 8 double-precision shared atomics per thread on 32 addresses -- shared fp64 atomics are compare-and-swap loops, and 16
 // lanes of every warp collide on each address.
@@ -729,7 +730,29 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   const int col = threadIdx.x % c4, pl = threadIdx.x / c4;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (pl < lanes) {
-    for (int p = p0 + pl; p < p1; p += lanes) {
+    int p = p0 + pl;
+    if (TREE) {
+      // four pixels per trip: the loads of a trip are independent (one 16-byte load in flight per thread and 4 CTAs per SM
+      // cover less than half of the bytes the HBM latency needs in flight)
+      for (; p + 3 * lanes < p1; p += 4 * lanes) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t o = ((size_t)b * HW + p + u * lanes) * in_cstride + col * 4;
+          v[u] = *reinterpret_cast<const float4*>(x + o);
+          if (x2) {
+            const float4 w = *reinterpret_cast<const float4*>(x2 + o);
+            v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+          q[0] += v[u].x * v[u].x; q[1] += v[u].y * v[u].y; q[2] += v[u].z * v[u].z; q[3] += v[u].w * v[u].w;
+        }
+      }
+    }
+    for (; p < p1; p += lanes) {
       const size_t o = ((size_t)b * HW + p) * in_cstride + col * 4;
       float4 v = *reinterpret_cast<const float4*>(x + o);
       if (x2) {

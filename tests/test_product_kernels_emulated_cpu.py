@@ -147,10 +147,12 @@ def test_emulated_groupnorm_elu_and_head_conv(emulated_kernels):
     torch.manual_seed(4)
     # (C, tree): tree = the staged shuffle reduction of the statistics kernel (pn_set_tuning PN_TUNE_GN_TREE): one float4
     # column per group (64), two (128), four columns over two warps per pixel (256); 16 and 32 fall back to the atomics
-    for C, tree in ((16, 0), (64, 0), (16, 1), (32, 1), (64, 1), (128, 1), (256, 1)):
+    # (80, 120): 65 pixels per CTA -> the four-pixel trips of the TREE kernel also run at C = 64 (16 pixel lanes)
+    for C, tree, hw in ((16, 0, (6, 10)), (64, 0, (6, 10)), (16, 1, (6, 10)), (32, 1, (6, 10)), (64, 1, (6, 10)), (128, 1, (6, 10)),
+                        (256, 1, (6, 10)), (64, 1, (80, 120))):
         _lib.set_tuning(_lib.PN_TUNE_GN_TREE, tree)
-        x = (torch.rand(2, 6, 10, C) * 2 - 0.7).requires_grad_(True)
-        x2 = (torch.rand(2, 6, 10, C) - 0.5).requires_grad_(True)
+        x = (torch.rand(2, hw[0], hw[1], C) * 2 - 0.7).requires_grad_(True)
+        x2 = (torch.rand(2, hw[0], hw[1], C) - 0.5).requires_grad_(True)
         g = (torch.rand(C) + 0.5).requires_grad_(True)
         bt = (torch.rand(C) - 0.5).requires_grad_(True)
         for second in (None, x2):
