@@ -22,6 +22,8 @@ for flags in "" "--loss-grouped" "--im2col-first" "--stage-flat" "--gn-tree" "--
 done
 timeout 300 python tools/step_profile.py             > ${O}_step_breakdown.txt 2>&1
 timeout 300 python tools/step_profile.py --pack-fold > ${O}_step_breakdown_fold.txt 2>&1
+timeout 300 python tools/step_profile.py --staged-small > ${O}_step_breakdown_staged_small.txt 2>&1
+timeout 300 python tools/step_profile.py --staged-all > ${O}_step_breakdown_staged_all.txt 2>&1
 head -30 ${O}_step_breakdown_fold.txt
 timeout 600 python tools/conv_sweep.py > ${O}_conv_sweep.txt 2>&1; tail -5 ${O}_conv_sweep.txt
 # BASELINE configs[2] shape on one GPU (B=2, 384x1280): never run on the B200 in round 1

@@ -17,8 +17,17 @@ ap.add_argument("--width", type=int, default=640)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--top", type=int, default=45)
 ap.add_argument("--pack-fold", action="store_true", help="folded pack layers (packnet_sfm_b200/folded.py)")
+ap.add_argument("--staged-all", action="store_true", help="every staged variant of DESIGN.md section 7 (as bench.py --staged-all)")
+ap.add_argument("--staged-small", action="store_true", help="the staged variants except the pack fold")
 a = ap.parse_args()
-PF.set_pack_fold(a.pack_fold)
+PF.set_pack_fold(a.pack_fold or a.staged_all)
+if a.staged_all or a.staged_small:
+    from packnet_sfm_b200 import _lib, losses
+    losses.set_grouped_kernel(True)
+    PF.set_im2col_first(True)
+    PF.set_unpack_tiled(True)
+    _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 1)
+    _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
 
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
