@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--staged-all", action="store_true",
                     help="every staged variant at once (pack fold, grouped loss, im2col first layer, flat staging, GroupNorm tree, "
                          "tiled unpack) -- not --graph, which is orthogonal")
+    ap.add_argument("--staged-small", action="store_true", help="every staged variant except the pack fold")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged-probe", action="store_true",
@@ -349,7 +350,9 @@ def staged_probe(args):
 
 def run_ours(args):
     if args.staged_all:
-        args.pack_fold = args.loss_grouped = args.im2col_first = args.stage_flat = args.gn_tree = args.unpack_tiled = True
+        args.pack_fold = True
+    if args.staged_all or args.staged_small:
+        args.loss_grouped = args.im2col_first = args.stage_flat = args.gn_tree = args.unpack_tiled = True
     import torch.distributed as dist
     from packnet_sfm_b200 import _lib, functional as PF, parallel
     from packnet_sfm_b200.models import SelfSupModel

@@ -15,7 +15,7 @@ tail -5 ${O}_tests_default.log ${O}_tests_folded.log ${O}_tests_loss_grouped.log
 timeout 300 python tools/loss_only.py > ${O}_loss_only_tile.txt 2>&1; PN_LOSS_GROUPED=1 timeout 300 python tools/loss_only.py > ${O}_loss_only_grouped.txt 2>&1
 tail -3 ${O}_loss_only_tile.txt ${O}_loss_only_grouped.txt
 timeout 300 python tools/head_bench.py > ${O}_head_bench.txt 2>&1; tail -8 ${O}_head_bench.txt
-for flags in "" "--loss-grouped" "--im2col-first" "--stage-flat" "--gn-tree" "--unpack-tiled" "--pack-fold" "--graph" "--staged-all" "--graph --staged-all"; do
+for flags in "" "--loss-grouped" "--im2col-first" "--stage-flat" "--gn-tree" "--unpack-tiled" "--pack-fold" "--graph" "--staged-small" "--staged-all" "--graph --staged-all"; do
   tag=$(echo "default $flags" | tr -d ' -' )
   timeout 600 python bench.py --no-cpu-baseline --no-staged-probe $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
   echo "bench [$flags]: $? $(cut -c1-400 ${O}_bench_${tag}.log)"
