@@ -1,9 +1,13 @@
 #!/bin/bash
 # First GPU call of round 2: everything written after the round-1 GPU budget ran out, in one gpurun.
-#   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
+#   gpurun --timeout 3000 -- 'bash tools/round2_first_call.sh'      (about 35-45 minutes of box time)
 # 1) default -m gpu tier (the measured path must still be green)
-# 2) experimental tier: fold kernels, folded pack block, PackNet01 with folded pack layers; the grouped-scale loss program
-# 3) bench: default / --pack-fold / --graph / both; CUPTI step breakdown with and without the fold
+# 2) experimental tiers (PN_EXPERIMENTAL=1): folded pack block + CUDA graph, grouped-scale loss program, re-compositions /
+#    flat staging / GroupNorm tree / tiled unpack (tests/test_recompose_gpu.py)
+# 3) kernel timings: loss tile vs grouped, head convolution default vs flat staging
+# 4) bench lines: default, --staged-small, --pack-fold, --staged-all, --graph, --graph --staged-all, then one per variant
+# 5) CUPTI step breakdowns, conv tile-height sweep, the 384x1280 B=2 shape
+# Read gpurun_out/r02a_* afterwards; DESIGN.md 7.4 says which result flips which default.
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 O=gpurun_out/r02a
@@ -15,7 +19,8 @@ tail -5 ${O}_tests_default.log ${O}_tests_folded.log ${O}_tests_loss_grouped.log
 timeout 300 python tools/loss_only.py > ${O}_loss_only_tile.txt 2>&1; PN_LOSS_GROUPED=1 timeout 300 python tools/loss_only.py > ${O}_loss_only_grouped.txt 2>&1
 tail -3 ${O}_loss_only_tile.txt ${O}_loss_only_grouped.txt
 timeout 300 python tools/head_bench.py > ${O}_head_bench.txt 2>&1; tail -8 ${O}_head_bench.txt
-for flags in "" "--loss-grouped" "--im2col-first" "--stage-flat" "--gn-tree" "--unpack-tiled" "--pack-fold" "--graph" "--staged-small" "--staged-all" "--graph --staged-all"; do
+# the combined runs first (they decide the defaults), then one line per variant
+for flags in "" "--staged-small" "--pack-fold" "--staged-all" "--graph" "--graph --staged-all" "--loss-grouped" "--im2col-first" "--stage-flat" "--gn-tree" "--unpack-tiled"; do
   tag=$(echo "default $flags" | tr -d ' -' )
   timeout 600 python bench.py --no-cpu-baseline --no-staged-probe $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
   echo "bench [$flags]: $? $(cut -c1-400 ${O}_bench_${tag}.log)"
