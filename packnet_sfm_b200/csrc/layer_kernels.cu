@@ -397,19 +397,22 @@ __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, i
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int ncell = nr * nc, total = ncell * dq;
   const int step = (int)blockDim.x;
+  // item `it` = (cell, q) = (it / dq, it % dq), cell = (r, c) = (cell / nc, cell % nc): the divisions are done once, the
+  // thread then walks its items (it, it + step, ...) with carries
+  const int step_q = step % dq, step_cell = step / dq;
+  const int step_c = step_cell % nc, step_r = step_cell / nc;
+  int q = (int)threadIdx.x % dq, cell0 = (int)threadIdx.x / dq;
+  int c = cell0 % nc, r = cell0 / nc;
   for (int base = threadIdx.x; base < total; base += step * U) {
     float4 v[U];
-    int off[U];   // shared-memory float offset of the item's float4, -1: no item
+    int off[U];   // shared-memory float offset of the item's float4 (low bit set: first float4 of its cell), -1: no item
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int it = base + u * step;
       v[u] = z4;
       off[u] = -1;
-      if (it < total) {
-        const int q = it % dq, cell = it / dq;
-        const int c = cell % nc, r = cell / nc;
+      if (base + u * step < total) {
         const int hh = h0 + r, ww = w0 + c;
-        off[u] = cell * PITCH + SPAD + 4 * q;
+        off[u] = ((r * nc + c) * PITCH + SPAD + 4 * q) | (q == 0 ? 1 : 0);
         if ((hh >= 0) && (hh < H) && (ww >= 0) && (ww < W)) {
           if (S2D) {
             const size_t rowstride = (size_t)2 * W * pixstride;
@@ -420,13 +423,21 @@ __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, i
             v[u] = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + chan0) + q);
           }
         }
+        // advance (q, c, r) by `step` items
+        q += step_q;
+        int carry = 0;
+        if (q >= dq) { q -= dq; carry = 1; }
+        c += step_c + carry;
+        r += step_r;
+        if (c >= nc) { c -= nc; r += 1; }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (off[u] >= 0) {
-        *reinterpret_cast<float4*>(s + off[u]) = v[u];
-        if (((off[u] - SPAD) % PITCH) == 0) *reinterpret_cast<float4*>(s + off[u] - SPAD) = z4;   // q == 0: the cell's front pad
+        const int o = off[u] & ~1;   // offsets are multiples of 4 floats
+        *reinterpret_cast<float4*>(s + o) = v[u];
+        if (off[u] & 1) *reinterpret_cast<float4*>(s + o - SPAD) = z4;   // the cell's front pad
       }
     }
   }
