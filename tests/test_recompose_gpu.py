@@ -156,3 +156,63 @@ def test_weight_grad_unpack_tiled_is_bit_identical(cout, cin, k):
                "unpack tiled")
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("fold", [False, True], ids=["staged_small", "staged_all"])
+def test_packnet01_and_loss_with_every_staged_variant(fold):
+    """bench.py --staged-small / --staged-all as a parity test: PackNet01 depth maps against the reference's golden vectors
+    (bar 1e-3) and one loss forward + backward against the default kernels, with every staged switch on."""
+    import ast
+    from packnet_sfm_b200 import _lib, functional as PF, losses
+    from packnet_sfm_b200.geometry import Pose
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    from packnet_sfm_b200.networks import PackNet01
+    z = load_golden("packnet01_64x96")
+    net = PackNet01(version="1A")
+    net.load_state_dict(PO.packnet01_state_dict(seed=42, randomize_affine=True), strict=True)
+    net = net.to(DEV).train()
+    zl = load_golden("loss_fullres")
+    meta = ast.literal_eval(str(zl["meta"]))
+
+    def loss_and_grads():
+        inv = [zl["inv%d" % i].to(DEV).requires_grad_(True) for i in range(meta["num_scales"])]
+        mats = [zl["pose%d" % j].to(DEV).requires_grad_(True) for j in range(2)]
+        K = zl["K"].to(DEV)
+        out = MultiViewPhotometricLoss(**meta)(zl["rgb"].to(DEV), [zl["ctx0"].to(DEV), zl["ctx1"].to(DEV)], inv, K, K,
+                                               [Pose(m) for m in mats])
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        return float(out["loss"]), [d.grad.cpu() for d in inv]
+
+    l_ref, g_ref = loss_and_grads()
+    prev = (PF.pack_fold_enabled(), PF.set_im2col_first(True), PF.set_unpack_tiled(True), losses.set_grouped_kernel(True),
+            PF._state["pack_fold_min_pixels"])
+    PF.set_pack_fold(fold, min_pixels=0)
+    _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 1)
+    _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
+    try:
+        x = z["rgb"].to(DEV).requires_grad_(False)
+        out = net(x)["inv_depths"]
+        sum(d.sum() for d in out).backward()      # every backward kernel of the staged path runs once
+        torch.cuda.synchronize()
+        for i, d in enumerate(out):
+            ref = z["disp%d" % (i + 1)]
+            rel = ((d.detach().cpu() - ref).abs() / ref.abs()).max().item()
+            print("staged disp%d max-rel %.3e" % (i + 1, rel))
+            assert rel < 1e-3
+        for p in net.parameters():
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all())
+        l_new, g_new = loss_and_grads()
+        assert abs(l_new - l_ref) <= 1e-5 * abs(l_ref)
+        for a, b in zip(g_new, g_ref):
+            err = (a.double() - b.double()).abs()
+            outl = err > 1e-3 * float(b.abs().max())
+            assert float(outl.double().mean()) <= max(1e-3, 21.0 / err.numel())
+            assert rel_l2(a[~outl], b[~outl]) < 1e-3
+    finally:
+        PF.set_pack_fold(prev[0], min_pixels=prev[4])
+        PF.set_im2col_first(prev[1])
+        PF.set_unpack_tiled(prev[2])
+        losses.set_grouped_kernel(prev[3])
+        _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 0)
+        _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 0)
