@@ -56,6 +56,8 @@ def parse():
                     help="STAGED (DESIGN.md 7.7): shuffle reduction in the GroupNorm statistics kernel (pn_set_tuning)")
     ap.add_argument("--unpack-tiled", action="store_true",
                     help="STAGED (DESIGN.md 7.9): weight-gradient re-layout through shared memory")
+    ap.add_argument("--pack-tiled", action="store_true",
+                    help="STAGED (DESIGN.md 7.9): per-step weight packing through shared memory")
     ap.add_argument("--staged-all", action="store_true",
                     help="every staged variant at once (pack fold, grouped loss, im2col first layer, flat staging, GroupNorm tree, "
                          "tiled unpack) -- not --graph, which is orthogonal")
@@ -352,7 +354,7 @@ def run_ours(args):
     if args.staged_all:
         args.pack_fold = True
     if args.staged_all or args.staged_small:
-        args.loss_grouped = args.im2col_first = args.stage_flat = args.gn_tree = args.unpack_tiled = True
+        args.loss_grouped = args.im2col_first = args.stage_flat = args.gn_tree = args.unpack_tiled = args.pack_tiled = True
     import torch.distributed as dist
     from packnet_sfm_b200 import _lib, functional as PF, parallel
     from packnet_sfm_b200.models import SelfSupModel
@@ -391,6 +393,8 @@ def run_ours(args):
         _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
     if args.unpack_tiled:
         PF.set_unpack_tiled(True)
+    if args.pack_tiled:
+        PF.set_pack_tiled(True)
     B, H, W = args.batch, args.height, args.width
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)
@@ -526,7 +530,7 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
                 "loss": state.get("loss_host"), "cuda_graph": graph_info, "pack_fold": bool(args.pack_fold),
-                "loss_grouped": bool(args.loss_grouped), "im2col_first": bool(args.im2col_first), "stage_flat": bool(args.stage_flat), "gn_tree": bool(args.gn_tree), "unpack_tiled": bool(args.unpack_tiled)}
+                "loss_grouped": bool(args.loss_grouped), "im2col_first": bool(args.im2col_first), "stage_flat": bool(args.stage_flat), "gn_tree": bool(args.gn_tree), "unpack_tiled": bool(args.unpack_tiled), "pack_tiled": bool(args.pack_tiled)}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)

@@ -162,6 +162,10 @@ int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const void* x_lo,
 int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, int precision, size_t* elems);
 int pn_conv2d_pack_weight(const float* w_oihw, void* w_packed, void* w_packed_lo, int cout, int cin, int ksize,
                           int transposed, int precision, pn_stream_t stream);
+/* STAGED alternative of pn_conv2d_pack_weight for the bf16 precisions (same bytes out): the re-layout through shared memory,
+ * one CTA per (8 rows, 64-wide reduction chunk).  rows_pad = pn_conv2d_packed_weight_elems / (chunks * k*k * 64). */
+int pn_conv2d_pack_weight_tiled(const float* w_oihw, void* w_packed, void* w_packed_lo, int cout, int cin, int ksize,
+                                int transposed, int rows_pad, pn_stream_t stream);
 
 /* Weight gradient (autograd backward of nn.Conv2d w.r.t. weight).  x [B,H,W,Cin] and g = dL/dy [B,H,W,Cout]
  * are the NHWC tensors themselves (read as MN-major operand tiles; the reduction runs over pixels); x_lo / g_lo

@@ -61,6 +61,8 @@ def declare(lib):
         getattr(lib, name).restype = c.c_int
     lib.pn_conv2d_wgrad.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]
     lib.pn_conv2d_unpack_weight_grad.argtypes = [vp, vp, i, i, i, i, vp]
+    lib.pn_conv2d_pack_weight_tiled.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
+    lib.pn_conv2d_pack_weight_tiled.restype = c.c_int
     lib.pn_conv2d_unpack_weight_grad_tiled.argtypes = [vp, vp, i, i, i, i, vp]
     lib.pn_conv2d_unpack_weight_grad_tiled.restype = c.c_int
     lib.pn_conv2d_wgrad.restype = c.c_int

@@ -22,7 +22,15 @@ from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_T
 _state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": os.environ.get("PN_PACK_FOLD", "0") == "1",
           "pack_fold_min_pixels": int(os.environ.get("PN_PACK_FOLD_MIN_PIXELS", "1920")),
           "im2col_first": os.environ.get("PN_IM2COL_FIRST", "0") == "1",
-          "unpack_tiled": os.environ.get("PN_UNPACK_TILED", "0") == "1"}
+          "unpack_tiled": os.environ.get("PN_UNPACK_TILED", "0") == "1",
+          "pack_tiled": os.environ.get("PN_PACK_TILED", "0") == "1"}
+
+
+def set_pack_tiled(on):
+    """STAGED (off by default): per-step weight packing of the bf16 precisions through shared memory
+    (pn_conv2d_pack_weight_tiled) instead of the strided element-per-thread gather."""
+    prev, _state["pack_tiled"] = _state["pack_tiled"], bool(on)
+    return prev
 
 
 def set_unpack_tiled(on):
@@ -131,6 +139,12 @@ def _pack_weight(w, transposed, precision):
     dt = torch.bfloat16 if is_bf16(precision) else torch.float32
     wp = torch.empty(int(n.value), dtype=dt, device=w.device)
     lo = torch.empty_like(wp) if is_split(precision) else None
+    if _state["pack_tiled"] and is_bf16(precision):
+        kred = cout if transposed else cin
+        rows_pad = int(n.value) // (((kred + 63) // 64) * k * k * 64)
+        _lib.check(lib.pn_conv2d_pack_weight_tiled(_lib.ptr(w), _lib.ptr(wp), _p(lo), cout, cin, k, int(transposed), rows_pad, _stream()),
+                   "pn_conv2d_pack_weight_tiled")
+        return wp, lo
     _lib.check(lib.pn_conv2d_pack_weight(_lib.ptr(w), _lib.ptr(wp), _p(lo), cout, cin, k, int(transposed), precision, _stream()),
                "pn_conv2d_pack_weight")
     return wp, lo

@@ -26,6 +26,7 @@ extern "C" const char* pn_last_error_string(void) { return pn::g_err; }
 #include "../../packnet_sfm_b200/csrc/frame_kernels.cu"
 #include "../../packnet_sfm_b200/csrc/layer_kernels.cu"
 #include "../../packnet_sfm_b200/csrc/loss_kernels.cu"
+#include "../../packnet_sfm_b200/csrc/pack_kernels.cu"
 
 // The tcgen05 / TMA convolution engine has no host emulation (tensor-core instructions): its entry points exist so that
 // the ctypes declarations of packnet_sfm_b200/_lib_conv.py resolve, and refuse to run.

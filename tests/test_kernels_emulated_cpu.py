@@ -133,3 +133,45 @@ def test_weight_grad_unpack_tiled_emulated(emulated_kernels):
         assert rc == 0, lib.pn_last_error_string()
         want = dwp[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, k, k)
         assert torch.equal(out, want), (cout, cin, k, kpad)
+
+
+def _packed_weight_mirror(w, transposed, rows_pad):
+    """the packed bf16 layout of conv_engine.cu (pack_weight_kernel), element for element, in PyTorch"""
+    import torch
+    cout, cin, k, _ = w.shape
+    taps = k * k
+    rows, kred = (cin, cout) if transposed else (cout, cin)
+    cchunks = (kred + 63) // 64
+    wf = w.reshape(cout, cin, taps)
+    hi = torch.zeros(cchunks, taps, rows_pad, 64)
+    for cc in range(cchunks):
+        for r in range(rows):
+            for e in range(64):
+                kk = cc * 64 + (((e // 8) ^ (r & 7)) * 8 + e % 8)
+                if kk >= kred:
+                    continue
+                hi[cc, :, r, e] = wf[kk, r].flip(0) if transposed else wf[r, kk]
+    h = hi.to(torch.bfloat16)
+    lo = (hi - h.float()).to(torch.bfloat16)
+    return h.reshape(-1), lo.reshape(-1)
+
+
+def test_weight_pack_tiled_emulated(emulated_kernels):
+    """pn_conv2d_pack_weight_tiled (staged shared-memory weight packing, bf16 hi/lo, SWIZZLE_128B rows) from its real source
+    under the host emulation against a PyTorch mirror of the documented layout: both orientations, ragged rows / chunks."""
+    import torch
+    from packnet_sfm_b200 import _lib
+    lib = _lib.lib()
+    torch.manual_seed(1)
+    for cout, cin, k, transposed, rows_pad in ((5, 7, 3, 0, 8), (5, 7, 3, 1, 8), (16, 70, 1, 0, 16), (70, 20, 3, 1, 24), (9, 130, 5, 0, 16),
+                                               (66, 9, 5, 1, 16), (3, 3, 7, 0, 8)):
+        w = torch.rand(cout, cin, k, k) - 0.5
+        kred = cout if transposed else cin
+        n = ((kred + 63) // 64) * k * k * rows_pad * 64
+        hi = torch.full((n,), float("nan")).to(torch.bfloat16)
+        lo = torch.full((n,), float("nan")).to(torch.bfloat16)
+        rc = lib.pn_conv2d_pack_weight_tiled(_lib.ptr(w), _lib.ptr(hi), _lib.ptr(lo), cout, cin, k, transposed, rows_pad, None)
+        assert rc == 0, lib.pn_last_error_string()
+        want_hi, want_lo = _packed_weight_mirror(w, bool(transposed), rows_pad)
+        assert torch.equal(hi.view(torch.int16), want_hi.view(torch.int16)), (cout, cin, k, transposed)
+        assert torch.equal(lo.view(torch.int16), want_lo.view(torch.int16)), (cout, cin, k, transposed)

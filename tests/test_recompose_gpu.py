@@ -186,7 +186,7 @@ def test_packnet01_and_loss_with_every_staged_variant(fold):
 
     l_ref, g_ref = loss_and_grads()
     prev = (PF.pack_fold_enabled(), PF.set_im2col_first(True), PF.set_unpack_tiled(True), losses.set_grouped_kernel(True),
-            PF._state["pack_fold_min_pixels"])
+            PF._state["pack_fold_min_pixels"], PF.set_pack_tiled(True))
     PF.set_pack_fold(fold, min_pixels=0)
     _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 1)
     _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
@@ -213,6 +213,28 @@ def test_packnet01_and_loss_with_every_staged_variant(fold):
         PF.set_pack_fold(prev[0], min_pixels=prev[4])
         PF.set_im2col_first(prev[1])
         PF.set_unpack_tiled(prev[2])
+        PF.set_pack_tiled(prev[5])
         losses.set_grouped_kernel(prev[3])
         _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 0)
         _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 0)
+
+
+@pytest.mark.parametrize("cout,cin,k", [(64, 2048, 5), (512, 16384, 3), (64, 136, 3), (64, 64, 7), (128, 64, 1), (64, 8, 5), (136, 64, 3)])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_weight_pack_tiled_is_bit_identical(cout, cin, k, transposed):
+    """pn_conv2d_pack_weight_tiled against the default element-per-thread packing (bf16x3: hi and lo), both orientations, on
+    the network's layer shapes."""
+    from packnet_sfm_b200 import functional as PF
+    if not PF.is_bf16(PF.get_precision()):
+        pytest.skip("the tiled packing covers the bf16 precisions")
+    w = (torch.rand(cout, cin, k, k, device=DEV) - 0.5) * 0.1
+    prev = PF.set_pack_tiled(False)
+    try:
+        a_hi, a_lo = PF._pack_weight(w, transposed, PF.get_precision())
+        PF.set_pack_tiled(True)
+        b_hi, b_lo = PF._pack_weight(w, transposed, PF.get_precision())
+        torch.cuda.synchronize()
+    finally:
+        PF.set_pack_tiled(prev)
+    assert torch.equal(a_hi.view(torch.int16), b_hi.view(torch.int16))
+    assert torch.equal(a_lo.view(torch.int16), b_lo.view(torch.int16))

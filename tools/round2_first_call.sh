@@ -20,7 +20,7 @@ timeout 300 python tools/loss_only.py > ${O}_loss_only_tile.txt 2>&1; PN_LOSS_GR
 tail -3 ${O}_loss_only_tile.txt ${O}_loss_only_grouped.txt
 timeout 300 python tools/head_bench.py > ${O}_head_bench.txt 2>&1; tail -8 ${O}_head_bench.txt
 # the combined runs first (they decide the defaults), then one line per variant
-for flags in "" "--staged-small" "--pack-fold" "--staged-all" "--graph" "--graph --staged-all" "--loss-grouped" "--im2col-first" "--stage-flat" "--gn-tree" "--unpack-tiled"; do
+for flags in "" "--staged-small" "--pack-fold" "--staged-all" "--graph" "--graph --staged-all" "--loss-grouped" "--im2col-first" "--stage-flat" "--gn-tree" "--unpack-tiled" "--pack-tiled"; do
   tag=$(echo "default $flags" | tr -d ' -' )
   timeout 600 python bench.py --no-cpu-baseline --no-staged-probe $flags > ${O}_bench_${tag}.log 2> ${O}_bench_${tag}.err
   echo "bench [$flags]: $? $(cut -c1-400 ${O}_bench_${tag}.log)"

@@ -26,6 +26,7 @@ if a.staged_all or a.staged_small:
     losses.set_grouped_kernel(True)
     PF.set_im2col_first(True)
     PF.set_unpack_tiled(True)
+    PF.set_pack_tiled(True)
     _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 1)
     _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
 
