@@ -99,16 +99,23 @@ __device__ __forceinline__ void gemm_tile(int K2, int K1, int K0, int m0, int n0
   for (int k2 = 0; k2 < K2; ++k2)
     for (int k1 = 0; k1 < K1; ++k1)
       for (int kb = 0; kb < K0; kb += BK) {
+        // all eight global loads of the stage first, then the shared stores: left interleaved (load, store, load, ...) every
+        // store waits for its own load and the stage costs eight serial round trips instead of one
+        float av[LD], bv[LD];
 #pragma unroll
         for (int i = 0; i < LD; ++i) {
           const int k0 = kb + a_kk[i];
-          As[a_kk[i]][a_mm[i]] = (k0 < K0) ? la(ca[i], k2, k1, k0) : 0.f;
+          av[i] = (k0 < K0) ? la(ca[i], k2, k1, k0) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < LD; ++i) {
           const int k0 = kb + b_kk[i];
-          Bs[b_kk[i]][b_nn[i]] = (k0 < K0) ? lb(cb[i], k2, k1, k0) : 0.f;
+          bv[i] = (k0 < K0) ? lb(cb[i], k2, k1, k0) : 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < LD; ++i) As[a_kk[i]][a_mm[i]] = av[i];
+#pragma unroll
+        for (int i = 0; i < LD; ++i) Bs[b_kk[i]][b_nn[i]] = bv[i];
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
