@@ -97,13 +97,37 @@ def ptr_array(tensors):
     return arr
 
 
-def current_stream():
+def current_stream(device=None):
+    """The caller's stream ON THE TENSORS' DEVICE (the library only enqueues on the stream it is handed)."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def require_cuda(*tensors):
+    """Every operand must be a CUDA tensor on the CURRENT device (one process per GPU: the wrapper never switches devices
+    and the kernels are enqueued on that device's current stream); a tensor of another GPU would be reached from the wrong
+    context: raise instead."""
+    import torch
+    cur = None
     for t in tensors:
+        if t is None:
+            continue
         if not t.is_cuda:
             raise RuntimeError("packnet_sfm_b200 ops run on CUDA tensors only (got %s); there is no CPU path"
                                % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError("packnet_sfm_b200 ops run on the current CUDA device (cuda:%d); got a tensor on %s -- call "
+                               "torch.cuda.set_device() first (one process per GPU)" % (cur, t.device))
+
+
+def require_f32(*tensors):
+    """require_cuda + every operand fp32.  A model cast with .half() / .double() (the reference's `--half` switches) or an
+    autocast output would otherwise be read through the raw pointer as 4-byte floats: out-of-bounds garbage, silently."""
+    import torch
+    require_cuda(*tensors)
+    for t in tensors:
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError("packnet_sfm_b200 kernels are fp32 (got %s): cast the module / inputs back with .float(); "
+                               "half / double / autocast tensors are not reinterpreted silently" % t.dtype)

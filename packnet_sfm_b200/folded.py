@@ -135,7 +135,7 @@ class _FoldSetCUDA(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w2, w3):
         from . import _lib
-        _lib.require_cuda(w2, w3)
+        _lib.require_f32(w2, w3)
         co, c8, k, _ = w2.shape
         n = c8 // 8
         m = k // 2
@@ -324,7 +324,7 @@ class _FrameApplyCUDA(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, top, bot, left, right, Wt, Wb, Wl, Wr, Wtl, Wtr, Wbl, Wbr, dB, k):
         from . import _lib
-        _lib.require_cuda(z, top, dB)
+        _lib.require_f32(z, top, dB)
         n = top.shape[2]
         lines = {"top": top.contiguous(), "bottom": bot.contiguous(), "left": left.contiguous(), "right": right.contiguous()}
         weights = dict(zip(FOLD_ORDER[1:], (t.contiguous() for t in (Wt, Wb, Wl, Wr, Wtl, Wtr, Wbl, Wbr))))

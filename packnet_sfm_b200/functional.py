@@ -173,7 +173,7 @@ class _Conv2d(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        _lib.require_cuda(x, weight)
+        _lib.require_f32(x, weight)
         x = x.contiguous()
         precision = _state["precision"]
         cout, cin_w, k, _ = weight.shape
@@ -263,18 +263,21 @@ def conv2d_im2col(x, weight, bias=None, conv=None, align=None):
 
 # The GroupNorm backward already reduces its dx over the pixels; the convolution that consumes dx as its output
 # gradient takes its bias gradient from here instead of re-reading the tensor.  An entry is valid only while the
-# producing tensor object is alive (weak reference): then no other tensor can own that storage.
+# producing tensor object is alive (weak reference), IS the tensor handed to the convolution's backward, and has not been
+# written since (autograd version counter).
 _channel_sums = []
 
 
 def _remember_channel_sum(dx, dsum):
-    _channel_sums.append((weakref.ref(dx), dx.data_ptr(), tuple(dx.shape), dsum))
+    _channel_sums.append((weakref.ref(dx), dx.data_ptr(), tuple(dx.shape), dx._version, dsum))
     del _channel_sums[:-8]
 
 
 def _lookup_channel_sum(g):
-    for ref, ptr, shape, dsum in reversed(_channel_sums):
-        if ref() is not None and ptr == g.data_ptr() and shape == tuple(g.shape) and g.is_contiguous():
+    for ref, ptr, shape, version, dsum in reversed(_channel_sums):
+        # the SAME tensor object, unmodified since the GroupNorm backward wrote it: a second consumer's gradient accumulated
+        # in place by autograd (or a hook editing dx) bumps the version counter and the cached sum is not used
+        if ref() is g and ptr == g.data_ptr() and shape == tuple(g.shape) and g._version == version and g.is_contiguous():
             return dsum
     return None
 
@@ -284,7 +287,7 @@ class _GroupNormELU(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x2, gamma, beta, eps):
-        _lib.require_cuda(x, gamma, beta)
+        _lib.require_f32(x, gamma, beta)
         x = x.contiguous()
         x2c = x2.contiguous() if x2 is not None else None
         B, H, W, C = x.shape
@@ -324,7 +327,7 @@ def groupnorm_elu(x, gamma, beta, eps=1e-5, x2=None):
 class _FeatureStencil(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w3, b3, pack):
-        _lib.require_cuda(x, w3, b3)
+        _lib.require_f32(x, w3, b3)
         x = x.contiguous()
         B = x.shape[0]
         if pack:
@@ -362,7 +365,7 @@ class _HeadConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        _lib.require_cuda(x, weight, bias)
+        _lib.require_f32(x, weight, bias)
         x = x.contiguous()
         B, H, W, C = x.shape
         wt = weight.detach().reshape(C, 9).t().contiguous()          # [9][C] tap-major

@@ -1,53 +1,37 @@
-"""Host-side mirror of the reference's tiny pose helpers (PyTorch, differentiable).
+"""The one piece of pose algebra the hot path needs on the host: PoseNet's 6-vector -> [B,4,4] rigid transform.
 
-  Pose                <- packnet_sfm/geometry/pose.py:9-101
-  euler2mat           <- packnet_sfm/geometry/pose_utils.py:8-37   (R = Rx @ Ry @ Rz)
-  pose_vec2mat        <- packnet_sfm/geometry/pose_utils.py:41-51
-  invert_pose         <- packnet_sfm/geometry/pose_utils.py:55-60
-
-north_star keeps PoseNet and the pose algebra in PyTorch host code; the fused loss kernel consumes
-Pose.mat ([B,4,4]) directly and returns its gradient, so autograd carries on into these ops."""
+The fused loss consumes `Pose.mat` and returns dL/dmat, so this module only has to (a) hold the matrix under the
+attribute name the reference's loss reads (`pose.mat`, packnet_sfm/geometry/pose.py:18) and (b) build it from
+[tx,ty,tz,rx,ry,rz] with the reference's convention R = Rx(rx)·Ry(ry)·Rz(rz) (pose_utils.py:8-37), differentiably.
+The rotation is written in closed form (one stack of nine products of sines / cosines) instead of three batched
+matrix products.  With the reference on the path (dropin.install()) its own `packnet_sfm.geometry.pose.Pose` is used
+and this shim is not imported by the glue."""
 import torch
 
 
-def euler2mat(angle):
-    B = angle.size(0)
-    x, y, z = angle[:, 0], angle[:, 1], angle[:, 2]
-    cosz, sinz = torch.cos(z), torch.sin(z)
-    zeros = z.detach() * 0
-    ones = zeros.detach() + 1
-    zmat = torch.stack([cosz, -sinz, zeros, sinz, cosz, zeros, zeros, zeros, ones], dim=1).view(B, 3, 3)
-    cosy, siny = torch.cos(y), torch.sin(y)
-    ymat = torch.stack([cosy, zeros, siny, zeros, ones, zeros, -siny, zeros, cosy], dim=1).view(B, 3, 3)
-    cosx, sinx = torch.cos(x), torch.sin(x)
-    xmat = torch.stack([ones, zeros, zeros, zeros, cosx, -sinx, zeros, sinx, cosx], dim=1).view(B, 3, 3)
-    return xmat.bmm(ymat).bmm(zmat)
-
-
-def pose_vec2mat(vec, mode="euler"):
-    if mode is None:
-        return vec
-    trans, rot = vec[:, :3].unsqueeze(-1), vec[:, 3:]
-    if mode != "euler":
-        raise ValueError("Rotation mode not supported {}".format(mode))
-    return torch.cat([euler2mat(rot), trans], dim=2)
-
-
-def invert_pose(T):
-    Tinv = torch.eye(4, device=T.device, dtype=T.dtype).repeat([len(T), 1, 1])
-    Tinv[:, :3, :3] = torch.transpose(T[:, :3, :3], -2, -1)
-    Tinv[:, :3, -1] = torch.bmm(-1.0 * Tinv[:, :3, :3], T[:, :3, -1].unsqueeze(-1)).squeeze(-1)
-    return Tinv
+def rigid_from_vec(vec):
+    """[B,6] (translation, XYZ Euler angles) -> [B,4,4]."""
+    t, a = vec[:, :3], vec[:, 3:]
+    s, c = torch.sin(a), torch.cos(a)
+    sx, sy, sz = s.unbind(1)
+    cx, cy, cz = c.unbind(1)
+    sxsy, cxsy = sx * sy, cx * sy
+    zero, one = torch.zeros_like(sx), torch.ones_like(sx)
+    rows = [cy * cz, -(cy * sz), sy, t[:, 0],
+            sxsy * cz + cx * sz, cx * cz - sxsy * sz, -(sx * cy), t[:, 1],
+            sx * sz - cxsy * cz, cxsy * sz + sx * cz, cx * cy, t[:, 2],
+            zero, zero, zero, one]
+    return torch.stack(rows, 1).view(-1, 4, 4)
 
 
 class Pose:
-    """[B,4,4] rigid transform wrapper with the reference's interface."""
+    """Holder of a [B,4,4] transform under the reference's attribute name (`.mat`)."""
 
     def __init__(self, mat):
-        assert tuple(mat.shape[-2:]) == (4, 4)
         if mat.dim() == 2:
             mat = mat.unsqueeze(0)
-        assert mat.dim() == 3
+        if mat.dim() != 3 or tuple(mat.shape[-2:]) != (4, 4):
+            raise ValueError("Pose needs a [B,4,4] tensor, got %s" % (tuple(mat.shape),))
         self.mat = mat
 
     def __len__(self):
@@ -55,49 +39,14 @@ class Pose:
 
     @classmethod
     def identity(cls, N=1, device=None, dtype=torch.float):
-        return cls(torch.eye(4, device=device, dtype=dtype).repeat([N, 1, 1]))
+        return cls(torch.eye(4, device=device, dtype=dtype).expand(N, 4, 4).contiguous())
 
     @classmethod
-    def from_vec(cls, vec, mode):
-        mat = pose_vec2mat(vec, mode)
-        pose = torch.eye(4, device=vec.device, dtype=vec.dtype).repeat([len(vec), 1, 1])
-        pose[:, :3, :3] = mat[:, :3, :3]
-        pose[:, :3, -1] = mat[:, :3, -1]
-        return cls(pose)
-
-    @property
-    def shape(self):
-        return self.mat.shape
-
-    def item(self):
-        return self.mat
-
-    def repeat(self, *args, **kwargs):
-        self.mat = self.mat.repeat(*args, **kwargs)
-        return self
-
-    def inverse(self):
-        return Pose(invert_pose(self.mat))
+    def from_vec(cls, vec, mode="euler"):
+        if mode != "euler":
+            raise ValueError("Rotation mode not supported {}".format(mode))
+        return cls(rigid_from_vec(vec))
 
     def to(self, *args, **kwargs):
         self.mat = self.mat.to(*args, **kwargs)
         return self
-
-    def transform_pose(self, pose):
-        assert tuple(pose.shape[-2:]) == (4, 4)
-        return Pose(self.mat.bmm(pose.item()))
-
-    def transform_points(self, points):
-        assert points.shape[1] == 3
-        B, _, H, W = points.shape
-        out = self.mat[:, :3, :3].bmm(points.view(B, 3, -1)) + self.mat[:, :3, -1].unsqueeze(-1)
-        return out.view(B, 3, H, W)
-
-    def __matmul__(self, other):
-        if isinstance(other, Pose):
-            return self.transform_pose(other)
-        if isinstance(other, torch.Tensor):
-            if other.shape[1] == 3 and other.dim() > 2:
-                return self.transform_points(other)
-            raise ValueError("Unknown tensor dimensions {}".format(other.shape))
-        raise NotImplementedError()

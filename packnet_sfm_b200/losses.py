@@ -86,7 +86,7 @@ class _FusedLoss(torch.autograd.Function):
         inv = [t.contiguous() for t in tensors[N:N + n]]
         poses = [t.contiguous() for t in tensors[N + n:]]
         image, K, ref_K = image.contiguous(), K.contiguous(), ref_K.contiguous()
-        _lib.require_cuda(image, K, ref_K, *context, *inv, *poses)
+        _lib.require_f32(image, K, ref_K, *context, *inv, *poses)
         B, _, H, W = image.shape
         desc = _make_desc(B, H, W, N, [tuple(d.shape[-2:]) for d in inv], cfg["ssim_w"], cfg["smooth_w"],
                           cfg["C1"], cfg["C2"], cfg["reduce_min"], cfg["automask"])
@@ -178,7 +178,7 @@ def warp_tap_indices(inv_depth, K, ref_K, pose, full_width=None):
     [B,h,w,2] for one scale / one context, from the device function the loss kernels use."""
     inv_depth, K, ref_K = inv_depth.contiguous(), K.contiguous().float(), ref_K.contiguous().float()
     pose = (pose.mat if hasattr(pose, "mat") else pose).contiguous()
-    _lib.require_cuda(inv_depth, K, ref_K, pose)
+    _lib.require_f32(inv_depth, K, ref_K, pose)
     B, _, h, w = inv_depth.shape
     W = w if full_width is None else full_width
     H = h if full_width is None else h * (W // w)

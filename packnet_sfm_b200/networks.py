@@ -86,11 +86,10 @@ class InvDepth(nn.Module):
         self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1)
 
     def forward(self, x):
-        if x.shape[3] % 4 == 0 and self.conv1.out_channels == 1:
-            y = PF.head_conv(x, self.conv1.weight, self.conv1.bias).unsqueeze(1)
-        else:   # odd channel counts (never in PackNet01): cuDNN on the NHWC storage viewed as channels_last
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=PF.get_precision() == PF.PRECISION_TF32X1):
-                y = F.conv2d(x.permute(0, 3, 1, 2), self.conv1.weight, self.conv1.bias, padding=1)
+        if x.shape[3] % 4 or self.conv1.out_channels != 1:
+            raise NotImplementedError("InvDepth: the head kernel takes C %% 4 == 0 input channels and one output channel "
+                                      "(got %d -> %d); there is no library fallback" % (x.shape[3], self.conv1.out_channels))
+        y = PF.head_conv(x, self.conv1.weight, self.conv1.bias).unsqueeze(1)
         return torch.sigmoid(y) / self.min_depth          # [B,1,H,W] (NCHW == NHWC for one channel)
 
 

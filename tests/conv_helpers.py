@@ -1,16 +1,16 @@
-"""Thin Python wrappers over the C-ABI layer ops (include/packnet_b200.h).  CUDA tensors only."""
+"""Test / probe helper: one-call convolution through the C-ABI (packs the weight and splits the activation every call)."""
 import ctypes
 
 import torch
 
-from . import _lib
-from ._lib_conv import (ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3,  # noqa: F401
+from packnet_sfm_b200 import _lib
+from packnet_sfm_b200._lib_conv import (ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3,  # noqa: F401
                         MODE_AUTO, MODE_PER_TAP, MODE_HALO)
 
 
 def conv2d_nhwc(x, w_oihw, bias=None, precision=None, mode=MODE_AUTO, debug_flags=0, error_flag=None):
     """Convenience (tests / probes): packs the weight and splits the activation on every call."""
-    from . import functional as PF
+    from packnet_sfm_b200 import functional as PF
     precision = PF.get_precision() if precision is None else precision
     x = x.contiguous()
     wp, wlo = PF._pack_weight(PF._pad_channels(w_oihw.contiguous(), x.shape[3]), False, precision)

@@ -61,14 +61,21 @@ def test_loss_class_surface_and_no_cpu_fallback():
              [Pose.identity(1), Pose.identity(1)])
 
 
-def test_pose_mirror_matches_oracle():
+def test_pose_shim_matches_oracle():
+    """The closed-form R = Rx·Ry·Rz of geometry.rigid_from_vec against the oracle's restatement of pose_utils.py:8-51
+    (values and the gradient that reaches PoseNet)."""
     from packnet_sfm_b200.geometry import Pose
     from oracle import loss_oracle as LO
-    vec = torch.rand(3, 6) - 0.5
-    assert torch.equal(Pose.from_vec(vec, "euler").mat, LO.pose_from_vec(vec))
-    p = Pose.from_vec(vec, "euler")
-    ident = (p @ p.inverse()).mat
-    assert torch.allclose(ident, torch.eye(4).repeat(3, 1, 1), atol=1e-6)
+    vec = (torch.rand(3, 6) - 0.5).requires_grad_(True)
+    ours, ref = Pose.from_vec(vec, "euler").mat, LO.pose_from_vec(vec)
+    assert torch.allclose(ours, ref, atol=1e-7, rtol=0)
+    w = torch.rand(3, 4, 4)
+    g1, = torch.autograd.grad((ours * w).sum(), vec)
+    g2, = torch.autograd.grad((ref * w).sum(), vec)
+    assert torch.allclose(g1, g2, atol=1e-6, rtol=0)
+    assert len(Pose.identity(2)) == 2 and torch.equal(Pose.identity(2).mat[1], torch.eye(4))
+    with pytest.raises(ValueError):
+        Pose.from_vec(vec, "quat")
 
 
 def test_fold_and_frame_descriptors_reach_the_c_side_intact():
@@ -104,3 +111,24 @@ def test_fold_and_frame_descriptors_reach_the_c_side_intact():
     fd = folded._FrameApplyCUDA._desc((B, h, w, co), n, k, lines, weights)
     if not torch.cuda.is_available():
         assert lib.pn_pack_frame_forward(ctypes.byref(fd), _lib.ptr(dB), _lib.ptr(z), None) > 0
+
+
+def test_half_and_double_tensors_are_rejected_not_reinterpreted(monkeypatch):
+    """the reference's `--half` switches cast model and images; the kernels read raw fp32 pointers, so any other
+    dtype must raise before a pointer is taken (the device check is bypassed here so that the dtype check is what fires)."""
+    from packnet_sfm_b200 import _lib, functional as PF
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    from packnet_sfm_b200.geometry import Pose
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    x = torch.rand(1, 8, 8, 16)
+    w = torch.rand(16, 16, 3, 3)
+    for bad in (torch.float16, torch.float64, torch.bfloat16):
+        with pytest.raises(RuntimeError, match="fp32"):
+            PF.conv2d(x.to(bad), w.to(bad), None)
+        with pytest.raises(RuntimeError, match="fp32"):
+            PF.groupnorm_elu(x.to(bad), torch.ones(16, dtype=bad), torch.zeros(16, dtype=bad))
+    loss = MultiViewPhotometricLoss(num_scales=1, photometric_reduce_op="min", clip_loss=0.0, automask_loss=True)
+    img = torch.rand(1, 3, 8, 16)
+    with pytest.raises(RuntimeError, match="fp32"):
+        loss(img.half(), [img.half(), img.half()], [torch.rand(1, 1, 8, 16).half()], torch.eye(3)[None], torch.eye(3)[None],
+             [Pose.identity(1), Pose.identity(1)])

@@ -77,7 +77,7 @@ def test_conv2d_forward_backward(case, precision):
 @pytest.mark.parametrize("mode", [1, 2])
 def test_conv2d_staging_modes_agree(mode):
     """PER_TAP (reload per tap) and HALO (patch reuse through shifted descriptors) give the same numbers."""
-    from packnet_sfm_b200 import ops
+    import conv_helpers as ops
     torch.manual_seed(5)
     x = torch.rand(2, 48, 40, 64, device=DEV) - 0.5
     w = (torch.rand(64, 64, 5, 5, device=DEV) - 0.5) * 0.05
