@@ -129,9 +129,105 @@ def packnet_case():
     print("packnet01", [tuple(d.shape) for d in out], float(out[0].mean()))
 
 
+def strided_index(numel, n):
+    """n evenly spaced flat indices (integer arithmetic: the tests rebuild exactly the same ones)."""
+    n = min(n, numel)
+    return (torch.arange(n, dtype=torch.int64) * (numel - 1)) // max(n - 1, 1)
+
+
+def _grad_samples(named_grads, arrays, prefix, n=64):
+    """Per parameter: float64 L2 norm and `n` evenly strided elements of the flattened gradient (keeps a 128 M-parameter
+    gradient in a fixture of a few hundred KB while still touching every tensor)."""
+    for k, g in named_grads:
+        flat = g.detach().reshape(-1)
+        idx = strided_index(flat.numel(), n)
+        arrays[prefix + "norm/" + k] = np.float64(flat.double().norm().item())
+        arrays[prefix + "samp/" + k] = flat[idx].numpy()
+
+
+def packnet_baseline_case(B=4, H=192, W=640, name="packnet01_192x640_b4"):
+    """PackNet01 at BASELINE configs[1] (B=4, 192x640): the engine paths that the 64x96 fixture cannot reach (persistent
+    tile loop, batch folding, split-K thresholds).  Depth maps in full (fp32), the gradient of sum_i <disp_i, gy_i> for a
+    seeded gy as per-parameter norms + strided samples.  The input is regenerated from its seed by the test; a checksum
+    guards against an RNG change."""
+    sd = PO.packnet01_state_dict(seed=42, randomize_affine=True)
+    net = PackNet01(version="1A")
+    _load(net, sd)
+    net.train()
+    x = synthetic.make_frames(B, H, W, seed=77)["rgb"]
+    out = net(x)["inv_depths"]
+    g = torch.Generator().manual_seed(78)
+    arrays = {"seed_rgb": np.int64(77), "seed_gy": np.int64(78), "rgb_sum": np.float64(x.double().sum().item()),
+              "rgb_probe": x.reshape(-1)[::100003].numpy()}
+    obj = 0.0
+    for i, d in enumerate(out):
+        gy = torch.rand(d.shape, generator=g) - 0.5
+        obj = obj + (d * gy).sum()
+        arrays["disp%d" % (i + 1)] = d.detach().numpy()
+    obj.backward()
+    _grad_samples([(k, p.grad) for k, p in net.named_parameters()], arrays, "g")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+    print(name, [tuple(d.shape) for d in out], float(out[0].mean()))
+
+
+def step_case(B=2, H=64, W=96, name="step_2x64x96"):
+    """Two optimizer steps of the reference's own SelfSupModel (models/SelfSupModel.py:63-97 over SfmModel.py:81-127) with
+    the reference's PackNet01 / PoseNet / loss, Adam(lr 2e-4) as model_wrapper.py:128-166: step 0 without the left-right
+    flip, step 1 with it.  Stored: both losses and metrics, the depth / pose outputs of step 0, per-parameter gradient
+    norms + samples of step 0, and strided parameter samples after each step (8 depth-net tensors + all of PoseNet)."""
+    from oracle.step_oracle import posenet_state_dict
+    from packnet_sfm.models.SelfSupModel import SelfSupModel
+    from packnet_sfm.networks.pose.PoseNet import PoseNet
+    depth = PackNet01(version="1A")
+    _load(depth, PO.packnet01_state_dict(seed=42, randomize_affine=True))
+    pose = PoseNet(nb_ref_imgs=2, rotation_mode="euler")
+    _load(pose, posenet_state_dict(43))
+    model = SelfSupModel(depth_net=depth, pose_net=pose, rotation_mode="euler", flip_lr_prob=0.0, upsample_depth_maps=True,
+                         **YACS_LOSS_DEFAULTS)
+    model.train()
+    opt = torch.optim.Adam([{"params": depth.parameters(), "lr": 2e-4}, {"params": pose.parameters(), "lr": 2e-4}])
+    fr = synthetic.make_frames(B, H, W, seed=91)
+    batch = {"rgb": fr["rgb"], "rgb_context": fr["rgb_context"], "rgb_original": fr["rgb"],
+             "rgb_context_original": fr["rgb_context"], "intrinsics": fr["intrinsics"]}
+    arrays = {"seed_frames": np.int64(91), "B": np.int64(B), "H": np.int64(H), "W": np.int64(W)}
+    watch = ["pre_calc.conv_base.weight", "conv1.conv_base.weight", "pack1.conv3d.weight", "pack1.conv.conv_base.weight",
+             "pack5.conv.conv_base.weight", "conv5.2.conv3.weight", "unpack3.conv.normalize.weight", "disp1_layer.conv1.weight"]
+    for step, flip in enumerate((0.0, 1.0)):
+        model.flip_lr_prob = flip
+        opt.zero_grad(set_to_none=True)
+        out = model(batch)
+        out["loss"].backward()
+        arrays["loss%d" % step] = out["loss"].detach().numpy()
+        arrays["photometric_loss%d" % step] = out["metrics"]["photometric_loss"].numpy()
+        arrays["smoothness_loss%d" % step] = out["metrics"]["smoothness_loss"].numpy()
+        if step == 0:
+            arrays["inv_depth0_step0"] = out["inv_depths"][0].detach().numpy()
+            for j, pz in enumerate(out["poses"]):
+                arrays["pose%d_step0" % j] = pz.mat.detach().numpy()
+            _grad_samples([("depth." + k, p.grad) for k, p in depth.named_parameters()] +
+                          [("pose." + k, p.grad) for k, p in pose.named_parameters()], arrays, "g0")
+        opt.step()
+        named = dict(depth.named_parameters())
+        for k in watch:
+            flat = named[k].detach().reshape(-1)
+            idx = strided_index(flat.numel(), 4096)
+            arrays["p%d/depth.%s" % (step, k)] = flat[idx].numpy().copy()
+        for k, p_ in pose.named_parameters():
+            flat = p_.detach().reshape(-1)
+            idx = strided_index(flat.numel(), 512)
+            arrays["p%d/pose.%s" % (step, k)] = flat[idx].numpy().copy()
+        print(name, "step", step, "flip", flip, float(out["loss"]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]
+    if only:            # python oracle/gen_golden.py step_case packnet_baseline_case
+        for fn in only:
+            globals()[fn]()
+        sys.exit(0)
     loss_case("loss_fullres", 2, 32, 64, True)
     loss_case("loss_multires", 2, 32, 64, False)
     loss_case("loss_mean_noautomask", 1, 24, 40, True, photometric_reduce_op="mean", automask_loss=False,
@@ -140,3 +236,5 @@ if __name__ == "__main__":
     loss_case("loss_progressive", 1, 32, 64, False, progressive_scaling=0.2)
     block_cases()
     packnet_case()
+    step_case()
+    packnet_baseline_case()

@@ -47,7 +47,7 @@ def pose_from_vec(vec):
     """Pose.from_vec(vec, 'euler'), pose.py:39-46 + pose_utils.py:41-51 -> [B,4,4]."""
     trans, rot = vec[:, :3].unsqueeze(-1), vec[:, 3:]
     mat = torch.cat([euler2mat(rot), trans], dim=2)
-    pose = torch.eye(4, dtype=vec.dtype).repeat([len(vec), 1, 1])
+    pose = torch.eye(4, dtype=vec.dtype, device=vec.device).repeat([len(vec), 1, 1])
     pose[:, :3, :3] = mat[:, :3, :3]
     pose[:, :3, -1] = mat[:, :3, -1]
     return pose
@@ -81,10 +81,10 @@ def K_inverse(K):
     return Kinv
 
 
-def image_grid(B, H, W, dtype):
+def image_grid(B, H, W, dtype, device=None):
     """image.py:218-282 -- [B,3,H,W] of (x, y, 1) with x in 0..W-1."""
-    xs = torch.linspace(0, W - 1, W, dtype=dtype)
-    ys = torch.linspace(0, H - 1, H, dtype=dtype)
+    xs = torch.linspace(0, W - 1, W, dtype=dtype, device=device)
+    ys = torch.linspace(0, H - 1, H, dtype=dtype, device=device)
     ys, xs = torch.meshgrid([ys, xs], indexing="ij")
     xs, ys = xs.repeat([B, 1, 1]), ys.repeat([B, 1, 1])
     return torch.stack([xs, ys, torch.ones_like(xs)], dim=1)
@@ -94,7 +94,7 @@ def reconstruct(depth, K):
     """Camera.reconstruct(depth, 'w') for the identity-pose target camera, camera.py:112-148.
     Twc of the identity pose is the identity, and R=I, t=0 leaves Xc bit-identical."""
     B, _, H, W = depth.shape
-    flat_grid = image_grid(B, H, W, depth.dtype).view(B, 3, -1)
+    flat_grid = image_grid(B, H, W, depth.dtype, depth.device).view(B, 3, -1)
     xnorm = K_inverse(K).bmm(flat_grid).view(B, 3, H, W)
     return xnorm * depth
 
@@ -245,7 +245,7 @@ def multiview_photometric_loss(image, context, inv_depths, K, ref_K, poses, num_
     photometric = sum([reduce_fn(photometric_losses[i]) for i in range(n)]) / n
     loss = photometric
     photometric_metric = photometric.detach()
-    smoothness = torch.zeros(())
+    smoothness = torch.zeros((), device=loss.device)
     if smooth_loss_weight > 0.0:
         # calc_smoothness_loss, :257-283
         sx, sy = calc_smoothness(inv_depths, images, n)

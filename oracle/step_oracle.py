@@ -46,9 +46,12 @@ def posenet_forward(image, context, sd, nb_ref_imgs=2):
 
 
 class StepOracle:
-    def __init__(self, depth_sd=None, pose_sd=None, lr=2e-4):
-        self.depth = {k: v.clone().requires_grad_(True) for k, v in (depth_sd or PO.packnet01_state_dict(42)).items()}
-        self.pose = {k: v.clone().requires_grad_(True) for k, v in (pose_sd or posenet_state_dict(43)).items()}
+    def __init__(self, depth_sd=None, pose_sd=None, lr=2e-4, device="cpu"):
+        """device="cuda": the same plain-PyTorch program on the GPU's library kernels (cuDNN / ATen) -- bench.py's
+        `stock_torch_gpu` leg, the number BASELINE.md asks the product to beat; never a parity reference."""
+        mk = lambda v: v.clone().to(device).requires_grad_(True)      # noqa: E731
+        self.depth = {k: mk(v) for k, v in (depth_sd or PO.packnet01_state_dict(42)).items()}
+        self.pose = {k: mk(v) for k, v in (pose_sd or posenet_state_dict(43)).items()}
         self.opt = torch.optim.Adam(list(self.depth.values()) + list(self.pose.values()), lr=lr)
 
     def forward_loss(self, batch, flip=False):

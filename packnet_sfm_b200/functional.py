@@ -263,7 +263,7 @@ def conv2d_im2col(x, weight, bias=None, conv=None, align=None):
 
 # The GroupNorm backward already reduces its dx over the pixels; the convolution that consumes dx as its output
 # gradient takes its bias gradient from here instead of re-reading the tensor.  An entry is valid only while the
-# producing tensor object is alive (weak reference), IS the tensor handed to the convolution's backward, and has not been
+# producing tensor object is alive (weak reference: no other tensor can own that storage) and has not been
 # written since (autograd version counter).
 _channel_sums = []
 
@@ -277,7 +277,7 @@ def _lookup_channel_sum(g):
     for ref, ptr, shape, version, dsum in reversed(_channel_sums):
         # the SAME tensor object, unmodified since the GroupNorm backward wrote it: a second consumer's gradient accumulated
         # in place by autograd (or a hook editing dx) bumps the version counter and the cached sum is not used
-        if ref() is g and ptr == g.data_ptr() and shape == tuple(g.shape) and g._version == version and g.is_contiguous():
+        if ref() is not None and ptr == g.data_ptr() and shape == tuple(g.shape) and g._version == version and g.is_contiguous():
             return dsum
     return None
 

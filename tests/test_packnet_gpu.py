@@ -84,3 +84,51 @@ def test_eval_mode_contract_and_shape_errors():
     assert torch.is_tensor(out["inv_depths"]) and out["inv_depths"].shape == (1, 1, 32, 64)
     with pytest.raises(ValueError):
         net(torch.rand(1, 3, 30, 64, device=DEV))
+
+
+def strided_index(numel, n):
+    """the sample positions of oracle/gen_golden.py::strided_index"""
+    n = min(n, numel)
+    return (torch.arange(n, dtype=torch.int64) * (numel - 1)) // max(n - 1, 1)
+
+
+def test_packnet01_baseline_config_matches_reference_golden():
+    """BASELINE configs[1] (B=4, 192x640): the engine paths the 64x96 fixture does not reach -- persistent tile loop with
+    hundreds of work items, batch folding on the small maps, the split-K thresholds -- against the LIVE reference's depth
+    maps (tests/golden/packnet01_192x640_b4.npz: fp32 maps in full, gradients of sum_i <disp_i, gy_i> as per-parameter
+    norms + 64 strided samples).  Bar: depth 1e-3 max-relative (north_star); gradients 2e-3 of the tensor's norm."""
+    from packnet_sfm_b200 import synthetic
+    z = load_golden("packnet01_192x640_b4")
+    x = synthetic.make_frames(4, 192, 640, seed=int(z["seed_rgb"]))["rgb"]
+    assert abs(float(x.double().sum()) - float(z["rgb_sum"])) < 1e-6 * float(z["rgb_sum"])       # same synthetic input
+    assert torch.equal(x.reshape(-1)[::100003], z["rgb_probe"])
+    net = _net(PO.packnet01_state_dict(seed=42, randomize_affine=True))
+    out = net(x.to(DEV))["inv_depths"]
+    g = torch.Generator().manual_seed(int(z["seed_gy"]))
+    gys = [torch.rand(d.shape, generator=g) - 0.5 for d in out]
+    worst = 0.0
+    for i, d in enumerate(out):
+        ref = z["disp%d" % (i + 1)]
+        assert d.shape == ref.shape
+        rel = ((d.detach().cpu() - ref).abs() / ref.abs()).max().item()
+        worst = max(worst, rel)
+        print("disp%d %s max-rel %.3e rel-l2 %.3e" % (i + 1, tuple(d.shape), rel, rel_l2(d.detach().cpu(), ref)))
+    assert worst < 1e-3
+    torch.autograd.backward(out, [t.to(DEV) for t in gys])
+    torch.cuda.synchronize()
+    worst_g = ("", 0.0)
+    for k, p in net.named_parameters():
+        norm_ref = float(z["gnorm/" + k])
+        samp_ref = z["gsamp/" + k].double()
+        flat = p.grad.reshape(-1)
+        got = flat[strided_index(flat.numel(), 64).to(DEV)].cpu().double()
+        norm_got = float(flat.double().norm())
+        # a sample of n elements carries about sqrt(n / numel) of the tensor's norm: scale the bound the same way
+        bound = 5e-3 * float(samp_ref.norm()) + 2e-3 * norm_ref * (got.numel() / flat.numel()) ** 0.5 + 1e-7
+        err = float((got - samp_ref).norm())
+        score = max(err / bound, abs(norm_got - norm_ref) / (2e-3 * norm_ref + 1e-6))
+        if score > worst_g[1]:
+            worst_g = (k, score)
+        assert abs(norm_got - norm_ref) <= 2e-3 * norm_ref + 1e-6, (k, norm_got, norm_ref)
+        assert err <= bound, (k, err, bound)
+    print("worst parameter-gradient error/bound at B=4 192x640: %s %.3f" % worst_g)
