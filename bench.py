@@ -41,34 +41,14 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "tf32x3", "tf32x1"],
                     help="tensor-core GEMM mode; bf16x3 and tf32x3 meet the 1e-3 depth parity bar, tf32x1 does not")
-    ap.add_argument("--graph", action="store_true",
-                    help="capture the whole step (fwd+loss+bwd+all-reduce+Adam) in two CUDA graphs (flip / no flip) and replay; "
-                         "experimental until measured on the B200")
-    ap.add_argument("--pack-fold", action="store_true",
-                    help="pack layers as one folded convolution (packnet_sfm_b200/folded.py); experimental until measured")
-    ap.add_argument("--loss-grouped", action="store_true",
-                    help="STAGED (DESIGN.md 7.5): the grouped-scale loss tile program (PN_LOSS_FLAG_GROUPED) instead of the default one")
-    ap.add_argument("--im2col-first", action="store_true",
-                    help="STAGED (DESIGN.md 7.6): first convolution (3 -> 64, 5x5) as a 1x1 convolution over its im2col tensor")
-    ap.add_argument("--stage-flat", action="store_true",
-                    help="STAGED (DESIGN.md 7.7): all-threads tile staging in the head convolution kernels (pn_set_tuning)")
-    ap.add_argument("--gn-tree", action="store_true",
-                    help="STAGED (DESIGN.md 7.7): shuffle reduction in the GroupNorm statistics kernel (pn_set_tuning)")
-    ap.add_argument("--unpack-tiled", action="store_true",
-                    help="STAGED (DESIGN.md 7.9): weight-gradient re-layout through shared memory")
-    ap.add_argument("--pack-tiled", action="store_true",
-                    help="STAGED (DESIGN.md 7.9): per-step weight packing through shared memory")
-    ap.add_argument("--staged-all", action="store_true",
-                    help="every staged variant at once (pack fold, grouped loss, im2col first layer, flat staging, GroupNorm tree, "
-                         "tiled unpack) -- not --graph, which is orthogonal")
-    ap.add_argument("--staged-small", action="store_true", help="every staged variant except the pack fold")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="enqueue every step eagerly instead of replaying the captured whole-step CUDA graphs (flip / no flip)")
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=0|1",
+                    help="A/B switch of a kernel variant against its library default: pack_fold, loss_grouped, im2col_first, "
+                         "stage_flat, gn_tree, unpack_tiled, pack_tiled (e.g. --set pack_fold=0 --set loss_grouped=0 = the round-1 path)")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock-torch", action="store_true", help="skip the stock-PyTorch-on-the-GPU leg (oracle step on cuda)")
-    ap.add_argument("--staged-probe", action="store_true",
-                    help="OPT-IN (also PN_STAGED_PROBE=1): after the N=1 run's own work, run the staged (not yet default) variants in "
-                         "isolated child processes and append their summaries as `staged` (adds up to ~8 minutes)")
-    ap.add_argument("--no-staged-probe", action="store_true", help="accepted for compatibility; the probe is off by default")
     return ap.parse_args()
 
 
@@ -355,65 +335,26 @@ def time_kernels(args, dev, pk):
     return res
 
 
-def staged_probe(args):
-    """Measure the STAGED variants of the step (folded pack layers, whole-step CUDA graph) in isolated
-    child processes, after every CUDA call of this process is done.  They are off by default because they were written
-    after the round-1 GPU budget was spent; each child runs this same script with the variant's flags for a few steps
-    and its JSON line (or its failure) is recorded under `staged` -- the headline `value` never depends on them, and a
-    child that faults or hangs (killed at the timeout) cannot take this process's result with it."""
-    out = {}
-    deadline = time.time() + 500.0
-    base = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
-            "--no-staged-probe", "--batch", str(args.batch), "--height", str(args.height), "--width", str(args.width),
-            "--precision", args.precision]
-    env = dict(os.environ)
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
-        env.pop(k, None)
-    # parity first: the experimental GPU tier of the folded path (fold / frame kernels against their PyTorch definition, the
-    # folded block on the engine against float64, block and network against the reference's golden vectors)
-    t0 = time.time()
-    try:
-        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_folded_gpu.py"),
-                            os.path.join(ROOT, "tests", "test_graph_gpu.py"), "-m", "gpu", "-q",
-                            "-p", "no:cacheprovider"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200.0,
-                           env=dict(env, PN_EXPERIMENTAL="1"), cwd=ROOT)
-        tail = [ln for ln in r.stdout.splitlines() if ln.strip()][-6:]
-        out["tests_experimental_gpu"] = {"exit_code": r.returncode, "summary": tail[-1] if tail else "", "tail": tail}
-    except subprocess.TimeoutExpired:
-        out["tests_experimental_gpu"] = {"failed": "timeout"}
-    except Exception as e:
-        out["tests_experimental_gpu"] = {"failed": repr(e)[:300]}
-    log("staged probe tests: %.0f s -> %s" % (time.time() - t0, json.dumps(out["tests_experimental_gpu"])[:300]))
-    for tag, flags in (("pack_fold", ["--pack-fold"]), ("cuda_graph", ["--graph"]), ("pack_fold+cuda_graph", ["--pack-fold", "--graph"]),
-                       ("loss_grouped", ["--loss-grouped"])):
-        left = deadline - time.time()
-        if left < 45.0:
-            out[tag] = {"skipped": "probe time budget used up"}
-            continue
-        t0 = time.time()
-        try:
-            r = subprocess.run(base + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=min(120.0, left), env=env)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            if r.returncode == 0 and lines:
-                j = json.loads(lines[-1])
-                out[tag] = {k: j.get(k) for k in ("value", "ms_per_step", "loss", "gpu_launches", "host_enqueue_ms_per_step", "cuda_graph",
-                                                  "pack_fold", "roofline_pack1_folded", "loss_grouped", "roofline_loss")}
-                out[tag]["e2e_value"] = (j.get("e2e") or {}).get("value")
-            else:
-                out[tag] = {"failed": "exit code %d" % r.returncode, "stderr_tail": r.stderr[-600:]}
-        except subprocess.TimeoutExpired:
-            out[tag] = {"failed": "timeout"}
-        except Exception as e:    # a probe must never cost the main result
-            out[tag] = {"failed": repr(e)[:300]}
-        log("staged probe %s: %.0f s -> %s" % (tag, time.time() - t0, json.dumps(out[tag])[:200]))
-    return out
+def apply_variants(settings, PF, _lib, _losses):
+    """--set KEY=0|1 overrides; returns the EFFECTIVE setting of every variant (library defaults where not overridden)."""
+    setters = {"pack_fold": lambda v: PF.set_pack_fold(v), "loss_grouped": _losses.set_grouped_kernel,
+               "im2col_first": PF.set_im2col_first, "unpack_tiled": PF.set_unpack_tiled, "pack_tiled": PF.set_pack_tiled,
+               "stage_flat": lambda v: _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, int(v)),
+               "gn_tree": lambda v: _lib.set_tuning(_lib.PN_TUNE_GN_TREE, int(v))}
+    eff = {"pack_fold": PF.pack_fold_enabled(), "loss_grouped": bool(_losses._grouped), "im2col_first": PF.im2col_first_enabled(),
+           "unpack_tiled": PF._state["unpack_tiled"], "pack_tiled": PF._state["pack_tiled"],
+           "stage_flat": os.environ.get("PN_STAGE_FLAT", "1") != "0", "gn_tree": os.environ.get("PN_GN_TREE", "1") != "0"}
+    for kv in settings:
+        k, _, v = kv.partition("=")
+        if k not in setters or v not in ("0", "1"):
+            raise SystemExit("--set %s: expected one of %s with =0 or =1" % (kv, sorted(setters)))
+        setters[k](v == "1")
+        eff[k] = v == "1"
+    return eff
 
 
 def run_ours(args):
-    if args.staged_all:
-        args.pack_fold = True
-    if args.staged_all or args.staged_small:
-        args.loss_grouped = args.im2col_first = args.stage_flat = args.gn_tree = args.unpack_tiled = args.pack_tiled = True
+    args.graph = not args.no_graph
     import torch.distributed as dist
     from packnet_sfm_b200 import _lib, functional as PF, parallel
     from packnet_sfm_b200.models import SelfSupModel
@@ -424,6 +365,11 @@ def run_ours(args):
         raise SystemExit("bench.py (ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Everything runs on ONE non-default stream from the first kernel on.  Autograd binds a parameter's AccumulateGrad node to
+    # the stream of the first forward; nodes born on the legacy default stream make the later whole-step capture fail
+    # ("operation would make the legacy stream depend on a capturing blocking stream", gpurun r02a).
+    main_stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(main_stream)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     PF.set_precision({"bf16x3": PF.PRECISION_BF16X3, "tf32x3": PF.PRECISION_TF32X3, "tf32x1": PF.PRECISION_TF32X1}[args.precision])
@@ -439,21 +385,8 @@ def run_ours(args):
     groups = [{"name": "Depth", "params": list(model.depth_net.parameters()), "lr": 2e-4},
               {"name": "Pose", "params": list(model.pose_net.parameters()), "lr": 2e-4}]
     opt = torch.optim.Adam(groups, fused=True, capturable=bool(args.graph))
-    if args.pack_fold:
-        PF.set_pack_fold(True)
-    if args.loss_grouped:
-        from packnet_sfm_b200 import losses as _losses
-        _losses.set_grouped_kernel(True)
-    if args.im2col_first:
-        PF.set_im2col_first(True)
-    if args.stage_flat:
-        _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 1)
-    if args.gn_tree:
-        _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
-    if args.unpack_tiled:
-        PF.set_unpack_tiled(True)
-    if args.pack_tiled:
-        PF.set_pack_tiled(True)
+    from packnet_sfm_b200 import losses as _losses
+    variants = apply_variants(args.set, PF, _lib, _losses)
     B, H, W = args.batch, args.height, args.width
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)
@@ -495,13 +428,9 @@ def run_ours(args):
         # Gradients are freed before each capture so that the backward allocates them from the graph's pool.
         flip_prob = model.flip_lr_prob
         graphs = {}
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for fl in (False, True):
-                model.flip_lr_prob = 1.0 if fl else 0.0
-                eager_step(dbatch)
-        torch.cuda.current_stream().wait_stream(side)
+        for fl in (False, True):
+            model.flip_lr_prob = 1.0 if fl else 0.0
+            eager_step(dbatch)
         torch.cuda.synchronize()
         per_graph_launches = 0
         for fl in (False, True):
@@ -585,17 +514,13 @@ def run_ours(args):
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
-                "loss": state.get("loss_host"), "cuda_graph": graph_info, "pack_fold": bool(args.pack_fold),
-                "loss_grouped": bool(args.loss_grouped), "im2col_first": bool(args.im2col_first), "stage_flat": bool(args.stage_flat), "gn_tree": bool(args.gn_tree), "unpack_tiled": bool(args.unpack_tiled), "pack_tiled": bool(args.pack_tiled)}
+                "loss": state.get("loss_host"), "cuda_graph": graph_info, "variants": variants}
         line.update(extra)
         if world == 1 and not args.no_stock_torch:
             line["stock_torch_gpu"] = stock_torch_gpu(args, dev)
             log("stock torch on the GPU: %s" % json.dumps(line["stock_torch_gpu"])[:300])
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)
-        if world == 1 and not args.no_staged_probe and (args.staged_probe or os.environ.get("PN_STAGED_PROBE") == "1"):
-            torch.cuda.synchronize()          # nothing of this process touches the GPU after this point
-            line["staged"] = staged_probe(args)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -19,29 +19,37 @@ import torch
 from . import _lib
 from ._lib_conv import ConvDesc, PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3, MODE_AUTO
 
-_state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": os.environ.get("PN_PACK_FOLD", "0") == "1",
+# Defaults since round 2 = what the B200 measured faster (gpurun r02a, B=4 192x640, ms per step): pack fold 37.9 -> 30.9, im2col
+# first layer -0.2, tiled weight-gradient unpack -0.2; the tiled weight PACK was not faster (1.85 vs 1.90 ms) and stays off.
+# PN_<NAME>=0 / =1 in the environment overrides a default for A/B runs.
+def _env(name, default):
+    v = os.environ.get(name)
+    return default if v is None else v == "1"
+
+
+_state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": _env("PN_PACK_FOLD", True),
           "pack_fold_min_pixels": int(os.environ.get("PN_PACK_FOLD_MIN_PIXELS", "1920")),
-          "im2col_first": os.environ.get("PN_IM2COL_FIRST", "0") == "1",
-          "unpack_tiled": os.environ.get("PN_UNPACK_TILED", "0") == "1",
-          "pack_tiled": os.environ.get("PN_PACK_TILED", "0") == "1"}
+          "im2col_first": _env("PN_IM2COL_FIRST", True),
+          "unpack_tiled": _env("PN_UNPACK_TILED", True),
+          "pack_tiled": _env("PN_PACK_TILED", False)}
 
 
 def set_pack_tiled(on):
-    """STAGED (off by default): per-step weight packing of the bf16 precisions through shared memory
-    (pn_conv2d_pack_weight_tiled) instead of the strided element-per-thread gather."""
+    """Off by default (measured on the B200: not faster than the gather): per-step weight packing of the bf16
+    precisions through shared memory (pn_conv2d_pack_weight_tiled) instead of the strided element-per-thread gather."""
     prev, _state["pack_tiled"] = _state["pack_tiled"], bool(on)
     return prev
 
 
 def set_unpack_tiled(on):
-    """STAGED (off by default): weight-gradient re-layout [Cout][tap][Cin] -> OIHW through shared memory
+    """On by default since round 2: weight-gradient re-layout [Cout][tap][Cin] -> OIHW through shared memory
     (pn_conv2d_unpack_weight_grad_tiled) instead of the strided element-per-thread gather."""
     prev, _state["unpack_tiled"] = _state["unpack_tiled"], bool(on)
     return prev
 
 
 def set_im2col_first(on):
-    """STAGED (off by default): evaluate the network's first convolution (3 -> 64, 5x5) as a 1x1 convolution
+    """On by default since round 2: evaluate the network's first convolution (3 -> 64, 5x5) as a 1x1 convolution
     over its im2col tensor (conv2d_im2col) instead of 25 tap items that each fill 3 of 64 reduction lanes."""
     prev, _state["im2col_first"] = _state["im2col_first"], bool(on)
     return prev
@@ -53,7 +61,7 @@ def im2col_first_enabled():
 
 def set_pack_fold(on, min_pixels=None):
     """Pack layers as ONE folded convolution of the space-to-depth tensor (packnet_sfm_b200/folded.py) instead of
-    feature stencil + convolution over the 8x-inflated channel count.  Off by default until measured on the B200.
+    feature stencil + convolution over the 8x-inflated channel count.  ON by default since round 2 (B200: 37.9 -> 30.9 ms/step).
     min_pixels: fold only layers whose packed map has at least that many pixels -- on the small maps (pack4: 12x40,
     pack5: 6x20 at 192x640) the frame is 20-40 % of the map and the layer is bound by streaming its weights, which the
     fold has to read once more (default 1920 = pack1..pack3 at 192x640)."""

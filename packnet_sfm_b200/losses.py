@@ -52,13 +52,13 @@ class LossBase(nn.Module):
         self._metrics[key] = val.detach()
 
 
-_grouped = os.environ.get("PN_LOSS_GROUPED") == "1"
+_grouped = os.environ.get("PN_LOSS_GROUPED", "1") == "1"     # default since round 2 (B200: fwd 0.193 -> 0.145, bwd 0.599 -> 0.436 ms)
 
 
 def set_grouped_kernel(on):
     """Select the grouped-scale tile program (csrc/loss_group_kernel.cuh, PN_LOSS_FLAG_GROUPED) for the descriptors built
-    from now on.  STAGED: off by default until it has been measured on a B200; PN_LOSS_GROUPED=1 sets
-    the initial value.  Returns the previous setting."""
+    from now on (the default since round 2; PN_LOSS_GROUPED=0 in the environment or set_grouped_kernel(False) selects the
+    first-generation tile program, which stays tested).  Returns the previous setting."""
     global _grouped
     prev, _grouped = _grouped, bool(on)
     return prev

@@ -16,11 +16,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=["tile", "grouped"])
 def loss_program(request):
-    """Every test of this file runs on the default tile program; with PN_EXPERIMENTAL=1 also on the staged grouped-scale
-    program (csrc/loss_group_kernel.cuh, PN_LOSS_FLAG_GROUPED) -- same assertions."""
+    """Every test of this file runs on both tile programs: the grouped-scale one (csrc/loss_group_kernel.cuh,
+    PN_LOSS_FLAG_GROUPED; the default since round 2) and the first-generation one -- same assertions."""
     from packnet_sfm_b200 import losses
-    if request.param == "grouped" and os.environ.get("PN_EXPERIMENTAL") != "1":
-        pytest.skip("staged grouped-scale loss program: set PN_EXPERIMENTAL=1")
     prev = losses.set_grouped_kernel(request.param == "grouped")
     yield request.param
     losses.set_grouped_kernel(prev)

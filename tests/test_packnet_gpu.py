@@ -10,6 +10,20 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=["default", "fold_all", "unfolded"])
+def pack_path(request):
+    """default = pack1..3 folded into one (k+2)x(k+2) convolution where the map has >= 1920 pixels (policy of round 2);
+    unfolded = feature stencil + convolution over the 8x-inflated channel count everywhere (the round-1 path, which still
+    serves pack4 / pack5)."""
+    from packnet_sfm_b200 import functional as PF
+    if request.param == "unfolded":
+        PF.set_pack_fold(False)
+    elif request.param == "fold_all":      # every pack layer whose map is larger than the frame (also the small test maps)
+        PF.set_pack_fold(True, min_pixels=0)
+    yield request.param
+    PF.set_pack_fold(True, min_pixels=1920)
+
+
 def _net(sd):
     from packnet_sfm_b200.networks import PackNet01
     net = PackNet01(version="1A")
@@ -17,7 +31,7 @@ def _net(sd):
     return net.to(DEV).train()
 
 
-def test_packnet01_depth_maps_match_reference_golden():
+def test_packnet01_depth_maps_match_reference_golden(pack_path):
     z = load_golden("packnet01_64x96")
     net = _net(PO.packnet01_state_dict(seed=42, randomize_affine=True))
     with torch.no_grad():
@@ -50,7 +64,7 @@ def test_packnet01_other_precisions():
         PF.set_precision(PF.PRECISION_BF16X3)
 
 
-def test_packnet01_gradients_match_oracle_autograd():
+def test_packnet01_gradients_match_oracle_autograd(pack_path):
     """Full backward through every custom kernel against CPU autograd of the oracle restatement."""
     from packnet_sfm_b200 import synthetic
     sd = PO.packnet01_state_dict(seed=7, randomize_affine=True)
@@ -92,7 +106,7 @@ def strided_index(numel, n):
     return (torch.arange(n, dtype=torch.int64) * (numel - 1)) // max(n - 1, 1)
 
 
-def test_packnet01_baseline_config_matches_reference_golden():
+def test_packnet01_baseline_config_matches_reference_golden(pack_path):
     """BASELINE configs[1] (B=4, 192x640): the engine paths the 64x96 fixture does not reach -- persistent tile loop with
     hundreds of work items, batch folding on the small maps, the split-K thresholds -- against the LIVE reference's depth
     maps (tests/golden/packnet01_192x640_b4.npz: fp32 maps in full, gradients of sum_i <disp_i, gy_i> as per-parameter
