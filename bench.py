@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--set", action="append", default=[], metavar="KEY=0|1",
                     help="A/B switch of a kernel variant against its library default: pack_fold, loss_grouped, im2col_first, "
                          "stage_flat, gn_tree, unpack_tiled, pack_tiled (e.g. --set pack_fold=0 --set loss_grouped=0 = the round-1 path)")
+    ap.add_argument("--torch-adam", action="store_true",
+                    help="A/B: torch.optim.Adam(fused) + per-call weight packing instead of packnet_sfm_b200.optim.FlatAdam")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock-torch", action="store_true", help="skip the stock-PyTorch-on-the-GPU leg (oracle step on cuda)")
@@ -381,22 +383,28 @@ def run_ours(args):
     model = SelfSupModel().to(dev).train()
     log("model on device")
     parallel.broadcast_parameters(model)
-    bucket = parallel.FlatBucket(model.parameters())
-    groups = [{"name": "Depth", "params": list(model.depth_net.parameters()), "lr": 2e-4},
-              {"name": "Pose", "params": list(model.pose_net.parameters()), "lr": 2e-4}]
-    opt = torch.optim.Adam(groups, fused=True, capturable=bool(args.graph))
-    from packnet_sfm_b200 import losses as _losses
+    from packnet_sfm_b200 import losses as _losses, optim
+    from packnet_sfm_b200.networks import native_conv_weights
     variants = apply_variants(args.set, PF, _lib, _losses)
     B, H, W = args.batch, args.height, args.width
+    groups = [{"name": "Depth", "params": list(model.depth_net.parameters()), "lr": 2e-4},
+              {"name": "Pose", "params": list(model.pose_net.parameters()), "lr": 2e-4}]
+    if args.torch_adam:      # A/B: ATen's fused multi-tensor Adam + per-call weight packing + flat gradient bucket (round 1)
+        bucket = parallel.FlatBucket(model.parameters())
+        opt = torch.optim.Adam(groups, fused=True, capturable=bool(args.graph))
+        zero_grad, reduce_grads = bucket.zero_grad, bucket.allreduce_mean
+    else:                    # flat parameters / gradients / moments, one Adam launch that also writes the engine's weight tiles
+        opt = optim.FlatAdam(groups, native=native_conv_weights(model.depth_net, (H, W)))
+        zero_grad, reduce_grads = opt.zero_grad, opt.allreduce_mean
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)
     state = {}
 
     def step(batch):
-        bucket.zero_grad()
+        zero_grad()
         out = model(batch)
         out["loss"].backward()
-        bucket.allreduce_mean()
+        reduce_grads()
         opt.step()
         state["loss"] = out["loss"]
 
@@ -435,13 +443,13 @@ def run_ours(args):
         per_graph_launches = 0
         for fl in (False, True):
             model.flip_lr_prob = 1.0 if fl else 0.0
-            bucket.zero_grad()
+            zero_grad()
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 out = model(dbatch)
                 out["loss"].backward()
-                bucket.allreduce_mean()
+                reduce_grads()
                 opt.step()
             per_graph_launches = _lib.launch_count() - l0
             graphs[fl] = (g, out["loss"])
@@ -514,7 +522,8 @@ def run_ours(args):
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "host_cpu_ms_per_step": cpu_ms, "host_enqueue_ms_per_step": enqueue_ms, "clocks": clk.summary(),
-                "loss": state.get("loss_host"), "cuda_graph": graph_info, "variants": variants}
+                "loss": state.get("loss_host"), "cuda_graph": graph_info, "variants": variants,
+                "optimizer": "torch.optim.Adam(fused)" if args.torch_adam else "packnet_sfm_b200.optim.FlatAdam"}
         line.update(extra)
         if world == 1 and not args.no_stock_torch:
             line["stock_torch_gpu"] = stock_torch_gpu(args, dev)

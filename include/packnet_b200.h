@@ -154,6 +154,14 @@ int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const void* x_lo,
                       const void* w_packed_lo, const float* bias, float* y, uint32_t* error_flag,
                       pn_stream_t stream);
 
+/* Data gradient (autograd backward of nn.Conv2d w.r.t. its input, layers01.py:28-30) from the layer's FORWARD packing:
+ *   gx[B,H,W,Cin] = sum_{tap,co} g[pixel - tap + pad, co] * w[co, ci, tap]
+ * desc describes the LAYER (cin = channels of gx, cout = channels of g); w_packed / w_packed_lo are what pn_conv2d_forward
+ * took (pn_conv2d_pack_weight with transposed=0, or the tiles pn_adam_step writes).  bf16 precisions only: the [co][64 ci]
+ * tiles are read as MN-major tensor-core operands, so the transposed packing (transposed=1) is never built. */
+int pn_conv2d_dgrad(const pn_conv_desc* desc, const void* g, const void* g_lo, const void* w_packed, const void* w_packed_lo,
+                    float* gx, uint32_t* error_flag, pn_stream_t stream);
+
 /* Weight packing: OIHW fp32 [Cout,Cin,k,k] (nn.Conv2d.weight) -> the shared-memory image of every B-operand tile,
  * [channel chunk][tap][rows padded to the N tile][128 bytes, SWIZZLE_128B applied], so that the kernel fetches a
  * tile with one contiguous bulk copy.  transposed=0: rows = Cout (fprop); transposed=1: rows = Cin, taps flipped
@@ -186,6 +194,35 @@ int pn_conv2d_unpack_weight_grad_tiled(const float* dw_packed, float* dw_oihw, i
 int pn_tf32_residual(const float* x, float* lo, size_t n, pn_stream_t stream);
 /* hi[i] = bf16_rn(x[i]), lo[i] = bf16_rn(x[i] - hi[i]); n % 4 == 0. */
 int pn_split_bf16(const float* x, void* hi, void* lo, size_t n, pn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step on flat buffers, fused with the weight re-layout of the convolution engine
+ *   replaces torch.optim.Adam over the 'Depth' and 'Pose' parameter groups (packnet_sfm/models/model_wrapper.py:128-166)
+ *   and every per-step pn_conv2d_pack_weight / pn_conv2d_unpack_weight_grad of a stored weight.
+ * Layout contract (packnet_sfm_b200/optim.py builds it):
+ *   params / grads / exp_avg / exp_avg_sq: fp32 [numel], numel a multiple of PN_ADAM_BLOCK; block b = elements
+ *   [b*PN_ADAM_BLOCK, (b+1)*PN_ADAM_BLOCK) belongs to ONE parameter group and to at most one stored convolution weight:
+ *   block_info[b] = (group << 16) | (segment index + 1, 0 = plain elements).
+ *   A stored convolution weight occupies [offset, offset + cout*taps*kpad) as [cout][tap][kpad] (kpad = Cin rounded up to 64,
+ *   the padding stays zero) -- the layout pn_conv2d_wgrad accumulates, so `grads + offset` IS its dw_packed -- and its
+ *   forward tiles (the operand of pn_conv2d_forward AND pn_conv2d_dgrad) are (re)written at packed_hi/lo + packed_offset:
+ *   [kpad/64][tap][rows_pad][128 bytes, SWIZZLE_128B], bf16 hi = rn(w), lo = rn(w - hi).  Tile rows >= cout are never
+ *   written: the caller zeroes the tile buffers once.
+ *   hyper (device, fp32[16]): [0] step count (incremented here), [1] beta1, [2] beta2, [3] eps, [4] 1-beta1^t, [5] sqrt(1-beta2^t)
+ *   (both written here), [8+2g] lr and [9+2g] weight_decay (L2) of group g < 4.  Device-resident so that a captured CUDA graph
+ *   replays with the current step count and learning rates.
+ * update = 1: one Adam step (torch.optim.Adam semantics, no amsgrad) + tiles of the new values; update = 0: tiles only. */
+#define PN_ADAM_BLOCK 2048
+typedef struct {
+  int64_t offset;          /* first element of the weight in the flat buffers (multiple of PN_ADAM_BLOCK) */
+  int64_t packed_offset;   /* byte offset of its tiles in packed_hi / packed_lo (multiple of 1024) */
+  int32_t cout, taps, kpad, rows_pad;
+} pn_adam_conv_seg;
+int pn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                 const int32_t* block_info, const pn_adam_conv_seg* segs, float* hyper, void* packed_hi, void* packed_lo,
+                 int update, pn_stream_t stream);
+/* Rows of a forward tile group for `cout` output channels (cout rounded up to the N tile and to 64). */
+int pn_conv2d_rows_pad(int cout);
 
 /* ------------------------------------------------------------------------------------------------
  * Pack / unpack feature stencil: Conv3d(1->8, 3x3x3, pad 1) fused with space-to-depth (pack) or

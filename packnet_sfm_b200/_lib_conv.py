@@ -43,6 +43,10 @@ def declare(lib):
     c = ctypes
     vp, sz = c.c_void_p, c.c_size_t
     lib.pn_conv2d_forward.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pn_conv2d_dgrad.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]
+    lib.pn_conv2d_dgrad.restype = c.c_int
+    lib.pn_conv2d_rows_pad.argtypes = [c.c_int]
+    lib.pn_conv2d_rows_pad.restype = c.c_int
     lib.pn_conv2d_packed_weight_elems.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(sz)]
     lib.pn_conv2d_pack_weight.argtypes = [vp, vp, vp, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, vp]
     lib.pn_tf32_residual.argtypes = [vp, vp, sz, vp]

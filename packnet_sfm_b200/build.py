@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpacknet_b200.so")
-SOURCES = ["api.cu", "loss_kernels.cu", "conv_engine.cu", "layer_kernels.cu", "fold_kernels.cu", "frame_kernels.cu", "pack_kernels.cu"]
+SOURCES = ["api.cu", "loss_kernels.cu", "conv_engine.cu", "layer_kernels.cu", "fold_kernels.cu", "frame_kernels.cu", "pack_kernels.cu", "optim_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -61,6 +61,7 @@ struct KernelParams {
   const uint8_t* wp;       // packed, pre-swizzled weight tiles [cchunk][tap][rows_pad][128 B] (see pack_weight kernels)
   const uint8_t* wp_lo;
   int rows_pad;            // rows of one (cchunk, tap) tile group: Cout rounded up to a multiple of bn
+  int bt_nchunks;          // BT (data gradient from the forward packing): 64-channel chunks of the layer's Cin in the packing
   const float* bias;
   float* out;
   unsigned int* error_flag;
@@ -220,7 +221,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_b
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <bool BF16, bool SPLIT, bool HALO>
+// BT = data gradient read from the layer's FORWARD weight packing: the reduction runs over the layer's output channels,
+// which are the ROWS of a forward tile [co][64 ci x 2 B, SWIZZLE_128B]; read as an MN-major B operand (K = rows, 64 N
+// elements contiguous -- the layout conv_wgrad_kernel reads its dZ tiles in) the tile IS the transposed weight, so no
+// second packing exists.  A K chunk = 64 rows = one contiguous 8 KB run per 64-wide N block; the taps are walked flipped.
+template <bool BF16, bool SPLIT, bool HALO, bool BT = false>
 __global__ void __launch_bounds__(NTHREADS_IGEMM, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const KernelParams P) {
@@ -342,10 +347,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   tma_load_4d(dst, &tmA, fb, cc * P.kc, T.x0 + dx - P.pad, T.y0 + dy - P.pad, T.b0);
                   if (nops == 2) tma_load_4d(dst + P.a_stage_bytes, &tmAlo, fb, cc * P.kc, T.x0 + dx - P.pad, T.y0 + dy - P.pad, T.b0);
                 }
+                if (BT) {
+                  // rows [cc*64, cc*64+64) of the forward tiles (chunk = 64-wide N block, flipped tap): 8 KB runs
+                  const int nb64 = P.bn >> 6, wtap = taps - 1 - tap;
+                  for (int i = 0; i < nb64; ++i) {
+                    const int nc = min((T.n0 >> 6) + i, P.bt_nchunks - 1);   // columns past the layer's Cin are never stored
+                    const size_t woff = ((size_t)(nc * taps + wtap) * P.rows_pad + (size_t)cc * 64) * 128u;
+                    bulk_load_1d(dst + b_off + (uint32_t)i * 8192u, P.wp + woff, 8192u, fb);
+                    if (nops == 2) bulk_load_1d(dst + b_off + P.b_stage_bytes + (uint32_t)i * 8192u, P.wp_lo + woff, 8192u, fb);
+                  }
+                } else {
                 // the weight tile of (channel chunk, tap, N block) is ONE contiguous, pre-swizzled run of bn*128 bytes
                 const size_t woff = ((size_t)(cc * taps + tap) * P.rows_pad + T.n0) * 128u;
                 bulk_load_1d(dst + b_off, P.wp + woff, P.b_stage_bytes, fb);
                 if (nops == 2) bulk_load_1d(dst + b_off + P.b_stage_bytes, P.wp_lo + woff, P.b_stage_bytes, fb);
+                }
                 dst += item_bytes;
                 if (++tap == taps) { tap = 0; if (!HALO) ++cc; }
               }
@@ -378,6 +394,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       auto lo_of = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); };
+      // BT: MN-major B -- LBO = 8 KB between 64-wide N blocks (B_lo's blocks follow B_hi's at the same stride, so the
+      // N = 2*bn instruction still covers [B_hi ; B_lo]), SBO = 1024 B between 8-row K groups, 16 rows = 2048 B per K step
+      constexpr uint32_t lbo_bt = ((8192u >> 4) - 1u) << 16;      // lo_of() already carries LBO field = 1
+      constexpr uint32_t kstep_b = BT ? 128u : 2u;
       auto desc = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
       const uint32_t item_step = item_bytes >> 4, alo_step = (HALO ? P.patch_bytes : P.a_stage_bytes) >> 4;
       const int nouter = HALO ? ncc : 1;
@@ -418,19 +438,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // profiles/r01_conv_probe.txt), exactly like the TMA write, so a 128-B-shifted start keeps base_offset 0
                 // and the 8-row groups may sit at any multiple of 128 B (SBO = patch pitch).
                 const uint32_t la = HALO ? pbase + (uint32_t)(dy * P.pitch + dx) * 8u : it;
-                const uint32_t lb = it + (b_off >> 4);
+                const uint32_t lb = it + (b_off >> 4) + (BT ? lbo_bt : 0u);
                 if (elect_one()) {
                   if (nops == 2) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // one UMMA_K (8 tf32 / 16 bf16) = 32 bytes inside the 128-byte swizzle row
                       const uint32_t a1 = k ? 1u : acc;
-                      umma_k<BF16>(tm_d2, desc(hi_a, la + alo_step + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, a1);   // A_lo x B_hi
-                      umma_k<BF16>(tm_d, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc2, a1);              // A_hi x [B_hi;B_lo]
+                      umma_k<BF16>(tm_d2, desc(hi_a, la + alo_step + 2u * k), desc(hi_b, lb + kstep_b * k), P.idesc, a1);   // A_lo x B_hi
+                      umma_k<BF16>(tm_d, desc(hi_a, la + 2u * k), desc(hi_b, lb + kstep_b * k), P.idesc2, a1);              // A_hi x [B_hi;B_lo]
                     }
                   } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                      umma_k<BF16>(tm_d, desc(hi_a, la + 2u * k), desc(hi_b, lb + 2u * k), P.idesc, k ? 1u : acc);
+                      umma_k<BF16>(tm_d, desc(hi_a, la + 2u * k), desc(hi_b, lb + kstep_b * k), P.idesc, k ? 1u : acc);
                   }
                 }
                 acc = 1u;
@@ -865,7 +885,13 @@ int kc_of(int precision) { return is_bf16(precision) ? 64 : 32; }
 int kpad_of(int c, int precision) { const int kc = kc_of(precision); return (c + kc - 1) / kc * kc; }
 // N tile of the forward/dgrad kernel and the row padding of the packed weight (a multiple of the N tile)
 int bn_of(int rows) { const int r16 = (rows + 15) / 16 * 16; return r16 < 128 ? r16 : 128; }
-int rows_pad_of(int rows) { const int bn = bn_of(rows); return (rows + bn - 1) / bn * bn; }
+// ... and of 64: the data gradient reads the forward packing in 64-ROW reduction chunks (BT), whose tail must be zero rows
+int rows_pad_of(int rows) {
+  const int bn = bn_of(rows);
+  int r = (rows + bn - 1) / bn * bn;
+  while (r % 64) r += bn;
+  return r;
+}
 size_t packed_weight_elems(int rows, int kred, int ksize, int precision) {
   const int kc = kc_of(precision);
   return (size_t)((kred + kc - 1) / kc) * ksize * ksize * rows_pad_of(rows) * kc;
@@ -873,7 +899,7 @@ size_t packed_weight_elems(int rows, int kred, int ksize, int precision) {
 
 // x [B,H,W,Cin] NHWC, wp [Cout][k*k][kpad(Cin)] -> y [B,H,W,Cout]
 static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, const void* wp, const void* wp_lo,
-                        const float* bias, float* y, unsigned int* error_flag, cudaStream_t stream) {
+                        const float* bias, float* y, unsigned int* error_flag, cudaStream_t stream, bool bt = false) {
   PN_REQUIRE(d && x && wp && y, PN_ERR_BAD_ARGUMENT, "pn_conv2d: null argument");
   PN_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0 && d->cin > 0 && d->cout > 0, PN_ERR_BAD_ARGUMENT,
              "pn_conv2d: bad shape");
@@ -882,6 +908,7 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
              PN_ERR_BAD_ARGUMENT, "pn_conv2d: precision %d", d->precision);
   const bool bf16 = is_bf16(d->precision);
   const int esize = bf16 ? 2 : 4, kc = kc_of(d->precision);
+  PN_REQUIRE(!bt || bf16, PN_ERR_UNSUPPORTED, "pn_conv2d_dgrad: the forward packing is read as an MN-major operand in the bf16 precisions only");
   PN_REQUIRE(d->cin % (16 / esize) == 0 && d->cout % 4 == 0, PN_ERR_UNSUPPORTED,
              "pn_conv2d: Cin (%d) must be a multiple of %d (16-byte TMA pitch) and Cout (%d) of 4", d->cin, 16 / esize, d->cout);
   PN_REQUIRE(!is_split(d->precision) || (x_lo && wp_lo), PN_ERR_BAD_ARGUMENT,
@@ -912,9 +939,11 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   P.tiles_y = (d->height + P.th - 1) / P.th;
   const int bgroups = (d->batch + P.nb - 1) / P.nb;
   // N tile (<= 128, multiple of 16); the packed weight is padded to a multiple of it
-  const int bn = bn_of(d->cout);
+  // (BT: whole 64-wide N blocks of the forward packing; its rows are the reduction dimension d->cin here)
+  const int bn = bt ? (d->cout <= 64 ? 64 : 128) : bn_of(d->cout);
   P.bn = bn;
-  P.rows_pad = rows_pad_of(d->cout);
+  P.rows_pad = bt ? rows_pad_of(d->cin) : rows_pad_of(d->cout);
+  P.bt_nchunks = (d->cout + 63) / 64;
   P.wp = static_cast<const uint8_t*>(wp);
   P.wp_lo = static_cast<const uint8_t*>(wp_lo ? wp_lo : wp);
   P.cchunks = (d->cin + kc - 1) / kc;
@@ -927,8 +956,9 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   P.set_cols = (int)pow2_cols(P.nsplit == 3 ? 3 * bn : bn);
   // instruction descriptor: fp32 accumulate, A/B format 2 = TF32 (kind::tf32) or 1 = BF16 (kind::f16), K-major, M = 128
   const uint32_t fmt = bf16 ? 1u : 2u;
-  P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  P.idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t bmaj = bt ? (1u << 16) : 0u;     // B operand MN-major
+  P.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | bmaj | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  P.idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | bmaj | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   P.bias = bias; P.out = y; P.error_flag = error_flag;
 
   const uint32_t patch_region = P.halo ? 2u * nops * P.patch_bytes : 0u;
@@ -993,8 +1023,12 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
     return 0;
   };
   int lrc;
-  const int variant = (P.bf16 ? 4 : 0) | (P.nsplit == 3 ? 2 : 0) | (P.halo ? 1 : 0);
+  const int variant = (bt ? 8 : 0) | (P.bf16 ? 4 : 0) | (P.nsplit == 3 ? 2 : 0) | (P.halo ? 1 : 0);
   switch (variant) {
+    case 12: lrc = launch(conv_igemm_kernel<true, false, false, true>); break;
+    case 13: lrc = launch(conv_igemm_kernel<true, false, true, true>); break;
+    case 14: lrc = launch(conv_igemm_kernel<true, true, false, true>); break;
+    case 15: lrc = launch(conv_igemm_kernel<true, true, true, true>); break;
     case 0: lrc = launch(conv_igemm_kernel<false, false, false>); break;
     case 1: lrc = launch(conv_igemm_kernel<false, false, true>); break;
     case 2: lrc = launch(conv_igemm_kernel<false, true, false>); break;
@@ -1127,6 +1161,19 @@ extern "C" int pn_conv2d_forward(const pn_conv_desc* desc, const void* x, const 
                 desc ? desc->height : 0, desc ? desc->width : 0, desc ? desc->cin : 0, desc ? desc->cout : 0, desc ? desc->ksize : 0,
                 desc ? desc->precision : 0);
   return conv::conv_forward(desc, x, x_lo, w_packed, w_packed_lo, bias, y, error_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pn_conv2d_rows_pad(int cout) { return cout > 0 ? conv::rows_pad_of(cout) : 0; }
+
+extern "C" int pn_conv2d_dgrad(const pn_conv_desc* desc, const void* g, const void* g_lo, const void* w_packed,
+                               const void* w_packed_lo, float* gx, uint32_t* error_flag, pn_stream_t stream) {
+  PN_REQUIRE(desc, PN_ERR_BAD_ARGUMENT, "pn_conv2d_dgrad: null descriptor");
+  TraceScope ts(reinterpret_cast<cudaStream_t>(stream), "conv_dgrad B%d H%d W%d Cin%d Cout%d k%d prec%d", desc->batch, desc->height,
+                desc->width, desc->cout, desc->cin, desc->ksize, desc->precision);
+  pn_conv_desc dd = *desc;           // the convolution that runs: g [.., Cout] -> gx [.., Cin]
+  dd.cin = desc->cout;
+  dd.cout = desc->cin;
+  return conv::conv_forward(&dd, g, g_lo, w_packed, w_packed_lo, nullptr, gx, error_flag, reinterpret_cast<cudaStream_t>(stream), true);
 }
 
 extern "C" int pn_conv2d_packed_weight_elems(int cout, int cin, int ksize, int transposed, int precision, size_t* elems) {

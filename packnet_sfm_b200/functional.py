@@ -175,22 +175,54 @@ def _pad_channels(w, cin_tensor):
     return torch.cat([w, pad], 1).contiguous()
 
 
+def _conv_dgrad(g_hi, g_lo, wp, wp_lo, B, H, W, cin, cout, ksize, precision):
+    """gx [B,H,W,cin] from the layer's FORWARD tiles (pn_conv2d_dgrad: MN-major reads, bf16 precisions)."""
+    gx = torch.empty(B, H, W, cin, dtype=torch.float32, device=g_hi.device)
+    d = ConvDesc(B, H, W, cin, cout, ksize, precision, _state["mode"], 0)
+    _lib.check(_lib.lib().pn_conv2d_dgrad(ctypes.byref(d), _lib.ptr(g_hi), _p(g_lo), _lib.ptr(wp), _p(wp_lo), _lib.ptr(gx),
+                                          _lib.ptr(error_flag()), _stream()), "pn_conv2d_dgrad")
+    return gx
+
+
+def _stored_weight(weight, cin_tensor, precision):
+    """The NativeWeight of a parameter that packnet_sfm_b200.optim stores in the engine's layout, with current tiles -- or None
+    (plain OIHW tensor: pack per call)."""
+    nat = getattr(weight, "_pn_native", None)
+    if nat is None or precision != PRECISION_BF16X3 or not nat.accepts(cin_tensor):
+        return None
+    if weight._version != nat.version:      # written through PyTorch since the tiles were made (load_state_dict, init)
+        nat.owner.repack()
+    return nat
+
+
 class _Conv2d(torch.autograd.Function):
     """y = conv2d(x, weight, stride 1, zero pad k//2) + bias on NHWC tensors (nn.Conv2d + ConstantPad2d,
-    layers01.py:28-30,36)."""
+    layers01.py:28-30,36).
+
+    Two weight paths.  (1) A parameter stored by optim.FlatAdam in the engine's layout: the forward and the data gradient
+    read the bf16 tiles the optimizer step wrote, the weight gradient is accumulated straight into the flat gradient buffer
+    (returned gradient: None -- `weight.grad` is a view of that buffer).  (2) Any other OIHW tensor (folded effective weights,
+    tests, a model without the flat optimizer): packed per call, gradient returned in OIHW.  In the bf16 precisions the data
+    gradient reads the FORWARD tiles in both paths (pn_conv2d_dgrad), so the transposed packing only exists for tf32."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        _lib.require_f32(x, weight)
+        _lib.require_f32(x, weight, bias)
         x = x.contiguous()
         precision = _state["precision"]
         cout, cin_w, k, _ = weight.shape
-        w_eff = _pad_channels(weight.detach().contiguous(), x.shape[3])
-        wp, wp_lo = _pack_weight(w_eff, False, precision)
+        nat = _stored_weight(weight, x.shape[3], precision)
+        if nat is not None:
+            wp, wp_lo = nat.hi, nat.lo
+        else:
+            w_eff = _pad_channels(weight.detach().contiguous(), x.shape[3])
+            wp, wp_lo = _pack_weight(w_eff, False, precision)
         x_hi, x_lo = _operands(x, precision)
         y = _conv_raw(x_hi, x_lo, wp, wp_lo, bias.detach().contiguous() if bias is not None else None, cout, k, precision)
         # the weight gradient needs exactly the operand pair the forward used
         ctx.save_for_backward(x_hi, x_lo, weight)
+        ctx.packed = (wp, wp_lo) if is_bf16(precision) else None
+        ctx.nat = nat
         ctx.has_bias = bias is not None
         ctx.precision = precision
         return y
@@ -207,28 +239,35 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             # the output gradient has `cout` channels; bf16 operands need a multiple of 8
             g_hi, g_lo = _operands(gy, precision)
-        w_eff = _pad_channels(weight.detach().contiguous(), Cin)
         if ctx.needs_input_grad[0]:
-            # data gradient: correlation of gy with the flipped kernel, contraction over Cout
-            wt, wt_lo = _pack_weight(w_eff, True, precision)
-            gx = _conv_raw(g_hi, g_lo, wt, wt_lo, None, Cin, k, precision)
+            if ctx.packed is not None:
+                gx = _conv_dgrad(g_hi, g_lo, ctx.packed[0], ctx.packed[1], B, H, W, Cin, cout, k, precision)
+            else:
+                # tf32: correlation of gy with the flipped kernel through the transposed packing, contraction over Cout
+                wt, wt_lo = _pack_weight(_pad_channels(weight.detach().contiguous(), Cin), True, precision)
+                gx = _conv_raw(g_hi, g_lo, wt, wt_lo, None, Cin, k, precision)
         if ctx.needs_input_grad[1]:
             # weight gradient: reduction over pixels, operands read in place as MN-major tiles
-            n = ctypes.c_size_t(0)
-            _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, Cin, k, precision, ctypes.byref(n)), "wgrad_packed_elems")
-            dwp = torch.empty(int(n.value), dtype=torch.float32, device=gy.device)
             d = ConvDesc(B, H, W, Cin, cout, k, precision, 0, 0)
-            _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
-                                           _lib.ptr(dwp), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
-            gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=gy.device)
-            if _state["unpack_tiled"]:
-                _lib.check(lib.pn_conv2d_unpack_weight_grad_tiled(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k,
-                                                                  int(n.value) // (cout * k * k), _stream()),
-                           "pn_conv2d_unpack_weight_grad_tiled")
+            if ctx.nat is not None:
+                # [Cout][tap][kpad] IS the stored layout: accumulate into the flat gradient buffer, nothing to return
+                _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
+                                               _lib.ptr(ctx.nat.grad_flat), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
             else:
-                _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, precision, _stream()),
-                           "pn_conv2d_unpack_weight_grad")
-            gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
+                n = ctypes.c_size_t(0)
+                _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, Cin, k, precision, ctypes.byref(n)), "wgrad_packed_elems")
+                dwp = torch.empty(int(n.value), dtype=torch.float32, device=gy.device)
+                _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
+                                               _lib.ptr(dwp), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
+                gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=gy.device)
+                if _state["unpack_tiled"]:
+                    _lib.check(lib.pn_conv2d_unpack_weight_grad_tiled(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k,
+                                                                      int(n.value) // (cout * k * k), _stream()),
+                               "pn_conv2d_unpack_weight_grad_tiled")
+                else:
+                    _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, precision, _stream()),
+                               "pn_conv2d_unpack_weight_grad")
+                gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = _lookup_channel_sum(gy)
             if gb is None:

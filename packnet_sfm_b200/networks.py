@@ -102,10 +102,14 @@ class PackLayerConv3d(nn.Module):
         self.conv = Conv2D(in_channels * (r ** 2) * d, in_channels, kernel_size, 1)
         self.conv3d = nn.Conv3d(1, d, kernel_size=(3, 3, 3), stride=(1, 1, 1), padding=(1, 1, 1))
 
-    def forward(self, x):
+    def folds(self, h, w):
+        """whether the layer is evaluated as one folded convolution on a packed map of h x w pixels (policy + geometry)"""
         k = self.conv.kernel_size
+        return PF.pack_fold_enabled(h * w) and k in (3, 5) and min(h, w) >= 2 * (k // 2) + 1
+
+    def forward(self, x):
         h, w = x.shape[1] // 2, x.shape[2] // 2
-        if PF.pack_fold_enabled(h * w) and k in (3, 5) and min(h, w) >= 2 * (k // 2) + 1:
+        if self.folds(h, w):
             # conv3d and conv2d composed into one (k+2)x(k+2) convolution of the space-to-depth tensor + exact frame terms
             z = folded.pack_conv_folded(x, self.conv.conv_base.weight, self.conv.conv_base.bias, self.conv3d.weight,
                                         self.conv3d.bias, PF.conv2d)
@@ -126,6 +130,29 @@ class UnpackLayerConv3d(nn.Module):
     def forward(self, x):
         u = self.conv(x)
         return PF.unpack_features(u, self.conv3d.weight, self.conv3d.bias)
+
+
+def native_conv_weights(net, image_hw=None):
+    """The convolution weights of `net` that reach the tensor-core engine AS PARAMETERS (functional.conv2d on the parameter
+    itself): optim.FlatAdam stores these in the engine's [Cout][tap][kpad] layout.  Not in the list: InvDepth heads (SIMT
+    kernels), the Conv3d stencils, the first layer when it runs through its im2col re-composition, and the Conv2d of a pack
+    layer that is evaluated FOLDED at the given image size (its weight is an operand of the fold kernels, in OIHW)."""
+    out = []
+    folded_convs = set()
+    if isinstance(net, PackNet01) and image_hw is not None:
+        H, W = image_hw
+        for i, name in enumerate(("pack1", "pack2", "pack3", "pack4", "pack5")):
+            layer = getattr(net, name)
+            h, w = H >> (i + 1), W >> (i + 1)
+            if layer.folds(h, w):
+                folded_convs.add(id(layer.conv))
+    skip_first = isinstance(net, PackNet01) and PF.im2col_first_enabled()
+    for m in net.modules():
+        if isinstance(m, Conv2D) and id(m) not in folded_convs and not (skip_first and m is net.pre_calc):
+            out.append(m.conv_base.weight)
+        elif isinstance(m, ResidualConv):
+            out.append((m.conv3[0] if m.dropout else m.conv3).weight)
+    return out
 
 
 class PackNet01(nn.Module):

@@ -69,7 +69,7 @@ def _emu_sources():
     csrc = os.path.join(ROOT, "packnet_sfm_b200", "csrc")
     return [os.path.join(EMU_DIR, "emu_kernels.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
             os.path.join(ROOT, "include", "packnet_b200.h")] + \
-           [os.path.join(csrc, f) for f in ("common.cuh", "fold_kernels.cu", "frame_kernels.cu", "layer_kernels.cu", "loss_kernels.cu", "loss_group_kernel.cuh", "pack_kernels.cu")]
+           [os.path.join(csrc, f) for f in ("common.cuh", "fold_kernels.cu", "frame_kernels.cu", "layer_kernels.cu", "loss_kernels.cu", "loss_group_kernel.cuh", "pack_kernels.cu", "optim_kernels.cu")]
 
 
 @pytest.fixture(scope="session")

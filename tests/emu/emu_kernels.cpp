@@ -27,6 +27,7 @@ extern "C" const char* pn_last_error_string(void) { return pn::g_err; }
 #include "../../packnet_sfm_b200/csrc/layer_kernels.cu"
 #include "../../packnet_sfm_b200/csrc/loss_kernels.cu"
 #include "../../packnet_sfm_b200/csrc/pack_kernels.cu"
+#include "../../packnet_sfm_b200/csrc/optim_kernels.cu"
 
 // The tcgen05 / TMA convolution engine has no host emulation (tensor-core instructions): its entry points exist so that
 // the ctypes declarations of packnet_sfm_b200/_lib_conv.py resolve, and refuse to run.
@@ -37,6 +38,7 @@ extern "C" const char* pn_last_error_string(void) { return pn::g_err; }
   }
 PN_EMU_UNSUPPORTED(pn_conv2d_forward, const pn_conv_desc*, const void*, const void*, const void*, const void*, const float*, float*,
                    uint32_t*, pn_stream_t)
+PN_EMU_UNSUPPORTED(pn_conv2d_dgrad, const pn_conv_desc*, const void*, const void*, const void*, const void*, float*, uint32_t*, pn_stream_t)
 PN_EMU_UNSUPPORTED(pn_conv2d_packed_weight_elems, int, int, int, int, int, size_t*)
 PN_EMU_UNSUPPORTED(pn_conv2d_pack_weight, const float*, void*, void*, int, int, int, int, int, pn_stream_t)
 PN_EMU_UNSUPPORTED(pn_conv2d_wgrad, const pn_conv_desc*, const void*, const void*, const void*, const void*, float*, uint32_t*, pn_stream_t)
@@ -44,6 +46,13 @@ PN_EMU_UNSUPPORTED(pn_conv2d_wgrad_packed_elems, int, int, int, int, size_t*)
 PN_EMU_UNSUPPORTED(pn_conv2d_unpack_weight_grad, const float*, float*, int, int, int, int, pn_stream_t)
 PN_EMU_UNSUPPORTED(pn_tf32_residual, const float*, float*, size_t, pn_stream_t)
 PN_EMU_UNSUPPORTED(pn_split_bf16, const float*, void*, void*, size_t, pn_stream_t)
+extern "C" int pn_conv2d_rows_pad(int cout) {   // conv_engine.cu: rows_pad_of (N tile = min(128, ceil16(cout)), then a multiple of 64)
+  if (cout <= 0) return 0;
+  const int r16 = (cout + 15) / 16 * 16, bn = r16 < 128 ? r16 : 128;
+  int r = (cout + bn - 1) / bn * bn;
+  while (r % 64) r += bn;
+  return r;
+}
 extern "C" int pn_version(void) { return 100; }
 extern "C" uint64_t pn_launch_count(void) { return 0; }
 extern "C" void pn_trace_enable(int) {}

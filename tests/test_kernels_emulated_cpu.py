@@ -175,3 +175,63 @@ def test_weight_pack_tiled_emulated(emulated_kernels):
         want_hi, want_lo = _packed_weight_mirror(w, bool(transposed), rows_pad)
         assert torch.equal(hi.view(torch.int16), want_hi.view(torch.int16)), (cout, cin, k, transposed)
         assert torch.equal(lo.view(torch.int16), want_lo.view(torch.int16)), (cout, cin, k, transposed)
+
+
+def test_flat_adam_emulated_matches_torch_adam_and_writes_the_forward_tiles(emulated_kernels):
+    """optim.FlatAdam + pn_adam_step from their real source under the host emulation: three steps against torch.optim.Adam
+    on the same values (two groups with different learning rates, one stored convolution weight with ragged Cin / Cout, plain
+    tensors of odd sizes), the parameter views keep shape / values / state_dict semantics, the stored weight's gradient view
+    has the [Cout][tap][kpad] layout of the weight-gradient kernel, and the bf16 hi/lo forward tiles equal the mirror of the
+    layout conv_engine.cu documents after every step."""
+    import torch
+    from packnet_sfm_b200 import optim
+    torch.manual_seed(0)
+    cout, cin, k = 20, 70, 3
+    conv_w = torch.nn.Parameter(torch.rand(cout, cin, k, k) - 0.5)
+    plain = [torch.nn.Parameter(torch.rand(*s) - 0.5) for s in ((7,), (3, 5), (1, 13, 3, 3), (2050,))]
+    other = [torch.nn.Parameter(torch.rand(33) - 0.5)]
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in [conv_w] + plain + other]
+    ref = torch.optim.Adam([{"params": ref_params[:5], "lr": 2e-4}, {"params": ref_params[5:], "lr": 1e-3}])
+    opt = optim.FlatAdam([{"params": [conv_w] + plain, "lr": 2e-4}, {"params": other, "lr": 1e-3}], native=[conv_w])
+    nat = conv_w._pn_native
+    assert nat.kpad == 128 and nat.rows_pad == 64 and conv_w.shape == (cout, cin, k, k)
+    assert torch.equal(conv_w.detach(), ref_params[0].detach())           # values preserved by the re-layout
+    assert conv_w.stride() == (9 * 128, 1, 3 * 128, 128)
+
+    def check_tiles():
+        want_hi, want_lo = _packed_weight_mirror(conv_w.detach().contiguous(), False, nat.rows_pad)
+        # the mirror packs ceil(cin/64) chunks; the stored layout has kpad/64 of them (the same here)
+        assert torch.equal(nat.hi.view(torch.int16), want_hi.view(torch.int16))
+        assert torch.equal(nat.lo.view(torch.int16), want_lo.view(torch.int16))
+
+    check_tiles()
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        grads = [torch.rand(p.shape, generator=g) - 0.5 for p in ref_params]
+        for p, gr in zip(ref_params, grads):
+            p.grad = gr.clone()
+        ref.step()
+        opt.zero_grad()
+        # the weight-gradient kernel's output: [Cout][tap][kpad] accumulated in the flat gradient buffer
+        nat.grad_flat.view(cout, k * k, nat.kpad).zero_()
+        nat.grad_flat.view(cout, k * k, nat.kpad)[:, :, :cin] = grads[0].reshape(cout, cin, k * k).permute(0, 2, 1)
+        assert torch.equal(conv_w.grad, grads[0])                          # ... read back through the parameter's view
+        for p, gr in zip(plain + other, grads[1:]):
+            p.grad = gr.clone()
+        opt.step()
+        for p, q in zip([conv_w] + plain + other, ref_params):
+            assert torch.allclose(p.detach(), q.detach(), rtol=0, atol=2e-7), (step, float((p - q).abs().max()))
+        check_tiles()
+    # padding of the stored layout never moves
+    pad = torch.as_strided(opt.flat_param, (cout, k * k, nat.kpad - cin), (k * k * nat.kpad, nat.kpad, 1),
+                           conv_w.storage_offset() + cin)
+    assert float(pad.abs().max()) == 0.0
+    # writing the weights through PyTorch is noticed (version counter) and the tiles are rebuilt on demand
+    with torch.no_grad():
+        conv_w.mul_(0.5)
+    assert conv_w._version != nat.version
+    opt.repack()
+    check_tiles()
+    # learning-rate schedule: device-resident, takes effect without rebuilding anything
+    opt.set_lr([1e-4, 5e-4])
+    assert abs(float(opt.hyper[8]) - 1e-4) < 1e-10 and abs(float(opt.hyper[10]) - 5e-4) < 1e-10

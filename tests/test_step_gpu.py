@@ -34,7 +34,7 @@ def _batch(z):
     return b
 
 
-@pytest.mark.parametrize("optimizer", ["fused_flat", "torch"])
+@pytest.mark.parametrize("optimizer", ["flat_native", "flat_plain", "torch"])
 def test_two_training_steps_match_the_reference(optimizer):
     z = load_golden("step_2x64x96")
     model, batch = _model(), _batch(z)
@@ -43,7 +43,13 @@ def test_two_training_steps_match_the_reference(optimizer):
         opt = torch.optim.Adam([{"params": model.depth_net.parameters(), "lr": 2e-4},
                                 {"params": model.pose_net.parameters(), "lr": 2e-4}])
     else:
-        opt = optim.FlatAdam(model.parameters(), lr=2e-4)
+        from packnet_sfm_b200.networks import native_conv_weights
+        # flat_native: the convolution weights stored in the engine's layout (tiles written by the optimizer launch, weight
+        # gradients accumulated in place, data gradients from the forward tiles); flat_plain: same optimizer, OIHW storage
+        native = native_conv_weights(model.depth_net, (int(z["H"]), int(z["W"]))) if optimizer == "flat_native" else ()
+        opt = optim.FlatAdam([{"params": list(model.depth_net.parameters())}, {"params": list(model.pose_net.parameters())}],
+                             lr=2e-4, native=native)
+        assert (len(native) > 40) == (optimizer == "flat_native")
     for step, flip in enumerate((0.0, 1.0)):
         model.flip_lr_prob = flip
         opt.zero_grad(set_to_none=True)

@@ -14,8 +14,9 @@ from packnet_sfm_b200.models import SelfSupModel  # noqa: E402
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
 model = SelfSupModel().to(dev).train()
-bucket = parallel.FlatBucket(model.parameters())
-opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)
+from packnet_sfm_b200 import optim  # noqa: E402
+from packnet_sfm_b200.networks import native_conv_weights  # noqa: E402
+opt = optim.FlatAdam(model.parameters(), lr=2e-4, native=native_conv_weights(model.depth_net, (192, 640)))
 batch = bench.to_device(bench.make_host_batch(4, 192, 640, 0), dev)
 lib = _lib.lib()
 lib.pn_trace_enable.argtypes = [ctypes.c_int]
@@ -24,7 +25,7 @@ lib.pn_trace_dump.restype = ctypes.c_int
 
 
 def step():
-    bucket.zero_grad()
+    opt.zero_grad()
     out = model(batch)
     out["loss"].backward()
     opt.step()

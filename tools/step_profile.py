@@ -16,30 +16,26 @@ ap.add_argument("--height", type=int, default=192)
 ap.add_argument("--width", type=int, default=640)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--top", type=int, default=45)
-ap.add_argument("--pack-fold", action="store_true", help="folded pack layers (packnet_sfm_b200/folded.py)")
-ap.add_argument("--staged-all", action="store_true", help="every staged variant of DESIGN.md section 7 (as bench.py --staged-all)")
-ap.add_argument("--staged-small", action="store_true", help="the staged variants except the pack fold")
+ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam + per-call weight packing (round-1 optimizer path)")
 a = ap.parse_args()
-PF.set_pack_fold(a.pack_fold or a.staged_all)
-if a.staged_all or a.staged_small:
-    from packnet_sfm_b200 import _lib, losses
-    losses.set_grouped_kernel(True)
-    PF.set_im2col_first(True)
-    PF.set_unpack_tiled(True)
-    PF.set_pack_tiled(True)
-    _lib.set_tuning(_lib.PN_TUNE_STAGE_FLAT, 1)
-    _lib.set_tuning(_lib.PN_TUNE_GN_TREE, 1)
 
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
 model = SelfSupModel().to(dev).train()
-bucket = parallel.FlatBucket(model.parameters())
-opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)
+if a.torch_adam:
+    bucket = parallel.FlatBucket(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)
+    zero_grad = bucket.zero_grad
+else:
+    from packnet_sfm_b200 import optim
+    from packnet_sfm_b200.networks import native_conv_weights
+    opt = optim.FlatAdam(model.parameters(), lr=2e-4, native=native_conv_weights(model.depth_net, (a.height, a.width)))
+    zero_grad = opt.zero_grad
 batch = bench.to_device(bench.make_host_batch(a.batch, a.height, a.width, 0), dev)
 
 
 def step():
-    bucket.zero_grad()
+    zero_grad()
     out = model(batch)
     out["loss"].backward()
     opt.step()
