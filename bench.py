@@ -260,7 +260,8 @@ def time_kernels(args, dev, pk):
 
     # fused warp + SSIM + L1 + automask-min + smoothness (HBM bound). Algorithmic bytes: SURVEY.md §8(d)
     fr = synthetic.make_frames(B, H, W, seed=5)
-    inv = [d.to(dev).requires_grad_(True) for d in synthetic.make_inv_depths(B, H, W, seed=6)]
+    # as the step calls it: the four maps at their own resolution, read nearest-upsampled by the kernel (a8 fused)
+    inv = [d.to(dev).requires_grad_(True) for d in synthetic.make_inv_depths(B, H, W, seed=6, full_res=False)]
     vec = synthetic.make_pose_vecs(B, seed=7).to(dev)
     mats = [Pose.from_vec(vec[:, j], "euler").mat.requires_grad_(True) for j in range(2)]
     loss_fn = MultiViewPhotometricLoss(**YACS_LOSS_DEFAULTS)
@@ -268,7 +269,7 @@ def time_kernels(args, dev, pk):
     out = {}
 
     def fwd():
-        out["o"] = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats])
+        out["o"] = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats], nearest_upsample=True)
 
     def bwd():
         torch.autograd.grad(out["o"]["loss"], inv + mats, retain_graph=True)

@@ -74,6 +74,10 @@ typedef struct {
   int32_t reduce_min;             /* 1: photometric_reduce_op='min', 0: 'mean' */
   int32_t automask;               /* 1: add the un-warped candidates (requires reduce_min) */
   int32_t flags;                  /* PN_LOSS_FLAG_*; 0 = the default tile program */
+  int32_t inv_shift[PN_MAX_SCALES]; /* s > 0: inv_depths[i] is stored at (scale_h >> s) x (scale_w >> s) and read through nearest
+                                     up-sampling (index >> s) -- SfmModel's upsample_output(mode='nearest'), models/model_utils.py:
+                                     152-180 with SfmModel.py:87-88, without the full-resolution copies; grad_inv_depths[i] then has
+                                     the stored shape and receives the sum over each 2^s x 2^s block.  0 = map at the scale's size. */
 } pn_loss_desc;
 
 /* flags: run the grouped-scale tile program (csrc/loss_group_kernel.cuh): one CTA carries a tile through every scale that

@@ -22,6 +22,7 @@ class LossDesc(ctypes.Structure):
         ("ssim_loss_weight", ctypes.c_float), ("smooth_loss_weight", ctypes.c_float),
         ("C1", ctypes.c_float), ("C2", ctypes.c_float),
         ("reduce_min", ctypes.c_int32), ("automask", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("inv_shift", ctypes.c_int32 * PN_MAX_SCALES),
     ]
 
 

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
   for (int js = 0; js < G.ns; ++js) {
     const int s = G.scale[js];
     const ScaleParams& S = P.sc[s];
-    const float* inv_b = S.inv + (size_t)b * plane;
+    const float* inv_b = S.inv + (size_t)b * (plane >> (2 * S.sh));   // stored at (h >> sh) x (w >> sh), read nearest-upsampled
     __syncthreads();  // the previous scale's readers of s_inv / s_warp / s_coef are done
 
     // ---- warp every context frame over the region -------------------------------------------------
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
       const int i = idx % GRW, j = idx / GRW;
       const int x = rx0 + i, y = ry0 + j;
       const bool inside = (x >= 0) && (x < w) && (y >= 0) && (y < h);
-      const float inv = inside ? __ldg(inv_b + (size_t)y * w + x) : 0.0f;
+      const float inv = inside ? __ldg(inv_b + (size_t)(y >> S.sh) * S.iw + (x >> S.sh)) : 0.0f;
       s_inv[idx] = inv;
       float X = 0.0f, Y = 0.0f, Zc = 0.0f;
       if (inside) backproject(Kinv, (float)x, (float)y, depth_from_inv(inv), X, Y, Zc);
@@ -597,7 +597,11 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
           }
         }
       }
-      if (GRAD) S.ginv[(size_t)b * plane + (size_t)y * w + x] = ginv_acc[slot] + go * gq * inv_mcl + bs_const;
+      if (GRAD) {
+        const float gv = ginv_acc[slot] + go * gq * inv_mcl + bs_const;
+        if (S.sh == 0) S.ginv[(size_t)b * plane + (size_t)y * w + x] = gv;
+        else atomicAdd(S.ginv + (size_t)b * (plane >> (2 * S.sh)) + (size_t)(y >> S.sh) * S.iw + (x >> S.sh), gv);   // nearest backward
+      }
     }
     if (!GRAD && do_smooth) {
       const float ss = block_sum(smooth_acc, s_red);

@@ -34,10 +34,11 @@ constexpr int CAM_STRIDE_BASE = 18;  // Kinv[9], Kref[9]; then per context R[9],
 struct ScaleParams {
   int h, w;
   int tiles_x, tiles_y, tile_base;
-  const float* inv;                   // [B,1,h,w]
+  const float* inv;                   // [B,1,h>>sh,w>>sh]: read through nearest up-sampling (index >> sh), model_utils.py:152-180
+  int sh, iw;                         // log2 of that up-sampling factor; row pitch of the map (w >> sh)
   const float* img;                   // [B,3,h,w] target at this scale
   const float* ctx[PN_MAX_CONTEXT];   // [B,3,h,w] context frames at this scale
-  float* ginv;                        // backward: [B,1,h,w]
+  float* ginv;                        // backward: [B,1,h>>sh,w>>sh]; sh > 0: pre-zeroed, the 2^sh x 2^sh block is summed (red.add)
   float photo_coef;                   // 1 / (B*h*w*n)            (x 1/#candidates in 'mean' mode)
   float sx_coef, sy_coef;             // smooth_w / (n*2^s) / (B*h*(w-1)),  .. / (B*(h-1)*w)
 };
@@ -173,7 +174,7 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 8 floats */
 // ---------------------------------------------------------------------------------------------------
 struct PrepParams {
   int B, N, n, W;
-  int h[PN_MAX_SCALES], w[PN_MAX_SCALES];
+  int h[PN_MAX_SCALES], w[PN_MAX_SCALES], sh[PN_MAX_SCALES];
   const float* inv[PN_MAX_SCALES];
   const float* K;
   const float* ref_K;
@@ -197,13 +198,14 @@ __global__ void __launch_bounds__(256) loss_prep_kernel(PrepParams P) {
   __shared__ float red[8];
   const int sb = blockIdx.y;
   const int s = sb / P.B, b = sb % P.B;
-  const int hw = P.h[s] * P.w[s];
+  // the sum over the (virtually) up-sampled map = 4^sh x the sum over the stored one
+  const int hw = (P.h[s] >> P.sh[s]) * (P.w[s] >> P.sh[s]);
   const float* inv = P.inv[s] + (size_t)b * hw;
   float acc = 0.0f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) acc += __ldg(inv + i);
   float tot = block_sum(acc, red);
   if (threadIdx.x == 0) {
-    atomicAdd(P.invsum + sb, (double)tot);
+    atomicAdd(P.invsum + sb, (double)tot * (double)(1 << (2 * P.sh[s])));
     if (blockIdx.x == 0) {
       const int stride = CAM_STRIDE_BASE + 12 * P.N;
       float* cam = P.cams + (size_t)sb * stride;
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
   const float* Kinv = s_cam;
   const float* Kref = s_cam + 9;
 
-  const float* inv_b = S.inv + (size_t)b * plane;
+  const float* inv_b = S.inv + (size_t)b * (plane >> (2 * S.sh));
   const float* img_b = S.img + (size_t)b * 3 * plane;
 
   // ---- phase 1: load the region, warp every context frame ------------------------------------------
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
     float inv = 0.0f, tg[3] = {0.0f, 0.0f, 0.0f};
     if (inside) {
       const size_t o = (size_t)y * w + x;
-      inv = __ldg(inv_b + o);
+      inv = __ldg(inv_b + (size_t)(y >> S.sh) * S.iw + (x >> S.sh));
 #pragma unroll
       for (int c = 0; c < 3; ++c) tg[c] = __ldg(img_b + c * plane + o);
     }
@@ -650,7 +652,11 @@ __global__ void __launch_bounds__(NT) loss_tile_kernel(const Params P) {
           }
         }
       }
-      if (GRAD) S.ginv[(size_t)b * plane + (size_t)y * w + x] = ginv_acc[slot] + go * gq * inv_mcl + bs_const;
+      if (GRAD) {
+        const float gv = ginv_acc[slot] + go * gq * inv_mcl + bs_const;
+        if (S.sh == 0) S.ginv[(size_t)b * plane + (size_t)y * w + x] = gv;
+        else atomicAdd(S.ginv + (size_t)b * (plane >> (2 * S.sh)) + (size_t)(y >> S.sh) * S.iw + (x >> S.sh), gv);   // nearest backward
+      }
     }
   }
 
@@ -772,6 +778,11 @@ static int validate(const pn_loss_desc* d) {
              "multiview_photometric_loss.py:216-217; not implemented)");
   PN_REQUIRE(!(d->automask && !d->reduce_min), PN_ERR_BAD_ARGUMENT,
              "pn_loss: automask requires photometric_reduce_op='min' (multiview_photometric_loss.py:112-114)");
+  for (int i = 0; i < d->num_scales; ++i) {
+    const int sh = d->inv_shift[i];
+    PN_REQUIRE(sh >= 0 && sh <= 5 && (d->scale_h[i] & ((1 << sh) - 1)) == 0 && (d->scale_w[i] & ((1 << sh) - 1)) == 0,
+               PN_ERR_BAD_ARGUMENT, "pn_loss: inv_shift[%d] = %d does not divide the %dx%d scale", i, sh, d->scale_h[i], d->scale_w[i]);
+  }
   PN_REQUIRE(d->batch <= 65535, PN_ERR_UNSUPPORTED, "pn_loss: batch > 65535");
   PN_REQUIRE((d->flags & ~PN_LOSS_FLAG_GROUPED) == 0, PN_ERR_BAD_ARGUMENT, "pn_loss: unknown flags 0x%x", d->flags);
   return PN_OK;
@@ -916,6 +927,7 @@ static int setup(const pn_loss_desc* d, const float* image, const float* const* 
     tile_base += S.tiles_x * S.tiles_y;
     PN_REQUIRE(inv_depths[i] != nullptr && aligned16(inv_depths[i]), PN_ERR_BAD_ARGUMENT, "pn_loss: inv_depths[%d]", i);
     S.inv = inv_depths[i];
+    S.sh = d->inv_shift[i]; S.iw = S.w >> S.sh;
     const bool full = (S.h == d->height && S.w == d->width);
     S.img = full ? image : reinterpret_cast<const float*>(base + ws.resized_img[i]);
     for (int j = 0; j < d->num_context; ++j) {
@@ -953,7 +965,7 @@ static int setup(const pn_loss_desc* d, const float* image, const float* const* 
   }
   PrepParams Q{};
   Q.B = d->batch; Q.N = d->num_context; Q.n = d->num_scales; Q.W = d->width;
-  for (int i = 0; i < d->num_scales; ++i) { Q.h[i] = d->scale_h[i]; Q.w[i] = d->scale_w[i]; Q.inv[i] = inv_depths[i]; }
+  for (int i = 0; i < d->num_scales; ++i) { Q.h[i] = d->scale_h[i]; Q.w[i] = d->scale_w[i]; Q.sh[i] = d->inv_shift[i]; Q.inv[i] = inv_depths[i]; }
   Q.K = K; Q.ref_K = ref_K;
   for (int j = 0; j < d->num_context; ++j) Q.poses[j] = poses[j];
   Q.cams = reinterpret_cast<float*>(base + ws.cams);
@@ -1013,6 +1025,9 @@ extern "C" int pn_loss_backward(const pn_loss_desc* desc, const float* image, co
   for (int i = 0; i < desc->num_scales; ++i) {
     PN_REQUIRE(grad_inv_depths[i] != nullptr, PN_ERR_BAD_ARGUMENT, "pn_loss_backward: grad_inv_depths[%d] null", i);
     P.sc[i].ginv = grad_inv_depths[i];
+    if (desc->inv_shift[i] > 0)   // the block sums of the nearest-upsample backward are accumulated
+      PN_CUDA(cudaMemsetAsync(grad_inv_depths[i], 0, sizeof(float) * desc->batch * (desc->scale_h[i] >> desc->inv_shift[i]) *
+                                                        (desc->scale_w[i] >> desc->inv_shift[i]), stream));
   }
   for (int j = 0; j < desc->num_context; ++j) {
     PN_REQUIRE(grad_poses[j] != nullptr, PN_ERR_BAD_ARGUMENT, "pn_loss_backward: grad_poses[%d] null", j);
@@ -1036,6 +1051,7 @@ extern "C" int pn_loss_warp_indices(const pn_loss_desc* desc, int scale, const f
   pn_loss_desc one = *desc;
   one.num_scales = 1; one.num_context = 1;
   one.scale_h[0] = desc->scale_h[scale]; one.scale_w[0] = desc->scale_w[scale];
+  one.inv_shift[0] = 0;      // the hook takes the map at the scale's own resolution
   Workspace ws;
   layout(&one, ws);
   PN_REQUIRE(workspace_bytes >= ws.total, PN_ERR_WORKSPACE, "pn_loss_warp_indices: workspace %zu < %zu", workspace_bytes,
@@ -1044,7 +1060,7 @@ extern "C" int pn_loss_warp_indices(const pn_loss_desc* desc, int scale, const f
   PN_CUDA(cudaMemsetAsync(base, 0, ws.cams, stream));
   PrepParams Q{};
   Q.B = one.batch; Q.N = 1; Q.n = 1; Q.W = one.width;
-  Q.h[0] = one.scale_h[0]; Q.w[0] = one.scale_w[0]; Q.inv[0] = inv_depth;
+  Q.h[0] = one.scale_h[0]; Q.w[0] = one.scale_w[0]; Q.sh[0] = 0; Q.inv[0] = inv_depth;
   Q.K = K; Q.ref_K = ref_K; Q.poses[0] = pose;
   Q.cams = reinterpret_cast<float*>(base + ws.cams);
   Q.invsum = reinterpret_cast<double*>(base + ws.invsum);

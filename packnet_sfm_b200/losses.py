@@ -64,12 +64,19 @@ def set_grouped_kernel(on):
     return prev
 
 
-def _make_desc(B, H, W, num_context, shapes, ssim_w, smooth_w, C1, C2, reduce_min, automask):
+def _make_desc(B, H, W, num_context, shapes, ssim_w, smooth_w, C1, C2, reduce_min, automask, nearest_upsample=False):
     d = _lib.LossDesc()
     d.flags = _lib.PN_LOSS_FLAG_GROUPED if _grouped else 0
     d.batch, d.height, d.width = B, H, W
     d.num_context, d.num_scales = num_context, len(shapes)
     for i, (h, w) in enumerate(shapes):
+        if nearest_upsample and (h, w) != (H, W):
+            # the map stays at its own resolution and is read as upsample_output(mode='nearest') would have made it
+            sh = (H // h).bit_length() - 1
+            if h << sh != H or w << sh != W:
+                raise ValueError("nearest_upsample: %dx%d is not a power-of-two reduction of %dx%d" % (h, w, H, W))
+            d.scale_h[i], d.scale_w[i], d.inv_shift[i] = H, W, sh
+            continue
         d.scale_h[i], d.scale_w[i] = h, w
     d.ssim_loss_weight, d.smooth_loss_weight, d.C1, d.C2 = ssim_w, smooth_w, C1, C2
     d.reduce_min, d.automask = int(reduce_min), int(automask)
@@ -89,7 +96,7 @@ class _FusedLoss(torch.autograd.Function):
         _lib.require_f32(image, K, ref_K, *context, *inv, *poses)
         B, _, H, W = image.shape
         desc = _make_desc(B, H, W, N, [tuple(d.shape[-2:]) for d in inv], cfg["ssim_w"], cfg["smooth_w"],
-                          cfg["C1"], cfg["C2"], cfg["reduce_min"], cfg["automask"])
+                          cfg["C1"], cfg["C2"], cfg["reduce_min"], cfg["automask"], cfg.get("nearest_upsample", False))
         lib = _lib.lib()
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.pn_loss_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "pn_loss_workspace_bytes")
@@ -152,7 +159,11 @@ class MultiViewPhotometricLoss(LossBase):
     def logs(self):
         return {'num_scales': self.n}
 
-    def forward(self, image, context, inv_depths, K, ref_K, poses, return_logs=False, progress=0.0):
+    def forward(self, image, context, inv_depths, K, ref_K, poses, return_logs=False, progress=0.0, nearest_upsample=False):
+        """nearest_upsample=True (not in the reference's signature; its callers never pass it): `inv_depths` are the network's
+        maps at H, H/2, H/4, H/8 and the loss reads them as SfmModel's upsample_output(mode='nearest') would have delivered
+        them (models/model_utils.py:152-180, SfmModel.py:87-88) -- index >> s in the kernel's load, the 2^s x 2^s block sum in
+        its backward -- instead of three full-resolution copies and their backward passes."""
         if self.clip_loss > 0.0:
             raise NotImplementedError("clip_loss > 0 is not implemented in the fused kernel (training default is 0.0, "
                                       "configs/default_config.py:99)")
@@ -165,7 +176,7 @@ class MultiViewPhotometricLoss(LossBase):
         mats = [p.mat if hasattr(p, "mat") else p for p in poses]
         cfg = dict(N=len(context), n=n, ssim_w=float(self.ssim_loss_weight), smooth_w=float(self.smooth_loss_weight),
                    C1=float(self.C1), C2=float(self.C2), reduce_min=self.photometric_reduce_op == 'min',
-                   automask=bool(self.automask_loss))
+                   automask=bool(self.automask_loss), nearest_upsample=bool(nearest_upsample))
         out = _FusedLoss.apply(cfg, image, K.float(), ref_K.float(), *context, *inv_depths[:n], *mats)
         self.add_metric('photometric_loss', out[1])
         if self.smooth_loss_weight > 0.0:

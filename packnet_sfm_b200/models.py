@@ -56,6 +56,14 @@ class PoseNet(nn.Module):
         return 0.01 * pose.view(pose.size(0), self.nb_ref_imgs, 6)
 
 
+def require_fp32_library_convolutions():
+    """PoseNet stays on the library's convolutions (north_star).  PyTorch lets cuDNN run them in TF32 by default
+    (torch.backends.cudnn.allow_tf32 = True), which moves the predicted poses by ~1e-4 relative to the fp32 reference --
+    measured on the B200 against tests/golden/step_2x64x96.npz -- and the photometric loss with them.  The parity bar of this
+    path is fp32, so the step harness switches the library to fp32 convolutions (PoseNet is 0.2 % of the step's FLOPs)."""
+    torch.backends.cudnn.allow_tf32 = False
+
+
 YACS_LOSS_DEFAULTS = dict(num_scales=4, ssim_loss_weight=0.85, occ_reg_weight=0.1, smooth_loss_weight=0.001,
                           C1=1e-4, C2=9e-4, photometric_reduce_op='min', disp_norm=True, clip_loss=0.0,
                           progressive_scaling=0.0, padding_mode='zeros', automask_loss=True)
@@ -70,8 +78,13 @@ class SelfSupModel(nn.Module):
     SelfSupModel.forward (:63-97).  Defaults = the yacs training defaults (configs/default_config.py:88-103)."""
 
     def __init__(self, depth_net=None, pose_net=None, rotation_mode='euler', flip_lr_prob=0.5,
-                 upsample_depth_maps=True, **loss_kwargs):
+                 upsample_depth_maps=True, fuse_upsample=True, **loss_kwargs):
+        """fuse_upsample: with upsample_depth_maps, hand the four maps to the loss at their own resolution and let its kernel
+        read them nearest-upsampled (losses.MultiViewPhotometricLoss.forward(nearest_upsample=True)); False = the three
+        F.interpolate copies of the reference's glue.  forward() returns 'inv_depths' at the network's resolutions then."""
         super().__init__()
+        require_fp32_library_convolutions()
+        self.fuse_upsample = fuse_upsample
         self.depth_net = depth_net if depth_net is not None else PackNet01(version='1A')
         self.pose_net = pose_net if pose_net is not None else PoseNet(nb_ref_imgs=2, rotation_mode=rotation_mode)
         self.rotation_mode = rotation_mode
@@ -91,7 +104,7 @@ class SelfSupModel(nn.Module):
         inv = out['inv_depths']
         if flip:
             inv = [torch.flip(d, [3]) for d in inv] if isinstance(inv, (list, tuple)) else torch.flip(inv, [3])
-        if self.training and self.upsample_depth_maps:
+        if self.training and self.upsample_depth_maps and not self.fuse_upsample:
             shape = inv[0].shape[-2:]
             inv = [F.interpolate(d, shape, mode='nearest') for d in inv]   # model_utils.py:152-180
         return inv
@@ -108,5 +121,6 @@ class SelfSupModel(nn.Module):
             return out
         loss = self._photometric_loss(batch['rgb_original'], batch['rgb_context_original'], inv_depths,
                                       batch['intrinsics'], batch['intrinsics'], poses,
-                                      return_logs=return_logs, progress=progress)
+                                      return_logs=return_logs, progress=progress,
+                                      nearest_upsample=self.upsample_depth_maps and self.fuse_upsample)
         return {'loss': loss['loss'], 'metrics': loss['metrics'], **out}

@@ -227,3 +227,66 @@ def test_unsupported_options_fail_loudly():
         loss_fn = MultiViewPhotometricLoss(clip_loss=0.0)
         K = fr["intrinsics"]
         loss_fn(fr["rgb"], fr["rgb_context"], inv, K, K, mats)
+
+
+def test_nearest_upsample_folded_into_the_kernel_matches_reference_golden(golden):
+    """a8 (SfmModel.py:87-88 -> model_utils.upsample_output 'nearest'): the loss reads the four maps at their own resolution
+    with index >> s.  tests/golden/loss_fullres.npz holds the LIVE reference's loss and gradients for maps that were nearest
+    up-sampled to HxW, so the stored maps are its [::2^s] sub-samples, the loss must match the golden one and the gradient of
+    a stored pixel is the sum of the golden gradient over its 2^s x 2^s block (the backward of the up-sampling)."""
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    from packnet_sfm_b200.geometry import Pose
+    z = golden("loss_fullres")
+    dev = torch.device("cuda:0")
+    native = []
+    for i in range(4):
+        full = z["inv%d" % i]
+        sub = full[..., ::1 << i, ::1 << i].contiguous()
+        assert torch.equal(torch.nn.functional.interpolate(sub, full.shape[-2:], mode="nearest"), full)   # fixture sanity
+        native.append(sub.to(dev).requires_grad_(True))
+    mats = [z["pose%d" % j].to(dev).requires_grad_(True) for j in range(2)]
+    loss_fn = MultiViewPhotometricLoss(num_scales=4, ssim_loss_weight=0.85, smooth_loss_weight=0.001, photometric_reduce_op="min",
+                                       clip_loss=0.0, automask_loss=True)
+    K = z["K"].to(dev)
+    out = loss_fn(z["rgb"].to(dev), [z["ctx0"].to(dev), z["ctx1"].to(dev)], native, K, K, [Pose(m) for m in mats],
+                  nearest_upsample=True)
+    out["loss"].backward()
+    want = float(z["loss"])
+    assert abs(float(out["loss"].item()) - want) <= LOSS_TOL * abs(want)
+    for i in range(4):
+        g = z["ginv%d" % i]
+        k = 1 << i
+        block = torch.nn.functional.avg_pool2d(g, k) * (k * k) if i else g
+        assert native[i].grad.shape == block.shape
+        assert_field_close(native[i].grad, block, ("ginv", i))
+    for j in range(2):
+        assert rel_l2(mats[j].grad.cpu(), z["gpose%d" % j]) < POSE_TOL
+
+
+def test_fused_and_explicit_upsampling_agree_at_the_bench_shape():
+    """B=4, 192x640: maps at H, H/2, H/4, H/8 through the fused read against F.interpolate(nearest) + the plain kernel."""
+    from packnet_sfm_b200 import synthetic
+    B, H, W = 4, 192, 640
+    fr, _, mats = _synthetic_case(B, H, W, seed=11)
+    native = synthetic.make_inv_depths(B, H, W, seed=211, full_res=False)
+    full = [torch.nn.functional.interpolate(d, (H, W), mode="nearest") if i else d for i, d in enumerate(native)]
+    out_f, inv_f, mats_f = _run_cuda(fr, full, mats)
+    out_f["loss"].backward()
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    from packnet_sfm_b200.geometry import Pose
+    dev = torch.device("cuda:0")
+    loss_fn = MultiViewPhotometricLoss(num_scales=4, ssim_loss_weight=0.85, smooth_loss_weight=0.001, photometric_reduce_op="min",
+                                       clip_loss=0.0, automask_loss=True)
+    inv_n = [d.to(dev).requires_grad_(True) for d in native]
+    mats_n = [m.to(dev).requires_grad_(True) for m in mats]
+    K = fr["intrinsics"].to(dev)
+    out_n = loss_fn(fr["rgb"].to(dev), [c.to(dev) for c in fr["rgb_context"]], inv_n, K, K, [Pose(m) for m in mats_n],
+                    nearest_upsample=True)
+    out_n["loss"].backward()
+    assert abs(float(out_n["loss"].item()) - float(out_f["loss"].item())) <= 1e-6 * abs(float(out_f["loss"].item()))
+    for i in range(4):
+        k = 1 << i
+        want = torch.nn.functional.avg_pool2d(inv_f[i].grad, k) * (k * k) if i else inv_f[i].grad
+        assert rel_l2(inv_n[i].grad, want) < 1e-5, (i, rel_l2(inv_n[i].grad, want))
+    for a, b in zip(mats_n, mats_f):
+        assert rel_l2(a.grad, b.grad) < 1e-4

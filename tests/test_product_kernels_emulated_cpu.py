@@ -251,3 +251,33 @@ def test_emulated_packnet01_forward_matches_reference_golden():
                        stderr=subprocess.STDOUT, text=True, timeout=500)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "disp4 max-rel" in r.stdout
+
+
+def test_emulated_loss_reads_the_maps_nearest_upsampled(emulated_kernels, loss_program):
+    """a8 folded into the kernel (pn_loss_desc.inv_shift): the four maps at their own resolution, read with index >> s, against the
+    LIVE reference's golden loss / gradients for the nearest up-sampled maps (tests/golden/loss_fullres.npz): same loss, and the
+    gradient of a stored pixel = the golden gradient summed over its 2^s x 2^s block."""
+    import torch.nn.functional as F
+    from packnet_sfm_b200.geometry import Pose
+    from packnet_sfm_b200.losses import MultiViewPhotometricLoss
+    z = load_golden("loss_fullres")
+    meta = ast.literal_eval(str(z["meta"]))
+    native = []
+    for i in range(4):
+        full = z["inv%d" % i]
+        sub = full[..., ::1 << i, ::1 << i].contiguous()
+        assert torch.equal(F.interpolate(sub, full.shape[-2:], mode="nearest"), full)
+        native.append(sub.requires_grad_(True))
+    mats = [z["pose%d" % j].clone().requires_grad_(True) for j in range(2)]
+    out = MultiViewPhotometricLoss(**meta)(z["rgb"], [z["ctx0"], z["ctx1"]], native, z["K"], z["K"], [Pose(m) for m in mats],
+                                           nearest_upsample=True)
+    out["loss"].backward()
+    ref, got = float(z["loss"]), float(out["loss"].item())
+    assert abs(got - ref) <= 1e-5 * abs(ref), (got, ref)
+    for i in range(4):
+        k = 1 << i
+        want = F.avg_pool2d(z["ginv%d" % i], k) * (k * k) if i else z["ginv%d" % i]
+        assert native[i].grad.shape == want.shape
+        _field_close(native[i].grad, want, ("ginv", i))
+    for j, m in enumerate(mats):
+        assert rel_l2(m.grad, z["gpose%d" % j]) < 2e-2

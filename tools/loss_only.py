@@ -13,13 +13,15 @@ from packnet_sfm_b200.models import YACS_LOSS_DEFAULTS  # noqa: E402
 B, H, W = 4, 192, 640
 dev = torch.device("cuda:0")
 fr = synthetic.make_frames(B, H, W, seed=5)
-inv = [d.to(dev).requires_grad_(True) for d in synthetic.make_inv_depths(B, H, W, seed=6)]
+# the product's default: maps at H, H/2, H/4, H/8 read nearest-upsampled by the kernel (a8 fused); PN_LOSS_FULLRES=1 = pre-upsampled
+FULL = os.environ.get("PN_LOSS_FULLRES") == "1"
+inv = [d.to(dev).requires_grad_(True) for d in synthetic.make_inv_depths(B, H, W, seed=6, full_res=FULL)]
 vec = synthetic.make_pose_vecs(B, seed=7).to(dev)
 mats = [Pose.from_vec(vec[:, j], "euler").mat.requires_grad_(True) for j in range(2)]
 loss_fn = MultiViewPhotometricLoss(**YACS_LOSS_DEFAULTS)
 img, ctx, K = fr["rgb"].to(dev), [c.to(dev) for c in fr["rgb_context"]], fr["intrinsics"].to(dev)
 for _ in range(3):
-    out = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats])
+    out = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats], nearest_upsample=not FULL)
     torch.autograd.grad(out["loss"], inv + mats)
 torch.cuda.synchronize()
 print("loss", float(out["loss"]))
@@ -47,7 +49,7 @@ state = {}
 
 
 def fwd():
-    state["o"] = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats])
+    state["o"] = loss_fn(img, ctx, inv, K, K, [Pose(m) for m in mats], nearest_upsample=not FULL)
 
 
 def bwd():
@@ -58,4 +60,4 @@ fwd()
 t_f, t_b = timed(fwd), timed(bwd)
 P_s = B * H * W * 4
 print("program %s: fwd %.4f ms (%.0f GB/s algorithmic), bwd %.4f ms (%.0f GB/s algorithmic)" % (
-    "grouped" if os.environ.get("PN_LOSS_GROUPED") == "1" else "tile", t_f, 48 * P_s / t_f / 1e6, t_b, 44 * P_s / t_b / 1e6))
+    "grouped" if os.environ.get("PN_LOSS_GROUPED", "1") == "1" else "tile", t_f, 48 * P_s / t_f / 1e6, t_b, 44 * P_s / t_b / 1e6))
