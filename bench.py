@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--set", action="append", default=[], metavar="KEY=0|1",
                     help="A/B switch of a kernel variant against its library default: pack_fold, loss_grouped, im2col_first, "
                          "stage_flat, gn_tree, unpack_tiled, pack_tiled (e.g. --set pack_fold=0 --set loss_grouped=0 = the round-1 path)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="A/B (N > 1): ONE gradient all-reduce after the backward instead of buckets launched from the backward")
     ap.add_argument("--torch-adam", action="store_true",
                     help="A/B: torch.optim.Adam(fused) + per-call weight packing instead of packnet_sfm_b200.optim.FlatAdam")
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -385,7 +387,7 @@ def run_ours(args):
     log("model on device")
     parallel.broadcast_parameters(model)
     from packnet_sfm_b200 import losses as _losses, optim
-    from packnet_sfm_b200.networks import native_conv_weights
+    from packnet_sfm_b200.networks import gradient_buckets, native_conv_weights
     variants = apply_variants(args.set, PF, _lib, _losses)
     B, H, W = args.batch, args.height, args.width
     groups = [{"name": "Depth", "params": list(model.depth_net.parameters()), "lr": 2e-4},
@@ -395,7 +397,8 @@ def run_ours(args):
         opt = torch.optim.Adam(groups, fused=True, capturable=bool(args.graph))
         zero_grad, reduce_grads = bucket.zero_grad, bucket.allreduce_mean
     else:                    # flat parameters / gradients / moments, one Adam launch that also writes the engine's weight tiles
-        opt = optim.FlatAdam(groups, native=native_conv_weights(model.depth_net, (H, W)))
+        opt = optim.FlatAdam(groups, native=native_conv_weights(model.depth_net, (H, W)),
+                             buckets=gradient_buckets(model.depth_net, (H, W)) if world > 1 and not args.no_overlap else None)
         zero_grad, reduce_grads = opt.zero_grad, opt.allreduce_mean
     hb = make_host_batch(B, H, W, rank)
     dbatch = to_device(hb, dev)

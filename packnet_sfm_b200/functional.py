@@ -253,6 +253,7 @@ class _Conv2d(torch.autograd.Function):
                 # [Cout][tap][kpad] IS the stored layout: accumulate into the flat gradient buffer, nothing to return
                 _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
                                                _lib.ptr(ctx.nat.grad_flat), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
+                ctx.nat.owner.grad_ready(ctx.nat)      # data parallel: may start the all-reduce of a completed bucket
             else:
                 n = ctypes.c_size_t(0)
                 _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, Cin, k, precision, ctypes.byref(n)), "wgrad_packed_elems")

@@ -155,6 +155,29 @@ def native_conv_weights(net, image_hw=None):
     return out
 
 
+def gradient_buckets(net, image_hw=None):
+    """Stored weights grouped by WHEN their gradients complete in the backward (reverse forward order, PackNet01.py:106-176):
+    [decoder: iconv1 .. unpack5] then [pack5, conv5, pack4: 110 M of the 128 M parameters, complete while the high-resolution
+    half of the encoder's backward is still to run].  optim.FlatAdam launches each bucket's all-reduce from the backward."""
+    native = {id(p) for p in native_conv_weights(net, image_hw)}
+    if not isinstance(net, PackNet01):
+        return []
+
+    def weights(*mods):
+        out = []
+        for m in mods:
+            for sub in m.modules():
+                for p in sub.parameters(recurse=False):
+                    if id(p) in native and all(p is not q for q in out):
+                        out.append(p)
+        return out
+
+    decoder = weights(net.iconv1, net.unpack1, net.iconv2, net.unpack2, net.iconv3, net.unpack3, net.iconv4, net.unpack4,
+                      net.iconv5, net.unpack5)
+    deep = weights(net.pack5, net.conv5, net.pack4)
+    return [decoder, deep]
+
+
 class PackNet01(nn.Module):
     """PackNet network with 3d convolutions (version 01, from the CVPR paper) -- PackNet01.py:7-185.
 

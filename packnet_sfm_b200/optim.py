@@ -54,9 +54,12 @@ class NativeWeight:
 
 class FlatAdam:
     """Adam on flat buffers.  `params`: an iterable of parameters or of torch-style groups ({'params': [...], 'lr': ...,
-    'weight_decay': ...}); `native`: the 4-D convolution weights to store in the engine's layout (networks.native_conv_weights)."""
+    'weight_decay': ...}); `native`: the 4-D convolution weights to store in the engine's layout (networks.native_conv_weights);
+    `buckets`: lists of native weights in the order their gradients complete during the backward (networks.gradient_buckets):
+    each list becomes one contiguous range at the front of the flat buffers whose all-reduce is launched from the backward
+    as soon as its last weight gradient has been enqueued; everything else is reduced by allreduce_mean() after the backward."""
 
-    def __init__(self, params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, native=()):
+    def __init__(self, params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, native=(), buckets=None):
         groups = list(params)
         if groups and not isinstance(groups[0], dict):
             groups = [{"params": groups}]
@@ -76,10 +79,42 @@ class FlatAdam:
         dev = every[0].device
         assert all(p.device == dev and p.dtype == torch.float32 for p in every), "fp32 parameters on one device"
         lib = _lib.lib()
-        # ---- layout: [group 0 plain | group 1 plain | ...] each padded to a block, then the stored convolution weights
+        # ---- layout: [bucket 0 natives | bucket 1 natives | ... | other natives | group 0 plain | group 1 plain | ...],
+        # every stored weight and every group padded to whole blocks
+        group_of = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
+        ordered, bucket_sizes = [], []
+        for bl in (buckets or []):
+            bl = [p for p in bl if id(p) in native_ids and id(p) not in {id(q) for q in ordered}]
+            if bl:
+                ordered += bl
+                bucket_sizes.append(len(bl))
+        ordered += [p for p in every if id(p) in native_ids and id(p) not in {id(q) for q in ordered}]
         self._slots = []                       # (param, offset, numel_storage, group, native index or -1)
         block_info = []
+        segs, packed_bytes = [], 0
         off = 0
+        self._bucket_ranges, self._bucket_of = [], {}
+        bstart, bcount, bi = 0, 0, 0
+        for p in ordered:
+            assert p.dim() == 4 and p.shape[2] == p.shape[3], "native weights are [Cout,Cin,k,k]"
+            gi = group_of[id(p)]
+            cout, cin, k, _ = p.shape
+            kpad, rows_pad = _round_up(cin, 64), int(lib.pn_conv2d_rows_pad(cout))
+            n = cout * k * k * kpad
+            seg = ConvSeg(off, packed_bytes, cout, k * k, kpad, rows_pad)
+            if bi < len(bucket_sizes):
+                self._bucket_of[len(segs)] = bi
+            self._slots.append((p, off, n, gi, len(segs)))
+            segs.append(seg)
+            nb = _round_up(n, BLOCK) // BLOCK
+            block_info += [(gi << 16) | len(segs)] * nb
+            off += nb * BLOCK
+            packed_bytes += _round_up((kpad // 64) * k * k * rows_pad * 128, 1024)
+            bcount += 1
+            while bi < len(bucket_sizes) and bcount == bucket_sizes[bi]:
+                self._bucket_ranges.append((bstart, off, bucket_sizes[bi]))
+                bstart, bcount, bi = off, 0, bi + 1
+        self._tail_start = self._bucket_ranges[-1][1] if self._bucket_ranges else 0
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 if id(p) in native_ids:
@@ -89,22 +124,6 @@ class FlatAdam:
             end = _round_up(off, BLOCK)
             block_info += [gi << 16] * ((end - len(block_info) * BLOCK) // BLOCK)
             off = end
-        segs, packed_bytes = [], 0
-        for gi, g in enumerate(self.param_groups):
-            for p in g["params"]:
-                if id(p) not in native_ids:
-                    continue
-                assert p.dim() == 4 and p.shape[2] == p.shape[3], "native weights are [Cout,Cin,k,k]"
-                cout, cin, k, _ = p.shape
-                kpad, rows_pad = _round_up(cin, 64), int(lib.pn_conv2d_rows_pad(cout))
-                n = cout * k * k * kpad
-                seg = ConvSeg(off, packed_bytes, cout, k * k, kpad, rows_pad)
-                self._slots.append((p, off, n, gi, len(segs)))
-                segs.append(seg)
-                nb = _round_up(n, BLOCK) // BLOCK
-                block_info += [(gi << 16) | len(segs)] * nb
-                off += nb * BLOCK
-                packed_bytes += _round_up((kpad // 64) * k * k * rows_pad * 128, 1024)
         assert len(segs) < 0xFFFF
         self.numel = off
         assert len(block_info) * BLOCK == off
@@ -147,7 +166,9 @@ class FlatAdam:
                     p._pn_native = nat
                     self.natives.append((p, nat))
         self._collected = False
-        self._buckets = None
+        self._pending = [n for (_, _, n) in self._bucket_ranges]     # weight gradients still missing per bucket, this step
+        self._works = []
+        self._launched = [False] * len(self._bucket_ranges)
         self.repack()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -190,6 +211,8 @@ class FlatAdam:
         for p, _ in self._plain:
             p.grad = None
         self._collected = False
+        self._pending = [n for (_, _, n) in self._bucket_ranges]
+        self._launched = [False] * len(self._bucket_ranges)
 
     def collect_grads(self):
         """Gather the gradients autograd produced for the plain parameters into the flat buffer (one multi-tensor copy)."""
@@ -208,16 +231,50 @@ class FlatAdam:
             p.grad = v
         self._collected = True
 
+    @staticmethod
+    def _distributed(group=None):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def _reduce_range(self, start, end, group=None):
+        """launch the averaging all-reduce of flat_grad[start:end]; NCCL orders it after the work enqueued so far on the
+        current stream and runs it on its own stream, i.e. concurrently with whatever the backward enqueues next"""
+        if end <= start:
+            return
+        view = self.flat_grad[start:end]
+        if dist.get_backend(group) == "nccl":
+            self._works.append((dist.all_reduce(view, op=dist.ReduceOp.AVG, group=group, async_op=True), None))
+        else:
+            self._works.append((dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group, async_op=True), view))
+
+    def grad_ready(self, nat, group=None):
+        """Called by functional._Conv2d.backward after it enqueued the weight gradient of a stored weight: when that
+        completes a bucket, the bucket's all-reduce starts NOW and overlaps the rest of the backward (the reference's Horovod
+        optimizer does the same per tensor, trainers/horovod_trainer.py:46-48)."""
+        bi = self._bucket_of.get(nat.index)
+        if bi is None or not self._distributed(group):
+            return
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and not self._launched[bi]:
+            self._launched[bi] = True
+            self._reduce_range(self._bucket_ranges[bi][0], self._bucket_ranges[bi][1], group)
+
     def allreduce_mean(self, group=None):
-        """Average the flat gradient buffer over the ranks (Horovod's op=Average): ONE collective over NVLink."""
-        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        """Average the gradients over the ranks (Horovod's op=Average): the buckets not yet launched from the backward plus
+        the tail of the flat buffer (remaining stored weights and all plain parameters), then wait for every collective."""
+        if not self._distributed(group):
             return
         self.collect_grads()
-        if dist.get_backend(group) == "nccl":
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=group)
-        else:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
-            self.flat_grad.div_(dist.get_world_size(group))
+        for bi, (start, end, _) in enumerate(self._bucket_ranges):
+            if not self._launched[bi]:
+                self._launched[bi] = True
+                self._reduce_range(start, end, group)
+        self._reduce_range(self._tail_start, self.numel, group)
+        world = dist.get_world_size(group)
+        for work, view in self._works:
+            work.wait()
+            if view is not None:
+                view.div_(world)
+        self._works = []
 
     def step(self):
         self.collect_grads()
