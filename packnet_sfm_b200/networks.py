@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from . import folded
 from . import functional as PF
 
@@ -262,9 +263,7 @@ class PackNet01(nn.Module):
         return up.permute(0, 2, 3, 1)
 
     def forward(self, rgb):
-        if not rgb.is_cuda:
-            raise RuntimeError("packnet_sfm_b200.PackNet01 runs on CUDA tensors only (got %s); there is no CPU path"
-                               % rgb.device)
+        _lib.require_f32(rgb)          # CUDA fp32 only: there is no CPU path and no silent dtype reinterpretation
         B, _, H, W = rgb.shape
         if H % 32 or W % 32:
             raise ValueError("PackNet01 needs H and W divisible by 32 (got %dx%d)" % (H, W))
