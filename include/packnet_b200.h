@@ -263,6 +263,15 @@ int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, c
                               float* dx_lo, float* dgamma, float* dbeta, float* dx_channel_sum, int batch, int hw,
                               int channels, int y_cstride, int y_coffset, int dy_cstride, int dy_coffset,
                               pn_stream_t stream);
+/* The same two passes, additionally emitting the bf16 operand pair (hi = rn(v), lo = rn(v - hi), contiguous [B,HW,C]) of the
+ * output for the tensor-core convolution that consumes it -- y in the forward, dx (the convolution's output gradient) in the
+ * backward -- so that no separate pn_split_bf16 launch re-reads the tensor.  No channel windows. */
+int pn_groupnorm_elu_forward_split(const float* x, const float* x2, const float* gamma, const float* beta, float eps, float* y,
+                                   void* y_hi_bf16, void* y_lo_bf16, double* stats, int batch, int hw, int channels,
+                                   pn_stream_t stream);
+int pn_groupnorm_elu_backward_split(const float* x, const float* x2, const float* y, const float* dy, const float* gamma, float eps,
+                                    const double* stats, double* bc, float* dx, void* dx_hi_bf16, void* dx_lo_bf16, float* dgamma,
+                                    float* dbeta, float* dx_channel_sum, int batch, int hw, int channels, pn_stream_t stream);
 
 /* out[c] = sum over pixels of g[pixel][c] (conv bias gradient), g dense [pixels, channels]. */
 int pn_channel_sum(const float* g, float* out, size_t pixels, int channels, pn_stream_t stream);

@@ -57,6 +57,9 @@ def declare(lib):
     lib.pn_feature_stencil_backward.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     lib.pn_groupnorm_elu_forward.argtypes = [vp, vp, vp, vp, f, vp, vp, vp, i, i, i, i, i, vp]
     lib.pn_groupnorm_elu_backward.argtypes = [vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.pn_groupnorm_elu_forward_split.argtypes = [vp, vp, vp, vp, f, vp, vp, vp, vp, i, i, i, vp]
+    lib.pn_groupnorm_elu_backward_split.argtypes = [vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.pn_groupnorm_elu_forward_split.restype = lib.pn_groupnorm_elu_backward_split.restype = c.c_int
     lib.pn_channel_sum.argtypes = [vp, vp, sz, i, vp]
     lib.pn_head_conv_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.pn_head_conv_backward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]

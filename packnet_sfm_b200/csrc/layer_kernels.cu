@@ -16,6 +16,12 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#ifdef PN_EMULATE
+#include <cmath>
+#include <cstring>
+#else
+#include <cuda_bf16.h>
+#endif
 
 namespace pn {
 namespace layers {
@@ -824,12 +830,58 @@ __global__ void gn_finalize_stats_kernel(const double* __restrict__ stats, float
   mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// y = ELU(gamma * (x - mean) * rstd + beta), written at (out_cstride, out_coffset); optional tf32 residual copy
+// bf16 pair of a value for the tensor-core engine: hi = rn_bf16(v), lo = rn_bf16(v - hi) (conv_engine.cu split_bf16_kernel)
+__device__ __forceinline__ void split_pair(float v, unsigned short& hi, unsigned short& lo) {
+#ifdef PN_EMULATE
+  unsigned u;
+  std::memcpy(&u, &v, 4);
+  auto rn = [](float f) { unsigned w; std::memcpy(&w, &f, 4); if ((w & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((w >> 16) | 0x0040u);
+                          w += 0x7fffu + ((w >> 16) & 1u); return (unsigned short)(w >> 16); };
+  hi = rn(v);
+  const unsigned hb = (unsigned)hi << 16;
+  float hf;
+  std::memcpy(&hf, &hb, 4);
+  lo = rn(v - hf);
+#else
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+#endif
+}
+__device__ __forceinline__ void store_split4(uint2* hi, uint2* lo, size_t i4, const float (&v)[4]) {
+  unsigned short h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) split_pair(v[k], h[k], l[k]);
+  hi[i4] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+  lo[i4] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+}
+
+// y = ELU(gamma * (x - mean) * rstd + beta), written at (out_cstride, out_coffset); optional tf32 residual copy.
+// Round 2: (mean, rstd) of every (sample, group) are derived from the fp64 sums in the kernel's prologue (the separate
+// finalize launch is gone; CTA 0 leaves the floats in `mr` for the backward), and the kernel can also emit the bf16 hi / lo
+// operand pair of y for the convolution that consumes it (y_hi / y_blo, contiguous [B,HW,C]): the split launch that re-read
+// y is gone as well.
 __global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restrict__ x, const float* __restrict__ x2, int HW, int C,
-                                                           int in_cstride, const float* __restrict__ mr,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                           float* __restrict__ y, float* __restrict__ y_lo, int out_cstride,
-                                                           int out_coffset, int B) {
+                                                           int in_cstride, float* __restrict__ mr, const double* __restrict__ sums,
+                                                           double cnt, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float eps, float* __restrict__ y, float* __restrict__ y_lo, int out_cstride,
+                                                           int out_coffset, int B, uint2* __restrict__ y_hi, uint2* __restrict__ y_blo) {
+  PN_DYNAMIC_SHARED(float, s_mr);     // [B*16][2]
+  for (int i = threadIdx.x; i < 16 * B; i += blockDim.x) {
+    float mean, rstd;
+    if (sums) {
+      const double m = sums[2 * i] / cnt;
+      double var = sums[2 * i + 1] / cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0) { mr[2 * i] = mean; mr[2 * i + 1] = rstd; }
+    } else {
+      mean = mr[2 * i]; rstd = mr[2 * i + 1];
+    }
+    s_mr[2 * i] = mean; s_mr[2 * i + 1] = rstd;
+  }
+  __syncthreads();
   const int c4 = C / 4, cg = C / 16;
   const size_t total = (size_t)B * HW * c4;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -846,7 +898,7 @@ __global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restri
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = col * 4 + k, g = c / cg;
-      const float mean = __ldg(mr + ((size_t)b * 16 + g) * 2 + 0), rstd = __ldg(mr + ((size_t)b * 16 + g) * 2 + 1);
+      const float mean = s_mr[(b * 16 + g) * 2 + 0], rstd = s_mr[(b * 16 + g) * 2 + 1];
       const float z = (in[k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
       out[k] = z > 0.0f ? z : expm1f(z);   // nn.ELU(alpha=1)
     }
@@ -855,6 +907,7 @@ __global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restri
     if (y_lo)
       *reinterpret_cast<float4*>(y_lo + oo) = make_float4(out[0] - tf32_trunc(out[0]), out[1] - tf32_trunc(out[1]),
                                                           out[2] - tf32_trunc(out[2]), out[3] - tf32_trunc(out[3]));
+    if (y_hi) store_split4(y_hi, y_blo, idx, out);
   }
 }
 
@@ -967,20 +1020,48 @@ __global__ void __launch_bounds__(256) gn_elu_bwd_reduce4_kernel(const float* __
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(bc + (size_t)b * C * 2 + i, (double)s_red[i]);
 }
 
+// Round 2: the finalize launch between the two passes is folded in -- every CTA derives the two group means of ITS sample from
+// the channel sums `bc` (16 threads x C/16 channels), the first CTA column also writes dgamma / dbeta -- and the kernel can
+// emit the bf16 hi / lo pair of dx, the output-gradient operand of the convolution that produced x.
 __global__ void __launch_bounds__(256) gn_elu_bwd_apply4_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                                 const float* __restrict__ y, const float* __restrict__ dy, int HW, int C,
                                                                 int in_cstride, int y_cstride, int y_coffset, int dy_cstride,
                                                                 int dy_coffset, const float* __restrict__ mr,
-                                                                const float* __restrict__ gmeans, const float* __restrict__ gamma,
+                                                                const double* __restrict__ bc, double cnt, const float* __restrict__ gamma,
                                                                 int pixels_per_cta, float* __restrict__ dx, float* __restrict__ dx_lo,
-                                                                float* __restrict__ dsum) {
+                                                                float* __restrict__ dsum, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta, int B, uint2* __restrict__ dx_hi,
+                                                                uint2* __restrict__ dx_blo) {
   __shared__ float s_red[1024];
+  __shared__ float s_gm[32];
   const int b = blockIdx.y, cg = C / 16, c4 = C / 4;
   const int p0 = blockIdx.x * pixels_per_cta, p1 = min(p0 + pixels_per_cta, HW);
+  if (threadIdx.x < 16) {
+    // (mean_g(gamma*dz), mean_g(gamma*dz*xhat)) over the HW * C/16 elements of group g of sample b
+    const int g = threadIdx.x;
+    double m1 = 0.0, m2 = 0.0;
+    for (int k = 0; k < cg; ++k) {
+      const int cc = g * cg + k;
+      const double gmv = (double)gamma[cc];
+      m1 += gmv * bc[((size_t)b * C + cc) * 2 + 0];
+      m2 += gmv * bc[((size_t)b * C + cc) * 2 + 1];
+    }
+    s_gm[2 * g + 0] = (float)(m1 / cnt);
+    s_gm[2 * g + 1] = (float)(m2 / cnt);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    // dgamma[c] = sum_b bc[b][c][1], dbeta[c] = sum_b bc[b][c][0]
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double a = 0.0, d = 0.0;
+      for (int bb = 0; bb < B; ++bb) { d += bc[((size_t)bb * C + c) * 2 + 0]; a += bc[((size_t)bb * C + c) * 2 + 1]; }
+      dgamma[c] = (float)a;
+      dbeta[c] = (float)d;
+    }
+  }
   if (dsum) {
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_red[i] = 0.0f;
-    __syncthreads();
   }
+  __syncthreads();
   const int lanes = blockDim.x / c4 > 0 ? blockDim.x / c4 : 1;
   const int col = threadIdx.x % c4, pl = threadIdx.x / c4;
   if (pl < lanes) {
@@ -990,8 +1071,8 @@ __global__ void __launch_bounds__(256) gn_elu_bwd_apply4_kernel(const float* __r
       const int c = col * 4 + k, g = c / cg;
       mean[k] = __ldg(mr + ((size_t)b * 16 + g) * 2 + 0);
       rstd[k] = __ldg(mr + ((size_t)b * 16 + g) * 2 + 1);
-      m1[k] = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 0);
-      m2[k] = __ldg(gmeans + ((size_t)b * 16 + g) * 2 + 1);
+      m1[k] = s_gm[2 * g + 0];
+      m2[k] = s_gm[2 * g + 1];
       gm[k] = __ldg(gamma + c);
     }
     for (int p = p0 + pl; p < p1; p += lanes) {
@@ -1017,6 +1098,7 @@ __global__ void __launch_bounds__(256) gn_elu_bwd_apply4_kernel(const float* __r
       if (dx_lo)
         *reinterpret_cast<float4*>(dx_lo + o) = make_float4(r[0] - tf32_trunc(r[0]), r[1] - tf32_trunc(r[1]),
                                                             r[2] - tf32_trunc(r[2]), r[3] - tf32_trunc(r[3]));
+      if (dx_hi) store_split4(dx_hi, dx_blo, o >> 2, r);
     }
     if (dsum) {
 #pragma unroll
@@ -1448,14 +1530,15 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   return check_launch("stencil_wgrad_kernel");
 }
 
-extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const float* gamma, const float* beta, float eps, float* y,
-                                        float* y_lo, double* stats, int batch, int hw, int channels, int out_cstride, int out_coffset,
-                                        pn_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int groupnorm_elu_forward_impl(const float* x, const float* x2, const float* gamma, const float* beta, float eps, float* y,
+                                      float* y_lo, double* stats, int batch, int hw, int channels, int out_cstride, int out_coffset,
+                                      void* y_hi_bf16, void* y_lo_bf16, cudaStream_t stream) {
   PN_REQUIRE(x && gamma && beta && y && stats && batch > 0 && hw > 0, PN_ERR_BAD_ARGUMENT, "pn_groupnorm_elu_forward: bad argument");
   PN_REQUIRE(channels % 16 == 0 && channels % 4 == 0 && channels <= 1024, PN_ERR_UNSUPPORTED,
              "pn_groupnorm_elu_forward: channels %d (need a multiple of 16, <= 1024)", channels);
   PN_REQUIRE(out_cstride % 4 == 0 && out_coffset % 4 == 0, PN_ERR_ALIGNMENT, "pn_groupnorm_elu_forward: output channel window");
+  PN_REQUIRE((!y_hi_bf16) == (!y_lo_bf16) && (!y_hi_bf16 || ((reinterpret_cast<uintptr_t>(y_hi_bf16) | reinterpret_cast<uintptr_t>(y_lo_bf16)) & 7) == 0),
+             PN_ERR_BAD_ARGUMENT, "pn_groupnorm_elu_forward: the bf16 pair needs both 8-byte aligned pointers");
   PN_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * 16 * batch, stream));
   int ppc = (hw + 147) / 148;
   if (ppc < 32) ppc = 32;
@@ -1467,22 +1550,35 @@ extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const f
   }
   count_launch();
   float* mr = reinterpret_cast<float*>(stats + (size_t)2 * 16 * batch);   // (mean, rstd) floats behind the doubles
-  PN_LAUNCH(gn_finalize_stats_kernel, (16 * batch + 127) / 128, 128, 0, stream, stats, mr, 16 * batch, (double)hw * (channels / 16), eps);
-  count_launch();
   const size_t total = (size_t)batch * hw * (channels / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  PN_LAUNCH(gn_elu_apply_kernel, blocks, 256, 0, stream, x, x2, hw, channels, channels, mr, gamma, beta, eps, y, y_lo, out_cstride,
-                                                  out_coffset, batch);
+  PN_LAUNCH(gn_elu_apply_kernel, blocks, 256, sizeof(float) * 2 * 16 * batch, stream, x, x2, hw, channels, channels, mr,
+            static_cast<const double*>(stats), (double)hw * (channels / 16), gamma, beta, eps, y, y_lo, out_cstride, out_coffset, batch,
+            static_cast<uint2*>(y_hi_bf16), static_cast<uint2*>(y_lo_bf16));
   count_launch();
   return check_launch("gn_elu_apply_kernel");
 }
 
-extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, const float* dy, const float* gamma,
-                                         float eps, const double* stats, double* bc, float* dx, float* dx_lo, float* dgamma,
-                                         float* dbeta, float* dx_channel_sum, int batch, int hw, int channels, int y_cstride,
-                                         int y_coffset, int dy_cstride, int dy_coffset, pn_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+extern "C" int pn_groupnorm_elu_forward(const float* x, const float* x2, const float* gamma, const float* beta, float eps, float* y,
+                                        float* y_lo, double* stats, int batch, int hw, int channels, int out_cstride, int out_coffset,
+                                        pn_stream_t stream_) {
+  return groupnorm_elu_forward_impl(x, x2, gamma, beta, eps, y, y_lo, stats, batch, hw, channels, out_cstride, out_coffset, nullptr,
+                                    nullptr, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int pn_groupnorm_elu_forward_split(const float* x, const float* x2, const float* gamma, const float* beta, float eps,
+                                              float* y, void* y_hi_bf16, void* y_lo_bf16, double* stats, int batch, int hw,
+                                              int channels, pn_stream_t stream_) {
+  return groupnorm_elu_forward_impl(x, x2, gamma, beta, eps, y, nullptr, stats, batch, hw, channels, channels, 0, y_hi_bf16, y_lo_bf16,
+                                    reinterpret_cast<cudaStream_t>(stream_));
+}
+
+static int groupnorm_elu_backward_impl(const float* x, const float* x2, const float* y, const float* dy, const float* gamma,
+                                       float eps, const double* stats, double* bc, float* dx, float* dx_lo, float* dgamma,
+                                       float* dbeta, float* dx_channel_sum, int batch, int hw, int channels, int y_cstride,
+                                       int y_coffset, int dy_cstride, int dy_coffset, void* dx_hi_bf16, void* dx_lo_bf16,
+                                       cudaStream_t stream) {
   PN_REQUIRE(x && y && dy && gamma && stats && bc && dx && dgamma && dbeta && batch > 0 && hw > 0, PN_ERR_BAD_ARGUMENT,
              "pn_groupnorm_elu_backward: bad argument");
   PN_REQUIRE(channels % 16 == 0 && channels <= 1024, PN_ERR_UNSUPPORTED, "pn_groupnorm_elu_backward: channels %d", channels);
@@ -1496,15 +1592,15 @@ extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const 
   const bool vec = aligned16(x) && (!x2 || aligned16(x2)) && aligned16(y) && aligned16(dy) && aligned16(dx) && (!dx_lo || aligned16(dx_lo)) &&
                    y_cstride % 4 == 0 && y_coffset % 4 == 0 && dy_cstride % 4 == 0 && dy_coffset % 4 == 0;
   if (dx_channel_sum) PN_CUDA(cudaMemsetAsync(dx_channel_sum, 0, sizeof(float) * channels, stream));
+  PN_REQUIRE((!dx_hi_bf16) == (!dx_lo_bf16) && (!dx_hi_bf16 || vec), PN_ERR_BAD_ARGUMENT,
+             "pn_groupnorm_elu_backward: the bf16 pair needs both pointers and 16-byte aligned tensors");
   if (vec) {
     PN_LAUNCH(gn_elu_bwd_reduce4_kernel, g1, 256, 0, stream, x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride,
                                                       dy_coffset, mr, ppc, bc);
     count_launch();
-    PN_LAUNCH(gn_bwd_finalize_kernel, (batch * 16 + channels + 127) / 128, 128, 0, stream, bc, gamma, batch, channels,
-                                                                                   (double)hw * (channels / 16), gmeans, dgamma, dbeta);
-    count_launch();
     PN_LAUNCH(gn_elu_bwd_apply4_kernel, g1, 256, 0, stream, x, x2, y, dy, hw, channels, channels, y_cstride, y_coffset, dy_cstride, dy_coffset,
-                                                     mr, gmeans, gamma, ppc, dx, dx_lo, dx_channel_sum);
+              mr, static_cast<const double*>(bc), (double)hw * (channels / 16), gamma, ppc, dx, dx_lo, dx_channel_sum, dgamma, dbeta, batch,
+              static_cast<uint2*>(dx_hi_bf16), static_cast<uint2*>(dx_lo_bf16));
     count_launch();
     return check_launch("gn_elu_bwd kernels");
   }
@@ -1527,6 +1623,22 @@ extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const 
     count_launch();
   }
   return check_launch("gn_elu_bwd kernels");
+}
+
+extern "C" int pn_groupnorm_elu_backward(const float* x, const float* x2, const float* y, const float* dy, const float* gamma,
+                                         float eps, const double* stats, double* bc, float* dx, float* dx_lo, float* dgamma,
+                                         float* dbeta, float* dx_channel_sum, int batch, int hw, int channels, int y_cstride,
+                                         int y_coffset, int dy_cstride, int dy_coffset, pn_stream_t stream_) {
+  return groupnorm_elu_backward_impl(x, x2, y, dy, gamma, eps, stats, bc, dx, dx_lo, dgamma, dbeta, dx_channel_sum, batch, hw, channels,
+                                     y_cstride, y_coffset, dy_cstride, dy_coffset, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int pn_groupnorm_elu_backward_split(const float* x, const float* x2, const float* y, const float* dy, const float* gamma,
+                                               float eps, const double* stats, double* bc, float* dx, void* dx_hi_bf16, void* dx_lo_bf16,
+                                               float* dgamma, float* dbeta, float* dx_channel_sum, int batch, int hw, int channels,
+                                               pn_stream_t stream_) {
+  return groupnorm_elu_backward_impl(x, x2, y, dy, gamma, eps, stats, bc, dx, nullptr, dgamma, dbeta, dx_channel_sum, batch, hw, channels,
+                                     channels, 0, channels, 0, dx_hi_bf16, dx_lo_bf16, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int pn_conv2d_unpack_weight_grad_tiled(const float* dw_packed, float* dw_oihw, int cout, int cin, int ksize, int kpad,

@@ -31,7 +31,9 @@ _state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": _env("P
           "pack_fold_min_pixels": int(os.environ.get("PN_PACK_FOLD_MIN_PIXELS", "1920")),
           "im2col_first": _env("PN_IM2COL_FIRST", True),
           "unpack_tiled": _env("PN_UNPACK_TILED", True),
-          "pack_tiled": _env("PN_PACK_TILED", False)}
+          "pack_tiled": _env("PN_PACK_TILED", False),
+          # GroupNorm+ELU kernels write the bf16 operand pair of their output for the convolution that consumes it
+          "gn_emit_split": _env("PN_GN_EMIT_SPLIT", True)}
 
 
 def set_pack_tiled(on):
@@ -129,8 +131,18 @@ def _residual(x):
     return lo
 
 
+def _attach_split(t, hi, lo):
+    """remember the bf16 operand pair the producing kernel wrote next to a tensor (valid while the tensor is unmodified)"""
+    t._pn_split = (hi, lo, t._version)
+
+
 def _operands(x, precision):
-    """fp32 NHWC tensor -> (hi, lo) tensor-core operands of the given precision (lo is None for the X1 modes)."""
+    """fp32 NHWC tensor -> (hi, lo) tensor-core operands of the given precision (lo is None for the X1 modes).  A tensor whose
+    producer (GroupNorm+ELU forward / backward) already emitted its bf16 pair carries it along: no split launch."""
+    if precision == PRECISION_BF16X3:
+        pair = getattr(x, "_pn_split", None)
+        if pair is not None and pair[2] == x._version and pair[0].shape == x.shape:
+            return pair[0], pair[1]
     if is_bf16(precision):
         hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
         lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
@@ -341,10 +353,21 @@ class _GroupNormELU(torch.autograd.Function):
         B, H, W, C = x.shape
         y = torch.empty_like(x)
         stats = torch.empty(B * 16 * 3, dtype=torch.float64, device=x.device)   # sums (double) + mean/rstd (float)
-        _lib.check(_lib.lib().pn_groupnorm_elu_forward(_lib.ptr(x), _p(x2c), _lib.ptr(gamma.detach().contiguous()),
-                                                       _lib.ptr(beta.detach().contiguous()), float(eps), _lib.ptr(y), None,
-                                                       _lib.ptr(stats), B, H * W, C, C, 0, _stream()),
-                   "pn_groupnorm_elu_forward")
+        ctx.emit = _state["precision"] == PRECISION_BF16X3 and _state["gn_emit_split"]
+        if ctx.emit:
+            # the consumer of y is (almost always) a tensor-core convolution: write its bf16 operand pair in the same pass
+            hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            _lib.check(_lib.lib().pn_groupnorm_elu_forward_split(_lib.ptr(x), _p(x2c), _lib.ptr(gamma.detach().contiguous()),
+                                                                 _lib.ptr(beta.detach().contiguous()), float(eps), _lib.ptr(y),
+                                                                 _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(stats), B, H * W, C, _stream()),
+                       "pn_groupnorm_elu_forward_split")
+            _attach_split(y, hi, lo)
+        else:
+            _lib.check(_lib.lib().pn_groupnorm_elu_forward(_lib.ptr(x), _p(x2c), _lib.ptr(gamma.detach().contiguous()),
+                                                           _lib.ptr(beta.detach().contiguous()), float(eps), _lib.ptr(y), None,
+                                                           _lib.ptr(stats), B, H * W, C, C, 0, _stream()),
+                       "pn_groupnorm_elu_forward")
         ctx.save_for_backward(x, x2c, y, gamma, stats)
         ctx.eps = float(eps)
         return y
@@ -359,11 +382,22 @@ class _GroupNormELU(torch.autograd.Function):
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
         bc = torch.empty(2 * C * B + 16 * B, dtype=torch.float64, device=x.device)   # doubles + float scratch tail
         dsum = torch.empty(C, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().pn_groupnorm_elu_backward(_lib.ptr(x), _p(x2), _lib.ptr(y), _lib.ptr(gy),
-                                                        _lib.ptr(gamma.detach().contiguous()), ctx.eps, _lib.ptr(stats),
-                                                        _lib.ptr(bc), _lib.ptr(dx), None, _lib.ptr(dgamma), _lib.ptr(dbeta),
-                                                        _lib.ptr(dsum), B, H * W, C, C, 0, C, 0, _stream()),
-                   "pn_groupnorm_elu_backward")
+        if ctx.emit:
+            # dx is the output gradient of the convolution that produced x: its bf16 pair comes out of the same pass
+            hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            _lib.check(_lib.lib().pn_groupnorm_elu_backward_split(_lib.ptr(x), _p(x2), _lib.ptr(y), _lib.ptr(gy),
+                                                                  _lib.ptr(gamma.detach().contiguous()), ctx.eps, _lib.ptr(stats),
+                                                                  _lib.ptr(bc), _lib.ptr(dx), _lib.ptr(hi), _lib.ptr(lo),
+                                                                  _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dsum), B, H * W, C,
+                                                                  _stream()), "pn_groupnorm_elu_backward_split")
+            _attach_split(dx, hi, lo)
+        else:
+            _lib.check(_lib.lib().pn_groupnorm_elu_backward(_lib.ptr(x), _p(x2), _lib.ptr(y), _lib.ptr(gy),
+                                                            _lib.ptr(gamma.detach().contiguous()), ctx.eps, _lib.ptr(stats),
+                                                            _lib.ptr(bc), _lib.ptr(dx), None, _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                                            _lib.ptr(dsum), B, H * W, C, C, 0, C, 0, _stream()),
+                       "pn_groupnorm_elu_backward")
         _remember_channel_sum(dx, dsum)
         return dx, (dx if x2 is not None else None), dgamma, dbeta, None
 

@@ -160,7 +160,21 @@ def test_emulated_groupnorm_elu_and_head_conv(emulated_kernels):
                 t.grad = None
             y = PF.groupnorm_elu(x, g, bt, 1e-5, x2=second)
             gy = torch.rand_like(y) - 0.5
+            # the bf16 operand pair the apply pass wrote for the consuming convolution: hi = rn(y), lo = rn(y - hi), bit for bit
+            hi, lo, ver = y._pn_split
+            assert ver == y._version and torch.equal(hi.view(torch.int16), y.detach().to(torch.bfloat16).view(torch.int16))
+            assert torch.equal(lo.view(torch.int16), (y.detach() - hi.float()).to(torch.bfloat16).view(torch.int16))
+            assert PF._operands(y, PF.PRECISION_BF16X3)[0] is hi
+            seen = {}
+            def hook(gr):
+                seen["dx"] = getattr(gr, "_pn_split", None)
+            h = x.register_hook(hook)
             y.backward(gy)
+            h.remove()
+            if seen.get("dx") is not None:       # ... and of dx in the backward (the attribute travels with the tensor object)
+                dh, dl, _ = seen["dx"]
+                assert torch.equal(dh.view(torch.int16), x.grad.to(torch.bfloat16).view(torch.int16))
+                assert torch.equal(dl.view(torch.int16), (x.grad - dh.float()).to(torch.bfloat16).view(torch.int16))
             xd, x2d, gd, bd = (t.detach().double().requires_grad_(True) for t in (x, x2, g, bt))
             inp = xd if second is None else xd + x2d
             yr = F.elu(F.group_norm(inp.permute(0, 3, 1, 2), 16, gd, bd, 1e-5)).permute(0, 2, 3, 1)

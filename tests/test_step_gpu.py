@@ -74,7 +74,9 @@ def test_two_training_steps_match_the_reference(optimizer):
                     norm_ref = float(z["g0norm/" + prefix + k])
                     flat = p.grad.reshape(-1)
                     norm_got = float(flat.double().norm())
-                    tol = 5e-3 * norm_ref + 1e-7
+                    # absolute floor: a Conv3d bias in front of Conv2d + GroupNorm has a gradient that is zero up to border effects
+                    # -- what is left is mostly rounding (7.7e-4 for pack3.conv3d.bias against ~1 for its neighbours)
+                    tol = 5e-3 * norm_ref + 5e-6
                     worst = max(worst, (prefix + k, abs(norm_got - norm_ref) / tol), key=lambda t: t[1])
                     assert abs(norm_got - norm_ref) <= tol, (prefix + k, norm_got, norm_ref)
             print("worst gradient-norm error/bound after step 0: %s %.3f" % worst)
