@@ -286,31 +286,36 @@ def time_kernels(args, dev, pk):
     grouped = bool(_losses._grouped)
     shape_tag = "%dx%dx%d" % (B, H, W)
     nm_loss = ncu_metrics("loss_%s_%s" % ("grouped" if grouped else "tile", shape_tag))
-    nm_conv = ncu_metrics("conv_pack1_%s_%s" % (args.precision, shape_tag))
     res["roofline_loss"] = {"bound": "hbm", "kernel": ("loss_group_kernel" if grouped else "loss_tile_kernel") + " fwd+bwd (incl. prep launches)",
                             "achieved": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9 / pk["hbm_gbs"],
                             "traffic": (nm_loss or {}).get("dram_bytes"), "traffic_source": (nm_loss or {}).get("source"),
                             "traffic_commit": (nm_loss or {}).get("commit"),
                             "fwd_ms": t_f, "bwd_ms": t_b, "algorithmic_bytes": bytes_f + bytes_b, "peak_source": pk["source"]}
-    # pack1 convolution (tensor bound): [B,96,320,2048] x [64,2048,5,5]
+    # pack1 (tensor bound).  Reference formulation: Conv2d(2048 -> 64, 5x5) over the Conv3d-inflated tensor at H/2 x W/2
+    # (201.3 GFLOP per image).  What the step launches for it since round 2 is the FOLDED 7x7 convolution
+    # 256 -> 64 of the space-to-depth tensor (12544/51200 of those MACs) -- the dominant conv_igemm launch of the step.
     h2, w2, cin, cout, k = H // 2, W // 2, 2048, 64, 5
-    x = torch.rand(B, h2, w2, cin, device=dev) - 0.5
-    w = (torch.rand(cout, cin, k, k, device=dev) - 0.5) * 0.01
-    with torch.no_grad():
-        for _ in range(2):
-            PF.conv2d(x, w, None)
-        prec = PF.get_precision()
-        wp, wlo = PF._pack_weight(w, False, prec)
-        xh, xlo = PF._operands(x, prec)
-        t_c = timed(lambda: PF._conv_raw(xh, xlo, wp, wlo, None, cout, k, prec), iters=5)
-    flops = 2.0 * B * h2 * w2 * cout * cin * k * k
+    prec = PF.get_precision()
+    flops_ref = 2.0 * B * h2 * w2 * cout * cin * k * k
     tf32_peak = pk["bf16_tflops"] / (1.0 if PF.is_bf16(prec) else 2.0)
-    if PF.pack_fold_enabled(h2 * w2):
-        # the same pack1 block evaluated as ONE folded 7x7 convolution of the space-to-depth tensor (folded.py): the nine
-        # weight folds + space-to-depth + operand split + weight packing + conv_igemm + frame terms, i.e. everything the
-        # forward of the block launches between its input x [B,H,W,64] and the GroupNorm.  Algorithmic FLOPs stay the
-        # reference's (Conv2d over the 8x-inflated channel count), the Conv3d stencil's 5.6 GFLOP not counted.
+    peak_source = pk["source"] + (" cuBLAS bf16" if PF.is_bf16(prec) else " cuBLAS bf16 / 2 (tf32 dense rate is half the bf16 rate)")
+    w = (torch.rand(cout, cin, k, k, device=dev) - 0.5) * 0.01
+    folded_path = PF.pack_fold_enabled(h2 * w2)
+    if folded_path:
+        kf, cf = k + 2, cin // 8
+        xs = torch.rand(B, h2, w2, cf, device=dev) - 0.5
+        wf = (torch.rand(cout, cf, kf, kf, device=dev) - 0.5) * 0.01
+        with torch.no_grad():
+            wp, wlo = PF._pack_weight(wf, False, prec)
+            xh, xlo = PF._operands(xs, prec)
+            for _ in range(2):
+                PF._conv_raw(xh, xlo, wp, wlo, None, cout, kf, prec)
+            t_c = timed(lambda: PF._conv_raw(xh, xlo, wp, wlo, None, cout, kf, prec), iters=5)
+        flops = 2.0 * B * h2 * w2 * cout * cf * kf * kf
+        kernel_name, tag = "conv_igemm_kernel (pack1 folded: %d -> %d, %dx%d at %dx%d, %s)" % (cf, cout, kf, kf, h2, w2, args.precision), "folded"
+        # the whole block as the step runs it: nine weight folds + space-to-depth + operand split + weight packing +
+        # conv_igemm + frame terms, against the REFERENCE formulation's FLOPs
         from packnet_sfm_b200 import folded
         x1 = torch.rand(B, H, W, 64, device=dev) - 0.5
         w3 = torch.rand(8, 1, 3, 3, 3, device=dev) - 0.5
@@ -319,24 +324,32 @@ def time_kernels(args, dev, pk):
             for _ in range(2):
                 folded.pack_conv_folded(x1, w, b2, w3, b3, PF.conv2d)
             t_fold = timed(lambda: folded.pack_conv_folded(x1, w, b2, w3, b3, PF.conv2d), iters=5)
-        res["roofline_pack1_folded"] = {"bound": "tensor", "kernel": "pack1 block forward, folded: fold + s2d + split + pack + "
-                                        "conv_igemm 7x7 (n=256 -> 64) + frame terms (%s)" % args.precision,
-                                        "achieved": flops / (t_fold * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                                        "frac": flops / (t_fold * 1e-3) / 1e12 / tf32_peak, "traffic": None, "ms": t_fold,
-                                        "algorithmic_flops": flops, "executed_mac_ratio": 12544.0 / 51200.0,
-                                        "note": "achieved counts the REFERENCE formulation's FLOPs; the folded convolution executes "
-                                                "12544/51200 of them (x3 bf16 products)"}
-    res["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (pack1 conv2d, %s)" % args.precision,
+        res["roofline_pack1_block"] = {"bound": "tensor", "kernel": "pack1 block forward as launched: folds + s2d + split + pack + "
+                                       "conv_igemm 7x7 + frame terms (%s)" % args.precision,
+                                       "achieved": flops_ref / (t_fold * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                                       "frac": flops_ref / (t_fold * 1e-3) / 1e12 / tf32_peak, "traffic": None, "ms": t_fold,
+                                       "algorithmic_flops": flops_ref, "executed_mac_ratio": 12544.0 / 51200.0,
+                                       "note": "achieved counts the REFERENCE formulation's FLOPs (Conv2d over the 8x-inflated "
+                                               "channel count); the folded convolution executes 12544/51200 of them"}
+    else:
+        x = torch.rand(B, h2, w2, cin, device=dev) - 0.5
+        with torch.no_grad():
+            wp, wlo = PF._pack_weight(w, False, prec)
+            xh, xlo = PF._operands(x, prec)
+            for _ in range(2):
+                PF._conv_raw(xh, xlo, wp, wlo, None, cout, k, prec)
+            t_c = timed(lambda: PF._conv_raw(xh, xlo, wp, wlo, None, cout, k, prec), iters=5)
+        flops = flops_ref
+        kernel_name, tag = "conv_igemm_kernel (pack1 conv2d 2048 -> 64, 5x5, %s)" % args.precision, "pack1"
+    nm_conv = ncu_metrics("conv_%s_%s_%s" % (tag, args.precision, shape_tag))
+    res["roofline"] = {"bound": "tensor", "kernel": kernel_name,
                        "achieved": flops / (t_c * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                        "frac": flops / (t_c * 1e-3) / 1e12 / tf32_peak,
                        "traffic": (nm_conv or {}).get("dram_bytes"), "traffic_source": (nm_conv or {}).get("source"),
                        "traffic_commit": (nm_conv or {}).get("commit"),
                        "tensor_pipe_active_pct_ncu": (nm_conv or {}).get("tensor_pipe_active_pct"),
-                       "ms": t_c,
-                       "algorithmic_flops": flops,
-                       "mma_products_per_flop": 3 if PF.is_split(prec) else 1,
-                       "peak_source": pk["source"] + (" cuBLAS bf16" if PF.is_bf16(prec) else
-                                                      " cuBLAS bf16 / 2 (tf32 dense rate is half the bf16 rate)")}
+                       "ms": t_c, "algorithmic_flops": flops,
+                       "mma_products_per_flop": 3 if PF.is_split(prec) else 1, "peak_source": peak_source}
     return res
 
 
