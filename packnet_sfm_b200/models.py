@@ -6,6 +6,7 @@ the self-supervised step can run where /root/reference is absent (the GPU box):
 
 With the reference on PYTHONPATH, packnet_sfm_b200.dropin.install() makes the reference's own SfmModel /
 SelfSupModel / ModelWrapper use PackNet01 and MultiViewPhotometricLoss from this package unchanged."""
+import os
 import random
 
 import torch
@@ -78,13 +79,15 @@ class SelfSupModel(nn.Module):
     SelfSupModel.forward (:63-97).  Defaults = the yacs training defaults (configs/default_config.py:88-103)."""
 
     def __init__(self, depth_net=None, pose_net=None, rotation_mode='euler', flip_lr_prob=0.5,
-                 upsample_depth_maps=True, fuse_upsample=True, **loss_kwargs):
+                 upsample_depth_maps=True, fuse_upsample=True, pose_stream=True, **loss_kwargs):
         """fuse_upsample: with upsample_depth_maps, hand the four maps to the loss at their own resolution and let its kernel
         read them nearest-upsampled (losses.MultiViewPhotometricLoss.forward(nearest_upsample=True)); False = the three
         F.interpolate copies of the reference's glue.  forward() returns 'inv_depths' at the network's resolutions then."""
         super().__init__()
         require_fp32_library_convolutions()
         self.fuse_upsample = fuse_upsample
+        self.pose_stream = pose_stream and os.environ.get("PN_POSE_STREAM", "1") != "0"
+        self._side_stream = None
         self.depth_net = depth_net if depth_net is not None else PackNet01(version='1A')
         self.pose_net = pose_net if pose_net is not None else PoseNet(nb_ref_imgs=2, rotation_mode=rotation_mode)
         self.rotation_mode = rotation_mode
@@ -114,8 +117,26 @@ class SelfSupModel(nn.Module):
         return [Pose.from_vec(pose_vec[:, i], self.rotation_mode) for i in range(pose_vec.shape[1])]
 
     def forward(self, batch, return_logs=False, progress=0.0):
+        poses = None
+        side = None
+        if 'rgb_context' in batch and self.pose_stream and batch['rgb'].is_cuda:
+            # PoseNet (library convolutions: 1.9 ms of small launches that leave most SMs idle) shares nothing with the depth
+            # network before the loss: run it on a second stream next to PackNet01.  Autograd replays each backward op on the
+            # stream of its forward, so the two backward passes overlap as well; a captured step keeps the fork / join.
+            cur = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                poses = self.compute_pose_net(batch['rgb'], batch['rgb_context'])
         inv_depths = self.compute_depth_net(batch['rgb'])
-        poses = self.compute_pose_net(batch['rgb'], batch['rgb_context']) if 'rgb_context' in batch else None
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            for p in poses:
+                p.mat.record_stream(torch.cuda.current_stream())
+        elif 'rgb_context' in batch:
+            poses = self.compute_pose_net(batch['rgb'], batch['rgb_context'])
         out = {'inv_depths': inv_depths, 'poses': poses}
         if not self.training:
             return out

@@ -68,18 +68,21 @@ def test_two_training_steps_match_the_reference(optimizer):
             for j, pz in enumerate(out["poses"]):
                 # PoseNet runs on the library's fp32 convolutions (models.require_fp32_library_convolutions)
                 assert torch.allclose(pz.mat.detach().cpu(), z["pose%d_step0" % j], atol=2e-6, rtol=1e-4)
-            worst = ("", 0.0)
+            # Gradient norms against the reference's.  The bound is NOT a rounding bound: a handful of pixels whose two best
+            # candidates of the per-pixel minimum tie to ~1e-6 resolve differently from run to run (split-K atomics reorder the
+            # forward sums) and on a 64x96 image each of them moves a decoder gradient by ~1e-3 of its norm; the tight
+            # comparison of the two weight storages below (same run-to-run noise, no reference) is the rounding-level check.
+            devs = []
             for prefix, net in (("depth.", model.depth_net), ("pose.", model.pose_net)):
                 for k, p in net.named_parameters():
                     norm_ref = float(z["g0norm/" + prefix + k])
-                    flat = p.grad.reshape(-1)
-                    norm_got = float(flat.double().norm())
-                    # absolute floor: a Conv3d bias in front of Conv2d + GroupNorm has a gradient that is zero up to border effects
-                    # -- what is left is mostly rounding (7.7e-4 for pack3.conv3d.bias against ~1 for its neighbours)
-                    tol = 5e-3 * norm_ref + 5e-6
-                    worst = max(worst, (prefix + k, abs(norm_got - norm_ref) / tol), key=lambda t: t[1])
-                    assert abs(norm_got - norm_ref) <= tol, (prefix + k, norm_got, norm_ref)
-            print("worst gradient-norm error/bound after step 0: %s %.3f" % worst)
+                    norm_got = float(p.grad.reshape(-1).double().norm())
+                    devs.append((abs(norm_got - norm_ref) / (1.5e-2 * norm_ref + 5e-6), prefix + k, norm_got, norm_ref))
+            devs.sort(reverse=True)
+            print("largest gradient-norm deviations from the reference after step 0 (error / bound, name, ours, reference):")
+            for d in devs[:6]:
+                print("   %.3f %s %.6e %.6e" % d)
+            assert devs[0][0] <= 1.0, devs[:3]
         opt.step()
         # Adam's first steps move every element by about lr * sign(g): elements whose gradient is within rounding of zero may
         # go the other way, so the bar is a fraction of samples within 10 % of lr, not a norm
@@ -88,8 +91,46 @@ def test_two_training_steps_match_the_reference(optimizer):
         keys = [k for k in z if k.startswith("p%d/" % step)]
         assert len(keys) >= 8
         for key in keys:
+            if float(z["g0norm/" + key.split("/", 1)[1]]) < 1e-6:
+                continue        # gradient = rounding noise (a bias in front of a one-channel-per-group GroupNorm): Adam moves it +-lr at random
             p = named[key.split("/", 1)[1]].detach().reshape(-1)
             n = z[key].numel()
             got = p[strided_index(p.numel(), n).to(DEV)].cpu()
             close = ((got - z[key]).abs() <= 2e-5).float().mean().item()
             assert close >= 0.97, (key, close)
+
+
+def test_stored_and_plain_weight_storage_give_the_same_gradients_and_step():
+    """The same model twice on the kernels of this repo: convolution weights stored in the engine's layout (tiles from the
+    optimizer launch, weight gradients accumulated in the flat buffer) against plain OIHW storage (packed per call, gradients
+    unpacked).  Same arithmetic, so every gradient must agree to the run-to-run noise of the split-K atomics, and so must the
+    parameters after one optimizer step (where |g| is above the noise)."""
+    from packnet_sfm_b200 import optim
+    from packnet_sfm_b200.networks import native_conv_weights
+    z = load_golden("step_2x64x96")
+    batch = _batch(z)
+    res = []
+    for stored in (True, False):
+        model = _model()
+        native = native_conv_weights(model.depth_net, (int(z["H"]), int(z["W"]))) if stored else ()
+        opt = optim.FlatAdam([{"params": list(model.depth_net.parameters())}, {"params": list(model.pose_net.parameters())}], lr=2e-4,
+                             native=native)
+        opt.zero_grad()
+        out = model(batch)
+        out["loss"].backward()
+        opt.collect_grads()
+        torch.cuda.synchronize()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        opt.step()
+        res.append((float(out["loss"].item()), grads, {k: p.detach().clone() for k, p in model.named_parameters()}))
+    (l1, g1, p1), (l0, g0, p0) = res
+    assert abs(l1 - l0) <= 1e-6 * abs(l0)
+    devs = sorted(((float((g1[k].double() - g0[k].double()).norm() / (g0[k].double().norm() + 1e-12)), k) for k in g0), reverse=True)
+    print("largest relative gradient differences stored vs plain:", [(round(d, 6), k) for d, k in devs[:5]])
+    assert devs[0][0] < 2e-3, devs[:5]
+    assert sorted(d for d, _ in devs)[len(devs) // 2] < 2e-5          # the typical tensor: rounding level
+    for k in p0:
+        moved = (p1[k] - p0[k]).abs()
+        big = g0[k].abs() > 1e-3 * g0[k].abs().max()
+        if big.any():      # where the gradient is above the noise both runs step the same way
+            assert float((moved[big] > 1e-5).float().mean()) < 0.02, (k, float(moved[big].max()))
