@@ -105,41 +105,42 @@ def test_two_training_steps_match_the_reference(optimizer):
 
 
 def test_stored_and_plain_weight_storage_give_the_same_gradients_and_step():
-    """The same model twice on the kernels of this repo: convolution weights stored in the engine's layout (tiles from the
-    optimizer launch, weight gradients accumulated in the flat buffer) against plain OIHW storage (packed per call, gradients
-    unpacked).  Same arithmetic, so every gradient must agree to the run-to-run noise of the split-K atomics, and so must the
-    parameters after one optimizer step (where |g| is above the noise)."""
-    from packnet_sfm_b200 import optim
+    """PackNet01 twice on the kernels of this repo with a FIXED output gradient: convolution weights stored in the engine's layout
+    (tiles from the optimizer launch, weight gradients accumulated in the flat buffer) against plain OIHW storage (packed per
+    call, gradients unpacked).  Same arithmetic: every gradient agrees to the run-to-run noise of the split-K / weight-gradient
+    atomics (measured with tools/determinism_probe.py: median 3e-5, worst 6e-5), and so do the parameters after one optimizer
+    step wherever |g| is above that noise.  (Through the photometric loss the comparison would be meaningless at this level:
+    its sign() terms turn the 5e-6 run-to-run noise of the depth maps into ~1 % of every gradient, in the reference as here.)"""
+    from packnet_sfm_b200 import optim, synthetic
     from packnet_sfm_b200.networks import native_conv_weights
-    z = load_golden("step_2x64x96")
-    batch = _batch(z)
+    x = synthetic.make_frames(2, 64, 96, seed=9)["rgb"].to(DEV)
+    g = torch.Generator().manual_seed(4)
+    gys = None
     res = []
     for stored in (True, False):
-        model = _model()
-        native = native_conv_weights(model.depth_net, (int(z["H"]), int(z["W"]))) if stored else ()
-        opt = optim.FlatAdam([{"params": list(model.depth_net.parameters())}, {"params": list(model.pose_net.parameters())}], lr=2e-4,
-                             native=native)
+        net = _model().depth_net
+        opt = optim.FlatAdam(net.parameters(), lr=2e-4, native=native_conv_weights(net, (64, 96)) if stored else ())
+        assert (len(opt.natives) > 40) == stored
         opt.zero_grad()
-        out = model(batch)
-        out["loss"].backward()
+        outs = net(x)["inv_depths"]
+        if gys is None:
+            gys = [(torch.rand(o.shape, generator=g) - 0.5).to(DEV) for o in outs]
+        torch.autograd.backward(outs, gys)
         opt.collect_grads()
         torch.cuda.synchronize()
-        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+        before = {k: p.detach().clone() for k, p in net.named_parameters()}
         opt.step()
-        res.append((float(out["loss"].item()), grads, {k: p.detach().clone() for k, p in model.named_parameters()}))
-    (l1, g1, p1), (l0, g0, p0) = res
-    assert abs(l1 - l0) <= 1e-6 * abs(l0)
+        res.append(([o.detach().clone() for o in outs], grads, {k: p.detach() - before[k] for k, p in net.named_parameters()}))
+    (o1, g1, d1), (o0, g0, d0) = res
+    for a, b in zip(o1, o0):
+        assert rel_l2(a, b) < 5e-5
     devs = sorted(((float((g1[k].double() - g0[k].double()).norm() / (g0[k].double().norm() + 1e-12)), k) for k in g0
-                   if float(g0[k].double().norm()) > 1e-6), reverse=True)          # (not the pure-noise gradients)
-    print("largest relative gradient differences stored vs plain:", [(round(d, 6), k) for d, k in devs[:5]])
-    # Two runs of the SAME arithmetic: the typical tensor agrees to rounding.  A few decoder tensors do not -- the photometric
-    # loss of a randomly initialised network has pixels whose projection passes close to the camera plane (huge d(ix)/d(depth))
-    # and whose winner of the per-pixel minimum flips with the last bit of the forward (split-K atomics): measured 2-4 % on
-    # unpack2 / disp2 / iconv2 at 64x96, in both storages alike.
-    assert sorted(d for d, _ in devs)[len(devs) // 2] < 2e-5
-    assert devs[0][0] < 8e-2, devs[:5]
-    for k in p0:
-        moved = (p1[k] - p0[k]).abs()
-        big = g0[k].abs() > 1e-3 * g0[k].abs().max()
-        if big.any():      # where the gradient is above the noise both runs step the same way
-            assert float((moved[big] > 1e-5).float().mean()) < 0.02, (k, float(moved[big].max()))
+                   if float(g0[k].double().norm()) > 1e-6), reverse=True)
+    print("largest relative gradient differences stored vs plain:", [(round(d, 7), k) for d, k in devs[:5]])
+    assert devs[0][0] < 5e-4, devs[:5]
+    assert sorted(d for d, _ in devs)[len(devs) // 2] < 1e-4
+    for k in d0:
+        big = g0[k].abs() > 1e-2 * g0[k].abs().max()
+        if big.any():      # where the gradient is above the noise both runs step the same way (first Adam step: -lr * sign(g))
+            assert float(((d1[k] - d0[k]).abs()[big] > 1e-5).float().mean()) < 0.01, k
