@@ -447,6 +447,7 @@ def run_ours(args):
         log("warm-up step %d: %.1f ms (loss %.5f)" % (i, (time.time() - t_w) * 1e3, float(state["loss"].item())))
     eager_step = step
     graph_info = None
+    graphs = None
     if args.graph:
         # Whole-step capture: the only host-side decision of a step is the random left-right flip of the depth
         # network (SfmModel.py:81-90) -> one graph per outcome, chosen every step by the same random.random() draw.
@@ -555,9 +556,22 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_steps)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        # NCCL wants every CUDA graph that captured one of its collectives destroyed before the communicator (gpurun r02i: with
+        # the step graphs alive destroy_process_group never returned and the ranks sat until the launcher's timeout)
+        step = None
+        if graphs is not None:
+            graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
+        bye = threading.Timer(20.0, lambda: os._exit(0))      # the JSON line is out: never let teardown hold the launcher
+        bye.daemon = True
+        bye.start()
         dist.destroy_process_group()
+        bye.cancel()
 
 
 if __name__ == "__main__":
