@@ -94,7 +94,7 @@ def test_two_training_steps_match_the_reference(optimizer):
         named.update({("pose." + k): p for k, p in model.pose_net.named_parameters()})
         keys = [k for k in z if k.startswith("p%d/" % step)]
         assert len(keys) >= 8
-        worst = []
+        worst, pooled = [], [0, 0]
         for key in keys:
             if float(z["g0norm/" + key.split("/", 1)[1]]) < 1e-6:
                 continue        # gradient = rounding noise (a bias in front of a one-channel-per-group GroupNorm): Adam moves it +-lr at random
@@ -103,10 +103,13 @@ def test_two_training_steps_match_the_reference(optimizer):
             got = p[strided_index(p.numel(), n).to(DEV)].cpu()
             close = ((got - z[key]).abs() <= 2e-5).float().mean().item()
             worst.append((close, key))
+            pooled[0] += int(((got - z[key]).abs() <= 2e-5).sum())
+            pooled[1] += n
             # step 1 is a second update on parameters that already differ by +-lr wherever step 0's gradient was noise, and its
-            # own gradient went through the flipped network: the fraction of untouched-by-noise samples falls from 0.97+ to
-            # 0.93-0.99 on the first layers (measured on the B200 over repeated runs: 0.947 on pre_calc.conv_base.weight)
-            assert close >= (0.97 if step == 0 else 0.90), (key, close)
+            # own gradient went through the flipped network: per tensor the fraction falls to 0.93-0.99 on the first layers and
+            # to 14/16 on a 16-element PoseNet bias (measured on the B200 over repeated runs); the pooled fraction stays > 0.98
+            assert close >= (0.97 if step == 0 else (0.90 if n >= 64 else 0.74)), (key, close)
+        assert pooled[0] >= 0.97 * pooled[1], pooled
         worst.sort()
         print("step %d: smallest fractions of parameter samples within 2e-5 of the reference:" % step, [(round(c, 4), k) for c, k in worst[:3]])
 
