@@ -29,6 +29,17 @@ int check_launch(const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+int sm_count() {
+  static std::atomic<int> cache[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  cache[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
 // ---- per-call device timing (diagnostics: pn_trace_enable / pn_trace_dump) ----
 struct TraceRec { char tag[112]; cudaEvent_t e0, e1; };
 static std::vector<TraceRec> g_trace;

@@ -25,6 +25,8 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 // launch accounting behind pn_launch_count()
 void count_launch(int n = 1);
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a B200): grid sizing / wave counting
+int sm_count();
 // device-time trace of one C-ABI call (no-op unless pn_trace_enable(1))
 struct TraceScope {
   TraceScope(cudaStream_t stream, const char* fmt, ...);

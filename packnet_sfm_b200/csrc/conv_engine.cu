@@ -921,14 +921,52 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   P.nsplit = is_split(d->precision) ? 3 : 1;
   P.kc = kc; P.bf16 = bf16 ? 1 : 0;
   const int nops = (P.nsplit == 3) ? 2 : 1;
-  // tile rows: tall tiles for big maps, batch folding for small ones
-  P.th = TILE_ROWS;
-  while (P.th > 1 && P.th / 2 >= d->height) P.th /= 2;
+  // Tile rows (th) x folded images (nb = 16 / th).  The default is the tallest tile that the map fills; on the small maps
+  // the choice is made by counting WAVES of the one-CTA-per-SM grid (r02l layer table: 512->512 3x3 at 12x40 ran 160 CTAs =
+  // two waves, the second one 12 CTAs wide, at 90 TFLOP/s; 4 rows x 4 images gives 15 full tiles -> 120 CTAs, one wave of
+  // half the length).  cost = (work items of the busiest CTA) x (its share of the reduction loop) + an epilogue term.
+  const int nblocks_c = bt ? (d->cout + (d->cout <= 64 ? 64 : 128) - 1) / (d->cout <= 64 ? 64 : 128)
+                           : (d->cout + bn_of(d->cout) - 1) / bn_of(d->cout);
+  const int cchunks_c = (d->cin + kc - 1) / kc;
+  const int sms = sm_count();
+  auto plan_of = [&](int th, int* ks_out) -> double {
+    const int nb = TILE_ROWS / th;
+    const int tiles = ((d->width + TILE_W - 1) / TILE_W) * ((d->height + th - 1) / th) * ((d->batch + nb - 1) / nb);
+    const int base = tiles * nblocks_c;
+    const int taps = d->ksize * d->ksize;
+    int ks = 1;
+    if (base < sms) {
+      ks = sms / base;
+      if (ks > cchunks_c) ks = cchunks_c;
+      const int per = (cchunks_c + ks - 1) / ks;
+      ks = (cchunks_c + per - 1) / per;   // no empty splits
+    }
+    *ks_out = ks;
+    const int per = (cchunks_c + ks - 1) / ks;
+    const int rounds = (base * ks + sms - 1) / sms;            // persistent loop / waves of the plain grid
+    const bool halo = (nb == 1 && d->ksize > 1);
+    // per-tap staging re-fetches the activation tile for every tap (L2 traffic, one TMA per item): a few per cent
+    const double item = halo ? 1.0 : 1.06;
+    return rounds * (per * taps * item + (ks > 1 ? 4.0 : 2.0));
+  };
+  int th_auto = TILE_ROWS;
+  while (th_auto > 1 && th_auto / 2 >= d->height) th_auto /= 2;
+  P.th = th_auto;
+  int ks_plan = 1;
+  if (!(d->debug_flags & 8192) && d->mode == PN_CONV_MODE_AUTO) {
+    double best = plan_of(th_auto, &ks_plan);
+    for (int th = th_auto / 2; th >= 1 && TILE_ROWS / th <= d->batch; th /= 2) {
+      int ks_c;
+      const double c = plan_of(th, &ks_c);
+      if (c < 0.93 * best) { best = c; P.th = th; ks_plan = ks_c; }
+    }
+  } else {
+    plan_of(P.th, &ks_plan);
+  }
   {
-    // tuning knob (debug_flags bits 16..19): force the tile height to 1, 2, 4 or 8 rows -- e.g. 4 rows x 2 images on a
-    // 12-row map fills every MMA row where the default 8-row tile leaves a quarter empty (but gives up halo staging)
+    // tuning knob (debug_flags bits 16..19): force the tile height to 1, 2, 4 or 8 rows
     const int forced_th = (d->debug_flags >> 16) & 15;
-    if (forced_th == 1 || forced_th == 2 || forced_th == 4 || forced_th == 8) P.th = forced_th;
+    if (forced_th == 1 || forced_th == 2 || forced_th == 4 || forced_th == 8) { P.th = forced_th; plan_of(P.th, &ks_plan); }
   }
   P.nb = TILE_ROWS / P.th;
   P.halo = (d->mode == PN_CONV_MODE_HALO) || (d->mode == PN_CONV_MODE_AUTO && P.nb == 1 && d->ksize > 1);
@@ -996,15 +1034,18 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
     rc = make_map(&tmAlo, x_lo ? x_lo : x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, bf16);
     if (rc) return rc;
   }
-  // small maps: split the channel-chunk loop so that the grid covers the 148 SMs
+  // small maps: split the channel-chunk loop so that the grid covers the SMs without spilling into a second wave
   {
-    const int base = P.tiles_x * P.tiles_y * bgroups * ((d->cout + bn - 1) / bn);
-    int ks = 1;
-    if (base < 120) ks = (148 + base - 1) / base;
-    if (ks > P.cchunks) ks = P.cchunks;
-    if (ks > 1) {
-      const int per = (P.cchunks + ks - 1) / ks;
-      ks = (P.cchunks + per - 1) / per;   // no empty splits
+    int ks = ks_plan;
+    if (d->debug_flags & 8192) {      // round-1 rule (A/B): round the split UP to at least 148 CTAs
+      const int base = P.tiles_x * P.tiles_y * bgroups * ((d->cout + bn - 1) / bn);
+      ks = 1;
+      if (base < 120) ks = (148 + base - 1) / base;
+      if (ks > P.cchunks) ks = P.cchunks;
+      if (ks > 1) {
+        const int per = (P.cchunks + ks - 1) / ks;
+        ks = (P.cchunks + per - 1) / per;   // no empty splits
+      }
     }
     P.ksplits = ks;
     if (ks > 1) PN_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)d->batch * d->height * d->width * d->cout, stream));
@@ -1013,10 +1054,10 @@ static int conv_forward(const pn_conv_desc* d, const void* x, const void* x_lo, 
   // with two accumulator sets in TMEM when they fit (debug flag 4096 forces one tile per CTA)
   P.nblocks = (d->cout + bn - 1) / bn;
   P.nwork = P.tiles_x * P.tiles_y * bgroups * P.nblocks;
-  const bool persistent = (P.ksplits == 1) && (P.nwork > 148) && !(d->debug_flags & 4096);
+  const bool persistent = (P.ksplits == 1) && (P.nwork > sms) && !(d->debug_flags & 4096);
   P.nsets = (persistent && 2 * P.set_cols <= 512) ? 2 : 1;
   P.tmem_cols = pow2_cols(P.nsets * P.set_cols);
-  dim3 grid(persistent ? 148 : P.nwork, 1, P.ksplits);
+  dim3 grid(persistent ? sms : P.nwork, 1, P.ksplits);
   auto launch = [&](auto kern) -> int {
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NTHREADS_IGEMM, smem, stream>>>(tmA, tmAlo, P);
@@ -1098,9 +1139,25 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* x_lo, co
   P.ntiles = d->batch * P.tiles_x * P.tiles_y;
   const int mblocks = (P.kpad + 127) / 128, nblocks = (d->cout + bn - 1) / bn;
   const int base_ctas = mblocks * P.tap_groups * nblocks;
-  int psplits = (2 * 148 + base_ctas - 1) / base_ctas;
-  if (psplits > P.ntiles) psplits = P.ntiles;
-  if (psplits < 1) psplits = 1;
+  // Pixel split: the kernel runs one CTA per SM, so the grid is counted in WAVES.  cost(ps) = waves x (pixel tiles per CTA +
+  // an epilogue term for the red.add of the CTA's accumulators); fewest splits among the near-best (fewer atomics).
+  // (round 1 aimed at 2 x 148 CTAs whatever the wave count: 512->512 3x3 at 12x40 ran 320 CTAs = 2.2 waves.)
+  int psplits = 1;
+  if (d->debug_flags & 8192) {
+    psplits = (2 * 148 + base_ctas - 1) / base_ctas;
+    if (psplits > P.ntiles) psplits = P.ntiles;
+    if (psplits < 1) psplits = 1;
+  } else {
+    const int sms = sm_count();
+    double best = 1e30;
+    for (int ps = 1; ps <= P.ntiles; ++ps) {
+      const int per = (P.ntiles + ps - 1) / ps;
+      if (ps > 1 && (P.ntiles + per - 1) / per != ps) continue;        // same work per CTA with fewer CTAs exists
+      const int waves = (base_ctas * ps + sms - 1) / sms;
+      const double c = waves * (per + 1.5);
+      if (c < 0.97 * best) { best = c; psplits = ps; }
+    }
+  }
   {
     const int per = (P.ntiles + psplits - 1) / psplits;
     psplits = (P.ntiles + per - 1) / per;

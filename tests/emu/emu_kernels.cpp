@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
 }
 int check_launch(const char*) { return 0; }
 void count_launch(int) {}
+int sm_count() { return 148; }
 TraceScope::TraceScope(cudaStream_t stream, const char*, ...) : stream_(stream), index_(-1) {}
 TraceScope::~TraceScope() {}
 }  // namespace pn
