@@ -1110,8 +1110,24 @@ static int conv_wgrad(const pn_conv_desc* d, const void* x, const void* x_lo, co
   if (tg > taps) tg = taps;
   if (d->debug_flags & 2) tg = 1;
   if (P.pair && tg > (taps + 1) / 2) tg = (taps + 1) / 2;
-  P.tg = tg;
-  P.tap_groups = P.pair ? ((taps + 1) / 2 + tg - 1) / tg : (taps + tg - 1) / tg;
+  {
+    // Balanced tap groups: every CTA of a (channel block, pixel split) loads the same tiles whatever its tap count, so a
+    // short last group (9 taps as 8 + 1: r02n ncu of 136 -> 64 3x3 at 192x640, SMs 60 % active) idles its SMs.  Among
+    // gmin .. gmin + 2 groups take the one with the least padded work groups x ceil(units / groups), fewest groups on ties.
+    const int units = P.pair ? (taps + 1) / 2 : taps;      // accumulators (taps or tap pairs) over all groups
+    const int gmin = (units + tg - 1) / tg;
+    int groups = gmin;
+    if (!(d->debug_flags & 8192)) {
+      int best = gmin * ((units + gmin - 1) / gmin);
+      for (int g = gmin + 1; g <= gmin + 2 && g <= units; ++g) {
+        const int padded = g * ((units + g - 1) / g);
+        if (padded < best) { best = padded; groups = g; }
+      }
+      tg = (units + groups - 1) / groups;
+    }
+    P.tg = tg;
+    P.tap_groups = (units + tg - 1) / tg;
+  }
   P.pitch = TILE_W + d->ksize - 1;
   // pixel tile height: as tall as shared memory allows with >= 2 stages (X-patch blocks + dZ blocks per stage, hi and lo
   // for the x3 precisions); bf16 consumes tile rows in pairs (K = 16 pixels per MMA), so its height is even
