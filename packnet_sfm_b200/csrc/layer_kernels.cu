@@ -21,6 +21,7 @@
 #include <cstring>
 #else
 #include <cuda_bf16.h>
+#include <cooperative_groups.h>
 #endif
 
 namespace pn {
@@ -911,6 +912,69 @@ __global__ void __launch_bounds__(256) gn_elu_apply_kernel(const float* __restri
   }
 }
 
+// The same pass with the thread <-> (pixel lane, float4 column) mapping of the backward kernels: one CTA per (pixel range,
+// sample), the four channels of a thread fixed -- gamma / beta / mean / rstd live in registers and the loop has no 64-bit
+// division (r02n ncu: the flat-index kernel above moved 3.0 TB/s on the 192x640 maps where the backward apply pass moves 5.1).
+__global__ void __launch_bounds__(256) gn_elu_apply4_kernel(const float* __restrict__ x, const float* __restrict__ x2, int HW, int C,
+                                                            float* __restrict__ mr, const double* __restrict__ sums, double cnt,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                            int pixels_per_cta, float* __restrict__ y, int out_cstride, int out_coffset,
+                                                            uint2* __restrict__ y_hi, uint2* __restrict__ y_blo) {
+  __shared__ float s_mr[32];
+  const int b = blockIdx.y, cg = C / 16, c4 = C / 4;
+  if (threadIdx.x < 16) {
+    const int i = b * 16 + threadIdx.x;
+    const double m = sums[2 * i] / cnt;
+    double var = sums[2 * i + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    s_mr[2 * threadIdx.x] = mean; s_mr[2 * threadIdx.x + 1] = rstd;
+    if (blockIdx.x == 0) { mr[2 * i] = mean; mr[2 * i + 1] = rstd; }
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pixels_per_cta, p1 = min(p0 + pixels_per_cta, HW);
+  const int lanes = blockDim.x / c4 > 0 ? blockDim.x / c4 : 1;
+  const int col = threadIdx.x % c4, pl = threadIdx.x / c4;
+  if (pl >= lanes) return;
+  float mean[4], rstd[4], gm[4], bt[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = col * 4 + k, g = c / cg;
+    mean[k] = s_mr[2 * g]; rstd[k] = s_mr[2 * g + 1];
+    gm[k] = __ldg(gamma + c); bt[k] = __ldg(beta + c);
+  }
+  auto load = [&](int p) {
+    const size_t o = ((size_t)b * HW + p) * C + col * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + o);
+    if (x2) {
+      const float4 u = *reinterpret_cast<const float4*>(x2 + o);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    return v;
+  };
+  auto apply = [&](int p, const float4& v) {
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float z = (in[k] - mean[k]) * rstd[k] * gm[k] + bt[k];
+      out[k] = z > 0.0f ? z : expm1f(z);   // nn.ELU(alpha=1)
+    }
+    const size_t pix = (size_t)b * HW + p;
+    *reinterpret_cast<float4*>(y + pix * out_cstride + out_coffset + col * 4) = make_float4(out[0], out[1], out[2], out[3]);
+    if (y_hi) store_split4(y_hi, y_blo, (pix * C + col * 4) >> 2, out);
+  };
+  int p = p0 + pl;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = load(p + u * lanes);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) apply(p + u * lanes, v[u]);
+  }
+  for (; p < p1; p += lanes) apply(p, load(p));
+}
+
 // backward, pass 1: per (b, c): sum dz, sum dz*xhat with dz = dy * ELU'(z) (ELU' = 1 for y>0 else y+1)
 //   -> bc[b][c][2] (double, zeroed)
 __global__ void __launch_bounds__(256) gn_elu_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ x2,
@@ -1530,6 +1594,10 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   return check_launch("stencil_wgrad_kernel");
 }
 
+#ifndef PN_EMULATE
+#include "gn_cluster_kernel.cuh"
+#endif
+
 static int groupnorm_elu_forward_impl(const float* x, const float* x2, const float* gamma, const float* beta, float eps, float* y,
                                       float* y_lo, double* stats, int batch, int hw, int channels, int out_cstride, int out_coffset,
                                       void* y_hi_bf16, void* y_lo_bf16, cudaStream_t stream) {
@@ -1539,6 +1607,24 @@ static int groupnorm_elu_forward_impl(const float* x, const float* x2, const flo
   PN_REQUIRE(out_cstride % 4 == 0 && out_coffset % 4 == 0, PN_ERR_ALIGNMENT, "pn_groupnorm_elu_forward: output channel window");
   PN_REQUIRE((!y_hi_bf16) == (!y_lo_bf16) && (!y_hi_bf16 || ((reinterpret_cast<uintptr_t>(y_hi_bf16) | reinterpret_cast<uintptr_t>(y_lo_bf16)) & 7) == 0),
              PN_ERR_BAD_ARGUMENT, "pn_groupnorm_elu_forward: the bf16 pair needs both 8-byte aligned pointers");
+#ifndef PN_EMULATE
+  {
+    // small / medium maps (the tensor fits the L2): one cluster launch, statistics through distributed shared memory
+    const GnClusterPlan plan = (y_lo || !aligned16(x) || (x2 && !aligned16(x2)) || !aligned16(y)) ? GnClusterPlan{0, 0, 0}
+                                                                                                 : gn_cluster_plan(batch, hw, channels);
+    if (plan.cl > 0) {
+      GnClusterParams P{};
+      P.x = x; P.x2 = x2; P.HW = hw; P.C = channels; P.cw = plan.cw; P.ppc = plan.ppc;
+      P.gamma = gamma; P.beta = beta; P.eps = eps;
+      P.mr = reinterpret_cast<float*>(stats + (size_t)2 * 16 * batch);
+      P.y = y; P.out_cstride = out_cstride; P.out_coffset = out_coffset;
+      P.hi = static_cast<uint2*>(y_hi_bf16); P.lo = static_cast<uint2*>(y_lo_bf16);
+      const int rc = gn_cluster_launch(false, P, batch, plan.cl, stream);
+      if (rc) return rc;
+      return check_launch("gn_elu_cluster_fwd_kernel");
+    }
+  }
+#endif
   PN_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * 16 * batch, stream));
   int ppc = (hw + 147) / 148;
   if (ppc < 32) ppc = 32;
@@ -1550,6 +1636,13 @@ static int groupnorm_elu_forward_impl(const float* x, const float* x2, const flo
   }
   count_launch();
   float* mr = reinterpret_cast<float*>(stats + (size_t)2 * 16 * batch);   // (mean, rstd) floats behind the doubles
+  if (!y_lo && aligned16(x) && (!x2 || aligned16(x2)) && aligned16(y) && channels / 4 <= 256) {
+    PN_LAUNCH(gn_elu_apply4_kernel, g1, 256, 0, stream, x, x2, hw, channels, mr, static_cast<const double*>(stats),
+              (double)hw * (channels / 16), gamma, beta, eps, ppc, y, out_cstride, out_coffset, static_cast<uint2*>(y_hi_bf16),
+              static_cast<uint2*>(y_lo_bf16));
+    count_launch();
+    return check_launch("gn_elu_apply4_kernel");
+  }
   const size_t total = (size_t)batch * hw * (channels / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -1582,6 +1675,35 @@ static int groupnorm_elu_backward_impl(const float* x, const float* x2, const fl
   PN_REQUIRE(x && y && dy && gamma && stats && bc && dx && dgamma && dbeta && batch > 0 && hw > 0, PN_ERR_BAD_ARGUMENT,
              "pn_groupnorm_elu_backward: bad argument");
   PN_REQUIRE(channels % 16 == 0 && channels <= 1024, PN_ERR_UNSUPPORTED, "pn_groupnorm_elu_backward: channels %d", channels);
+  PN_REQUIRE((!dx_hi_bf16) == (!dx_lo_bf16), PN_ERR_BAD_ARGUMENT, "pn_groupnorm_elu_backward: the bf16 pair needs both pointers");
+#ifndef PN_EMULATE
+  {
+    const bool vec0 = aligned16(x) && (!x2 || aligned16(x2)) && aligned16(y) && aligned16(dy) && aligned16(dx) && !dx_lo &&
+                      y_cstride % 4 == 0 && y_coffset % 4 == 0 && dy_cstride % 4 == 0 && dy_coffset % 4 == 0;
+    const GnClusterPlan plan = vec0 ? gn_cluster_plan(batch, hw, channels) : GnClusterPlan{0, 0, 0};
+    if (plan.cl > 0) {
+      // dgamma / dbeta / dsum meet over the samples with float atomics: one memset when the caller laid them out back to back
+      if (dbeta == dgamma + channels && dx_channel_sum == dbeta + channels) {
+        PN_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * 3 * channels, stream));
+      } else {
+        PN_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * channels, stream));
+        PN_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * channels, stream));
+        if (dx_channel_sum) PN_CUDA(cudaMemsetAsync(dx_channel_sum, 0, sizeof(float) * channels, stream));
+      }
+      GnClusterParams P{};
+      P.x = x; P.x2 = x2; P.HW = hw; P.C = channels; P.cw = plan.cw; P.ppc = plan.ppc;
+      P.gamma = gamma; P.eps = eps;
+      P.mr = const_cast<float*>(reinterpret_cast<const float*>(stats + (size_t)2 * 16 * batch));
+      P.yin = y; P.y_cstride = y_cstride; P.y_coffset = y_coffset;
+      P.dy = dy; P.dy_cstride = dy_cstride; P.dy_coffset = dy_coffset;
+      P.dx = dx; P.hi = static_cast<uint2*>(dx_hi_bf16); P.lo = static_cast<uint2*>(dx_lo_bf16);
+      P.dgamma = dgamma; P.dbeta = dbeta; P.dsum = dx_channel_sum;
+      const int rc = gn_cluster_launch(true, P, batch, plan.cl, stream);
+      if (rc) return rc;
+      return check_launch("gn_elu_cluster_bwd_kernel");
+    }
+  }
+#endif
   PN_CUDA(cudaMemsetAsync(bc, 0, sizeof(double) * 2 * channels * batch, stream));
   int ppc = (hw + 147) / 148;
   if (ppc < 32) ppc = 32;

@@ -378,10 +378,10 @@ class _GroupNormELU(torch.autograd.Function):
         gy = gy.contiguous()
         B, H, W, C = x.shape
         dx = torch.empty_like(x)
-        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        # dgamma | dbeta | dsum back to back: the cluster kernel zeroes the three with ONE memset
+        small = torch.empty(3, C, dtype=torch.float32, device=x.device)
+        dgamma, dbeta, dsum = small[0], small[1], small[2]
         bc = torch.empty(2 * C * B + 16 * B, dtype=torch.float64, device=x.device)   # doubles + float scratch tail
-        dsum = torch.empty(C, dtype=torch.float32, device=x.device)
         if ctx.emit:
             # dx is the output gradient of the convolution that produced x: its bf16 pair comes out of the same pass
             hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)

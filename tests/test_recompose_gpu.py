@@ -138,6 +138,49 @@ def test_groupnorm_tree_statistics_match_default(shape):
     assert rel_l2(res[1], yr) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(4, 96, 320, 64), (4, 96, 320, 32), (4, 48, 160, 128), (4, 24, 80, 256), (4, 12, 40, 512), (4, 6, 20, 256),
+                                   (1, 2, 3, 512), (2, 7, 9, 16), (3, 5, 11, 1024), (2, 6, 10, 48), (2, 192, 640, 64)])
+@pytest.mark.parametrize("residual", [False, True])
+def test_groupnorm_cluster_and_two_pass_kernels_match_float64(shape, residual):
+    """GroupNorm+ELU forward and backward on the one-launch cluster kernels (statistics through distributed shared memory;
+    every tensor that fits the L2) and on the two-pass kernels (PN_GN_CLUSTER=0; what the 192x640 maps run): both against
+    float64 PyTorch, on the network's layer shapes at B=4 192x640 plus ragged / odd ones (1024 channels = 64-wide groups, 48
+    channels = no cluster plan, one-pixel-per-CTA maps)."""
+    import os
+    from packnet_sfm_b200 import functional as PF
+    B, H, W, C = shape
+    g = torch.Generator().manual_seed(C * 7 + H)
+    x0 = (torch.rand(B, H, W, C, generator=g) * 2 - 0.7).to(DEV)
+    x20 = (torch.rand(B, H, W, C, generator=g) - 0.5).to(DEV)
+    gm0, bt0 = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.rand(C, generator=g) - 0.5).to(DEV)
+    gy = (torch.rand(B, H, W, C, generator=g) - 0.5).to(DEV)
+    xd, x2d, gd, bd = (t.detach().double().requires_grad_(True) for t in (x0, x20, gm0, bt0))
+    inp = xd + x2d if residual else xd
+    yr = F.elu(F.group_norm(inp.permute(0, 3, 1, 2), 16, gd, bd, 1e-5)).permute(0, 2, 3, 1)
+    yr.backward(gy.double())
+    prev = os.environ.get("PN_GN_CLUSTER")
+    try:
+        for cluster in ("1", "0"):
+            os.environ["PN_GN_CLUSTER"] = cluster
+            x, x2, gm, bt = (t.clone().requires_grad_(True) for t in (x0, x20, gm0, bt0))
+            y = PF.groupnorm_elu(x, gm, bt, 1e-5, x2=x2 if residual else None)
+            y.backward(gy)
+            torch.cuda.synchronize()
+            assert rel_l2(y, yr) < 1e-6, (cluster, rel_l2(y, yr))
+            assert rel_l2(x.grad, xd.grad) < 1e-5, (cluster, rel_l2(x.grad, xd.grad))
+            assert rel_l2(gm.grad, gd.grad) < 1e-5 and rel_l2(bt.grad, bd.grad) < 1e-5, cluster
+            if residual:
+                assert rel_l2(x2.grad, x2d.grad) < 1e-5
+            pair = getattr(y, "_pn_split", None)
+            if pair is not None:      # the bf16 operand pair written next to y: hi + lo reproduces y to 16 mantissa bits
+                assert rel_l2(pair[0].float() + pair[1].float(), y.detach()) < 2e-5
+    finally:
+        if prev is None:
+            os.environ.pop("PN_GN_CLUSTER", None)
+        else:
+            os.environ["PN_GN_CLUSTER"] = prev
+
+
 @pytest.mark.parametrize("cout,cin,k", [(64, 2048, 5), (512, 16384, 3), (64, 136, 3), (64, 64, 7), (128, 64, 1), (64, 8, 5)])
 def test_weight_grad_unpack_tiled_is_bit_identical(cout, cin, k):
     """pn_conv2d_unpack_weight_grad_tiled against the default element-per-thread gather on the network's layer shapes."""
