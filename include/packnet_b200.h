@@ -111,6 +111,25 @@ int pn_loss_backward(const pn_loss_desc* desc, const float* image, const float* 
                      const float* const* poses, const float* grad_out, float* const* grad_inv_depths,
                      float* const* grad_poses, void* workspace, size_t workspace_bytes, pn_stream_t stream);
 
+/* Training call (grouped program only: desc->flags & PN_LOSS_FLAG_GROUPED): ONE tile launch produces the loss (`out`, as
+ * pn_loss_forward) AND the gradients for dL/dloss = 1 -- MultiViewPhotometricLoss.forward followed by loss.backward()
+ * (models/model_wrapper.py:193-199 -> losses/multiview_photometric_loss.py:287-344) without evaluating the tile program twice.
+ *   unit_grad_inv_depths[i]  [B,1,h_i >> s_i,w_i >> s_i], unit_grad_poses[j] [B,4,4]: overwritten with the UNIT gradients
+ *                            (minus the per-sample smoothness constant that pn_loss_backward_finish adds)
+ *   grad_span_bytes          0, or the size of ONE allocation that starts at unit_grad_inv_depths[0] and holds every unit
+ *                            gradient output: the library then zeroes it with a single memset
+ * The workspace must be kept untouched until pn_loss_backward_finish ran. */
+int pn_loss_forward_backward(const pn_loss_desc* desc, const float* image, const float* const* context,
+                             const float* const* inv_depths, const float* K, const float* ref_K,
+                             const float* const* poses, float* out, float* const* unit_grad_inv_depths,
+                             float* const* unit_grad_poses, size_t grad_span_bytes, void* workspace,
+                             size_t workspace_bytes, pn_stream_t stream);
+/* Second half of the training call (autograd's backward of the loss node): grad = grad_out * (unit gradient + smoothness
+ * constant of the sample), out of place (the unit gradients stay valid: the call may be repeated). */
+int pn_loss_backward_finish(const pn_loss_desc* desc, const float* grad_out, const float* const* unit_grad_inv_depths,
+                            const float* const* unit_grad_poses, float* const* grad_inv_depths, float* const* grad_poses,
+                            void* workspace, size_t workspace_bytes, pn_stream_t stream);
+
 /* Test/inspection hook for the "warp pixel indices bit-exact" bar: writes, for one (scale, context),
  * the integer bilinear tap origin floor(ix), floor(iy) as int32 [B,h,w,2] and the unnormalised float
  * coordinates ix, iy as fp32 [B,h,w,2] -- produced by the SAME device function the loss kernels use. */

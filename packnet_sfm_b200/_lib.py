@@ -46,9 +46,14 @@ def _declare(lib):
                                     vp, sz, vp]
     lib.pn_loss_backward.argtypes = [c.POINTER(LossDesc), fp, c.POINTER(vp), c.POINTER(vp), fp, fp, c.POINTER(vp), fp,
                                      c.POINTER(vp), c.POINTER(vp), vp, sz, vp]
+    lib.pn_loss_forward_backward.argtypes = [c.POINTER(LossDesc), fp, c.POINTER(vp), c.POINTER(vp), fp, fp, c.POINTER(vp), fp,
+                                             c.POINTER(vp), c.POINTER(vp), sz, vp, sz, vp]
+    lib.pn_loss_backward_finish.argtypes = [c.POINTER(LossDesc), fp, c.POINTER(vp), c.POINTER(vp), c.POINTER(vp), c.POINTER(vp),
+                                            vp, sz, vp]
     lib.pn_loss_warp_indices.argtypes = [c.POINTER(LossDesc), c.c_int, fp, fp, fp, fp, vp, vp, vp, sz, vp]
     lib.pn_resize_bilinear_ac.argtypes = [fp, fp, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, vp]
-    for name in ("pn_loss_workspace_bytes", "pn_loss_forward", "pn_loss_backward", "pn_loss_warp_indices",
+    for name in ("pn_loss_workspace_bytes", "pn_loss_forward", "pn_loss_backward", "pn_loss_forward_backward",
+                 "pn_loss_backward_finish", "pn_loss_warp_indices",
                  "pn_resize_bilinear_ac"):
         getattr(lib, name).restype = c.c_int
     return lib

@@ -164,8 +164,14 @@ __device__ __forceinline__ float block_sum_vec(float (&v)[K], float* red /* >= 8
   return r;
 }
 
-template <int N, bool MIN, bool GRAD>
+// FUSED (GRAD only): the training call -- ONE launch produces the loss AND the gradients for dL/dloss = 1.  The backward
+// program recomputes the whole forward anyway; what it lacked were the loss sums (added here over its 30x14 core) and the
+// smoothness constant of the mean normalisation, -L_smooth(b,s) / (mean * pixels), which needs the finished sum over the
+// sample: it is the same for every pixel of (scale, sample), so loss_grad_finish_kernel adds it when it scales the stored unit
+// gradients by the incoming dL/dloss (pn_loss_backward_finish: one small launch instead of the second 0.36 ms tile pass).
+template <int N, bool MIN, bool GRAD, bool FUSED = false>
 __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GParams Q) {
+  static_assert(GRAD || !FUSED, "FUSED is a variant of the gradient program");
   using GG = GroupGeom<GRAD>;
   constexpr int CO = GG::CO, CWc = GG::CW, CHc = GG::CH, SLOTS = GG::SLOTS;
   const Params& P = Q.P;
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
   }
   __syncthreads();
 
-  const float go = GRAD ? __ldg(P.grad_out) : 1.0f;
+  const float go = (GRAD && !FUSED) ? __ldg(P.grad_out) : 1.0f;
   const float wS = P.ssim_w / 3.0f, wL = (1.0f - P.ssim_w) / 3.0f;  // channel means, :214-216
   const float c1 = 81.0f * P.C1, c2 = 81.0f * P.C2;
   const int ncand = P.automask ? 2 * N : N;
@@ -561,7 +567,7 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
     const float mcl = fmaxf(mean, 1e-6f);
     const float inv_mcl = 1.0f / mcl;
     float bs_const = 0.0f;
-    if (GRAD && do_smooth && mean >= 1e-6f)
+    if (GRAD && !FUSED && do_smooth && mean >= 1e-6f)
       bs_const = -go * (float)(P.smooth_bs[s * P.B + b] / ((double)mcl * (double)plane));
 #pragma unroll
     for (int slot = 0; slot < SLOTS; ++slot) {
@@ -603,14 +609,14 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
         else atomicAdd(S.ginv + (size_t)b * (plane >> (2 * S.sh)) + (size_t)(y >> S.sh) * S.iw + (x >> S.sh), gv);   // nearest backward
       }
     }
-    if (!GRAD && do_smooth) {
+    if ((!GRAD || FUSED) && do_smooth) {
       const float ss = block_sum(smooth_acc, s_red);
       if (threadIdx.x == 0) atomicAdd(P.smooth_bs + s * P.B + b, (double)ss);
     }
   }
 
   // ---- reductions ----------------------------------------------------------------------------------
-  if (!GRAD) {
+  if (!GRAD || FUSED) {
     // every scale of the group has the same photo_coef (same B, h, w, n): one sum, credited to the first scale
     const float ps = block_sum(photo_acc * S0.photo_coef, s_red);
     if (threadIdx.x == 0) {
@@ -632,7 +638,8 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
         P.out[3] = 0.0f;
       }
     }
-  } else {
+  }
+  if (GRAD) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const float v = block_sum_vec<12>(dPose[k], s_red);
@@ -642,6 +649,38 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
         // dPose = [dR row-major 3x3 | dT] -> the 4x4 pose matrix gradient
         atomicAdd(i < 9 ? gp + (i / 3) * 4 + (i % 3) : gp + (i - 9) * 4 + 3, v);
       }
+    }
+  }
+}
+
+
+// scales the unit gradients of the FUSED launch by dL/dloss and adds the smoothness constant (see loss_group_kernel)
+struct FinishParams {
+  int B, N, n;
+  const float* raw[PN_MAX_SCALES]; float* out[PN_MAX_SCALES];
+  int count[PN_MAX_SCALES];           // stored elements per sample: (h >> sh) * (w >> sh)
+  double plane[PN_MAX_SCALES];        // h * w of the (virtually up-sampled) map
+  float block[PN_MAX_SCALES];         // 4^sh: full-resolution pixels per stored element
+  int smooth[PN_MAX_SCALES];
+  const float* raw_pose[PN_MAX_CONTEXT]; float* out_pose[PN_MAX_CONTEXT];
+  const double* invsum; const double* smooth_bs; const float* grad_out;
+};
+
+__global__ void __launch_bounds__(256) loss_grad_finish_kernel(const FinishParams F) {
+  const float go = __ldg(F.grad_out);
+  const int sb = blockIdx.y, s = sb / F.B, b = sb % F.B;
+  float c = 0.0f;
+  if (F.smooth[s]) {
+    const float mean = (float)(F.invsum[sb] / F.plane[s]);
+    if (mean >= 1e-6f) c = -(float)(F.smooth_bs[sb] / ((double)fmaxf(mean, 1e-6f) * F.plane[s])) * F.block[s];
+  }
+  const float* raw = F.raw[s] + (size_t)b * F.count[s];
+  float* out = F.out[s] + (size_t)b * F.count[s];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F.count[s]; i += gridDim.x * blockDim.x) out[i] = go * (raw[i] + c);
+  if (sb == 0 && blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < F.N * F.B * 16; i += blockDim.x) {
+      const int j = i / (F.B * 16), r = i % (F.B * 16);
+      F.out_pose[j][r] = go * F.raw_pose[j][r];
     }
   }
 }

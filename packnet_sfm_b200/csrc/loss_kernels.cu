@@ -865,17 +865,17 @@ static void make_groups(const Params& P, GParams& Q) {
   Q.P.total_tiles = tile_base;
 }
 
-template <int N, bool MIN, bool GRAD>
+template <int N, bool MIN, bool GRAD, bool FUSED = false>
 static int launch_groups(const GParams& Q, int batch, cudaStream_t stream) {
   const size_t smem = group_smem_floats<N, GRAD>() * sizeof(float);
-  auto kern = loss_group_kernel<N, MIN, GRAD>;
+  auto kern = loss_group_kernel<N, MIN, GRAD, FUSED>;
   PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PN_LAUNCH(kern, dim3(Q.P.total_tiles, batch), GNT, smem, stream, Q);
   count_launch();
   return check_launch("loss_group_kernel");
 }
 
-template <bool GRAD>
+template <bool GRAD, bool FUSED = false>
 static int dispatch_groups(const pn_loss_desc* d, const Params& P, cudaStream_t stream) {
   PN_REQUIRE(3LL * d->height * d->width < (1LL << 31), PN_ERR_UNSUPPORTED,
              "pn_loss (grouped): 3*H*W must fit 32-bit tap offsets");
@@ -883,7 +883,7 @@ static int dispatch_groups(const pn_loss_desc* d, const Params& P, cudaStream_t 
   make_groups<GRAD>(P, Q);
 #define PN_CASE(NN)                                                                       \
   case NN:                                                                                \
-    return d->reduce_min ? launch_groups<NN, true, GRAD>(Q, d->batch, stream) : launch_groups<NN, false, GRAD>(Q, d->batch, stream);
+    return d->reduce_min ? launch_groups<NN, true, GRAD, FUSED>(Q, d->batch, stream) : launch_groups<NN, false, GRAD, FUSED>(Q, d->batch, stream);
   switch (d->num_context) {
     PN_CASE(1)
     PN_CASE(2)
@@ -1036,6 +1036,81 @@ extern "C" int pn_loss_backward(const pn_loss_desc* desc, const float* image, co
   }
   if (desc->flags & PN_LOSS_FLAG_GROUPED) return dispatch_groups<true>(desc, P, stream);
   return dispatch_tiles<true>(desc, P, dim3(P.total_tiles, desc->batch), stream);
+}
+
+extern "C" int pn_loss_forward_backward(const pn_loss_desc* desc, const float* image, const float* const* context,
+                                        const float* const* inv_depths, const float* K, const float* ref_K,
+                                        const float* const* poses, float* out, float* const* unit_grad_inv_depths,
+                                        float* const* unit_grad_poses, size_t grad_span_bytes, void* workspace,
+                                        size_t workspace_bytes, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PN_REQUIRE(desc && (desc->flags & PN_LOSS_FLAG_GROUPED), PN_ERR_UNSUPPORTED,
+             "pn_loss_forward_backward: the one-launch training call exists for the grouped program (PN_LOSS_FLAG_GROUPED)");
+  Params P;
+  Workspace ws;
+  int rc = setup(desc, image, context, inv_depths, K, ref_K, poses, workspace, workspace_bytes, stream, true, P, ws);
+  if (rc) return rc;
+  PN_REQUIRE(out && unit_grad_inv_depths && unit_grad_poses, PN_ERR_BAD_ARGUMENT, "pn_loss_forward_backward: null output pointer");
+  P.out = out;
+  for (int i = 0; i < desc->num_scales; ++i) {
+    PN_REQUIRE(unit_grad_inv_depths[i] != nullptr, PN_ERR_BAD_ARGUMENT, "pn_loss_forward_backward: unit_grad_inv_depths[%d] null", i);
+    P.sc[i].ginv = unit_grad_inv_depths[i];
+  }
+  for (int j = 0; j < desc->num_context; ++j) {
+    PN_REQUIRE(unit_grad_poses[j] != nullptr, PN_ERR_BAD_ARGUMENT, "pn_loss_forward_backward: unit_grad_poses[%d] null", j);
+    P.gpose[j] = unit_grad_poses[j];
+  }
+  if (grad_span_bytes) {
+    // the caller laid every gradient output out inside one allocation starting at unit_grad_inv_depths[0]: one memset node
+    PN_CUDA(cudaMemsetAsync(unit_grad_inv_depths[0], 0, grad_span_bytes, stream));
+  } else {
+    for (int i = 0; i < desc->num_scales; ++i)
+      if (desc->inv_shift[i] > 0)
+        PN_CUDA(cudaMemsetAsync(unit_grad_inv_depths[i], 0, sizeof(float) * desc->batch * (desc->scale_h[i] >> desc->inv_shift[i]) *
+                                                                (desc->scale_w[i] >> desc->inv_shift[i]), stream));
+    for (int j = 0; j < desc->num_context; ++j) PN_CUDA(cudaMemsetAsync(unit_grad_poses[j], 0, sizeof(float) * 16 * desc->batch, stream));
+  }
+  return dispatch_groups<true, true>(desc, P, stream);
+}
+
+extern "C" int pn_loss_backward_finish(const pn_loss_desc* desc, const float* grad_out, const float* const* unit_grad_inv_depths,
+                                       const float* const* unit_grad_poses, float* const* grad_inv_depths, float* const* grad_poses,
+                                       void* workspace, size_t workspace_bytes, pn_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = validate(desc);
+  if (rc) return rc;
+  PN_REQUIRE(grad_out && unit_grad_inv_depths && unit_grad_poses && grad_inv_depths && grad_poses && workspace, PN_ERR_BAD_ARGUMENT,
+             "pn_loss_backward_finish: null pointer argument");
+  Workspace ws;
+  layout(desc, ws);
+  PN_REQUIRE(workspace_bytes >= ws.total, PN_ERR_WORKSPACE, "pn_loss_backward_finish: workspace %zu < required %zu", workspace_bytes, ws.total);
+  char* base = static_cast<char*>(workspace);
+  FinishParams F{};
+  F.B = desc->batch; F.N = desc->num_context; F.n = desc->num_scales;
+  int maxcount = 1;
+  for (int i = 0; i < desc->num_scales; ++i) {
+    PN_REQUIRE(unit_grad_inv_depths[i] && grad_inv_depths[i], PN_ERR_BAD_ARGUMENT, "pn_loss_backward_finish: gradient pointer %d null", i);
+    const int sh = desc->inv_shift[i];
+    F.raw[i] = unit_grad_inv_depths[i]; F.out[i] = grad_inv_depths[i];
+    F.count[i] = (desc->scale_h[i] >> sh) * (desc->scale_w[i] >> sh);
+    F.plane[i] = (double)desc->scale_h[i] * desc->scale_w[i];
+    F.block[i] = (float)(1 << (2 * sh));
+    F.smooth[i] = desc->smooth_loss_weight > 0.0f ? 1 : 0;
+    if (F.count[i] > maxcount) maxcount = F.count[i];
+  }
+  for (int j = 0; j < desc->num_context; ++j) {
+    PN_REQUIRE(unit_grad_poses[j] && grad_poses[j], PN_ERR_BAD_ARGUMENT, "pn_loss_backward_finish: pose gradient pointer %d null", j);
+    F.raw_pose[j] = unit_grad_poses[j]; F.out_pose[j] = grad_poses[j];
+  }
+  F.invsum = reinterpret_cast<const double*>(base + ws.invsum);
+  F.smooth_bs = reinterpret_cast<const double*>(base + ws.smooth_bs);
+  F.grad_out = grad_out;
+  int bx = (maxcount + 256 * 8 - 1) / (256 * 8);
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  PN_LAUNCH(loss_grad_finish_kernel, dim3(bx, desc->num_scales * desc->batch), 256, 0, stream, F);
+  count_launch();
+  return check_launch("loss_grad_finish_kernel");
 }
 
 extern "C" int pn_loss_warp_indices(const pn_loss_desc* desc, int scale, const float* inv_depth, const float* K,

@@ -55,6 +55,18 @@ class LossBase(nn.Module):
 _grouped = os.environ.get("PN_LOSS_GROUPED", "1") == "1"     # default since round 2 (B200: fwd 0.193 -> 0.145, bwd 0.599 -> 0.436 ms)
 
 
+_fused_training = os.environ.get("PN_LOSS_FUSED", "1") == "1"
+
+
+def set_fused_training(on):
+    """One tile launch for the loss AND its unit gradients when an input requires a gradient (pn_loss_forward_backward; grouped
+    program only); off = forward launch + backward launch of the tile program (the round-1 call sequence).  Returns the
+    previous setting."""
+    global _fused_training
+    prev, _fused_training = _fused_training, bool(on)
+    return prev
+
+
 def set_grouped_kernel(on):
     """Select the grouped-scale tile program (csrc/loss_group_kernel.cuh, PN_LOSS_FLAG_GROUPED) for the descriptors built
     from now on (the default since round 2; PN_LOSS_GROUPED=0 in the environment or set_grouped_kernel(False) selects the
@@ -102,12 +114,27 @@ class _FusedLoss(torch.autograd.Function):
         _lib.check(lib.pn_loss_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "pn_loss_workspace_bytes")
         ws = torch.empty(max(int(nbytes.value), 16), dtype=torch.uint8, device=image.device)
         out = torch.empty(4, dtype=torch.float32, device=image.device)
+        ctx.desc, ctx.ws, ctx.N, ctx.n = desc, ws, N, n
+        ctx.saved = (image, K, ref_K, context, inv, poses)
+        ctx.unit = None
+        if _fused_training and (desc.flags & _lib.PN_LOSS_FLAG_GROUPED) and any(ctx.needs_input_grad[4 + N:]):
+            # training: ONE tile launch gives the loss and the unit gradients (pn_loss_forward_backward); backward() scales them.
+            # All unit gradients live in one buffer: the library zeroes it with a single memset.
+            sizes = [d.numel() for d in inv] + [p.numel() for p in poses]
+            offs = np.cumsum([0] + [(s + 3) // 4 * 4 for s in sizes])
+            flat = torch.empty(int(offs[-1]), dtype=torch.float32, device=image.device)
+            unit = [flat[int(o):int(o) + s].view(t.shape) for o, s, t in zip(offs[:-1], sizes, inv + poses)]
+            _lib.check(lib.pn_loss_forward_backward(ctypes.byref(desc), _lib.ptr(image), _lib.ptr_array(context),
+                                                    _lib.ptr_array(inv), _lib.ptr(K), _lib.ptr(ref_K), _lib.ptr_array(poses),
+                                                    _lib.ptr(out), _lib.ptr_array(unit[:n]), _lib.ptr_array(unit[n:]),
+                                                    flat.numel() * 4, _lib.ptr(ws), ws.numel(), _lib.current_stream()),
+                       "pn_loss_forward_backward")
+            ctx.unit = (flat, unit)
+            return out
         _lib.check(lib.pn_loss_forward(ctypes.byref(desc), _lib.ptr(image), _lib.ptr_array(context),
                                        _lib.ptr_array(inv), _lib.ptr(K), _lib.ptr(ref_K), _lib.ptr_array(poses),
                                        _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.current_stream()),
                    "pn_loss_forward")
-        ctx.desc, ctx.ws, ctx.N, ctx.n = desc, ws, N, n
-        ctx.saved = (image, K, ref_K, context, inv, poses)
         return out
 
     @staticmethod
@@ -117,6 +144,13 @@ class _FusedLoss(torch.autograd.Function):
         g = grad_out.contiguous().to(torch.float32)
         ginv = [torch.empty_like(d) for d in inv]
         gpose = [torch.empty_like(p) for p in poses]
+        if ctx.unit is not None:
+            unit = ctx.unit[1]
+            _lib.check(lib.pn_loss_backward_finish(ctypes.byref(ctx.desc), _lib.ptr(g), _lib.ptr_array(unit[:ctx.n]),
+                                                   _lib.ptr_array(unit[ctx.n:]), _lib.ptr_array(ginv), _lib.ptr_array(gpose),
+                                                   _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.current_stream()),
+                       "pn_loss_backward_finish")
+            return (None, None, None, None) + (None,) * ctx.N + tuple(ginv) + tuple(gpose)
         _lib.check(lib.pn_loss_backward(ctypes.byref(ctx.desc), _lib.ptr(image), _lib.ptr_array(context),
                                         _lib.ptr_array(inv), _lib.ptr(K), _lib.ptr(ref_K), _lib.ptr_array(poses),
                                         _lib.ptr(g), _lib.ptr_array(ginv), _lib.ptr_array(gpose), _lib.ptr(ctx.ws),

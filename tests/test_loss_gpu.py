@@ -14,14 +14,18 @@ import os
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tile", "grouped"])
+@pytest.fixture(autouse=True, params=["tile", "grouped", "grouped_two_launches"])
 def loss_program(request):
     """Every test of this file runs on both tile programs: the grouped-scale one (csrc/loss_group_kernel.cuh,
-    PN_LOSS_FLAG_GROUPED; the default since round 2) and the first-generation one -- same assertions."""
+    PN_LOSS_FLAG_GROUPED; the default since round 2) -- through the one-launch training call (pn_loss_forward_backward +
+    pn_loss_backward_finish, the default) and through separate forward / backward launches -- and the first-generation one:
+    same assertions."""
     from packnet_sfm_b200 import losses
-    prev = losses.set_grouped_kernel(request.param == "grouped")
-    yield request.param
+    prev = losses.set_grouped_kernel(request.param != "tile")
+    prev_f = losses.set_fused_training(request.param != "grouped_two_launches")
+    yield "tile" if request.param == "tile" else "grouped"
     losses.set_grouped_kernel(prev)
+    losses.set_fused_training(prev_f)
 
 LOSS_TOL = 1e-3        # north_star: photometric loss within 1e-3 relative fp32
 GRAD_TOL = 1e-3        # gradient fields: relative L2 over the inlier pixels

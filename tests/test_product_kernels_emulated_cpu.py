@@ -34,13 +34,16 @@ def _field_close(got, want, tag):
     assert rel < GRAD_TOL, (tag, rel)
 
 
-@pytest.fixture(params=[False, True], ids=["tile", "grouped"])
+@pytest.fixture(params=[(False, True), (True, True), (True, False)], ids=["tile", "grouped", "grouped_two_launches"])
 def loss_program(request):
-    """both generations of the loss tile program: the default one and the grouped-scale one (PN_LOSS_FLAG_GROUPED)"""
+    """both generations of the loss tile program: the first one and the grouped-scale one (PN_LOSS_FLAG_GROUPED), the latter
+    through the one-launch training call (pn_loss_forward_backward + pn_loss_backward_finish) and through two launches"""
     from packnet_sfm_b200 import losses
-    prev = losses.set_grouped_kernel(request.param)
-    yield request.param
+    prev = losses.set_grouped_kernel(request.param[0])
+    prev_f = losses.set_fused_training(request.param[1])
+    yield request.param[0]
     losses.set_grouped_kernel(prev)
+    losses.set_fused_training(prev_f)
 
 
 @pytest.mark.parametrize("case", ["loss_fullres", "loss_multires", "loss_mean_noautomask", "loss_bigmotion", "loss_progressive"])
