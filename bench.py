@@ -278,20 +278,37 @@ def time_kernels(args, dev, pk):
 
     for _ in range(3):
         fwd(); bwd()
-    t_f = timed(fwd)
-    t_b = timed(bwd)
+    torch.cuda.synchronize()
+    # as in the step: replayed CUDA graphs (the eager calls carry ~60 us of host enqueue gaps per call, which is not kernel time)
+    loss_timing = "cuda graph replay, L2 flushed before every replay"
+    try:
+        gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gf):
+            fwd()
+        with torch.cuda.graph(gb, pool=gf.pool()):
+            bwd()
+        torch.cuda.synchronize()
+        t_f, t_b = timed(gf.replay), timed(gb.replay)
+    except Exception as e:
+        log("loss graph capture failed (%s): eager timing" % repr(e)[:200])
+        loss_timing = "eager calls, L2 flushed before every call"
+        torch.cuda.synchronize()
+        t_f, t_b = timed(fwd), timed(bwd)
     P_s = B * H * W * 4
     bytes_f, bytes_b = 48 * P_s, 44 * P_s
     from packnet_sfm_b200 import losses as _losses
     grouped = bool(_losses._grouped)
     shape_tag = "%dx%dx%d" % (B, H, W)
     nm_loss = ncu_metrics("loss_%s_%s" % ("grouped" if grouped else "tile", shape_tag))
-    res["roofline_loss"] = {"bound": "hbm", "kernel": ("loss_group_kernel" if grouped else "loss_tile_kernel") + " fwd+bwd (incl. prep launches)",
+    res["roofline_loss"] = {"bound": "hbm", "kernel": ("loss_group_kernel" if grouped else "loss_tile_kernel") + " fwd+bwd (incl. prep / finish launches)",
                             "achieved": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": (bytes_f + bytes_b) / ((t_f + t_b) * 1e-3) / 1e9 / pk["hbm_gbs"],
                             "traffic": (nm_loss or {}).get("dram_bytes"), "traffic_source": (nm_loss or {}).get("source"),
                             "traffic_commit": (nm_loss or {}).get("commit"),
-                            "fwd_ms": t_f, "bwd_ms": t_b, "algorithmic_bytes": bytes_f + bytes_b, "peak_source": pk["source"]}
+                            "fwd_ms": t_f, "bwd_ms": t_b, "algorithmic_bytes": bytes_f + bytes_b, "peak_source": pk["source"],
+                            "timing": loss_timing,
+                            "calls": ("training call: pn_loss_forward_backward (loss + unit gradients in one tile launch) then pn_loss_backward_finish"
+                                      if (grouped and _losses._fused_training) else "pn_loss_forward then pn_loss_backward")}
     # pack1 (tensor bound).  Reference formulation: Conv2d(2048 -> 64, 5x5) over the Conv3d-inflated tensor at H/2 x W/2
     # (201.3 GFLOP per image).  What the step launches for it since round 2 is the FOLDED 7x7 convolution
     # 256 -> 64 of the space-to-depth tensor (12544/51200 of those MACs) -- the dominant conv_igemm launch of the step.

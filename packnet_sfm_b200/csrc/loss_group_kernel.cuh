@@ -52,8 +52,9 @@ struct GroupGeom {
 template <int N, bool GRAD>
 constexpr size_t group_smem_floats() {
   size_t f = (size_t)GRP * (1 + 3 + 3 * N + 3 * N);  // inv, tgt, ref, warp
-  if (GRAD) f += (size_t)GPP * 10;                    // 9 coefficients + winner id
-  return f + 8 * 12 * N + 16;                         // reduction scratch
+  if (GRAD) f += (size_t)GPP * 12;                    // per pixel: 9 coefficients + winner id (+ 2 pad) = three float4
+  if (GRAD) f += (size_t)GRP * 2 * N;                 // sampling coordinates (ix, iy) of the warp phase, re-used by the gather
+  return f + 8 * (12 * N + 1) + 16 + PN_MAX_SCALES;   // reduction scratch + per-scale smoothness sums
 }
 
 // project_point with the two exact simplifications the compiler does not make: x / 2 == x * 0.5 for every float, so the
@@ -141,6 +142,25 @@ __device__ __forceinline__ float ssim_loss_from_sums(float sx, float sxx, float 
   return __saturatef(fmaf(-0.5f, ssim, 0.5f));
 }
 
+// d SSIM / d (mu_x, E[x^2], E[xy]) from window sums, for the winner's coefficients of the backward.  Same formulas as
+// ssim_from_sums<true> with the divisions by nine as multiplications and one fast reciprocal: the derivative feeds a
+// gradient that is compared to 1e-3, only the forward's candidate ORDER is rounding-sensitive (and is not computed here).
+__device__ __forceinline__ void ssim_deriv_from_sums(float sx, float sxx, float sxy, float sy, float syy, float C1, float C2,
+                                                     float& half, float& a, float& b, float& c) {
+  constexpr float r9 = 1.0f / 9.0f;
+  const float mu_x = sx * r9, mu_y = sy * r9;
+  const float mxy = mu_x * mu_y, mxx = mu_x * mu_x, myy = mu_y * mu_y;
+  const float sig_x = fmaf(sxx, r9, -mxx), sig_y = fmaf(syy, r9, -myy), sig_xy = fmaf(sxy, r9, -mxy);
+  const float A1 = fmaf(2.0f, mxy, C1), A2 = fmaf(2.0f, sig_xy, C2);
+  const float B1 = mxx + myy + C1, B2 = sig_x + sig_y + C2;
+  const float invD = fast_rcp(B1 * B2);
+  const float ssim = A1 * A2 * invD;
+  half = (1.0f - ssim) * 0.5f;
+  a = (2.0f * mu_y * (A2 - A1) - ssim * 2.0f * mu_x * (B2 - B1)) * invD;
+  b = -ssim * B1 * invD;
+  c = 2.0f * A1 * invD;
+}
+
 // sums of K per-thread values over the block: thread i < K returns the i-th sum (other threads return 0)
 template <int K>
 __device__ __forceinline__ float block_sum_vec(float (&v)[K], float* red /* >= 8*K floats */) {
@@ -180,9 +200,10 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
   float* s_tgt = s_inv + GRP;             // [3][GRP]
   float* s_ref = s_tgt + 3 * GRP;         // [N][3][GRP]  un-warped context (auto-mask)
   float* s_warp = s_ref + 3 * N * GRP;    // [N][3][GRP]  warped context of the current scale
-  float* s_coef = s_warp + 3 * N * GRP;   // [9][GPP]     (GRAD)
-  float* s_selj = s_coef + (GRAD ? 9 * GPP : 0);  // [GPP] winner context as float (-1: none) (GRAD)
-  float* s_red = s_selj + (GRAD ? GPP : 0);       // [8*12*N + 16]
+  float* s_coef = s_warp + 3 * N * GRP;   // [GPP][12]: a/b/c x 3 channels, winner context as float (-1: none), 2 pad   (GRAD)
+  float* s_ixy = s_coef + (GRAD ? 12 * GPP : 0);    // [N][2][GRP] sampling coordinates of the warp phase   (GRAD)
+  float* s_red = s_ixy + (GRAD ? 2 * N * GRP : 0);  // [8*(12*N+1) + 16]
+  float* s_smooth = s_red + 8 * (12 * N + 1) + 16;  // [PN_MAX_SCALES] smoothness sums of the CTA, one per scale of the group
 
   // ---- which tile -------------------------------------------------------------------------------
   int gi = 0;
@@ -206,6 +227,7 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
   const float* cam = P.cams + (size_t)(s_first * P.B + b) * cam_stride;
   __shared__ float s_cam[CAM_STRIDE_BASE + 12 * PN_MAX_CONTEXT];
   if (threadIdx.x < cam_stride) s_cam[threadIdx.x] = cam[threadIdx.x];
+  if (threadIdx.x < PN_MAX_SCALES) s_smooth[threadIdx.x] = 0.0f;
   const float* Kinv = s_cam;
   const float* Kref = s_cam + 9;
 
@@ -363,6 +385,7 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
           const Projection pr = project_point_g(Kref, s_cam + CAM_STRIDE_BASE + 12 * k, X, Y, Zc, wm1, hm1);
           const Taps t = make_taps(pr.ix, pr.iy, w, h);
           sample3_g(ctx_b, (int)plane, w, pr.ix, pr.iy, t, wv);
+          if (GRAD) { s_ixy[(2 * k) * GRP + idx] = pr.ix; s_ixy[(2 * k + 1) * GRP + idx] = pr.iy; }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) s_warp[(k * 3 + c) * GRP + idx] = wv[c];
@@ -425,42 +448,54 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
       const int passes = MIN ? 1 : N;
       for (int pass = 0; pass < passes; ++pass) {
         if (pass > 0) __syncthreads();
-        // ---- SSIM derivative coefficients of the winner (min) / of context `pass` (mean) ----------------
+        // ---- SSIM derivative coefficients of the winner (min) / of context `pass` (mean): one 48-byte record per pixel ------
+        {
+          int kk[2];
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const int pidx = (2 * rp + o) * GW + col;
-          float coef[9];
+          for (int o = 0; o < 2; ++o) kk[o] = !pv[o] ? -1 : (MIN ? (((sel[o] >= 0) && !(sel[o] & 1)) ? (sel[o] >> 1) : -1) : pass);
+          float coef[2][9];
 #pragma unroll
-          for (int i = 0; i < 9; ++i) coef[i] = 0.0f;
-          float selj = -1.0f;
-          const int k = MIN ? (((sel[o] >= 0) && !(sel[o] & 1)) ? (sel[o] >> 1) : -1) : pass;
-          if (pv[o] && k >= 0) {
-            selj = (float)k;
-            const float up = go * S.photo_coef * cand_w;
+          for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) coef[o][i] = 0.0f;
+          const float up = go * S.photo_coef * cand_w;
+          if (kk[0] >= 0 || kk[1] >= 0) {
+            const bool same = (kk[0] == kk[1]) || kk[0] < 0 || kk[1] < 0;   // one plane serves both pixels (the usual case)
+            const int k0 = kk[0] >= 0 ? kk[0] : kk[1];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
+              float yv[4][3];
               const float* tg = s_tgt + c * GRP;
-              const float* src = s_warp + (k * 3 + c) * GRP;
-              float sx = 0.0f, sxx = 0.0f, sxy = 0.0f;
 #pragma unroll
-              for (int a = 0; a < 3; ++a)
+              for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                  const int off = ro[o + a] + co[d];
-                  const float v = src[off];
-                  sx += v; sxx += v * v; sxy += v * tg[off];
-                }
-              const SsimTerms t = ssim_from_sums<true>(sx, sxx, sxy, sy[c][o], syy[c][o], P.C1, P.C2);
-              const float half = (1.0f - t.ssim) * 0.5f;
-              const float g = (half >= 0.0f && half <= 1.0f) ? up * wS * (-0.5f) / 9.0f : 0.0f;
-              coef[c * 3 + 0] = g * t.a;
-              coef[c * 3 + 1] = g * 2.0f * t.b;
-              coef[c * 3 + 2] = g * t.c;
+                for (int d = 0; d < 3; ++d) yv[r][d] = tg[ro[r] + co[d]];
+              float sx[2], sxx[2], sxy[2], xc[2];
+              plane_sums(s_warp + (k0 * 3 + c) * GRP, ro, co, yv, sx, sxx, sxy, xc);
+              if (!same) {   // the second pixel's winner is the other context: its sums come from that plane
+                float sx2[2], sxx2[2], sxy2[2];
+                plane_sums(s_warp + (kk[1] * 3 + c) * GRP, ro, co, yv, sx2, sxx2, sxy2, xc);
+                sx[1] = sx2[1]; sxx[1] = sxx2[1]; sxy[1] = sxy2[1];
+              }
+#pragma unroll
+              for (int o = 0; o < 2; ++o) {
+                if (kk[o] < 0) continue;
+                float half, da, db, dc;
+                ssim_deriv_from_sums(sx[o], sxx[o], sxy[o], sy[c][o], syy[c][o], P.C1, P.C2, half, da, db, dc);
+                const float g = (half >= 0.0f && half <= 1.0f) ? up * wS * (-0.5f) / 9.0f : 0.0f;
+                coef[o][c * 3 + 0] = g * da;
+                coef[o][c * 3 + 1] = g * 2.0f * db;
+                coef[o][c * 3 + 2] = g * dc;
+              }
             }
           }
 #pragma unroll
-          for (int i = 0; i < 9; ++i) s_coef[i * GPP + pidx] = coef[i];
-          s_selj[pidx] = selj;
+          for (int o = 0; o < 2; ++o) {
+            float4* rec = reinterpret_cast<float4*>(s_coef + (size_t)((2 * rp + o) * GW + col) * 12);
+            rec[0] = make_float4(coef[o][0], coef[o][1], coef[o][2], coef[o][3]);
+            rec[1] = make_float4(coef[o][4], coef[o][5], coef[o][6], coef[o][7]);
+            rec[2] = make_float4(coef[o][8], (float)kk[o], 0.0f, 0.0f);
+          }
         }
         __syncthreads();
         // ---- gather the SSIM / L1 gradient onto the warped pixel, push it through the sampler ------------
@@ -472,70 +507,92 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
           const int x = cx0 + qi, y = cy0 + qj;
           if (x >= w || y >= h) continue;
           const int ridx = (qj + CO + 1) * GRW + (qi + CO + 1);
+          // window multiplicities of the 3x3 neighbours (reflection padding counts a border pixel's neighbour twice; 0 = outside)
+          float mxv[3], myv[3];
+#pragma unroll
+          for (int d = -1; d <= 1; ++d) {
+            const int px = x + d, py = y + d;
+            mxv[d + 1] = (px < 0 || px >= w) ? 0.0f : (((px == 0 && x == 1 && d == -1) || (px == w - 1 && x == w - 2 && d == 1)) ? 2.0f : 1.0f);
+            myv[d + 1] = (py < 0 || py >= h) ? 0.0f : (((py == 0 && y == 1 && d == -1) || (py == h - 1 && y == h - 2 && d == 1)) ? 2.0f : 1.0f);
+          }
+          float xq[N][3], yq[3], Gc[N][3];
+          bool any[N];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) yq[c] = s_tgt[c * GRP + ridx];
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            any[k] = false;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { xq[k][c] = s_warp[(k * 3 + c) * GRP + ridx]; Gc[k][c] = 0.0f; }
+          }
+          // ONE walk over the neighbours: a record belongs to exactly one context
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const float m = mxv[dx + 1] * myv[dy + 1];
+              if (m == 0.0f) continue;
+              const float4* rec = reinterpret_cast<const float4*>(s_coef + (size_t)((qj + CO + dy) * GW + (qi + CO + dx)) * 12);
+              const float4 r2 = rec[2];
+              if (r2.y < 0.0f) continue;
+              const float4 r0 = rec[0], r1 = rec[1];
+              const float ca[3] = {r0.x, r0.w, r1.z}, cb[3] = {r0.y, r1.x, r1.w}, cc[3] = {r0.z, r1.y, r2.x};
+#pragma unroll
+              for (int k = 0; k < N; ++k) {
+                if (r2.y != (float)k) continue;
+                any[k] = true;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Gc[k][c] += m * (ca[c] + cb[c] * xq[k][c] + cc[c] * yq[c]);
+              }
+              if (dx == 0 && dy == 0) {   // the L1 term of this pixel itself
+                const float upl = go * S.photo_coef * cand_w * wL;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                  if (r2.y != (float)k) continue;
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) Gc[k][c] += upl * sgnf(xq[k][c] - yq[c]);
+                }
+              }
+            }
+          }
           const float inv = s_inv[ridx];
           const float depth = depth_from_inv(inv);
-          float X, Y, Zc;
-          backproject(Kinv, (float)x, (float)y, depth, X, Y, Zc);
+          // X = ray * depth with ray = Kinv (x, y, 1): the values of the warp phase to rounding (the gradient does not need its bits)
+          const float rx = dot3_rn(Kinv + 0, (float)x, (float)y, 1.0f), ry = dot3_rn(Kinv + 3, (float)x, (float)y, 1.0f),
+                      rz = dot3_rn(Kinv + 6, (float)x, (float)y, 1.0f);
+          const float X = rx * depth, Y = ry * depth, Zc = rz * depth;
           float ddepth = 0.0f;
 #pragma unroll
           for (int k = 0; k < N; ++k) {
             if (!MIN && k != pass) continue;
-            float Gc[3] = {0.0f, 0.0f, 0.0f};
-            float xq[3], yq[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              xq[c] = s_warp[(k * 3 + c) * GRP + ridx];
-              yq[c] = s_tgt[c * GRP + ridx];
-            }
-            bool any = false;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-              const int py = y + dy;
-              if (py < 0 || py >= h) continue;
-              const float my = ((py == 0 && y == 1 && dy == -1) || (py == h - 1 && y == h - 2 && dy == 1)) ? 2.0f : 1.0f;
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx) {
-                const int px = x + dx;
-                if (px < 0 || px >= w) continue;
-                const float mx = ((px == 0 && x == 1 && dx == -1) || (px == w - 1 && x == w - 2 && dx == 1)) ? 2.0f : 1.0f;
-                const int cidx = (qj + CO + dy) * GW + (qi + CO + dx);
-                if (s_selj[cidx] != (float)k) continue;
-                any = true;
-                const float m = mx * my;
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                  Gc[c] += m * (s_coef[(c * 3 + 0) * GPP + cidx] + s_coef[(c * 3 + 1) * GPP + cidx] * xq[c] +
-                                s_coef[(c * 3 + 2) * GPP + cidx] * yq[c]);
-              }
-            }
-            const int cself = (qj + CO) * GW + (qi + CO);
-            if (s_selj[cself] == (float)k) {
-              any = true;
-              const float up = go * S.photo_coef * cand_w * wL;
-#pragma unroll
-              for (int c = 0; c < 3; ++c) Gc[c] += up * sgnf(xq[c] - yq[c]);
-            }
-            if (!any) continue;
-            // d warped / d (ix, iy): grid_sampler_2d backward w.r.t. the grid, in-bounds taps only
+            if (!any[k]) continue;
+            // d warped / d (ix, iy): grid_sampler_2d backward w.r.t. the grid, in-bounds taps only; the coordinates are the
+            // warp phase's own (bit-exact taps), the projection terms of the chain rule are re-evaluated with plain FMAs
             const float* Rt = s_cam + CAM_STRIDE_BASE + 12 * k;
-            const Projection pr = project_point_g(Kref, Rt, X, Y, Zc, wm1, hm1);
-            const Taps t = make_taps(pr.ix, pr.iy, w, h);
+            const float ix = s_ixy[(2 * k) * GRP + ridx], iy = s_ixy[(2 * k + 1) * GRP + ridx];
+            const Taps t = make_taps(ix, iy, w, h);
             const float x1f = t.x0f + 1.0f, y1f = t.y0f + 1.0f;
             const float* ctx_b = S.ctx[k] + (size_t)b * 3 * plane + (ptrdiff_t)t.yi * w + t.xi;
             float gix = 0.0f, giy = 0.0f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const float* pc = ctx_b + c * plane;
-              const float g = Gc[c];
-              if (t.nw) { const float v = __ldg(pc);         gix -= v * (y1f - pr.iy) * g; giy -= v * (x1f - pr.ix) * g; }
-              if (t.ne) { const float v = __ldg(pc + 1);     gix += v * (y1f - pr.iy) * g; giy -= v * (pr.ix - t.x0f) * g; }
-              if (t.sw) { const float v = __ldg(pc + w);     gix -= v * (pr.iy - t.y0f) * g; giy += v * (x1f - pr.ix) * g; }
-              if (t.se) { const float v = __ldg(pc + w + 1); gix += v * (pr.iy - t.y0f) * g; giy += v * (pr.ix - t.x0f) * g; }
+              const float g = Gc[k][c];
+              if (t.nw) { const float v = __ldg(pc);         gix -= v * (y1f - iy) * g; giy -= v * (x1f - ix) * g; }
+              if (t.ne) { const float v = __ldg(pc + 1);     gix += v * (y1f - iy) * g; giy -= v * (ix - t.x0f) * g; }
+              if (t.sw) { const float v = __ldg(pc + w);     gix -= v * (iy - t.y0f) * g; giy += v * (x1f - ix) * g; }
+              if (t.se) { const float v = __ldg(pc + w + 1); gix += v * (iy - t.y0f) * g; giy += v * (ix - t.x0f) * g; }
             }
+            const float wx = fmaf(Rt[0], X, fmaf(Rt[1], Y, fmaf(Rt[2], Zc, Rt[9])));
+            const float wy = fmaf(Rt[3], X, fmaf(Rt[4], Y, fmaf(Rt[5], Zc, Rt[10])));
+            const float wz = fmaf(Rt[6], X, fmaf(Rt[7], Y, fmaf(Rt[8], Zc, Rt[11])));
+            const float ppx = fmaf(Kref[0], wx, fmaf(Kref[1], wy, Kref[2] * wz));
+            const float ppy = fmaf(Kref[3], wx, fmaf(Kref[4], wy, Kref[5] * wz));
+            const float ppz = fmaf(Kref[6], wx, fmaf(Kref[7], wy, Kref[8] * wz));
             // ix == px/Z, iy == py/Z up to rounding (camera.py:181-182 then GridSampler unnormalise)
-            const float iZ = 1.0f / pr.Z;
+            const float iZ = fast_rcp(fmaxf(ppz, 1e-5f));
             const float dPx = gix * iZ, dPy = giy * iZ;
-            const float dPz = (pr.pz >= 1e-5f) ? -(gix * pr.px + giy * pr.py) * iZ * iZ : 0.0f;
+            const float dPz = (ppz >= 1e-5f) ? -(gix * ppx + giy * ppy) * iZ * iZ : 0.0f;
             float dXc[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) dXc[i] = Kref[0 + i] * dPx + Kref[3 + i] * dPy + Kref[6 + i] * dPz;
@@ -549,9 +606,6 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
             const float dX = Rt[0] * dXc[0] + Rt[3] * dXc[1] + Rt[6] * dXc[2];
             const float dY = Rt[1] * dXc[0] + Rt[4] * dXc[1] + Rt[7] * dXc[2];
             const float dZ = Rt[2] * dXc[0] + Rt[5] * dXc[1] + Rt[8] * dXc[2];
-            // X = ray * depth with ray = X / depth
-            const float rx = dot3_rn(Kinv + 0, (float)x, (float)y, 1.0f), ry = dot3_rn(Kinv + 3, (float)x, (float)y, 1.0f),
-                        rz = dot3_rn(Kinv + 6, (float)x, (float)y, 1.0f);
             ddepth += rx * dX + ry * dY + rz * dZ;
           }
           if (inv >= 1e-6f) ginv_acc[slot] += -ddepth * depth * depth;  // d(1/clamp(inv)) (depth.py:120)
@@ -610,8 +664,18 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
       }
     }
     if ((!GRAD || FUSED) && do_smooth) {
-      const float ss = block_sum(smooth_acc, s_red);
-      if (threadIdx.x == 0) atomicAdd(P.smooth_bs + s * P.B + b, (double)ss);
+      // warp tree + one shared atomic per warp: no block barrier per scale (the global add happens once, after the loop)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) smooth_acc += __shfl_xor_sync(0xffffffffu, smooth_acc, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_smooth[js], smooth_acc);
+    }
+  }
+  if (!GRAD || FUSED) {
+    __syncthreads();
+    if (threadIdx.x < G.ns) {
+      const ScaleParams& Sj = P.sc[G.scale[threadIdx.x]];
+      if ((Sj.sx_coef != 0.0f) || (Sj.sy_coef != 0.0f)) atomicAdd(P.smooth_bs + G.scale[threadIdx.x] * P.B + b, (double)s_smooth[threadIdx.x]);
+      __threadfence();     // before this CTA's ticket (taken by thread 0 behind the barriers of the photometric block sum)
     }
   }
 

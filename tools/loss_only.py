@@ -12,6 +12,7 @@ from packnet_sfm_b200.models import YACS_LOSS_DEFAULTS  # noqa: E402
 
 B, H, W = 4, 192, 640
 dev = torch.device("cuda:0")
+torch.cuda.set_stream(torch.cuda.Stream(dev))     # everything on one non-default stream (graph capture below; see bench.py)
 fr = synthetic.make_frames(B, H, W, seed=5)
 # the product's default: maps at H, H/2, H/4, H/8 read nearest-upsampled by the kernel (a8 fused); PN_LOSS_FULLRES=1 = pre-upsampled
 FULL = os.environ.get("PN_LOSS_FULLRES") == "1"
@@ -59,5 +60,16 @@ def bwd():
 fwd()
 t_f, t_b = timed(fwd), timed(bwd)
 P_s = B * H * W * 4
-print("program %s: fwd %.4f ms (%.0f GB/s algorithmic), bwd %.4f ms (%.0f GB/s algorithmic)" % (
-    "grouped" if os.environ.get("PN_LOSS_GROUPED", "1") == "1" else "tile", t_f, 48 * P_s / t_f / 1e6, t_b, 44 * P_s / t_b / 1e6))
+print("program %s, eager calls: fwd %.4f ms, bwd %.4f ms" % ("grouped" if os.environ.get("PN_LOSS_GROUPED", "1") == "1" else "tile", t_f, t_b))
+# replayed graphs: device time without the host's enqueue gaps (how the training step runs it)
+fwd(); bwd()
+torch.cuda.synchronize()
+gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+with torch.cuda.graph(gf):
+    fwd()
+with torch.cuda.graph(gb, pool=gf.pool()):
+    bwd()
+torch.cuda.synchronize()
+t_f, t_b = timed(gf.replay), timed(gb.replay)
+print("program %s, graph replay: fwd %.4f ms + bwd %.4f ms = %.4f ms -> %.0f GB/s algorithmic (%.1f MB)" % (
+    "grouped" if os.environ.get("PN_LOSS_GROUPED", "1") == "1" else "tile", t_f, t_b, t_f + t_b, 92 * P_s / (t_f + t_b) / 1e6, 92 * P_s / 1e6))
