@@ -145,7 +145,7 @@ def _grad_samples(named_grads, arrays, prefix, n=64):
         arrays[prefix + "samp/" + k] = flat[idx].numpy()
 
 
-def packnet_baseline_case(B=4, H=192, W=640, name="packnet01_192x640_b4"):
+def packnet_baseline_case(B=4, H=192, W=640, name="packnet01_192x640_b4", disp1_stride=1):
     """PackNet01 at BASELINE configs[1] (B=4, 192x640): the engine paths that the 64x96 fixture cannot reach (persistent
     tile loop, batch folding, split-K thresholds).  Depth maps in full (fp32), the gradient of sum_i <disp_i, gy_i> for a
     seeded gy as per-parameter norms + strided samples.  The input is regenerated from its seed by the test; a checksum
@@ -163,11 +163,18 @@ def packnet_baseline_case(B=4, H=192, W=640, name="packnet01_192x640_b4"):
     for i, d in enumerate(out):
         gy = torch.rand(d.shape, generator=g) - 0.5
         obj = obj + (d * gy).sum()
-        arrays["disp%d" % (i + 1)] = d.detach().numpy()
+        # the full-resolution map of the large fixtures is stored at every second pixel (fixture size)
+        arrays["disp%d" % (i + 1)] = d.detach()[..., ::disp1_stride, ::disp1_stride].numpy() if i == 0 else d.detach().numpy()
+    arrays["disp1_stride"] = np.int64(disp1_stride)
     obj.backward()
     _grad_samples([(k, p.grad) for k, p in net.named_parameters()], arrays, "g")
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
     print(name, [tuple(d.shape) for d in out], float(out[0].mean()))
+
+
+def packnet_config3_case():
+    """BASELINE configs[2]'s per-GPU shape: B=2, 384x1280."""
+    packnet_baseline_case(B=2, H=384, W=1280, name="packnet01_384x1280_b2", disp1_stride=2)
 
 
 def step_case(B=2, H=64, W=96, name="step_2x64x96"):
