@@ -75,6 +75,7 @@ struct GnClusterParams {
   float* dgamma; float* dbeta; float* dsum;   // [C] each, ZEROED by the caller (float atomics over samples / clusters)
 };
 
+template <int U>      // independent 16-byte loads in flight per thread and trip (4: small tensors; 8: keeps a 96x320 map streaming)
 __global__ void __launch_bounds__(GNC_THREADS, 1) gn_elu_cluster_fwd_kernel(const GnClusterParams P) {
   cgx::cluster_group cluster = cgx::this_cluster();
   __shared__ double s_part[2 * GNC_WARPS * GNC_MAXCW];
@@ -100,12 +101,12 @@ __global__ void __launch_bounds__(GNC_THREADS, 1) gn_elu_cluster_fwd_kernel(cons
   // ---- pass 1: sums ---------------------------------------------------------------------------------
   float acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
   int p = p0 + pl;
-  for (; p + 3 * lanes < p1; p += 4 * lanes) {
-    float4 v[4];
+  for (; p + (U - 1) * lanes < p1; p += U * lanes) {
+    float4 v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = load(p + u * lanes);
+    for (int u = 0; u < U; ++u) v[u] = load(p + u * lanes);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       acc[0][0] += v[u].x; acc[0][1] += v[u].y; acc[0][2] += v[u].z; acc[0][3] += v[u].w;
       acc[1][0] += v[u].x * v[u].x; acc[1][1] += v[u].y * v[u].y; acc[1][2] += v[u].z * v[u].z; acc[1][3] += v[u].w * v[u].w;
     }
@@ -165,12 +166,12 @@ __global__ void __launch_bounds__(GNC_THREADS, 1) gn_elu_cluster_fwd_kernel(cons
     if (P.hi) store_split4(P.hi, P.lo, (pix * C + c0 + col * 4) >> 2, out);
   };
   p = p0 + pl;
-  for (; p + 3 * lanes < p1; p += 4 * lanes) {
-    float4 v[4];
+  for (; p + (U - 1) * lanes < p1; p += U * lanes) {
+    float4 v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = load(p + u * lanes);
+    for (int u = 0; u < U; ++u) v[u] = load(p + u * lanes);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) apply(p + u * lanes, v[u]);
+    for (int u = 0; u < U; ++u) apply(p + u * lanes, v[u]);
   }
   for (; p < p1; p += lanes) apply(p, load(p));
 }
@@ -326,11 +327,15 @@ static int gn_cluster_launch(bool bwd, const GnClusterParams& P, int B, int cl, 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  const bool deep = P.ppc * (P.cw / 4) >= 8 * GNC_THREADS;     // at least one full trip of 8 loads per thread
   if (cl > 8) {
-    PN_CUDA(cudaFuncSetAttribute(bwd ? gn_elu_cluster_bwd_kernel : gn_elu_cluster_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (bwd) PN_CUDA(cudaFuncSetAttribute(gn_elu_cluster_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    else if (deep) PN_CUDA(cudaFuncSetAttribute(gn_elu_cluster_fwd_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    else PN_CUDA(cudaFuncSetAttribute(gn_elu_cluster_fwd_kernel<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   if (bwd) PN_CUDA(cudaLaunchKernelEx(&cfg, gn_elu_cluster_bwd_kernel, P));
-  else     PN_CUDA(cudaLaunchKernelEx(&cfg, gn_elu_cluster_fwd_kernel, P));
+  else if (deep) PN_CUDA(cudaLaunchKernelEx(&cfg, gn_elu_cluster_fwd_kernel<8>, P));
+  else     PN_CUDA(cudaLaunchKernelEx(&cfg, gn_elu_cluster_fwd_kernel<4>, P));
   count_launch();
   return 0;
 }

@@ -479,7 +479,13 @@ __global__ void __launch_bounds__(256, 2) stencil_fwd8_kernel(const StencilParam
   __syncthreads();
   const int ntiles = P.tw * (D >> 3);
   for (int it = threadIdx.x; it < ntiles; it += blockDim.x) {
-    const int pw = it % P.tw, d0 = (it / P.tw) << 3;
+    // pack: consecutive lanes = consecutive pixels (each thread stores whole 32-byte runs of its own pixel).  unpack: the
+    // depth-to-space store sends a thread's 8 depths to 2 channels x 4 pixels, so consecutive lanes take consecutive depth
+    // blocks of ONE pixel: D/8 lanes together write D/4 contiguous channels (32 bytes at D = 32: whole sectors; the
+    // pixel-major order wrote 4-byte pieces 512 bytes apart -- r02n: unpack1 forward 189 us for 126 MB).  Shared-memory reads
+    // stay conflict-free: a quarter-warp's float4 columns start at (lane / (D/8)) * (D + 4) + (lane % (D/8)) * 8 floats.
+    const int nd = D >> 3;
+    const int pw = PACK ? it % P.tw : it / nd, d0 = (PACK ? it / P.tw : it % nd) << 3;
     const int w = w0 + pw;
     if (w >= P.W) continue;
     float acc[8][8];
@@ -523,15 +529,26 @@ __global__ void __launch_bounds__(256, 2) stencil_fwd8_kernel(const StencilParam
         }
       }
     } else {
+      // v = f*D + d0 + k -> channel v >> 2 at output pixel (2h + ((v >> 1) & 1), 2w + (v & 1)); d0 and D are multiples of 8, so
+      // depths k and k + 4 of a thread are the adjacent channels co0, co0 + 1 of the same pixel: one 8-byte store
+      const bool vec2 = ((P.out_cstride | P.out_coffset) & 1) == 0;
 #pragma unroll
-      for (int f = 0; f < 8; ++f)
+      for (int f = 0; f < 8; ++f) {
+        const int co0 = (f * D + d0) >> 2;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int v = f * D + d0 + k, co = v >> 2, i = (v >> 1) & 1, j = v & 1;
-          const size_t o = (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.out_cstride + P.out_coffset + co;
-          P.out[o] = acc[f][k];
-          if (P.out_lo) P.out_lo[o] = acc[f][k] - tf32_trunc(acc[f][k]);
+        for (int ij = 0; ij < 4; ++ij) {
+          const int i = ij >> 1, j = ij & 1;
+          const size_t o = (((size_t)b * 2 * P.H + (2 * h + i)) * 2 * P.W + (2 * w + j)) * P.out_cstride + P.out_coffset + co0;
+          const float v0 = acc[f][ij], v1 = acc[f][4 + ij];
+          if (vec2) {
+            *reinterpret_cast<float2*>(P.out + o) = make_float2(v0, v1);
+            if (P.out_lo) *reinterpret_cast<float2*>(P.out_lo + o) = make_float2(v0 - tf32_trunc(v0), v1 - tf32_trunc(v1));
+          } else {
+            P.out[o] = v0; P.out[o + 1] = v1;
+            if (P.out_lo) { P.out_lo[o] = v0 - tf32_trunc(v0); P.out_lo[o + 1] = v1 - tf32_trunc(v1); }
+          }
         }
+      }
     }
   }
 }

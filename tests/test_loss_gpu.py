@@ -94,6 +94,7 @@ def test_loss_and_gradients_match_reference_golden(case):
         assert_field_close(d.grad, g, ("ginv", i))
     for j, m in enumerate(mats):
         g = z["gpose%d" % j]
+        print("POSE_REL %s gpose%d %.3e" % (case, j, rel_l2(m.grad.cpu(), g)))
         assert rel_l2(m.grad.cpu(), g) < POSE_TOL, ("gpose", j, rel_l2(m.grad.cpu(), g))
         assert float(m.grad[:, 3, :].abs().max()) == 0.0
 
@@ -165,6 +166,7 @@ def test_ragged_shapes_against_oracle(shape):
     for i, (a, b) in enumerate(zip(inv_d, inv_c)):
         assert_field_close(a.grad, b.grad, ("ginv", i))
     for a, b in zip(mats_d, mats_c):
+        print("POSE_REL configurations %.3e" % rel_l2(a.grad.cpu(), b.grad))
         assert rel_l2(a.grad.cpu(), b.grad) < POSE_TOL
 
 
@@ -185,6 +187,7 @@ def test_bench_shape_against_oracle():
     for i, (a, b) in enumerate(zip(inv_d, inv_c)):
         assert_field_close(a.grad, b.grad, ("ginv", i))
     for a, b in zip(mats_d, mats_c):
+        print("POSE_REL bench_shape %.3e" % rel_l2(a.grad.cpu(), b.grad))
         assert rel_l2(a.grad.cpu(), b.grad) < POSE_TOL
 
 
