@@ -396,9 +396,13 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int b,
 // cell per warp iteration.  With D = 64 the original keeps 16 of 32 lanes busy and issues one dependent 256-byte load per
 // warp iteration: the head convolution stages 340 cells = 43 serial round trips to DRAM per warp, which is what its
 // 0.22 ms at 192x640 (126 MB: 17 us at the HBM rate) amounts to; the unpack stencils (D = 32) keep 8 lanes busy.
-template <bool S2D>
+// PLANES: the nr "rows" of the tile are nr channel windows of ONE grid row h0 (row r reads channels chan0 + r * chan_step): the
+// eight feature planes of an output gradient staged by one call = one load phase (round 1 staged them with eight calls, i.e.
+// eight serial DRAM round trips per work item of the weight-gradient / data-gradient kernels).
+template <bool S2D, bool PLANES = false>
 __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, int b, int H, int W, int pixstride, int chan0, int D,
-                                                int h0, int nr, int w0, int nc, float* __restrict__ s) {
+                                                int h0, int nr, int w0, int nc, float* __restrict__ s, int chan_step = 0,
+                                                int start = 0) {
   constexpr int U = 8;   // items in flight per thread: all loads of a batch are issued before the first store
   const int PITCH = D + SPAD, dq = D >> 2;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -408,9 +412,10 @@ __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, i
   // thread then walks its items (it, it + step, ...) with carries
   const int step_q = step % dq, step_cell = step / dq;
   const int step_c = step_cell % nc, step_r = step_cell / nc;
-  int q = (int)threadIdx.x % dq, cell0 = (int)threadIdx.x / dq;
+  // `start` (a multiple of blockDim.x): the items before it were brought in by flat_prefetch / flat_store
+  int q = ((int)threadIdx.x + start) % dq, cell0 = ((int)threadIdx.x + start) / dq;
   int c = cell0 % nc, r = cell0 / nc;
-  for (int base = threadIdx.x; base < total; base += step * U) {
+  for (int base = threadIdx.x + start; base < total; base += step * U) {
     float4 v[U];
     int off[U];   // shared-memory float offset of the item's float4 (low bit set: first float4 of its cell), -1: no item
 #pragma unroll
@@ -418,16 +423,17 @@ __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, i
       v[u] = z4;
       off[u] = -1;
       if (base + u * step < total) {
-        const int hh = h0 + r, ww = w0 + c;
+        const int hh = PLANES ? h0 : h0 + r, ww = w0 + c;
+        const int ch = PLANES ? chan0 + r * chan_step : chan0;
         off[u] = ((r * nc + c) * PITCH + SPAD + 4 * q) | (q == 0 ? 1 : 0);
         if ((hh >= 0) && (hh < H) && (ww >= 0) && (ww < W)) {
           if (S2D) {
             const size_t rowstride = (size_t)2 * W * pixstride;
-            const float* p00 = src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + chan0;
+            const float* p00 = src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + ch;
             v[u].x = __ldg(p00 + q); v[u].y = __ldg(p00 + pixstride + q);
             v[u].z = __ldg(p00 + rowstride + q); v[u].w = __ldg(p00 + rowstride + pixstride + q);
           } else {
-            v[u] = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + chan0) + q);
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + ch) + q);
           }
         }
         // advance (q, c, r) by `step` items
@@ -451,6 +457,56 @@ __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, i
   if (threadIdx.x == 0) *reinterpret_cast<float4*>(s + (size_t)ncell * PITCH) = z4;   // depth D of the last cell
 }
 
+
+// Register prefetch of the FIRST U items per thread of a flat-staged region (same item order, addresses and shared-memory image
+// as stage_tile_flat): flat_prefetch issues the loads -- typically for the NEXT work item / feature plane, right before the FMAs
+// of the current one -- and flat_store writes them behind the barrier that ends those FMAs.  Regions with more than
+// U * blockDim.x items finish with stage_tile_flat(..., start = U * blockDim.x).
+template <int U>
+struct FlatRegs { float4 v[U]; int off[U]; };
+
+template <bool S2D, bool PLANES, int U>
+__device__ __forceinline__ void flat_prefetch(FlatRegs<U>& R, const float* __restrict__ src, int b, int H, int W, int pixstride, int chan0,
+                                              int D, int h0, int nr, int w0, int nc, int chan_step = 0) {
+  const int PITCH = D + SPAD, dq = D >> 2, total = nr * nc * dq;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int it = (int)threadIdx.x + u * (int)blockDim.x;
+    R.v[u] = z4;
+    R.off[u] = -1;
+    if (it < total) {
+      const int q = it % dq, cell = it / dq, c = cell % nc, r = cell / nc;
+      const int hh = PLANES ? h0 : h0 + r, ww = w0 + c;
+      const int ch = PLANES ? chan0 + r * chan_step : chan0;
+      R.off[u] = (cell * PITCH + SPAD + 4 * q) | (q == 0 ? 1 : 0);
+      if ((hh >= 0) && (hh < H) && (ww >= 0) && (ww < W)) {
+        if (S2D) {
+          const size_t rowstride = (size_t)2 * W * pixstride;
+          const float* p00 = src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + ch;
+          R.v[u].x = __ldg(p00 + q); R.v[u].y = __ldg(p00 + pixstride + q);
+          R.v[u].z = __ldg(p00 + rowstride + q); R.v[u].w = __ldg(p00 + rowstride + pixstride + q);
+        } else {
+          R.v[u] = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + hh) * W + ww) * pixstride + ch) + q);
+        }
+      }
+    }
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void flat_store(const FlatRegs<U>& R, float* __restrict__ s, int D, int ncell) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (R.off[u] >= 0) {
+      const int o = R.off[u] & ~1;
+      *reinterpret_cast<float4*>(s + o) = R.v[u];
+      if (R.off[u] & 1) *reinterpret_cast<float4*>(s + o - SPAD) = z4;   // the cell's front pad
+    }
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<float4*>(s + (size_t)ncell * (D + SPAD)) = z4;   // depth D of the last cell
+}
 
 // the 10 staged floats around depths [d0, d0+8) of one cell: vv[j] = depth d0 - 1 + j
 __device__ __forceinline__ void load_col10(const float* __restrict__ col, float vv[10]) {
@@ -562,7 +618,7 @@ struct StencilBwd8Params {
   int th;   // rows per CTA (even)
 };
 
-template <bool PACK, int MAXT, bool FLAT = false>
+template <bool PACK, int MAXT, bool FLAT = false, bool PRE = false>
 __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Params Q) {
   const StencilBwdParams& P = Q.p;
   PN_DYNAMIC_SHARED(float, sm);
@@ -579,16 +635,33 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
     for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[m][rr][k] = 0.0f;
+  // FLAT: the first UP items per thread of feature plane f+1 are loaded into registers before the FMAs of plane f (eight
+  // serial load phases per CTA otherwise); a plane with more items finishes behind the barrier as before.
+  constexpr int UP = 8;
+  FlatRegs<UP> RP;
+  const int plane_items = (TH + 2) * TWP * (D >> 2);
+  auto prefetch = [&](int f) {
+    if (PACK) flat_prefetch<false, false, UP>(RP, P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP);
+    else      flat_prefetch<true, false, UP>(RP, P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP);
+  };
+  if (PRE) prefetch(0);
   for (int f = 0; f < 8; ++f) {
     __syncthreads();   // the previous plane is consumed (and s_w is visible)
-    if (FLAT) {
+    if (FLAT && !PRE) {
       if (PACK) stage_tile_flat<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
       else      stage_tile_flat<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
+    } else if (PRE) {
+      flat_store<UP>(RP, s_g, D, (TH + 2) * TWP);
+      if (plane_items > UP * (int)blockDim.x) {
+        if (PACK) stage_tile_flat<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g, 0, UP * (int)blockDim.x);
+        else      stage_tile_flat<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g, 0, UP * (int)blockDim.x);
+      }
     } else {
       if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
       else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
     }
     __syncthreads();
+    if (PRE && f + 1 < 8) prefetch(f + 1);     // in flight during the FMAs of this plane
     float wr[27];
 #pragma unroll
     for (int t = 0; t < 27; ++t) wr[t] = s_w[f * 27 + t];
@@ -663,7 +736,7 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
 // weight / bias gradient.  Warp (fp, half): feature pair {2fp, 2fp+1}, half of the thread tiles; 54 + 2 partial sums in
 // registers over the whole persistent walk, one warp reduction + atomics at the end.
 // smem: s_v[3][tw+2][PITCH] + 4, s_gc[8][tw][PITCH]
-template <bool PACK, bool FLAT = false>
+template <bool PACK, bool FLAT = false, bool PRE = false>
 __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdParams P) {
   PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
@@ -678,22 +751,46 @@ __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdPar
   const int wtiles = (P.W + P.tw - 1) / P.tw;
   const int nwork = P.B * P.H * wtiles;
   const int ntiles = P.tw * (D >> 3);
+  // FLAT: the staging loads of work item i+1 are issued before the FMAs of work item i (register prefetch: UA + UG float4 per
+  // thread cover a whole work item at D = 32, tw = 16) -- round 1 paid nine serial DRAM round trips per work item (r02n:
+  // unpack1 weight gradient 241 us for 142 MB).
+  constexpr int UA = 4, UG = 8;
+  FlatRegs<UA> RA;
+  FlatRegs<UG> RG;
+  auto prefetch = [&](int work) {
+    const int wt = work % wtiles, row = work / wtiles;
+    const int b = row / P.H, h = row % P.H, w0 = wt * P.tw;
+    flat_prefetch<PACK, false, UA>(RA, P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP);
+    if (PACK) flat_prefetch<false, true, UG>(RG, P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, D);
+    else      flat_prefetch<true, true, UG>(RG, P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, D >> 2);
+  };
+  if (PRE && (int)blockIdx.x < nwork) prefetch(blockIdx.x);
   for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
     const int wt = work % wtiles, row = work / wtiles;
     const int b = row / P.H, h = row % P.H, w0 = wt * P.tw;
     __syncthreads();
-    if (FLAT) stage_tile_flat<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
-    else      stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
-    for (int f = 0; f < 8; ++f) {
-      if (FLAT) {
-        if (PACK) stage_tile_flat<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
-        else      stage_tile_flat<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
-      } else {
+    if (FLAT && !PRE) {
+      stage_tile_flat<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+      if (PACK) stage_tile_flat<false, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, s_gc, D);       // the eight planes:
+      else      stage_tile_flat<true, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, s_gc, D >> 2);    // ONE load phase
+    } else if (PRE) {
+      flat_store<UA>(RA, s_v, D, 3 * TWP);
+      flat_store<UG>(RG, s_gc, D, 8 * P.tw);
+      const int step = (int)blockDim.x;
+      if (3 * TWP * (D >> 2) > UA * step) stage_tile_flat<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v, 0, UA * step);
+      if (8 * P.tw * (D >> 2) > UG * step) {
+        if (PACK) stage_tile_flat<false, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, s_gc, D, UG * step);
+        else      stage_tile_flat<true, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, s_gc, D >> 2, UG * step);
+      }
+    } else {
+      stage_tile<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
+      for (int f = 0; f < 8; ++f) {
         if (PACK) stage_tile<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
         else      stage_tile<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h, 1, w0, P.tw, s_gc + (size_t)f * P.tw * PITCH);
       }
     }
     __syncthreads();
+    if (PRE && work + (int)gridDim.x < nwork) prefetch(work + gridDim.x);     // in flight during the FMAs below
     const float* gA = s_gc + (size_t)(2 * fp) * P.tw * PITCH + SPAD;
     const float* gB = gA + (size_t)P.tw * PITCH;
     for (int it = half * 32 + lane; it < ntiles; it += 64) {
@@ -1419,6 +1516,18 @@ __global__ void __launch_bounds__(256) unpack_weight_grad_tiled_kernel(const flo
   for (int i = threadIdx.x; i < n * taps; i += blockDim.x) out[i] = sm[i];
 }
 
+// register prefetch of the next work item / feature plane in the stencil backward kernels (A/B: PN_STENCIL_PREFETCH=0)
+static int stencil_prefetch() {
+  static std::atomic<int> v{-1};
+  int x = v.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = std::getenv("PN_STENCIL_PREFETCH");
+    x = (e && e[0] == '0') ? 0 : 1;
+    v.store(x, std::memory_order_relaxed);
+  }
+  return x;
+}
+
 static std::atomic<int> g_gn_tree{-1};
 static int gn_tree() {
   int v = g_gn_tree.load(std::memory_order_relaxed);
@@ -1538,7 +1647,10 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
         return 0;
       };
       int lrc;
-      if (stage_flat()) {
+      if (stage_flat() && stencil_prefetch()) {
+        if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1, true, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2, true, true>) : launch(stencil_bwd8_kernel<true, 4, true, true>);
+        else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1, true, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2, true, true>) : launch(stencil_bwd8_kernel<false, 4, true, true>);
+      } else if (stage_flat()) {
         if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2, true>) : launch(stencil_bwd8_kernel<true, 4, true>);
         else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2, true>) : launch(stencil_bwd8_kernel<false, 4, true>);
       } else {
@@ -1568,9 +1680,9 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
         PN_LAUNCH(kern, ctas, 256, smem8, stream, Q);
         return 0;
       };
-      const bool flat = stage_flat() != 0;
-      const int lrcw = pack ? (flat ? launchw(stencil_wgrad8_kernel<true, true>) : launchw(stencil_wgrad8_kernel<true>))
-                            : (flat ? launchw(stencil_wgrad8_kernel<false, true>) : launchw(stencil_wgrad8_kernel<false>));
+      const bool flat = stage_flat() != 0, pre = flat && stencil_prefetch();
+      const int lrcw = pack ? (pre ? launchw(stencil_wgrad8_kernel<true, true, true>) : flat ? launchw(stencil_wgrad8_kernel<true, true>) : launchw(stencil_wgrad8_kernel<true>))
+                            : (pre ? launchw(stencil_wgrad8_kernel<false, true, true>) : flat ? launchw(stencil_wgrad8_kernel<false, true>) : launchw(stencil_wgrad8_kernel<false>));
       if (lrcw) return lrcw;
       count_launch();
       return check_launch("stencil_wgrad8_kernel");
