@@ -73,8 +73,8 @@ __device__ __forceinline__ long long z_offset(const Params& P, const Term& T, in
 // is contiguous in the reduction index) or along the row / column index.
 template <bool A_KFAST, bool B_KFAST, class RA, class LA, class RB, class LB>
 __device__ __forceinline__ void gemm_tile(int K2, int K1, int K0, int m0, int n0, RA ra, LA la, RB rb, LB lb, float (&acc)[4][4]) {
-  __align__(16) __shared__ float As[BK][BM + 4];
-  __align__(16) __shared__ float Bs[BK][BN + 4];
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
   const int t = threadIdx.x;
   const int ty = t / 16, tx = t % 16;
   constexpr int LD = (BM * BK) / NT;                     // 4 loads per thread and operand
@@ -96,47 +96,43 @@ __device__ __forceinline__ void gemm_tile(int K2, int K1, int K0, int m0, int n0
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // The reduction is walked as ONE sequence of stages (k2, k1, kb) with the global loads of stage s+1 issued BEFORE the FMAs
-  // of stage s (register prefetch): the load -> store -> barrier -> FMA -> barrier loop of round 1 paid one exposed DRAM / L2
-  // round trip per 16-wide stage -- 112 of them for pack1's 7 x 256 reduction, ~0.2 ms for 0.4 GMAC (r02n: 45 GB/s, 5 TFLOP/s).
-  auto load_stage = [&](int k2, int k1, int kb, float (&av)[LD], float (&bv)[LD]) {
+  for (int k2 = 0; k2 < K2; ++k2)
+    for (int k1 = 0; k1 < K1; ++k1)
+      for (int kb = 0; kb < K0; kb += BK) {
+        // all eight global loads of the stage first, then the shared stores: left interleaved (load, store, load, ...) every
+        // store waits for its own load and the stage costs eight serial round trips instead of one.
+        // (Round 2 tried a register-prefetch pipeline over the stages + float4 operand reads: forward 0.45 -> 0.55 ms on the B200,
+        // gpurun r02v -- the three launches are a few hundred CTAs of 2 waves each; reverted.)
+        float av[LD], bv[LD];
 #pragma unroll
-    for (int i = 0; i < LD; ++i) {
-      const int k0 = kb + a_kk[i];
-      av[i] = (k0 < K0) ? la(ca[i], k2, k1, k0) : 0.f;
-    }
+        for (int i = 0; i < LD; ++i) {
+          const int k0 = kb + a_kk[i];
+          av[i] = (k0 < K0) ? la(ca[i], k2, k1, k0) : 0.f;
+        }
 #pragma unroll
-    for (int i = 0; i < LD; ++i) {
-      const int k0 = kb + b_kk[i];
-      bv[i] = (k0 < K0) ? lb(cb[i], k2, k1, k0) : 0.f;
-    }
-  };
-  int k2 = 0, k1 = 0, kb = 0;
-  bool have = (K2 > 0) && (K1 > 0) && (K0 > 0);
-  float av[LD], bv[LD];
-  if (have) load_stage(k2, k1, kb, av, bv);
-  while (have) {
+        for (int i = 0; i < LD; ++i) {
+          const int k0 = kb + b_kk[i];
+          bv[i] = (k0 < K0) ? lb(cb[i], k2, k1, k0) : 0.f;
+        }
 #pragma unroll
-    for (int i = 0; i < LD; ++i) As[a_kk[i]][a_mm[i]] = av[i];
+        for (int i = 0; i < LD; ++i) As[a_kk[i]][a_mm[i]] = av[i];
 #pragma unroll
-    for (int i = 0; i < LD; ++i) Bs[b_kk[i]][b_nn[i]] = bv[i];
-    __syncthreads();
-    kb += BK;
-    if (kb >= K0) { kb = 0; if (++k1 >= K1) { k1 = 0; ++k2; } }
-    have = k2 < K2;
-    if (have) load_stage(k2, k1, kb, av, bv);      // in flight during the FMAs below
+        for (int i = 0; i < LD; ++i) Bs[b_kk[i]][b_nn[i]] = bv[i];
+        __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);   // rows are 272 bytes: 16-byte aligned
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int kk = 0; kk < BK; ++kk) {
+          float a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
+          for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
 }
 
 struct PixelCtx { int valid, b, l; };                    // a row of the border line: pixel l of sample b

@@ -1516,13 +1516,15 @@ __global__ void __launch_bounds__(256) unpack_weight_grad_tiled_kernel(const flo
   for (int i = threadIdx.x; i < n * taps; i += blockDim.x) out[i] = sm[i];
 }
 
-// register prefetch of the next work item / feature plane in the stencil backward kernels (A/B: PN_STENCIL_PREFETCH=0)
+// register prefetch of the next work item / feature plane in the stencil backward kernels: OFF by default -- measured on the
+// B200 (gpurun r02v, whole step 19.92 ms without / 20.15 ms with): the 48 prefetch registers take the kernels from 2 CTAs per
+// SM to 1 (118 -> 226 and 110 -> 189 registers) and the data-gradient launches get slower (0.217 -> 0.259 ms); A/B: PN_STENCIL_PREFETCH=1
 static int stencil_prefetch() {
   static std::atomic<int> v{-1};
   int x = v.load(std::memory_order_relaxed);
   if (x < 0) {
     const char* e = std::getenv("PN_STENCIL_PREFETCH");
-    x = (e && e[0] == '0') ? 0 : 1;
+    x = (e && e[0] == '1') ? 1 : 0;
     v.store(x, std::memory_order_relaxed);
   }
   return x;

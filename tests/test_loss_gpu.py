@@ -29,7 +29,9 @@ def loss_program(request):
 
 LOSS_TOL = 1e-3        # north_star: photometric loss within 1e-3 relative fp32
 GRAD_TOL = 1e-3        # gradient fields: relative L2 over the inlier pixels
-POSE_TOL = 2e-2        # pose gradients are sums over all pixels, outliers included
+POSE_TOL = 1e-3        # pose gradients (sums over all pixels).  Measured on the B200 (r02v): 1.6e-5 .. 1.0e-4 on every fixture except
+POSE_TOL_KINK = 2e-2   # loss_bigmotion (5.6e-3): there a handful of per-pixel minima resolve the other way (full-size gradient each)
+POSE_TOL_ORACLE = 5e-3 # against the oracle on larger synthetic maps (configurations / bench shape: 2.2e-3 .. 2.4e-3 measured, same cause)
 
 
 def _kink_pixels():
@@ -95,7 +97,7 @@ def test_loss_and_gradients_match_reference_golden(case):
     for j, m in enumerate(mats):
         g = z["gpose%d" % j]
         print("POSE_REL %s gpose%d %.3e" % (case, j, rel_l2(m.grad.cpu(), g)))
-        assert rel_l2(m.grad.cpu(), g) < POSE_TOL, ("gpose", j, rel_l2(m.grad.cpu(), g))
+        assert rel_l2(m.grad.cpu(), g) < (POSE_TOL_KINK if case == "loss_bigmotion" else POSE_TOL), ("gpose", j, rel_l2(m.grad.cpu(), g))
         assert float(m.grad[:, 3, :].abs().max()) == 0.0
 
 
@@ -167,7 +169,7 @@ def test_ragged_shapes_against_oracle(shape):
         assert_field_close(a.grad, b.grad, ("ginv", i))
     for a, b in zip(mats_d, mats_c):
         print("POSE_REL configurations %.3e" % rel_l2(a.grad.cpu(), b.grad))
-        assert rel_l2(a.grad.cpu(), b.grad) < POSE_TOL
+        assert rel_l2(a.grad.cpu(), b.grad) < POSE_TOL_ORACLE
 
 
 def test_bench_shape_against_oracle():
@@ -188,7 +190,7 @@ def test_bench_shape_against_oracle():
         assert_field_close(a.grad, b.grad, ("ginv", i))
     for a, b in zip(mats_d, mats_c):
         print("POSE_REL bench_shape %.3e" % rel_l2(a.grad.cpu(), b.grad))
-        assert rel_l2(a.grad.cpu(), b.grad) < POSE_TOL
+        assert rel_l2(a.grad.cpu(), b.grad) < POSE_TOL_ORACLE
 
 
 def test_properties_full_size():
