@@ -431,13 +431,20 @@ class _FeatureStencil(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, w3 = ctx.saved_tensors
-        g = g.contiguous()
         B, h, w, C = ctx.dims
+        # The gradient usually arrives as a CHANNEL WINDOW of the gradient of a concatenation (torch.cat's backward hands out
+        # narrow() views): the kernels read it in place through their channel stride -- no contiguous copy of the window
+        cs = ctx.cs
+        if (not g.is_contiguous() and g.dim() == 4 and g.stride(3) == 1 and g.stride(2) % 4 == 0 and g.stride(2) >= g.shape[3]
+                and g.stride(1) == g.shape[2] * g.stride(2) and g.stride(0) == g.shape[1] * g.stride(1) and g.data_ptr() % 16 == 0):
+            cs = g.stride(2)
+        else:
+            g = g.contiguous()
         gin = torch.empty_like(x)
         gw3 = torch.empty(216, dtype=torch.float32, device=x.device)
         gb3 = torch.empty(8, dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().pn_feature_stencil_backward(int(ctx.pack), _lib.ptr(x), _lib.ptr(g), _lib.ptr(w3), _lib.ptr(gin),
-                                                          _lib.ptr(gw3), _lib.ptr(gb3), B, h, w, C, ctx.cs, 0, _stream()),
+                                                          _lib.ptr(gw3), _lib.ptr(gb3), B, h, w, C, cs, 0, _stream()),
                    "pn_feature_stencil_backward")
         return gin, gw3.view(8, 1, 3, 3, 3), gb3, None
 

@@ -133,7 +133,14 @@ def _feature_stencil_cases(PF):
         b3 = (torch.rand(8) - 0.5).requires_grad_(True)
         y = PF.pack_features(x, w3, b3) if pack else PF.unpack_features(x, w3, b3)
         gy = torch.rand_like(y) - 0.5
-        y.backward(gy)
+        if shape[-1] % 4 == 0 and not pack:
+            # as in the decoder: the output is concatenated with a skip tensor, so its gradient arrives as a channel WINDOW
+            # of the concatenation's gradient (a narrow() view), which the kernels read in place through their channel stride
+            skip = torch.rand(*y.shape[:3], 8 + y.shape[3])
+            gcat = torch.cat([gy, torch.rand_like(skip)], -1)
+            (torch.cat([y, skip], -1) * gcat).sum().backward()
+        else:
+            y.backward(gy)
         xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w3, b3))
         xn = xd.permute(0, 3, 1, 2)
         if pack:
