@@ -458,6 +458,81 @@ __device__ __forceinline__ void stage_tile_flat(const float* __restrict__ src, i
 }
 
 
+// ---- asynchronous staging (cp.async): global -> shared copies that need no registers and no load/store pairing ------------------
+// A work item's tiles are copied into the OTHER half of a double buffer while the FMAs of the current one run; rows outside the
+// grid are zero-filled by the copy itself (src-size 0).  The emulated host build performs the copy at issue time.
+__device__ __forceinline__ void pn_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+#ifdef PN_EMULATE
+  if (valid) std::memcpy(smem_dst, gsrc, 16); else std::memset(smem_dst, 0, 16);
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+#endif
+}
+__device__ __forceinline__ void pn_cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+#ifdef PN_EMULATE
+  if (valid) std::memcpy(smem_dst, gsrc, 4); else std::memset(smem_dst, 0, 4);
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+#endif
+}
+__device__ __forceinline__ void pn_cp_async_commit() {
+#ifndef PN_EMULATE
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void pn_cp_async_wait() {
+#ifndef PN_EMULATE
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// the zero cells of a staged region that no copy ever touches: front pad of every cell and depth D of the last one
+__device__ __forceinline__ void stage_pads_zero(float* __restrict__ s, int D, int ncell) {
+  const int PITCH = D + SPAD;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int cell = threadIdx.x; cell <= ncell; cell += blockDim.x) *reinterpret_cast<float4*>(s + (size_t)cell * PITCH) = z4;
+}
+
+// stage_tile_flat's region (same item order, addresses and shared-memory image, pads excluded: stage_pads_zero) as
+// asynchronous copies
+template <bool S2D, bool PLANES>
+__device__ __forceinline__ void stage_tile_async(const float* __restrict__ src, int b, int H, int W, int pixstride, int chan0, int D,
+                                                 int h0, int nr, int w0, int nc, float* __restrict__ s, int chan_step = 0) {
+  const int PITCH = D + SPAD, dq = D >> 2;
+  const int total = nr * nc * dq, step = (int)blockDim.x;
+  const int step_q = step % dq, step_cell = step / dq;
+  const int step_c = step_cell % nc, step_r = step_cell / nc;
+  int q = (int)threadIdx.x % dq, cell0 = (int)threadIdx.x / dq;
+  int c = cell0 % nc, r = cell0 / nc;
+  for (int it = threadIdx.x; it < total; it += step) {
+    const int hh = PLANES ? h0 : h0 + r, ww = w0 + c;
+    const int ch = PLANES ? chan0 + r * chan_step : chan0;
+    float* dst = s + (size_t)(r * nc + c) * PITCH + SPAD + 4 * q;
+    const bool inside = (hh >= 0) && (hh < H) && (ww >= 0) && (ww < W);
+    if (S2D) {
+      const size_t rowstride = (size_t)2 * W * pixstride;
+      const float* p00 = inside ? src + (((size_t)b * 2 * H + 2 * hh) * 2 * W + 2 * ww) * pixstride + ch + q : src;
+      pn_cp_async4(dst + 0, p00, inside);
+      pn_cp_async4(dst + 1, inside ? p00 + pixstride : src, inside);
+      pn_cp_async4(dst + 2, inside ? p00 + rowstride : src, inside);
+      pn_cp_async4(dst + 3, inside ? p00 + rowstride + pixstride : src, inside);
+    } else {
+      pn_cp_async16(dst, inside ? src + (((size_t)b * H + hh) * W + ww) * pixstride + ch + 4 * q : src, inside);
+    }
+    q += step_q;
+    int carry = 0;
+    if (q >= dq) { q -= dq; carry = 1; }
+    c += step_c + carry;
+    r += step_r;
+    if (c >= nc) { c -= nc; r += 1; }
+  }
+}
+
 // Register prefetch of the FIRST U items per thread of a flat-staged region (same item order, addresses and shared-memory image
 // as stage_tile_flat): flat_prefetch issues the loads -- typically for the NEXT work item / feature plane, right before the FMAs
 // of the current one -- and flat_store writes them behind the barrier that ends those FMAs.  Regions with more than
@@ -618,13 +693,14 @@ struct StencilBwd8Params {
   int th;   // rows per CTA (even)
 };
 
-template <bool PACK, int MAXT, bool FLAT = false, bool PRE = false>
+template <bool PACK, int MAXT, bool FLAT = false, bool PRE = false, bool ASYNC = false>
 __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Params Q) {
   const StencilBwdParams& P = Q.p;
   PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2, TH = Q.th;
+  const size_t g_floats = (size_t)(TH + 2) * TWP * PITCH + 4;
   float* s_g = sm;
-  float* s_w = sm + (TH + 2) * TWP * PITCH + 4;
+  float* s_w = sm + (ASYNC ? 2 : 1) * g_floats;     // ASYNC: two plane buffers (cp.async of plane f+1 during the FMAs of plane f)
   const int w0 = blockIdx.x * P.tw, h0 = blockIdx.y * TH, b = blockIdx.z;
   for (int i = threadIdx.x; i < 216; i += blockDim.x) s_w[i] = __ldg(P.w3 + i);
   const int ntiles = (TH >> 1) * P.tw * (D >> 3);
@@ -645,9 +721,27 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
     else      flat_prefetch<true, false, UP>(RP, P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP);
   };
   if (PRE) prefetch(0);
+  auto issue = [&](int f, int k) {
+    if (PACK) stage_tile_async<false, false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, sm + (size_t)k * g_floats);
+    else      stage_tile_async<true, false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, sm + (size_t)k * g_floats);
+    pn_cp_async_commit();
+  };
+  if (ASYNC) {
+    stage_pads_zero(sm, D, (TH + 2) * TWP);
+    stage_pads_zero(sm + g_floats, D, (TH + 2) * TWP);
+    issue(0, 0);
+  }
   for (int f = 0; f < 8; ++f) {
-    __syncthreads();   // the previous plane is consumed (and s_w is visible)
-    if (FLAT && !PRE) {
+    if (ASYNC) {
+      // buffer (f + 1) & 1 was read by plane f - 1, whose iteration ended with a barrier
+      if (f + 1 < 8) { issue(f + 1, (f + 1) & 1); pn_cp_async_wait<1>(); }
+      else pn_cp_async_wait<0>();
+      s_g = sm + (size_t)(f & 1) * g_floats;
+    } else {
+      __syncthreads();   // the previous plane is consumed (and s_w is visible)
+    }
+    if (ASYNC) {
+    } else if (FLAT && !PRE) {
       if (PACK) stage_tile_flat<false>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + f * D, D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
       else      stage_tile_flat<true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset + ((f * D) >> 2), D, h0 - 1, TH + 2, w0 - 1, TWP, s_g);
     } else if (PRE) {
@@ -693,10 +787,11 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
           }
       }
     }
+    if (ASYNC) __syncthreads();   // plane f is consumed before the copies of plane f + 2 refill its buffer
   }
   // transpose through shared memory so that the stores run along the channels of one pixel
   __syncthreads();
-  float* s_out = s_g;   // [TH][tw][D]
+  float* s_out = sm;   // [TH][tw][D] (the first plane buffer)
 #pragma unroll
   for (int m = 0; m < MAXT; ++m) {
     const int it = threadIdx.x + m * 256;
@@ -736,12 +831,16 @@ __global__ void __launch_bounds__(256) stencil_bwd8_kernel(const StencilBwd8Para
 // weight / bias gradient.  Warp (fp, half): feature pair {2fp, 2fp+1}, half of the thread tiles; 54 + 2 partial sums in
 // registers over the whole persistent walk, one warp reduction + atomics at the end.
 // smem: s_v[3][tw+2][PITCH] + 4, s_gc[8][tw][PITCH]
-template <bool PACK, bool FLAT = false, bool PRE = false>
+// ASYNC (default since round 2 where two buffers fit): the tiles of work item i+1 are copied with cp.async into the other half
+// of a double buffer while the FMAs of work item i run -- no staging registers (the register-prefetch variant PRE took the
+// kernel from 2 CTAs per SM to 1) and no exposed load phase (FLAT: nine, then two, serial DRAM round trips per work item).
+template <bool PACK, bool FLAT = false, bool PRE = false, bool ASYNC = false>
 __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdParams P) {
   PN_DYNAMIC_SHARED(float, sm);
   const int D = P.D, PITCH = D + SPAD, TWP = P.tw + 2;
+  const size_t v_floats = (size_t)3 * TWP * PITCH + 4, buf_floats = v_floats + (size_t)8 * P.tw * PITCH + 4;
   float* s_v = sm;
-  float* s_gc = sm + 3 * TWP * PITCH + 4;
+  float* s_gc = sm + v_floats;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fp = warp & 3, half = warp >> 2;
   float wa[27], wb[27];
@@ -765,11 +864,37 @@ __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdPar
     else      flat_prefetch<true, true, UG>(RG, P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, D >> 2);
   };
   if (PRE && (int)blockIdx.x < nwork) prefetch(blockIdx.x);
-  for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+  auto issue = [&](int work, int k) {      // ASYNC: all tiles of a work item -> buffer k, one commit group
     const int wt = work % wtiles, row = work / wtiles;
     const int b = row / P.H, h = row % P.H, w0 = wt * P.tw;
-    __syncthreads();
-    if (FLAT && !PRE) {
+    float* bv = sm + (size_t)k * buf_floats;
+    stage_tile_async<PACK, false>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, bv);
+    if (PACK) stage_tile_async<false, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, bv + v_floats, D);
+    else      stage_tile_async<true, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, bv + v_floats, D >> 2);
+    pn_cp_async_commit();
+  };
+  if (ASYNC) {
+    for (int k = 0; k < 2; ++k) {
+      stage_pads_zero(sm + (size_t)k * buf_floats, D, 3 * TWP);
+      stage_pads_zero(sm + (size_t)k * buf_floats + v_floats, D, 8 * P.tw);
+    }
+    if ((int)blockIdx.x < nwork) issue(blockIdx.x, 0);
+  }
+  int iter = 0;
+  for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++iter) {
+    const int wt = work % wtiles, row = work / wtiles;
+    const int b = row / P.H, h = row % P.H, w0 = wt * P.tw;
+    if (ASYNC) {
+      // buffer (iter + 1) & 1 was last read in iteration iter - 1, which ended with a barrier
+      if (work + (int)gridDim.x < nwork) { issue(work + gridDim.x, (iter + 1) & 1); pn_cp_async_wait<1>(); }
+      else pn_cp_async_wait<0>();
+      s_v = sm + (size_t)(iter & 1) * buf_floats;
+      s_gc = s_v + v_floats;
+    } else {
+      __syncthreads();
+    }
+    if (ASYNC) {
+    } else if (FLAT && !PRE) {
       stage_tile_flat<PACK>(P.in, b, P.H, P.W, P.C, 0, D, h - 1, 3, w0 - 1, TWP, s_v);
       if (PACK) stage_tile_flat<false, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, s_gc, D);       // the eight planes:
       else      stage_tile_flat<true, true>(P.g, b, P.H, P.W, P.g_cstride, P.g_coffset, D, h, 8, w0, P.tw, s_gc, D >> 2);    // ONE load phase
@@ -820,6 +945,7 @@ __global__ void __launch_bounds__(256) stencil_wgrad8_kernel(const StencilBwdPar
           }
         }
     }
+    if (ASYNC) __syncthreads();   // every thread is done with this buffer before the copies of iteration iter + 1 refill it
   }
 #pragma unroll
   for (int t = 0; t < 28; ++t) {
@@ -1530,6 +1656,18 @@ static int stencil_prefetch() {
   return x;
 }
 
+// cp.async double buffering of the stencil weight-gradient kernel (A/B: PN_STENCIL_ASYNC=0)
+static int stencil_async() {
+  static std::atomic<int> v{-1};
+  int x = v.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = std::getenv("PN_STENCIL_ASYNC");
+    x = (e && e[0] == '0') ? 0 : 1;
+    v.store(x, std::memory_order_relaxed);
+  }
+  return x;
+}
+
 static std::atomic<int> g_gn_tree{-1};
 static int gn_tree() {
   int v = g_gn_tree.load(std::memory_order_relaxed);
@@ -1640,7 +1778,9 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
       while (tw > 1 && (tw >> 1) >= P.W) tw >>= 1;
       PN_REQUIRE(tiles_of(tw) <= 1024 && smem_of(tw) <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large", P.D);
       Q8.p.tw = tw; Q8.th = th;
-      const size_t smem8 = smem_of(tw);
+      const size_t plane_bytes = ((size_t)(th + 2) * (tw + 2) * PITCH + 4) * sizeof(float);
+      const bool async8 = stage_flat() && !stencil_prefetch() && stencil_async() && smem_of(tw) + plane_bytes <= 200 * 1024;
+      const size_t smem8 = smem_of(tw) + (async8 ? plane_bytes : 0);
       const int maxt = (tiles_of(tw) + 255) / 256;
       dim3 grid8((P.W + tw - 1) / tw, (P.H + th - 1) / th, P.B);
       auto launch = [&](auto kern) -> int {
@@ -1649,7 +1789,10 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
         return 0;
       };
       int lrc;
-      if (stage_flat() && stencil_prefetch()) {
+      if (async8) {
+        if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1, true, false, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2, true, false, true>) : launch(stencil_bwd8_kernel<true, 4, true, false, true>);
+        else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1, true, false, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2, true, false, true>) : launch(stencil_bwd8_kernel<false, 4, true, false, true>);
+      } else if (stage_flat() && stencil_prefetch()) {
         if (pack) lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<true, 1, true, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<true, 2, true, true>) : launch(stencil_bwd8_kernel<true, 4, true, true>);
         else      lrc = (maxt <= 1) ? launch(stencil_bwd8_kernel<false, 1, true, true>) : (maxt <= 2) ? launch(stencil_bwd8_kernel<false, 2, true, true>) : launch(stencil_bwd8_kernel<false, 4, true, true>);
       } else if (stage_flat()) {
@@ -1673,7 +1816,9 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
       while (tw > 1 && (tw >> 1) >= P.W) tw >>= 1;
       PN_REQUIRE(smem_of(tw) <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d too large for the weight gradient", P.D);
       Q.tw = tw;
-      const size_t smem8 = smem_of(tw);
+      const bool flat = stage_flat() != 0, pre = flat && stencil_prefetch();
+      const bool async = flat && !pre && stencil_async() && 2 * smem_of(tw) <= 200 * 1024;     // double buffer
+      const size_t smem8 = async ? 2 * smem_of(tw) : smem_of(tw);
       const int nwork = Q.B * Q.H * ((Q.W + tw - 1) / tw);
       int ctas = (smem8 <= 110 * 1024) ? 148 * 2 : 148;
       if (ctas > nwork) ctas = nwork;
@@ -1682,9 +1827,8 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
         PN_LAUNCH(kern, ctas, 256, smem8, stream, Q);
         return 0;
       };
-      const bool flat = stage_flat() != 0, pre = flat && stencil_prefetch();
-      const int lrcw = pack ? (pre ? launchw(stencil_wgrad8_kernel<true, true, true>) : flat ? launchw(stencil_wgrad8_kernel<true, true>) : launchw(stencil_wgrad8_kernel<true>))
-                            : (pre ? launchw(stencil_wgrad8_kernel<false, true, true>) : flat ? launchw(stencil_wgrad8_kernel<false, true>) : launchw(stencil_wgrad8_kernel<false>));
+      const int lrcw = pack ? (async ? launchw(stencil_wgrad8_kernel<true, true, false, true>) : pre ? launchw(stencil_wgrad8_kernel<true, true, true>) : flat ? launchw(stencil_wgrad8_kernel<true, true>) : launchw(stencil_wgrad8_kernel<true>))
+                            : (async ? launchw(stencil_wgrad8_kernel<false, true, false, true>) : pre ? launchw(stencil_wgrad8_kernel<false, true, true>) : flat ? launchw(stencil_wgrad8_kernel<false, true>) : launchw(stencil_wgrad8_kernel<false>));
       if (lrcw) return lrcw;
       count_launch();
       return check_launch("stencil_wgrad8_kernel");
