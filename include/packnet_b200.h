@@ -350,7 +350,12 @@ int pn_pack_fold_set_backward(int cout, int n, int ksize, const float* w2, const
  * dB [2m+1][2m+1][Co] is the Conv3d-bias correction per border class (class(p) = p for p < m, m inside,
  * m+1+(p-(len-m)) for the last m).  All terms run in one launch and accumulate into z with atomics.
  * backward: dline (atomically accumulated; caller zeroes), dw (overwritten) per term; gdB accumulated (caller zeroes).
+ * flags: PN_FRAME_FLAG_DW_ZEROED -- the caller zeroed every term's dw: the weight-gradient GEMMs are then split over the
+ * samples and meet by atomic adds (4x the CTAs; the launches are latency bound); PN_FRAME_FLAG_NO_KSPLIT -- A/B: one CTA per
+ * output tile walks the whole reduction (the round-1 schedule).
  * ------------------------------------------------------------------------------------------------ */
+#define PN_FRAME_FLAG_DW_ZEROED 1
+#define PN_FRAME_FLAG_NO_KSPLIT 2
 typedef struct {
   const float* line;
   const float* w;
@@ -366,7 +371,7 @@ typedef struct {
 } pn_frame_term;
 typedef struct {
   int32_t batch, height, width; /* of z: the packed map */
-  int32_t cout, n, ksize, num_terms, reserved;
+  int32_t cout, n, ksize, num_terms, flags;
   pn_frame_term terms[8];
 } pn_frame_desc;
 int pn_pack_frame_forward(const pn_frame_desc* desc, const float* dB, float* z, pn_stream_t stream);

@@ -36,7 +36,7 @@ class FrameTerm(ctypes.Structure):
 class FrameDesc(ctypes.Structure):
     _fields_ = [("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
                 ("cout", ctypes.c_int32), ("n", ctypes.c_int32), ("ksize", ctypes.c_int32), ("num_terms", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("terms", FrameTerm * 8)]
+                ("flags", ctypes.c_int32), ("terms", FrameTerm * 8)]
 
 
 def declare(lib):

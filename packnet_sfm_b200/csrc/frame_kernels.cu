@@ -40,6 +40,7 @@ struct Term {
 
 struct Params {
   int B, h, w, Co, n, m, nterms;
+  int ksplit;                       // CTAs per output tile along the middle reduction index (taps e forward / line backward, samples for the weights)
   Term t[8];
   const float* dB;                  // [2m+1][2m+1][Co]
   float* z;                         // forward: [B][h][w][Co], accumulated
@@ -72,7 +73,7 @@ __device__ __forceinline__ long long z_offset(const Params& P, const Term& T, in
 // reduction triple ready-made.  A_KFAST / B_KFAST: whether consecutive threads of the tile load run along k0 (the operand
 // is contiguous in the reduction index) or along the row / column index.
 template <bool A_KFAST, bool B_KFAST, class RA, class LA, class RB, class LB>
-__device__ __forceinline__ void gemm_tile(int K2, int K1, int K0, int m0, int n0, RA ra, LA la, RB rb, LB lb, float (&acc)[4][4]) {
+__device__ __forceinline__ void gemm_tile(int K2, int K1b, int K1e, int K0, int m0, int n0, RA ra, LA la, RB rb, LB lb, float (&acc)[4][4]) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int t = threadIdx.x;
@@ -97,7 +98,7 @@ __device__ __forceinline__ void gemm_tile(int K2, int K1, int K0, int m0, int n0
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k2 = 0; k2 < K2; ++k2)
-    for (int k1 = 0; k1 < K1; ++k1)
+    for (int k1 = K1b; k1 < K1e; ++k1)
       for (int kb = 0; kb < K0; kb += BK) {
         // all eight global loads of the stage first, then the shared stores: left interleaved (load, store, load, ...) every
         // store waits for its own load and the stage costs eight serial round trips instead of one.
@@ -162,13 +163,19 @@ __device__ __forceinline__ float line_at(const Params& P, const Term& T, int b, 
 
 // forward: M = B*L pixels, N = A*Co columns (a, co), reduction (e, nn)
 __global__ void __launch_bounds__(NT) frame_forward_kernel(const __grid_constant__ Params P) {
+  // K split (round 2): the launch was ~300 CTAs walking 112 sixteen-wide stages each with one exposed L2 round trip per stage
+  // (0.45 ms for 0.4 GMAC); one CTA per (tile, tap e) gives 7x the CTAs with 16 stages each, partial sums meet in the atomicAdd
+  // the epilogue already used.
   const Term& T = P.t[blockIdx.z];
   const int M = P.B * T.L, N = T.A * P.Co;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (m0 >= M || n0 >= N) return;
+  const int ks = blockIdx.x % P.ksplit;
+  const int m0 = blockIdx.y * BM, n0 = (blockIdx.x / P.ksplit) * BN;
+  if (m0 >= M || n0 >= N || ks >= T.KE) return;
+  const int e_per = (T.KE + P.ksplit - 1) / P.ksplit, e0 = ks * e_per, e1 = min(T.KE, e0 + e_per);
+  if (e0 >= e1) return;
   float acc[4][4];
   gemm_tile<true, true>(
-      1, T.KE, P.n, m0, n0,
+      1, e0, e1, P.n, m0, n0,
       [&](int p) { return pixel_ctx(T, M, p); },
       [&](const PixelCtx& c, int, int e, int nn) -> float { return c.valid ? line_at(P, T, c.b, c.l + e - T.pad, nn) : 0.f; },
       [&](int c) { return weight_col_ctx(P, T, N, c); },
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(NT) frame_forward_kernel(const __grid_constant
       int row, col;
       const long long off = z_offset(P, T, b, a, l, &row, &col);
       float v = T.alpha * acc[i][j];
-      if (T.bias_mode == 1 || (T.bias_mode == 2 && row >= P.m && row < P.h - P.m))
+      if (ks == 0 && (T.bias_mode == 1 || (T.bias_mode == 2 && row >= P.m && row < P.h - P.m)))
         v += __ldg(P.dB + ((long long)border_class(row, P.h, P.m) * g + border_class(col, P.w, P.m)) * P.Co + co);
       atomicAdd(P.z + off + co, v);
     }
@@ -201,11 +208,14 @@ __global__ void __launch_bounds__(NT) frame_forward_kernel(const __grid_constant
 __global__ void __launch_bounds__(NT) frame_backward_line_kernel(const __grid_constant__ Params P) {
   const Term& T = P.t[blockIdx.z];
   const int M = P.B * T.L, N = P.n;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ks = blockIdx.x % P.ksplit;
+  const int m0 = blockIdx.y * BM, n0 = (blockIdx.x / P.ksplit) * BN;
   if (m0 >= M || n0 >= N) return;
+  const int e_per = (T.KE + P.ksplit - 1) / P.ksplit, e0 = ks * e_per, e1 = min(T.KE, e0 + e_per);
+  if (e0 >= e1) return;
   float acc[4][4];
   gemm_tile<true, false>(
-      T.A, T.KE, P.Co, m0, n0,
+      T.A, e0, e1, P.Co, m0, n0,
       [&](int p) { return pixel_ctx(T, M, p); },
       [&](const PixelCtx& c, int a, int e, int co) -> float {
         const int l = c.l - e + T.pad;
@@ -237,11 +247,14 @@ __global__ void __launch_bounds__(NT) frame_backward_line_kernel(const __grid_co
 __global__ void __launch_bounds__(NT) frame_backward_weight_kernel(const __grid_constant__ Params P) {
   const Term& T = P.t[blockIdx.z];
   const int M = T.A * P.Co, N = T.KE * P.n;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ks = blockIdx.x % P.ksplit;                 // split over the samples; dw is zeroed by the caller when ksplit > 1
+  const int m0 = blockIdx.y * BM, n0 = (blockIdx.x / P.ksplit) * BN;
   if (m0 >= M || n0 >= N) return;
+  const int b_per = (P.B + P.ksplit - 1) / P.ksplit, b0 = ks * b_per, b1 = min(P.B, b0 + b_per);
+  if (b0 >= b1) return;
   float acc[4][4];
   gemm_tile<false, false>(
-      1, P.B, T.L, m0, n0,
+      1, b0, b1, T.L, m0, n0,
       [&](int r) { return weight_col_ctx(P, T, M, r); },
       [&](const WeightColCtx& c, int, int b, int l) -> float {
         if (!c.valid) return 0.f;
@@ -268,7 +281,9 @@ __global__ void __launch_bounds__(NT) frame_backward_weight_kernel(const __grid_
       const int c = n0 + tx * 4 + j;
       if (c >= N) continue;
       const int e = c / P.n, nn = c - e * P.n;
-      T.dw[(long long)co * T.w_sco + (long long)a * T.w_sa + (long long)e * T.w_se + nn] = T.alpha * acc[i][j];
+      float* dst = T.dw + (long long)co * T.w_sco + (long long)a * T.w_sa + (long long)e * T.w_se + nn;
+      if (P.ksplit > 1) atomicAdd(dst, T.alpha * acc[i][j]);
+      else *dst = T.alpha * acc[i][j];
     }
   }
 }
@@ -349,7 +364,10 @@ extern "C" int pn_pack_frame_forward(const pn_frame_desc* desc, const float* dB,
     mmax = std::max<long long>(mmax, (long long)P.B * P.t[i].L);
     nmax = std::max<long long>(nmax, (long long)P.t[i].A * P.Co);
   }
-  PN_LAUNCH(frame::frame_forward_kernel, dim3(frame::cdiv(nmax, frame::BN), frame::cdiv(mmax, frame::BM), P.nterms), frame::NT, 0, stream, P);
+  int kemax = 1;
+  for (int i = 0; i < P.nterms; ++i) kemax = std::max(kemax, P.t[i].KE);
+  P.ksplit = (desc->flags & PN_FRAME_FLAG_NO_KSPLIT) ? 1 : kemax;
+  PN_LAUNCH(frame::frame_forward_kernel, dim3(frame::cdiv(nmax, frame::BN) * P.ksplit, frame::cdiv(mmax, frame::BM), P.nterms), frame::NT, 0, stream, P);
   count_launch();
   return check_launch("frame_forward_kernel");
 }
@@ -369,8 +387,14 @@ extern "C" int pn_pack_frame_backward(const pn_frame_desc* desc, const float* gz
     amax = std::max<long long>(amax, (long long)P.t[i].A * P.Co);
     kmax = std::max<long long>(kmax, (long long)P.t[i].KE * P.n);
   }
-  PN_LAUNCH(frame::frame_backward_line_kernel, dim3(frame::cdiv(P.n, frame::BN), frame::cdiv(pmax, frame::BM), P.nterms), frame::NT, 0, stream, P);
-  PN_LAUNCH(frame::frame_backward_weight_kernel, dim3(frame::cdiv(kmax, frame::BN), frame::cdiv(amax, frame::BM), P.nterms), frame::NT, 0, stream, P);
+  int kemax = 1;
+  for (int i = 0; i < P.nterms; ++i) kemax = std::max(kemax, P.t[i].KE);
+  const bool split = !(desc->flags & PN_FRAME_FLAG_NO_KSPLIT);
+  P.ksplit = split ? kemax : 1;
+  PN_LAUNCH(frame::frame_backward_line_kernel, dim3(frame::cdiv(P.n, frame::BN) * P.ksplit, frame::cdiv(pmax, frame::BM), P.nterms), frame::NT, 0, stream, P);
+  // weights: split over the samples only when the caller zeroed dw (PN_FRAME_FLAG_DW_ZEROED): partial sums meet by atomicAdd
+  P.ksplit = (split && (desc->flags & PN_FRAME_FLAG_DW_ZEROED)) ? P.B : 1;
+  PN_LAUNCH(frame::frame_backward_weight_kernel, dim3(frame::cdiv(kmax, frame::BN) * P.ksplit, frame::cdiv(amax, frame::BM), P.nterms), frame::NT, 0, stream, P);
   const int m = P.m;
   const long long total = (long long)P.B * ((long long)P.h * P.w - (long long)(P.h - 2 * m) * (P.w - 2 * m)) * P.Co;
   unsigned blocks = frame::cdiv(total, frame::NT);

@@ -350,9 +350,16 @@ class _FrameApplyCUDA(torch.autograd.Function):
         o1, o2, o3 = B * w * n, 2 * B * w * n, 2 * B * w * n + B * h * n
         dlines = {"top": flat[:o1].view(B, w, n), "bottom": flat[o1:o2].view(B, w, n),
                   "left": flat[o2:o3].view(B, h, n), "right": flat[o3:].view(B, h, n)}
-        dws = {name: torch.empty_like(t) for name, t in weights.items()}
+        # the eight weight gradients in ONE zeroed buffer: the library splits their GEMMs over the samples (atomic adds)
+        sizes = [(t.numel() + 3) // 4 * 4 for t in weights.values()]
+        wflat = torch.zeros(sum(sizes), dtype=torch.float32, device=gz.device)
+        dws, o = {}, 0
+        for (name, t), sz in zip(weights.items(), sizes):
+            dws[name] = wflat[o:o + t.numel()].view(t.shape)
+            o += sz
         gdB = torch.zeros(ctx.dB_shape, dtype=torch.float32, device=gz.device)
         d = _FrameApplyCUDA._desc((B, h, w, co), n, k, lines, weights, dlines, dws)
+        d.flags = 1      # PN_FRAME_FLAG_DW_ZEROED
         _lib.check(_lib.lib().pn_pack_frame_backward(ctypes.byref(d), _lib.ptr(gz), _lib.ptr(gdB), _lib.current_stream()),
                    "pn_pack_frame_backward")
         return (gz, dlines["top"], dlines["bottom"], dlines["left"], dlines["right"]) + tuple(dws[nm] for nm in FOLD_ORDER[1:]) \
