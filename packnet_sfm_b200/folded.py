@@ -281,6 +281,12 @@ def frame_term_specs(h, w, n, k):
     ]
 
 
+def _frame_flags():
+    """A/B switch of the frame GEMMs' K split (PN_FRAME_KSPLIT=0 -> PN_FRAME_FLAG_NO_KSPLIT: the round-1 schedule)"""
+    import os
+    return 2 if os.environ.get("PN_FRAME_KSPLIT") == "0" else 0
+
+
 class _FrameApplyCUDA(torch.autograd.Function):
     """z += frame terms, in place (one launch); backward: border-line, folded-weight and bias-class gradients
     (three launches).  weights = the eight channels-last frame folds in FOLD_ORDER[1:]."""
@@ -330,6 +336,7 @@ class _FrameApplyCUDA(torch.autograd.Function):
         weights = dict(zip(FOLD_ORDER[1:], (t.contiguous() for t in (Wt, Wb, Wl, Wr, Wtl, Wtr, Wbl, Wbr))))
         dBc = dB.detach().contiguous()
         d = _FrameApplyCUDA._desc(tuple(z.shape), n, k, lines, weights)
+        d.flags = _frame_flags()
         _lib.check(_lib.lib().pn_pack_frame_forward(ctypes.byref(d), _lib.ptr(dBc), _lib.ptr(z), _lib.current_stream()),
                    "pn_pack_frame_forward")
         ctx.mark_dirty(z)
@@ -359,7 +366,7 @@ class _FrameApplyCUDA(torch.autograd.Function):
             o += sz
         gdB = torch.zeros(ctx.dB_shape, dtype=torch.float32, device=gz.device)
         d = _FrameApplyCUDA._desc((B, h, w, co), n, k, lines, weights, dlines, dws)
-        d.flags = 1      # PN_FRAME_FLAG_DW_ZEROED
+        d.flags = 1 | _frame_flags()      # PN_FRAME_FLAG_DW_ZEROED
         _lib.check(_lib.lib().pn_pack_frame_backward(ctypes.byref(d), _lib.ptr(gz), _lib.ptr(gdB), _lib.current_stream()),
                    "pn_pack_frame_backward")
         return (gz, dlines["top"], dlines["bottom"], dlines["left"], dlines["right"]) + tuple(dws[nm] for nm in FOLD_ORDER[1:]) \
