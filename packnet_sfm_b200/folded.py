@@ -373,9 +373,20 @@ class _FrameApplyCUDA(torch.autograd.Function):
             + (gdB, None)
 
 
-def pack_conv_folded(x, w2, b2, w3, b3, conv):
+def prefold(w2, w3, b3, w_packed):
+    """The weight-only half of pack_conv_folded -- the nine folds, S and the Conv3d-bias classes -- for a packed map that is
+    `w_packed` pixels wide.  It depends on parameters alone, so networks.PackNet01 issues it on a side stream at the start
+    of the forward (0.31 ms of small launches per step, and through autograd's stream replay the 0.50 ms of fold backward
+    launches, next to the convolutions instead of between them).  -> (folds, beta, dB)"""
+    folds = fold_set(w2, w3)
+    beta, dB = bias_classes(folds[9], b3, w2.shape[2], w_packed, w2.device)
+    return folds, beta, dB
+
+
+def pack_conv_folded(x, w2, b2, w3, b3, conv, pre=None):
     """z = Conv2d(W2, b2)(pad(Conv3d(W3, b3)(packing(x)))) on NHWC maps: x [B,2h,2w,C] -> z [B,h,w,Co].
-    `conv(xs, weight, bias)` is the O(area) convolution (functional.conv2d on the GPU)."""
+    `conv(xs, weight, bias)` is the O(area) convolution (functional.conv2d on the GPU); `pre` = prefold(...) when the caller
+    computed the weight-only half ahead of time."""
     co, c8, k, _ = w2.shape
     m = k // 2
     B, H, W, C = x.shape
@@ -387,6 +398,10 @@ def pack_conv_folded(x, w2, b2, w3, b3, conv):
     if h < 2 * m + 1 or w < 2 * m + 1:
         raise ValueError("pack_conv_folded: packed map %dx%d smaller than the frame of a %dx%d kernel" % (h, w, k, k))
     xs, top, bot, left, right = space_to_depth_borders(x.contiguous())
+    if pre is not None and _use_kernels(x):
+        folds, beta, dB = pre
+        z = conv(xs, folds[0], b2 + beta)
+        return _FrameApplyCUDA.apply(z, top, bot, left, right, *folds[1:9], dB, k)
     folds = fold_set(w2, w3)
     if _use_kernels(x):
         beta, dB = bias_classes(folds[9], b3, k, w, x.device)

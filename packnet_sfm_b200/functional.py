@@ -76,6 +76,12 @@ def pack_fold_enabled(packed_pixels=None):
     return _state["pack_fold"] and (packed_pixels is None or packed_pixels >= _state["pack_fold_min_pixels"])
 
 
+def prefold_stream_enabled():
+    """Weight folds of the folded pack layers on a side stream at the start of PackNet01.forward (PN_PREFOLD_STREAM=0: inline,
+    on the main stream, where the layer runs)."""
+    return _env("PN_PREFOLD_STREAM", True)
+
+
 def set_precision(p):
     assert p in (PRECISION_TF32X1, PRECISION_BF16X1, PRECISION_TF32X3, PRECISION_BF16X3)
     _state["precision"] = p

@@ -108,12 +108,27 @@ class PackLayerConv3d(nn.Module):
         k = self.conv.kernel_size
         return PF.pack_fold_enabled(h * w) and k in (3, 5) and min(h, w) >= 2 * (k // 2) + 1
 
+    def prefold(self, w):
+        """weight-only half of the folded evaluation for a packed map of width w, on the CURRENT stream (PackNet01.forward calls
+        this under a side stream before the first layer runs)"""
+        self._pre = (folded.prefold(self.conv.conv_base.weight, self.conv3d.weight, self.conv3d.bias, w), torch.cuda.Event())
+        self._pre[1].record()
+
     def forward(self, x):
         h, w = x.shape[1] // 2, x.shape[2] // 2
         if self.folds(h, w):
             # conv3d and conv2d composed into one (k+2)x(k+2) convolution of the space-to-depth tensor + exact frame terms
+            pre = None
+            if getattr(self, "_pre", None) is not None:
+                (folds, beta, dB), ev = self._pre
+                self._pre = None
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                for t in tuple(folds) + (beta, dB):      # allocated on the side stream, consumed here
+                    t.record_stream(cur)
+                pre = (folds, beta, dB)
             z = folded.pack_conv_folded(x, self.conv.conv_base.weight, self.conv.conv_base.bias, self.conv3d.weight,
-                                        self.conv3d.bias, PF.conv2d)
+                                        self.conv3d.bias, PF.conv2d, pre=pre)
             return PF.groupnorm_elu(z, self.conv.normalize.weight, self.conv.normalize.bias, self.conv.normalize.eps)
         feats = PF.pack_features(x, self.conv3d.weight, self.conv3d.bias)
         return self.conv(feats)
@@ -270,6 +285,18 @@ class PackNet01(nn.Module):
         # NCHW image -> NHWC, zero-padded to the operand's channel multiple (TMA row pitch)
         cpad = PF.channel_align() - 3
         x_in = torch.cat([rgb.permute(0, 2, 3, 1), torch.zeros(B, H, W, cpad, dtype=rgb.dtype, device=rgb.device)], -1)
+        if PF.prefold_stream_enabled() and rgb.is_cuda:
+            # the weight folds of the folded pack layers depend on parameters only: a side stream computes them while the first
+            # layers run (autograd replays their backward on that stream too; a captured step keeps the fork / join)
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_fold_stream", None) is None:
+                self._fold_stream = torch.cuda.Stream()
+            self._fold_stream.wait_stream(cur)
+            with torch.cuda.stream(self._fold_stream):
+                for i, name in enumerate(("pack1", "pack2", "pack3", "pack4", "pack5")):
+                    layer = getattr(self, name)
+                    if layer.folds(H >> (i + 1), W >> (i + 1)):
+                        layer.prefold(W >> (i + 1))
         if PF.im2col_first_enabled():
             # staged: the 3 -> 64 5x5 layer as one 1x1 convolution over its im2col tensor (functional.conv2d_im2col)
             pc = self.pre_calc
