@@ -10,6 +10,7 @@ plain contiguous [B,H,W,C] CUDA tensor (the same bytes as a torch.channels_last 
 Precision of the tensor-core GEMMs (include/packnet_b200.h): PRECISION_BF16X3 (default: error-compensated bf16
 split, 16 mantissa bits, meets the 1e-3 depth parity bar at twice the tf32 MMA rate), PRECISION_TF32X3 (22 bits),
 PRECISION_TF32X1 (what cuDNN gives the reference on Ampere+ with PyTorch defaults; fails the parity bar)."""
+import contextlib
 import ctypes
 import os
 import weakref
@@ -33,7 +34,9 @@ _state = {"precision": PRECISION_BF16X3, "mode": MODE_AUTO, "pack_fold": _env("P
           "unpack_tiled": _env("PN_UNPACK_TILED", True),
           "pack_tiled": _env("PN_PACK_TILED", False),
           # GroupNorm+ELU kernels write the bf16 operand pair of their output for the convolution that consumes it
-          "gn_emit_split": _env("PN_GN_EMIT_SPLIT", True)}
+          "gn_emit_split": _env("PN_GN_EMIT_SPLIT", True),
+          # weight gradients of stored weights on a side stream during the backward (joined by an autograd end-of-backward callback)
+          "wgrad_stream": _env("PN_WGRAD_STREAM", True)}
 
 
 def set_pack_tiled(on):
@@ -74,6 +77,32 @@ def set_pack_fold(on, min_pixels=None):
 
 def pack_fold_enabled(packed_pixels=None):
     return _state["pack_fold"] and (packed_pixels is None or packed_pixels >= _state["pack_fold_min_pixels"])
+
+
+_wgrad_side = {"stream": None, "pending": False}
+
+
+def _wgrad_side_stream(cur):
+    """The side stream of the weight-gradient launches; the FIRST use inside a backward pass queues the join: when the pass
+    ends, the stream the backward ran on waits for the side stream, so that `loss.backward()` returns with every gradient
+    ordered before whatever the caller enqueues next (optimizer, all-reduce, a read of .grad)."""
+    if _wgrad_side["stream"] is None:
+        _wgrad_side["stream"] = torch.cuda.Stream()
+    side = _wgrad_side["stream"]
+    if not _wgrad_side["pending"]:
+        _wgrad_side["pending"] = True
+
+        def join():
+            _wgrad_side["pending"] = False
+            cur.wait_stream(side)
+
+        torch.autograd.Variable._execution_engine.queue_callback(join)
+    return side
+
+
+def set_wgrad_stream(on):
+    prev, _state["wgrad_stream"] = _state["wgrad_stream"], bool(on)
+    return prev
 
 
 def prefold_stream_enabled():
@@ -257,6 +286,16 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             # the output gradient has `cout` channels; bf16 operands need a multiple of 8
             g_hi, g_lo = _operands(gy, precision)
+        side = None
+        if ctx.needs_input_grad[1] and ctx.nat is not None and _state["wgrad_stream"] and gy.is_cuda:
+            # The weight gradient of a stored weight has no consumer inside the backward (it lands in the flat gradient buffer):
+            # it runs on a side stream, next to the data-gradient / GroupNorm / stencil chain that IS the critical path -- its
+            # CTAs fill the SMs the small-map launches leave idle and share SMs with the kernels that use no shared memory.
+            cur = torch.cuda.current_stream()
+            side = _wgrad_side_stream(cur)
+            ready = torch.cuda.Event()
+            ready.record(cur)                 # both operand pairs exist at this point of the main stream
+            side.wait_event(ready)
         if ctx.needs_input_grad[0]:
             if ctx.packed is not None:
                 gx = _conv_dgrad(g_hi, g_lo, ctx.packed[0], ctx.packed[1], B, H, W, Cin, cout, k, precision)
@@ -269,9 +308,14 @@ class _Conv2d(torch.autograd.Function):
             d = ConvDesc(B, H, W, Cin, cout, k, precision, 0, 0)
             if ctx.nat is not None:
                 # [Cout][tap][kpad] IS the stored layout: accumulate into the flat gradient buffer, nothing to return
-                _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
-                                               _lib.ptr(ctx.nat.grad_flat), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
-                ctx.nat.owner.grad_ready(ctx.nat)      # data parallel: may start the all-reduce of a completed bucket
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                    _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
+                                                   _lib.ptr(ctx.nat.grad_flat), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
+                    ctx.nat.owner.grad_ready(ctx.nat)      # data parallel: may start the all-reduce of a completed bucket (behind this launch)
+                if side is not None:
+                    for t in (x_hi, x_lo, g_hi, g_lo):     # read by the side stream after this node returned them to the allocator
+                        if t is not None:
+                            t.record_stream(side)
             else:
                 n = ctypes.c_size_t(0)
                 _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, Cin, k, precision, ctypes.byref(n)), "wgrad_packed_elems")
