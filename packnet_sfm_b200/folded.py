@@ -157,6 +157,8 @@ class _FoldSetCUDA(torch.autograd.Function):
         co, c8, k, _ = w2c.shape
         n = c8 // 8
         dev = w2c.device
+        from . import functional as PF
+        PF.wait_for_wgrad_stream(*grads)      # the interior fold's gradient may come from the weight-gradient side stream
         dw2 = torch.empty_like(w2c)
         dw3 = torch.zeros(216, dtype=torch.float32, device=dev)
         gs = [None if g is None else g.contiguous() for g in grads]      # named: the pointers must outlive the call

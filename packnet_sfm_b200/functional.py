@@ -100,6 +100,19 @@ def _wgrad_side_stream(cur):
     return side
 
 
+def wait_for_wgrad_stream(*tensors):
+    """For the consumer of a weight gradient produced with wgrad_side=True: order the current stream behind the side stream
+    and tell the allocator that `tensors` (allocated on the side stream) are used here."""
+    side = _wgrad_side["stream"]
+    if side is None or not torch.cuda.is_available():
+        return
+    cur = torch.cuda.current_stream()
+    cur.wait_stream(side)
+    for t in tensors:
+        if t is not None and t.is_cuda:
+            t.record_stream(cur)
+
+
 def set_wgrad_stream(on):
     prev, _state["wgrad_stream"] = _state["wgrad_stream"], bool(on)
     return prev
@@ -253,11 +266,12 @@ class _Conv2d(torch.autograd.Function):
     gradient reads the FORWARD tiles in both paths (pn_conv2d_dgrad), so the transposed packing only exists for tf32."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, wgrad_side=False):
         _lib.require_f32(x, weight, bias)
         x = x.contiguous()
         precision = _state["precision"]
         cout, cin_w, k, _ = weight.shape
+        ctx.wgrad_side = bool(wgrad_side)
         nat = _stored_weight(weight, x.shape[3], precision)
         if nat is not None:
             wp, wp_lo = nat.hi, nat.lo
@@ -287,7 +301,7 @@ class _Conv2d(torch.autograd.Function):
             # the output gradient has `cout` channels; bf16 operands need a multiple of 8
             g_hi, g_lo = _operands(gy, precision)
         side = None
-        if ctx.needs_input_grad[1] and ctx.nat is not None and _state["wgrad_stream"] and gy.is_cuda:
+        if ctx.needs_input_grad[1] and (ctx.nat is not None or ctx.wgrad_side) and _state["wgrad_stream"] and gy.is_cuda:
             # The weight gradient of a stored weight has no consumer inside the backward (it lands in the flat gradient buffer):
             # it runs on a side stream, next to the data-gradient / GroupNorm / stencil chain that IS the critical path -- its
             # CTAs fill the SMs the small-map launches leave idle and share SMs with the kernels that use no shared memory.
@@ -317,31 +331,39 @@ class _Conv2d(torch.autograd.Function):
                         if t is not None:
                             t.record_stream(side)
             else:
-                n = ctypes.c_size_t(0)
-                _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, Cin, k, precision, ctypes.byref(n)), "wgrad_packed_elems")
-                dwp = torch.empty(int(n.value), dtype=torch.float32, device=gy.device)
-                _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
-                                               _lib.ptr(dwp), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
-                gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=gy.device)
-                if _state["unpack_tiled"]:
-                    _lib.check(lib.pn_conv2d_unpack_weight_grad_tiled(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k,
-                                                                      int(n.value) // (cout * k * k), _stream()),
-                               "pn_conv2d_unpack_weight_grad_tiled")
-                else:
-                    _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, precision, _stream()),
-                               "pn_conv2d_unpack_weight_grad")
-                gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
+                # wgrad_side (the caller vouches that the ONLY consumer of this gradient waits for the side stream itself --
+                # folded._FoldSetCUDA.backward does): same side stream, tensors allocated there
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                    n = ctypes.c_size_t(0)
+                    _lib.check(lib.pn_conv2d_wgrad_packed_elems(cout, Cin, k, precision, ctypes.byref(n)), "wgrad_packed_elems")
+                    dwp = torch.empty(int(n.value), dtype=torch.float32, device=gy.device)
+                    _lib.check(lib.pn_conv2d_wgrad(ctypes.byref(d), _lib.ptr(x_hi), _p(x_lo), _lib.ptr(g_hi), _p(g_lo),
+                                                   _lib.ptr(dwp), _lib.ptr(error_flag()), _stream()), "pn_conv2d_wgrad")
+                    gw_full = torch.empty(cout, Cin, k, k, dtype=torch.float32, device=gy.device)
+                    if _state["unpack_tiled"]:
+                        _lib.check(lib.pn_conv2d_unpack_weight_grad_tiled(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k,
+                                                                          int(n.value) // (cout * k * k), _stream()),
+                                   "pn_conv2d_unpack_weight_grad_tiled")
+                    else:
+                        _lib.check(lib.pn_conv2d_unpack_weight_grad(_lib.ptr(dwp), _lib.ptr(gw_full), cout, Cin, k, precision, _stream()),
+                                   "pn_conv2d_unpack_weight_grad")
+                    gw = gw_full[:, :cin_w].contiguous() if cin_w != Cin else gw_full
+                if side is not None:
+                    for t in (x_hi, x_lo, g_hi, g_lo):
+                        if t is not None:
+                            t.record_stream(side)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = _lookup_channel_sum(gy)
             if gb is None:
                 gb = torch.empty(cout, dtype=torch.float32, device=gy.device)
                 _lib.check(lib.pn_channel_sum(_lib.ptr(gy), _lib.ptr(gb), B * H * W, cout, _stream()), "pn_channel_sum")
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
-def conv2d(x, weight, bias=None):
-    """x: [B,H,W,C] with C a multiple of channel_align(); weight may have fewer input channels (zero-padded)."""
-    return _Conv2d.apply(x, weight, bias)
+def conv2d(x, weight, bias=None, wgrad_side=False):
+    """x: [B,H,W,C] with C a multiple of channel_align(); weight may have fewer input channels (zero-padded).
+    wgrad_side: the weight gradient may be produced on the weight-gradient side stream (the caller's consumer waits for it)."""
+    return _Conv2d.apply(x, weight, bias, wgrad_side)
 
 
 def conv2d_im2col(x, weight, bias=None, conv=None, align=None):

@@ -7,6 +7,8 @@ The nn.Conv2d / nn.Conv3d / nn.GroupNorm members only HOLD the parameters (so ch
 load by name, packnet_sfm/utils/load.py:146-157); their own forward is never called.  Feature maps are NHWC
 tensors; every convolution runs on the tcgen05 implicit-GEMM kernel, the Conv3d feature stencils and
 GroupNorm+ELU on the fused HBM-bound kernels (packnet_sfm_b200/functional.py)."""
+import functools
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -127,8 +129,11 @@ class PackLayerConv3d(nn.Module):
                 for t in tuple(folds) + (beta, dB):      # allocated on the side stream, consumed here
                     t.record_stream(cur)
                 pre = (folds, beta, dB)
+            # with the folds on their own stream the effective weight's gradient has ONE consumer, the fold backward, which waits
+            # for the weight-gradient side stream itself: the largest weight-gradient launch of the step leaves the critical path
+            conv = functools.partial(PF.conv2d, wgrad_side=True) if pre is not None else PF.conv2d
             z = folded.pack_conv_folded(x, self.conv.conv_base.weight, self.conv.conv_base.bias, self.conv3d.weight,
-                                        self.conv3d.bias, PF.conv2d, pre=pre)
+                                        self.conv3d.bias, conv, pre=pre)
             return PF.groupnorm_elu(z, self.conv.normalize.weight, self.conv.normalize.bias, self.conv.normalize.eps)
         feats = PF.pack_features(x, self.conv3d.weight, self.conv3d.bias)
         return self.conv(feats)
