@@ -266,6 +266,12 @@ int pn_feature_stencil_forward(int pack, const float* in, const float* w3, const
 int pn_feature_stencil_backward(int pack, const float* in, const float* g, const float* w3, float* gin,
                                 float* gw3, float* gb3, int batch, int h_low, int w_low, int channels,
                                 int g_cstride, int g_coffset, pn_stream_t stream);
+/* The same, one half at a time: parts = 1 data gradient (gin), 2 weight / bias gradient (gw3, gb3), 3 both.  The halves are
+ * independent launches; a caller may enqueue the weight half on another stream (autograd of nn.Conv3d w.r.t. its parameters
+ * is off the critical path of the backward).  Pointers of a half that is not requested may be NULL. */
+int pn_feature_stencil_backward_parts(int pack, const float* in, const float* g, const float* w3, float* gin,
+                                      float* gw3, float* gb3, int batch, int h_low, int w_low, int channels,
+                                      int g_cstride, int g_coffset, int parts, pn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm(16, eps) + ELU on NHWC maps (layers01.py:31-32,37; with x2 != NULL the input is x + x2, the

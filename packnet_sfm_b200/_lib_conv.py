@@ -55,6 +55,7 @@ def declare(lib):
     i, f = c.c_int, c.c_float
     lib.pn_feature_stencil_forward.argtypes = [i, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     lib.pn_feature_stencil_backward.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.pn_feature_stencil_backward_parts.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.pn_groupnorm_elu_forward.argtypes = [vp, vp, vp, vp, f, vp, vp, vp, i, i, i, i, i, vp]
     lib.pn_groupnorm_elu_backward.argtypes = [vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.pn_groupnorm_elu_forward_split.argtypes = [vp, vp, vp, vp, f, vp, vp, vp, vp, i, i, i, vp]
@@ -63,7 +64,7 @@ def declare(lib):
     lib.pn_channel_sum.argtypes = [vp, vp, sz, i, vp]
     lib.pn_head_conv_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.pn_head_conv_backward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
-    for name in ("pn_feature_stencil_forward", "pn_feature_stencil_backward", "pn_groupnorm_elu_forward",
+    for name in ("pn_feature_stencil_forward", "pn_feature_stencil_backward", "pn_feature_stencil_backward_parts", "pn_groupnorm_elu_forward",
                  "pn_groupnorm_elu_backward", "pn_channel_sum", "pn_head_conv_forward", "pn_head_conv_backward"):
         getattr(lib, name).restype = c.c_int
     lib.pn_conv2d_wgrad.argtypes = [c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]

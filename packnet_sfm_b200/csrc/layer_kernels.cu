@@ -1750,24 +1750,27 @@ extern "C" int pn_feature_stencil_forward(int pack, const float* in, const float
   return check_launch("stencil_fwd_kernel");
 }
 
-extern "C" int pn_feature_stencil_backward(int pack, const float* in, const float* g, const float* w3, float* gin, float* gw3,
-                                           float* gb3, int batch, int h_low, int w_low, int channels, int g_cstride, int g_coffset,
-                                           pn_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PN_REQUIRE(in && g && w3 && gin && gw3 && gb3 && batch > 0 && h_low > 0 && w_low > 0 && channels > 0, PN_ERR_BAD_ARGUMENT,
-             "pn_feature_stencil_backward: bad argument");
+// parts: 1 = data gradient (gin), 2 = weight / bias gradient (gw3, gb3), 3 = both.  The two halves are independent launches:
+// the caller may put the weight half on another stream (the data half is the critical path of the backward).
+static int stencil_backward_impl(int pack, const float* in, const float* g, const float* w3, float* gin, float* gw3,
+                                 float* gb3, int batch, int h_low, int w_low, int channels, int g_cstride, int g_coffset,
+                                 int parts, cudaStream_t stream) {
+  PN_REQUIRE(in && g && w3 && batch > 0 && h_low > 0 && w_low > 0 && channels > 0 && (parts & 3) && (!(parts & 1) || gin) &&
+                 (!(parts & 2) || (gw3 && gb3)), PN_ERR_BAD_ARGUMENT, "pn_feature_stencil_backward: bad argument");
   TraceScope ts(stream, "stencil_bwd pack%d B%d H%d W%d C%d", pack, batch, h_low, w_low, channels);
   StencilBwdParams P{};
   P.B = batch; P.H = h_low; P.W = w_low; P.C = channels; P.D = pack ? 4 * channels : channels;
   P.in = in; P.g = g; P.w3 = w3; P.gin = gin; P.gw3 = gw3; P.gb3 = gb3;
   P.g_cstride = g_cstride; P.g_coffset = g_coffset;
-  PN_CUDA(cudaMemsetAsync(gw3, 0, sizeof(float) * 216, stream));
-  PN_CUDA(cudaMemsetAsync(gb3, 0, sizeof(float) * 8, stream));
-  const bool vec_ok = aligned16(in) && aligned16(g) && aligned16(gin) && g_cstride % 4 == 0 && g_coffset % 4 == 0;
+  if (parts & 2) {
+    PN_CUDA(cudaMemsetAsync(gw3, 0, sizeof(float) * 216, stream));
+    PN_CUDA(cudaMemsetAsync(gb3, 0, sizeof(float) * 8, stream));
+  }
+  const bool vec_ok = aligned16(in) && aligned16(g) && (!gin || aligned16(gin)) && g_cstride % 4 == 0 && g_coffset % 4 == 0;
   if (P.D % 8 == 0 && vec_ok) {   // register-tiled production path
     const int PITCH = P.D + SPAD;
     // data gradient
-    {
+    if (parts & 1) {
       StencilBwd8Params Q8{};
       Q8.p = P;
       int th = (P.H >= 3) ? 4 : 2, tw = 32;
@@ -1808,6 +1811,7 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
       if (rc8) return rc8;
     }
     // weight / bias gradient
+    if (!(parts & 2)) return PN_OK;
     {
       StencilBwdParams Q = P;
       int tw = 32;
@@ -1839,16 +1843,19 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   const size_t smem = stencil_smem_bytes(P.D, P.tw, true, !pack);
   PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_feature_stencil_backward: depth %d needs %zu bytes of shared memory", P.D, smem);
   dim3 grid((P.W + P.tw - 1) / P.tw, P.H, P.B);
-  if (pack) {
-    PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PN_LAUNCH((stencil_bwd_kernel<true>), grid, 256, smem, stream, P);
-  } else {
-    PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PN_LAUNCH((stencil_bwd_kernel<false>), grid, 256, smem, stream, P);
+  if (parts & 1) {
+    if (pack) {
+      PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PN_LAUNCH((stencil_bwd_kernel<true>), grid, 256, smem, stream, P);
+    } else {
+      PN_CUDA(cudaFuncSetAttribute(stencil_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PN_LAUNCH((stencil_bwd_kernel<false>), grid, 256, smem, stream, P);
+    }
+    count_launch();
+    int rc = check_launch("stencil_bwd_kernel");
+    if (rc) return rc;
   }
-  count_launch();
-  int rc = check_launch("stencil_bwd_kernel");
-  if (rc) return rc;
+  if (!(parts & 2)) return PN_OK;
   // weight / bias gradient
   StencilBwdParams Q = P;
   Q.tw = 8;
@@ -1867,6 +1874,20 @@ extern "C" int pn_feature_stencil_backward(int pack, const float* in, const floa
   }
   count_launch();
   return check_launch("stencil_wgrad_kernel");
+}
+
+extern "C" int pn_feature_stencil_backward(int pack, const float* in, const float* g, const float* w3, float* gin, float* gw3,
+                                           float* gb3, int batch, int h_low, int w_low, int channels, int g_cstride, int g_coffset,
+                                           pn_stream_t stream_) {
+  return stencil_backward_impl(pack, in, g, w3, gin, gw3, gb3, batch, h_low, w_low, channels, g_cstride, g_coffset, 3,
+                               reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int pn_feature_stencil_backward_parts(int pack, const float* in, const float* g, const float* w3, float* gin, float* gw3,
+                                                 float* gb3, int batch, int h_low, int w_low, int channels, int g_cstride,
+                                                 int g_coffset, int parts, pn_stream_t stream_) {
+  return stencil_backward_impl(pack, in, g, w3, gin, gw3, gb3, batch, h_low, w_low, channels, g_cstride, g_coffset, parts,
+                               reinterpret_cast<cudaStream_t>(stream_));
 }
 
 #ifndef PN_EMULATE

@@ -480,7 +480,7 @@ def groupnorm_elu(x, gamma, beta, eps=1e-5, x2=None):
 
 class _FeatureStencil(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w3, b3, pack):
+    def forward(ctx, x, w3, b3, pack, wgrad_side=False):
         _lib.require_f32(x, w3, b3)
         x = x.contiguous()
         B = x.shape[0]
@@ -498,6 +498,7 @@ class _FeatureStencil(torch.autograd.Function):
                    "pn_feature_stencil_forward")
         ctx.save_for_backward(x, w3c)
         ctx.pack, ctx.dims, ctx.cs = bool(pack), (B, h, w, C), cs
+        ctx.wgrad_side = bool(wgrad_side)
         return out
 
     @staticmethod
@@ -515,10 +516,29 @@ class _FeatureStencil(torch.autograd.Function):
         gin = torch.empty_like(x)
         gw3 = torch.empty(216, dtype=torch.float32, device=x.device)
         gb3 = torch.empty(8, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().pn_feature_stencil_backward(int(ctx.pack), _lib.ptr(x), _lib.ptr(g), _lib.ptr(w3), _lib.ptr(gin),
-                                                          _lib.ptr(gw3), _lib.ptr(gb3), B, h, w, C, cs, 0, _stream()),
-                   "pn_feature_stencil_backward")
-        return gin, gw3.view(8, 1, 3, 3, 3), gb3, None
+        lib = _lib.lib()
+        if ctx.wgrad_side and _state["wgrad_stream"] and g.is_cuda:
+            # The Conv3d's weight / bias gradient on the weight-gradient side stream.  The caller vouched (at forward time) that
+            # both parameters have no gradient yet: autograd's AccumulateGrad then only STORES these tensors -- no kernel reads
+            # them before the end-of-backward join (_wgrad_side_stream).
+            cur = torch.cuda.current_stream()
+            side = _wgrad_side_stream(cur)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            side.wait_event(ready)
+            _lib.check(lib.pn_feature_stencil_backward_parts(int(ctx.pack), _lib.ptr(x), _lib.ptr(g), _lib.ptr(w3), _lib.ptr(gin),
+                                                             None, None, B, h, w, C, cs, 0, 1, _stream()), "pn_feature_stencil_backward_parts")
+            with torch.cuda.stream(side):
+                _lib.check(lib.pn_feature_stencil_backward_parts(int(ctx.pack), _lib.ptr(x), _lib.ptr(g), _lib.ptr(w3), None,
+                                                                 _lib.ptr(gw3), _lib.ptr(gb3), B, h, w, C, cs, 0, 2, _stream()),
+                           "pn_feature_stencil_backward_parts")
+            for t in (x, g, gw3, gb3):
+                t.record_stream(side)
+        else:
+            _lib.check(lib.pn_feature_stencil_backward(int(ctx.pack), _lib.ptr(x), _lib.ptr(g), _lib.ptr(w3), _lib.ptr(gin),
+                                                       _lib.ptr(gw3), _lib.ptr(gb3), B, h, w, C, cs, 0, _stream()),
+                       "pn_feature_stencil_backward")
+        return gin, gw3.view(8, 1, 3, 3, 3), gb3, None, None
 
 
 class _HeadConv(torch.autograd.Function):
@@ -554,11 +574,17 @@ def head_conv(x, weight, bias):
     return _HeadConv.apply(x, weight, bias)
 
 
+def _grads_unset(*params):
+    """the parameters are leaves without a gradient so far (optimizer.zero_grad(set_to_none=True) ran): a gradient produced for
+    them is only stored by autograd, never added to -- the condition for producing it on the weight-gradient side stream"""
+    return all(p.is_leaf and p.grad is None for p in params)
+
+
 def pack_features(x, w3, b3):
     """[B,2h,2w,C] -> [B,h,w,32C]"""
-    return _FeatureStencil.apply(x, w3, b3, True)
+    return _FeatureStencil.apply(x, w3, b3, True, _grads_unset(w3, b3))
 
 
 def unpack_features(u, w3, b3):
     """[B,h,w,Cu] -> [B,2h,2w,2Cu]"""
-    return _FeatureStencil.apply(u, w3, b3, False)
+    return _FeatureStencil.apply(u, w3, b3, False, _grads_unset(w3, b3))
