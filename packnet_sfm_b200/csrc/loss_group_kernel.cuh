@@ -53,7 +53,7 @@ template <int N, bool GRAD>
 constexpr size_t group_smem_floats() {
   size_t f = (size_t)GRP * (1 + 3 + 3 * N + 3 * N);  // inv, tgt, ref, warp
   if (GRAD) f += (size_t)GPP * 12;                    // per pixel: 9 coefficients + winner id (+ 2 pad) = three float4
-  if (GRAD) f += (size_t)GRP * 2 * N;                 // sampling coordinates (ix, iy) of the warp phase, re-used by the gather
+  if (GRAD) f += (size_t)GroupGeom<true>::CW * GroupGeom<true>::CH * 2 * N;   // sampling coordinates (ix, iy) of the core pixels, kept from the warp phase for the gather
   return f + 8 * (12 * N + 1) + 16 + PN_MAX_SCALES;   // reduction scratch + per-scale smoothness sums
 }
 
@@ -189,8 +189,10 @@ __device__ __forceinline__ float block_sum_vec(float (&v)[K], float* red /* >= 8
 // smoothness constant of the mean normalisation, -L_smooth(b,s) / (mean * pixels), which needs the finished sum over the
 // sample: it is the same for every pixel of (scale, sample), so loss_grad_finish_kernel adds it when it scales the stored unit
 // gradients by the incoming dL/dloss (pn_loss_backward_finish: one small launch instead of the second 0.36 ms tile pass).
-template <int N, bool MIN, bool GRAD, bool FUSED = false>
-__global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GParams Q) {
+// MINB: CTAs per SM the register allocation aims at (gradient program: 2 = 128 registers; 3 = 80 registers with spills --
+// PN_LOSS_MINB=3 selects it for A/B, tools/loss_only.py)
+template <int N, bool MIN, bool GRAD, bool FUSED = false, int MINB = (GRAD ? 2 : 3)>
+__global__ void __launch_bounds__(GNT, MINB) loss_group_kernel(const GParams Q) {
   static_assert(GRAD || !FUSED, "FUSED is a variant of the gradient program");
   using GG = GroupGeom<GRAD>;
   constexpr int CO = GG::CO, CWc = GG::CW, CHc = GG::CH, SLOTS = GG::SLOTS;
@@ -201,8 +203,8 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
   float* s_ref = s_tgt + 3 * GRP;         // [N][3][GRP]  un-warped context (auto-mask)
   float* s_warp = s_ref + 3 * N * GRP;    // [N][3][GRP]  warped context of the current scale
   float* s_coef = s_warp + 3 * N * GRP;   // [GPP][12]: a/b/c x 3 channels, winner context as float (-1: none), 2 pad   (GRAD)
-  float* s_ixy = s_coef + (GRAD ? 12 * GPP : 0);    // [N][2][GRP] sampling coordinates of the warp phase   (GRAD)
-  float* s_red = s_ixy + (GRAD ? 2 * N * GRP : 0);  // [8*(12*N+1) + 16]
+  float* s_ixy = s_coef + (GRAD ? 12 * GPP : 0);    // [N][2][CW*CH] sampling coordinates of the core pixels (warp phase)   (GRAD)
+  float* s_red = s_ixy + (GRAD ? 2 * N * CWc * CHc : 0);  // [8*(12*N+1) + 16]
   float* s_smooth = s_red + 8 * (12 * N + 1) + 16;  // [PN_MAX_SCALES] smoothness sums of the CTA, one per scale of the group
 
   // ---- which tile -------------------------------------------------------------------------------
@@ -385,7 +387,13 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
           const Projection pr = project_point_g(Kref, s_cam + CAM_STRIDE_BASE + 12 * k, X, Y, Zc, wm1, hm1);
           const Taps t = make_taps(pr.ix, pr.iy, w, h);
           sample3_g(ctx_b, (int)plane, w, pr.ix, pr.iy, t, wv);
-          if (GRAD) { s_ixy[(2 * k) * GRP + idx] = pr.ix; s_ixy[(2 * k + 1) * GRP + idx] = pr.iy; }
+          if (GRAD) {
+            const int ci = i - 1 - CO, cj = j - 1 - CO;      // core coordinates of this region pixel
+            if (ci >= 0 && ci < CWc && cj >= 0 && cj < CHc) {
+              s_ixy[(2 * k) * (CWc * CHc) + cj * CWc + ci] = pr.ix;
+              s_ixy[(2 * k + 1) * (CWc * CHc) + cj * CWc + ci] = pr.iy;
+            }
+          }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) s_warp[(k * 3 + c) * GRP + idx] = wv[c];
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(GNT, GRAD ? 2 : 3) loss_group_kernel(const GPa
             // d warped / d (ix, iy): grid_sampler_2d backward w.r.t. the grid, in-bounds taps only; the coordinates are the
             // warp phase's own (bit-exact taps), the projection terms of the chain rule are re-evaluated with plain FMAs
             const float* Rt = s_cam + CAM_STRIDE_BASE + 12 * k;
-            const float ix = s_ixy[(2 * k) * GRP + ridx], iy = s_ixy[(2 * k + 1) * GRP + ridx];
+            const float ix = s_ixy[(2 * k) * (CWc * CHc) + qidx], iy = s_ixy[(2 * k + 1) * (CWc * CHc) + qidx];
             const Taps t = make_taps(ix, iy, w, h);
             const float x1f = t.x0f + 1.0f, y1f = t.y0f + 1.0f;
             const float* ctx_b = S.ctx[k] + (size_t)b * 3 * plane + (ptrdiff_t)t.yi * w + t.xi;

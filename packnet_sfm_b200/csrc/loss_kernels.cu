@@ -20,6 +20,7 @@
 // with one IEEE rounding per op (__fmul_rn/__fadd_rn/__fdiv_rn are never contracted into FMAs).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -868,6 +869,19 @@ static void make_groups(const Params& P, GParams& Q) {
 template <int N, bool MIN, bool GRAD, bool FUSED = false>
 static int launch_groups(const GParams& Q, int batch, cudaStream_t stream) {
   const size_t smem = group_smem_floats<N, GRAD>() * sizeof(float);
+#ifndef PN_EMULATE
+  if (GRAD && FUSED && N == 2 && MIN) {      // A/B of the register target of the training launch (PN_LOSS_MINB=3: 3 CTAs per SM)
+    static const int minb = [] { const char* e = std::getenv("PN_LOSS_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
+    if (minb == 3) {
+      auto kern3 = loss_group_kernel<N, MIN, GRAD, FUSED, 3>;
+      PN_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PN_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      PN_LAUNCH(kern3, dim3(Q.P.total_tiles, batch), GNT, smem, stream, Q);
+      count_launch();
+      return check_launch("loss_group_kernel");
+    }
+  }
+#endif
   auto kern = loss_group_kernel<N, MIN, GRAD, FUSED>;
   PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PN_LAUNCH(kern, dim3(Q.P.total_tiles, batch), GNT, smem, stream, Q);
