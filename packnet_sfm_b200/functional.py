@@ -79,35 +79,41 @@ def pack_fold_enabled(packed_pixels=None):
     return _state["pack_fold"] and (packed_pixels is None or packed_pixels >= _state["pack_fold_min_pixels"])
 
 
-_wgrad_side = {"stream": None, "pending": False}
+_wgrad_side = {}          # device index -> {"stream": side stream, "dirty": launches since the last join}
 
 
 def _wgrad_side_stream(cur):
-    """The side stream of the weight-gradient launches; the FIRST use inside a backward pass queues the join: when the pass
-    ends, the stream the backward ran on waits for the side stream, so that `loss.backward()` returns with every gradient
-    ordered before whatever the caller enqueues next (optimizer, all-reduce, a read of .grad)."""
-    if _wgrad_side["stream"] is None:
-        _wgrad_side["stream"] = torch.cuda.Stream()
-    side = _wgrad_side["stream"]
-    if not _wgrad_side["pending"]:
-        _wgrad_side["pending"] = True
+    """The side stream of the weight-gradient launches on `cur`'s device.  Every use inside a backward pass queues an
+    end-of-backward callback; the first one to run makes the stream the backward ran on wait for the side stream, so that
+    `loss.backward()` returns with every gradient ordered before whatever the caller enqueues next (optimizer, all-reduce, a
+    read of .grad).  (One callback per launch rather than one per pass: a pass that died with an exception must not leave a
+    stale "already queued" mark behind.)"""
+    st = _wgrad_side.get(cur.device.index)
+    if st is None:
+        with torch.cuda.device(cur.device):
+            st = _wgrad_side[cur.device.index] = {"stream": torch.cuda.Stream(), "dirty": False}
+    side = st["stream"]
+    st["dirty"] = True
 
-        def join():
-            _wgrad_side["pending"] = False
+    def join():
+        if st["dirty"]:
+            st["dirty"] = False
             cur.wait_stream(side)
 
-        torch.autograd.Variable._execution_engine.queue_callback(join)
+    torch.autograd.Variable._execution_engine.queue_callback(join)
     return side
 
 
 def wait_for_wgrad_stream(*tensors):
     """For the consumer of a weight gradient produced with wgrad_side=True: order the current stream behind the side stream
     and tell the allocator that `tensors` (allocated on the side stream) are used here."""
-    side = _wgrad_side["stream"]
-    if side is None or not torch.cuda.is_available():
+    if not torch.cuda.is_available():
         return
     cur = torch.cuda.current_stream()
-    cur.wait_stream(side)
+    st = _wgrad_side.get(cur.device.index)
+    if st is None:
+        return
+    cur.wait_stream(st["stream"])
     for t in tensors:
         if t is not None and t.is_cuda:
             t.record_stream(cur)
