@@ -366,7 +366,9 @@ def time_kernels(args, dev, pk):
                        "traffic_commit": (nm_conv or {}).get("commit"),
                        "tensor_pipe_active_pct_ncu": (nm_conv or {}).get("tensor_pipe_active_pct"),
                        "ms": t_c, "algorithmic_flops": flops,
-                       "mma_products_per_flop": 3 if PF.is_split(prec) else 1, "peak_source": peak_source}
+                       "mma_products_per_flop": 3 if PF.is_split(prec) else 1, "peak_source": peak_source,
+                       # the same launch counted in executed MMA work (bf16x3 issues three products per algorithmic product)
+                       "executed_mma_frac": flops / (t_c * 1e-3) / 1e12 / tf32_peak * (3 if PF.is_split(prec) else 1)}
     return res
 
 
